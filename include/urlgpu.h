@@ -1,0 +1,126 @@
+/*
+ * urlgpu.h — C ABI of the B200-native local-score engine (liburlgpu.so).
+ *
+ * This is the drop-in boundary for the local-score hot path of ninalu/urlearning-cpp.  All entry
+ * points are extern "C", take plain pointers and sizes, return 0 on success and a negative
+ * urlgpu_status on error (message via urlgpu_last_error).  There is NO CPU fallback: every scoring
+ * entry point fails with URLGPU_ERR_CUDA when no sm_100 device is usable.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference/urlearning/):
+ *
+ *   urlgpu_set_discrete      ADTree::initialize/createTree            ad_tree/ad_tree.cpp:17-31
+ *                            BayesianNetwork::getConsistentRecords    base/bayesian_network.cpp:146-169
+ *                            LogLikelihoodCalculator::getLogCache     scoring_function/log_likelihood_calculator.h:30-38
+ *                            BICScoringFunction ctor                  scoring_function/bic_scoring_function.cpp:11-18
+ *   urlgpu_set_continuous    BIC_OLS_Function ctor (standardise)      scoring_function/BIC_OLS.cpp:30-123
+ *   urlgpu_score_variable    ScoreCalculator::calculateScores         scoring_function/score_calculator.cpp:33-135
+ *                            (+ the per-set ScoringFunction::calculateScore calls it makes,
+ *                               scoring_function/scoring_function.h:19; bic_scoring_function.cpp:32-76;
+ *                               BIC_OLS.cpp:174-389; log_likelihood_calculator.cpp:22-77; ad_tree.cpp:95-164)
+ *                            and, with URLGPU_PRUNE_DOMINATED, ScoreCalculator::prune
+ *                                                                     scoring_function/score_calculator.cpp:150-197
+ *   urlgpu_score_one         ScoringFunction::calculateScore          scoring_function/scoring_function.h:19
+ *   urlgpu_contingency       ADTree::makeContab                       ad_tree/ad_tree.cpp:95-137
+ *   urlgpu_prune             ScoreCalculator::prune                   scoring_function/score_calculator.cpp:150-197
+ *   urlgpu_result_*          FloatMap iteration in scoringThread      score/score_main.cpp:187-200, base/typedefs.h:816
+ *
+ * varsets: the reference's varset is one uint64_t (base/typedefs.h:469,650).  Here a varset is
+ * `mask_words` little-endian uint64_t words (bit i of word i/64 = variable i), so p may exceed 63.
+ */
+#ifndef URLGPU_H
+#define URLGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct urlgpu_ctx urlgpu_ctx;
+typedef struct urlgpu_result urlgpu_result;
+
+typedef enum {
+    URLGPU_OK = 0,
+    URLGPU_ERR_ARG = -1,      /* bad argument / call order */
+    URLGPU_ERR_CUDA = -2,     /* CUDA runtime error or no usable device */
+    URLGPU_ERR_LIMIT = -3,    /* problem exceeds an engine limit (candidate count, table size, memory) */
+    URLGPU_ERR_INTERNAL = -4
+} urlgpu_status;
+
+typedef enum { URLGPU_BIC = 0, URLGPU_CBIC = 1 } urlgpu_score_t;
+
+/* filter_flags of urlgpu_score_variable (bit set) */
+enum {
+    URLGPU_KEEP_ALL = 0,          /* store rule of the shipped `score` only (score_calculator.cpp:59,111; BIC_OLS.cpp:213-249) */
+    URLGPU_PRUNE_DOMINATED = 2,   /* additionally drop S if a stored subset scores at least as well (score_calculator.cpp:150-197) */
+    URLGPU_CBIC_NO_ACCEPT = 4     /* cBIC: skip the in-line acceptance test, store every set's -the_score (diagnostics) */
+};
+
+/* One context = one device + one stream.  Thread-compatible: use one context per host thread. */
+int urlgpu_create(urlgpu_ctx **out, int device_id);
+int urlgpu_destroy(urlgpu_ctx *ctx);
+const char *urlgpu_last_error(urlgpu_ctx *ctx); /* ctx may be NULL: error of the failed urlgpu_create */
+int urlgpu_device_count(void);
+/* use a caller-owned stream (e.g. torch's current stream) instead of the context's own; NULL restores it */
+int urlgpu_set_stream(urlgpu_ctx *ctx, void *cuda_stream);
+int urlgpu_synchronize(urlgpu_ctx *ctx);
+
+/* Data is COPIED to the device; the caller keeps ownership.  Column-major: value of variable i in record r at
+ * [i*n + r].  codes are value indices < cardinality[i] (first-appearance order, base/variable.h:43-48). */
+int urlgpu_set_discrete(urlgpu_ctx *ctx, const uint8_t *codes_colmajor, int64_t n, int p, const int32_t *cardinality);
+/* same, but codes_colmajor is a DEVICE pointer on ctx's device (multi-GPU: data arrives by NCCL broadcast) */
+int urlgpu_set_discrete_device(urlgpu_ctx *ctx, const uint8_t *d_codes_colmajor, int64_t n, int p, const int32_t *cardinality);
+/* raw continuous data; the engine centres, scales by the sample std (N-1) and forms G = Z^T Z in FP64 */
+int urlgpu_set_continuous(urlgpu_ctx *ctx, const double *x_colmajor, int64_t n, int p);
+int urlgpu_set_continuous_device(urlgpu_ctx *ctx, const double *d_x_colmajor, int64_t n, int p);
+/* The Gram G = Z^T Z (p*p, symmetric) can be exported (oracle-side recomputation, multi-GPU broadcast) and
+ * installed without the raw data (a rank that only scores needs G and n, not the rows). */
+int urlgpu_get_gram(urlgpu_ctx *ctx, double *gram_rowmajor /* p*p */);
+int urlgpu_set_gram(urlgpu_ctx *ctx, const double *gram_rowmajor, int64_t n_total, int p);
+
+/* Score the whole candidate family of `variable`: every subset of neighbors\{variable} with 0..max_parents
+ * elements (score_calculator.cpp:54-135).  `neighbors` is the 2-hop mask the reference's scoringThread builds
+ * (score_main.cpp:145-155); max_parents is the EFFECTIVE limit (score_main.cpp:296-304).  Results stay on
+ * the device until fetched. */
+int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents,
+                          int score_type, double lambda, unsigned filter_flags, urlgpu_result **out);
+int urlgpu_result_count(urlgpu_result *res, uint64_t *n_stored);   /* stored entries (after filters) */
+int urlgpu_result_scored(urlgpu_result *res, uint64_t *n_scored);  /* candidate sets scored */
+/* canonical order: (|S| ascending, mask ascending as an integer).  masks: n*mask_words words. */
+int urlgpu_result_fetch(urlgpu_result *res, uint64_t offset, uint64_t n, uint64_t *masks, float *scores);
+int urlgpu_result_free(urlgpu_result *res);
+
+/* Single parent set, same value ScoringFunction::calculateScore returns (BIC: the score; cBIC: -the_score).
+ * value64 (optional): BIC: exact log-likelihood before the float rounding; cBIC: the_score in FP64. */
+int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *parents, int mask_words, int score_type,
+                     double lambda, float *score, double *value64);
+/* Dense contingency counts of (variable, parents): counts[x_v + r_v*paIdx], paIdx mixed radix over the parents in
+ * ascending variable index, lowest index least significant (log_likelihood_calculator.cpp:61-73). */
+int urlgpu_contingency(urlgpu_ctx *ctx, int variable, const uint64_t *parents, int mask_words, int32_t *counts,
+                       int64_t n_cells);
+/* Standalone prune of a caller-supplied cache (masks over <=30 distinct variables): keep[i]=0 iff some other
+ * entry j with masks[j] subset of masks[i] has scores[j] >= scores[i] (ties: the subset wins). */
+int urlgpu_prune(urlgpu_ctx *ctx, const uint64_t *masks, const float *scores, uint64_t n, int mask_words, uint8_t *keep);
+
+/* Measurement hooks: device time (CUDA events on the context's stream) and launch counts per kernel family,
+ * accumulated since the last reset. */
+typedef struct urlgpu_stats {
+    uint64_t launches_total;
+    uint64_t launches_count;   /* K1 row-count kernels */
+    uint64_t launches_cube;    /* K1 marginalise+score kernels */
+    uint64_t launches_cbic;    /* K3 */
+    uint64_t launches_accept;  /* K4 */
+    uint64_t launches_prune;   /* K5 */
+    uint64_t launches_other;
+    double ms_count, ms_cube, ms_cbic, ms_accept, ms_prune, ms_gram;
+    uint64_t sets_scored;
+    double algorithmic_bytes;  /* BIC: sum over scored sets of n*(|S|+1) */
+    double algorithmic_flops;  /* cBIC: sum over scored sets of k^3/3+2k^2+2k */
+} urlgpu_stats;
+int urlgpu_stats_reset(urlgpu_ctx *ctx);
+int urlgpu_stats_get(urlgpu_ctx *ctx, urlgpu_stats *out);
+/* enable (1) / disable (0) per-kernel CUDA-event timing (adds a stream sync per measured region) */
+int urlgpu_stats_enable_timing(urlgpu_ctx *ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,125 @@
+"""GPU parity: discrete BIC through the C ABI vs the CPU oracle (bit-exact counts, scores and stored lists)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _check_variable(pkg, orc, eng, codes, card, edges, v, K, flags=0):
+    p = codes.shape[0]
+    nb = pkg.two_hop_neighbors(edges, p, v)
+    res = eng.score_variable(v, nb, K, pkg.BIC, flags=flags)
+    masks, scores = res.fetch()
+    om = orc.enumerate_sets(v, nb, p, K)
+    osc = orc.bic_score_many(codes, card, v, om)
+    stored = np.array([(s < 1) if m == 0 else (s < 0) for m, s in zip(om, osc)])
+    om, osc = om[stored], osc[stored]
+    if flags & pkg.PRUNE_DOMINATED:
+        keep = orc.prune(om, osc, K)
+        om, osc = om[keep], osc[keep]
+    order = orc.canonical_order(om)
+    assert res.scored() == len(stored)
+    assert [int(m[0]) for m in masks] == [int(om[i]) for i in order]
+    assert np.array_equal(scores.view(np.uint32), osc[order].view(np.uint32))
+    res.free()
+    return len(order)
+
+
+def test_hepatitis_all_variables(pkg, orc, engine, data_dir):
+    t = orc.Table(os.path.join(data_dir, "hepatitis.clean.csv"), has_header=True)
+    codes = t.codes()
+    engine.set_discrete(codes, t.card)
+    K = pkg.effective_max_parents(0, t.p, t.n, True)
+    assert K == 3
+    total = sum(_check_variable(pkg, orc, engine, codes, t.card, None, v, K) for v in range(t.p))
+    assert total == 23200
+
+
+def test_contingency_counts_ragged_rows(pkg, orc, engine):
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=12, n=10007, seed=11, arities=(2, 3, 4))
+    engine.set_discrete(codes, card)
+    rng = np.random.default_rng(0)
+    for _ in range(25):
+        v = int(rng.integers(12))
+        k = int(rng.integers(0, 8))
+        others = [i for i in range(12) if i != v]
+        parents = sum(1 << int(i) for i in rng.choice(others, size=k, replace=False))
+        ref = orc.bic_counts(codes, card, v, parents)
+        got = engine.contingency(v, parents, len(ref))
+        assert got.sum() == 10007
+        assert np.array_equal(got, ref)
+        s, ll = engine.score_one(v, parents, pkg.BIC)
+        rs, rll = orc.bic_score(codes, card, v, parents)
+        assert s.view(np.uint32) == rs.view(np.uint32) and ll == rll
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 4097])
+def test_tiny_and_edge_row_counts(pkg, orc, engine, n):
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=6, n=max(n, 2), seed=n, arities=(2, 3))
+    codes = codes[:, :n].copy()
+    if n < 3:  # N=1: log(1)=0 -> the reference's BIC parent cap divides by zero; use N=2 instead
+        codes = np.array([[0, 1], [0, 0], [1, 0], [0, 1], [0, 0], [1, 1]], dtype=np.uint8)
+        card = np.array([2, 1, 2, 2, 1, 2], dtype=np.int32)
+    else:
+        card = np.array([max(1, int(c.max()) + 1) for c in codes], dtype=np.int32)
+    engine.set_discrete(codes, card)
+    for v in range(6):
+        _check_variable(pkg, orc, engine, codes, card, None, v, 5)
+
+
+def test_all_tiers_arity4(pkg, orc, engine):
+    """tables from 4 cells to 4^10 = 1M cells: small shared tier, one-CTA-per-SM shared tier and the global tier"""
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=11, n=20011, seed=5, arities=(4,), window=10, max_indegree=3)
+    engine.set_discrete(codes, card)
+    for v in (0, 5, 10):
+        _check_variable(pkg, orc, engine, codes, card, None, v, 9)
+
+
+def test_skeleton_two_hop_and_prune(pkg, orc, engine):
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=24, n=30000, seed=7, window=3, max_indegree=2)
+    engine.set_discrete(codes, card)
+    K = pkg.effective_max_parents(12, 24, 30000, True)
+    for v in (0, 3, 11, 23):
+        _check_variable(pkg, orc, engine, codes, card, edges, v, K)
+        _check_variable(pkg, orc, engine, codes, card, edges, v, K, flags=pkg.PRUNE_DOMINATED)
+
+
+def test_row_permutation_invariance_and_counts_sum(pkg, orc, engine):
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=10, n=50000, seed=9)
+    perm = np.random.default_rng(1).permutation(50000)
+    engine.set_discrete(codes, card)
+    a = engine.score_variable(4, (1 << 10) - 1, 6, pkg.BIC).fetch()
+    engine.set_discrete(codes[:, perm], card)
+    b = engine.score_variable(4, (1 << 10) - 1, 6, pkg.BIC).fetch()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_score_binary_matches_oracle_pss(pkg, orc, data_dir, tmp_path):
+    """the product `score` binary vs the oracle's restatement of score_main.cpp: identical bytes"""
+    exe = os.path.join(ROOT, "urlearning-cpp_b200", "score")
+    inp = os.path.join(data_dir, "hepatitis.clean.csv")
+    out = str(tmp_path / "gpu.pss")
+    ref = str(tmp_path / "ref.pss")
+    subprocess.check_call([exe, inp, out, "-s", "-f", "BIC", "--quiet"], stdout=subprocess.DEVNULL)
+    orc.score_file(inp, ref, "BIC", has_header=True)
+    gb, rb = open(out, "rb").read(), open(ref, "rb").read()
+    assert gb == rb
+    meta, variables = orc.parse_pss(out)
+    assert meta["num_records"] == "80" and meta["parent_limit"] == "3" and len(variables) == 20
+    # with pruning and 2 worker threads
+    subprocess.check_call([exe, inp, out, "-s", "--prune", "-t", "2", "--quiet"], stdout=subprocess.DEVNULL)
+    orc.score_file(inp, ref, "BIC", has_header=True, prune=True)
+    assert open(out, "rb").read() == open(ref, "rb").read()
+
+
+def test_errors_are_loud(pkg, engine):
+    with pytest.raises(pkg.UrlGpuError):
+        engine.score_variable(99, 1, 1, pkg.BIC)
+    codes = np.zeros((40, 100), dtype=np.uint8)
+    engine.set_discrete(codes, [1] * 40)
+    with pytest.raises(pkg.UrlGpuError, match="candidate"):
+        engine.score_variable(0, (1 << 40) - 1, 2, pkg.BIC)

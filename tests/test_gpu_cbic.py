@@ -1,0 +1,130 @@
+"""GPU parity: continuous cBIC (Gram + Schur sweeps + acceptance DP + prune) vs the CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-9  # BASELINE.json north_star: scores within 1e-9 relative (checked on the FP64 value before the float32 rounding)
+
+
+def ulp_diff(a, b):
+    a = np.asarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
+    b = np.asarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
+    a = np.where(a < 0, -(a & 0x7FFFFFFF), a)
+    b = np.where(b < 0, -(b & 0x7FFFFFFF), b)
+    return np.abs(a - b)
+
+
+def test_gram_matches_extended_precision(pkg, orc, engine):
+    x, _ = pkg.datagen.linear_gaussian_sem(p=13, n=20001, seed=2)
+    x[3] += 1e3  # a large mean must not hurt (two-pass centring)
+    engine.set_continuous(x)
+    g = engine.gram()
+    ref = orc.gram(orc.standardise(x))
+    assert np.allclose(np.diag(g), 20000.0, rtol=1e-12)
+    assert np.max(np.abs(g - ref)) <= 1e-12 * 20001
+    assert np.array_equal(g, g.T)
+
+
+@pytest.mark.parametrize("fig,fn", [("Figure_1", "raw_data_8000.csv"), ("Figure_2", "raw_data_5000.csv")])
+def test_figures_full_family(pkg, orc, engine, data_dir, fig, fn):
+    t = orc.Table(os.path.join(data_dir, fig, fn))
+    x = t.values()
+    assert x.shape == (4, 5000)
+    engine.set_continuous(x)
+    z = orc.standardise(x)
+    for v in range(4):
+        nb = pkg.two_hop_neighbors(None, 4, v)
+        om = orc.enumerate_sets(v, nb, 4, 3)
+        ts = np.array([orc.cbic_residual(z, v, int(m), 2.0) for m in om])
+        for m, r in zip(om, ts):
+            s, ts64 = engine.score_one(v, int(m), pkg.CBIC, 2.0)
+            assert abs(ts64 - r) <= TOL * max(1.0, abs(r))
+            assert ulp_diff(s, np.float32(-np.float32(r))) <= 1
+        stored, val = orc.cbic_accept(v, 4, om, ts.astype(np.float32))
+        res = engine.score_variable(v, nb, 3, pkg.CBIC, lam=2.0)
+        masks, scores = res.fetch()
+        order = [i for i in orc.canonical_order(om) if stored[i]]
+        assert [int(m[0]) for m in masks] == [int(om[i]) for i in order]
+        assert np.all(ulp_diff(scores, val[order]) <= 1)
+
+
+@pytest.mark.parametrize("p,n,K", [(9, 2000, 8), (13, 3000, 12), (14, 1500, 4), (17, 4000, 3)])
+def test_synthetic_exhaustive_and_limited(pkg, orc, engine, p, n, K):
+    x, _ = pkg.datagen.linear_gaussian_sem(p=p, n=n, seed=p)
+    engine.set_continuous(x)
+    g = engine.gram()
+    z = orc.standardise(x)
+    rng = np.random.default_rng(p)
+    for v in (0, p // 2, p - 1):
+        nb = (1 << p) - 1
+        om = orc.enumerate_sets(v, nb, p, K)
+        # every set's score without the acceptance filter
+        res = engine.score_variable(v, nb, K, pkg.CBIC, lam=2.0, flags=pkg.CBIC_NO_ACCEPT)
+        masks, neg_ts = res.fetch()
+        assert res.scored() == len(om) and len(masks) == len(om)
+        order = orc.canonical_order(om)
+        assert [int(m[0]) for m in masks] == [int(om[i]) for i in order]
+        gpu_ts = np.zeros(len(om), dtype=np.float32)
+        gpu_ts[order] = -neg_ts
+        # (i) against the Cholesky form on the engine's own Gram and (ii) against the reference's residual form
+        sample = rng.choice(len(om), size=min(len(om), 300), replace=False)
+        for i in sample:
+            r1 = orc.cbic_gram(g, n, v, int(om[i]), 2.0)
+            r2 = orc.cbic_residual(z, v, int(om[i]), 2.0)
+            s, ts64 = engine.score_one(v, int(om[i]), pkg.CBIC, 2.0)
+            assert abs(ts64 - r1) <= TOL * max(1.0, abs(r1))
+            assert abs(ts64 - r2) <= TOL * max(1.0, abs(r2))
+            assert ulp_diff(gpu_ts[i], np.float32(r2)) <= 1
+            assert ulp_diff(-s, gpu_ts[i]) == 0
+        # acceptance DP and prune: decisions bit-exact given the engine's float32 the_scores
+        stored, val = orc.cbic_accept(v, p, om, gpu_ts)
+        r = engine.score_variable(v, nb, K, pkg.CBIC, lam=2.0)
+        m2, s2 = r.fetch()
+        keep_order = [i for i in order if stored[i]]
+        assert [int(m[0]) for m in m2] == [int(om[i]) for i in keep_order]
+        assert np.array_equal(s2.view(np.uint32), val[keep_order].view(np.uint32))
+        km, ks = om[stored], val[stored]
+        keep = orc.prune(km, ks, K)
+        r3 = engine.score_variable(v, nb, K, pkg.CBIC, lam=2.0, flags=pkg.PRUNE_DOMINATED)
+        m3, s3 = r3.fetch()
+        po = [i for i in orc.canonical_order(km) if keep[i]]
+        assert [int(m[0]) for m in m3] == [int(km[i]) for i in po]
+        assert np.array_equal(s3.view(np.uint32), ks[po].view(np.uint32))
+        # RSS is monotone under set inclusion: the best score never gets worse... (property) prune is idempotent
+        again = engine.prune(m3, s3)
+        assert again.all()
+
+
+def test_standalone_prune_matches_literal(pkg, orc, engine):
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        c = int(rng.integers(3, 9))
+        m = int(rng.integers(1, 1 << c))
+        masks = rng.choice(1 << c, size=m, replace=False).astype(np.uint64)
+        masks = (masks << np.uint64(3))  # not starting at bit 0
+        scores = (-rng.integers(1, 12, size=m) * 7.25).astype(np.float32)  # many exact ties, |score| >= 4
+        keep = engine.prune(masks, scores)
+        ref = orc.prune(masks, scores)
+        assert np.array_equal(keep, ref)
+
+
+def test_score_binary_cbic_matches_oracle(pkg, orc, data_dir, tmp_path):
+    exe = os.path.join(ROOT, "urlearning-cpp_b200", "score")
+    skel = os.path.join(data_dir, "skeleton4_ones.csv")
+    for fig, fn in (("Figure_1", "raw_data_8000.csv"), ("Figure_2", "raw_data_5000.csv")):
+        inp = os.path.join(data_dir, fig, fn)
+        out, ref = str(tmp_path / "gpu.pss"), str(tmp_path / "ref.pss")
+        subprocess.check_call([exe, inp, out, "-k", skel, "-f", "cBIC", "--lambda=2", "--quiet"], stdout=subprocess.DEVNULL)
+        orc.score_file(inp, ref, "cBIC", skeleton=skel, lam=2.0)
+        mg, vg = orc.parse_pss(out)
+        mr, vr = orc.parse_pss(ref)
+        assert mg == mr
+        for (ng, ag, eg), (nr, ar, er) in zip(vg, vr):
+            assert (ng, ag) == (nr, ar)
+            assert [e[1] for e in eg] == [e[1] for e in er]
+            for a, b in zip(eg, er):
+                assert abs(float(a[0]) - float(b[0])) <= 1e-6 * max(1.0, abs(float(b[0])))

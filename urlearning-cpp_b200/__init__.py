@@ -1,0 +1,301 @@
+"""urlearning-cpp_b200 — B200-native local-score engine for URLearning (Python binding of liburlgpu.so).
+
+This module is a thin ctypes binding of the C ABI declared in ``include/urlgpu.h``; all computation happens in
+the hand-written sm_100a kernels under ``csrc/``.  There is no CPU fallback: importing works anywhere (so the
+symbol table can be checked without a GPU) but creating an :class:`Engine` raises :class:`UrlGpuError` when no
+Blackwell device is usable or the shared library has not been built.
+
+Host-side helpers mirror the reference's driver logic (paths relative to /root/reference/urlearning/):
+
+* :func:`two_hop_neighbors`      score/score_main.cpp:145-155
+* :func:`effective_max_parents`  score/score_main.cpp:296-304
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Iterable, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liburlgpu.so")
+
+BIC, CBIC = 0, 1
+KEEP_ALL, PRUNE_DOMINATED, CBIC_NO_ACCEPT = 0, 2, 4
+
+# every symbol include/urlgpu.h declares (tests check the built library exports all of them)
+ABI_SYMBOLS = [
+    "urlgpu_create", "urlgpu_destroy", "urlgpu_last_error", "urlgpu_device_count", "urlgpu_set_stream",
+    "urlgpu_synchronize", "urlgpu_set_discrete", "urlgpu_set_discrete_device", "urlgpu_set_continuous",
+    "urlgpu_set_continuous_device", "urlgpu_get_gram", "urlgpu_set_gram", "urlgpu_score_variable",
+    "urlgpu_result_count", "urlgpu_result_scored", "urlgpu_result_fetch", "urlgpu_result_free",
+    "urlgpu_score_one", "urlgpu_contingency", "urlgpu_prune", "urlgpu_stats_reset", "urlgpu_stats_get",
+    "urlgpu_stats_enable_timing",
+]
+
+
+class UrlGpuError(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("launches_total", C.c_uint64), ("launches_count", C.c_uint64), ("launches_cube", C.c_uint64),
+        ("launches_cbic", C.c_uint64), ("launches_accept", C.c_uint64), ("launches_prune", C.c_uint64),
+        ("launches_other", C.c_uint64),
+        ("ms_count", C.c_double), ("ms_cube", C.c_double), ("ms_cbic", C.c_double), ("ms_accept", C.c_double),
+        ("ms_prune", C.c_double), ("ms_gram", C.c_double),
+        ("sets_scored", C.c_uint64), ("algorithmic_bytes", C.c_double), ("algorithmic_flops", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library():
+    """Load liburlgpu.so (built in-tree by ``__graft_entry__.build()`` / ``make``).  Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UrlGpuError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+    P = C.POINTER
+    lib.urlgpu_create.argtypes = [P(vp), i32]
+    lib.urlgpu_destroy.argtypes = [vp]
+    lib.urlgpu_last_error.argtypes = [vp]
+    lib.urlgpu_last_error.restype = C.c_char_p
+    lib.urlgpu_device_count.argtypes = []
+    lib.urlgpu_set_stream.argtypes = [vp, vp]
+    lib.urlgpu_synchronize.argtypes = [vp]
+    lib.urlgpu_set_discrete.argtypes = [vp, vp, i64, i32, vp]
+    lib.urlgpu_set_discrete_device.argtypes = [vp, vp, i64, i32, vp]
+    lib.urlgpu_set_continuous.argtypes = [vp, vp, i64, i32]
+    lib.urlgpu_set_continuous_device.argtypes = [vp, vp, i64, i32]
+    lib.urlgpu_get_gram.argtypes = [vp, vp]
+    lib.urlgpu_set_gram.argtypes = [vp, vp, i64, i32]
+    lib.urlgpu_score_variable.argtypes = [vp, i32, vp, i32, i32, i32, C.c_double, C.c_uint, P(vp)]
+    lib.urlgpu_result_count.argtypes = [vp, P(u64)]
+    lib.urlgpu_result_scored.argtypes = [vp, P(u64)]
+    lib.urlgpu_result_fetch.argtypes = [vp, u64, u64, vp, vp]
+    lib.urlgpu_result_free.argtypes = [vp]
+    lib.urlgpu_score_one.argtypes = [vp, i32, vp, i32, i32, C.c_double, P(C.c_float), P(C.c_double)]
+    lib.urlgpu_contingency.argtypes = [vp, i32, vp, i32, vp, i64]
+    lib.urlgpu_prune.argtypes = [vp, vp, vp, u64, i32, vp]
+    lib.urlgpu_stats_reset.argtypes = [vp]
+    lib.urlgpu_stats_get.argtypes = [vp, P(Stats)]
+    lib.urlgpu_stats_enable_timing.argtypes = [vp, i32]
+    for name in ABI_SYMBOLS:
+        if name != "urlgpu_last_error":
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+# ------------------------------------------------------------------------------------------ host-side mirrors
+
+def mask_words_for(p: int) -> int:
+    return max(1, (p + 63) // 64)
+
+
+def mask_to_words(mask: int, words: int) -> np.ndarray:
+    return np.array([(mask >> (64 * w)) & 0xFFFFFFFFFFFFFFFF for w in range(words)], dtype=np.uint64)
+
+
+def words_to_mask(row: Sequence[int]) -> int:
+    m = 0
+    for w, x in enumerate(row):
+        m |= int(x) << (64 * w)
+    return m
+
+
+def two_hop_neighbors(edges: Sequence[int] | None, p: int, v: int) -> int:
+    """score_main.cpp:145-155: N(v) | U_{j in N(v), j != v} N(j); ``edges=None`` = no skeleton (all ones)."""
+    allbits = (1 << p) - 1
+    nb = (lambda i: allbits) if edges is None else (lambda i: int(edges[i]))
+    orig = nb(v)
+    out = orig
+    for j in range(p):
+        if (orig >> j) & 1 and j != v:
+            out |= nb(j)
+    return out
+
+
+def effective_max_parents(max_parents: int, p: int, n_records: int, is_bic: bool) -> int:
+    """score_main.cpp:296-304 (the BIC cap uses integer 2*N and natural logs, truncated)."""
+    if max_parents > p or max_parents < 1:
+        max_parents = p - 1
+    if is_bic:
+        cap = int(math.log((2 * n_records) / math.log(n_records)))
+        max_parents = min(max_parents, cap)
+    return max_parents
+
+
+# ------------------------------------------------------------------------------------------ engine
+
+class Result:
+    """One variable's score cache on the device (the reference's per-variable FloatMap)."""
+
+    def __init__(self, eng: "Engine", handle, words: int):
+        self._eng, self._h, self.words = eng, handle, words
+
+    def count(self) -> int:
+        n = C.c_uint64()
+        self._eng._check(self._eng.lib.urlgpu_result_count(self._h, C.byref(n)))
+        return n.value
+
+    def scored(self) -> int:
+        n = C.c_uint64()
+        self._eng._check(self._eng.lib.urlgpu_result_scored(self._h, C.byref(n)))
+        return n.value
+
+    def fetch(self):
+        """-> (masks uint64[n, words], scores float32[n]) in canonical (|S|, mask) order."""
+        n = self.count()
+        masks = np.zeros((n, self.words), dtype=np.uint64)
+        scores = np.zeros(n, dtype=np.float32)
+        self._eng._check(self._eng.lib.urlgpu_result_fetch(self._h, 0, n, masks.ctypes.data, scores.ctypes.data))
+        return masks, scores
+
+    def free(self):
+        if self._h is not None:
+            self._eng.lib.urlgpu_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One urlgpu context = one B200 + one stream (ScoringFunction + ScoreCalculator of the reference)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.urlgpu_create(C.byref(h), device)
+        if rc != 0:
+            raise UrlGpuError(self.lib.urlgpu_last_error(None).decode())
+        self._h = h
+        self.p = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.urlgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise UrlGpuError(self.lib.urlgpu_last_error(self._h).decode())
+
+    # data --------------------------------------------------------------------------------
+    def set_discrete(self, codes: np.ndarray, card: Iterable[int]):
+        """codes: uint8 [p, n] (row i = all records of variable i, i.e. column-major records)."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        card = np.ascontiguousarray(list(card), dtype=np.int32)
+        p, n = codes.shape
+        self._check(self.lib.urlgpu_set_discrete(self._h, codes.ctypes.data, n, p, card.ctypes.data))
+        self.p = p
+
+    def set_discrete_device(self, dev_ptr: int, n: int, p: int, card: Iterable[int]):
+        card = np.ascontiguousarray(list(card), dtype=np.int32)
+        self._check(self.lib.urlgpu_set_discrete_device(self._h, C.c_void_p(dev_ptr), n, p, card.ctypes.data))
+        self.p = p
+
+    def set_continuous(self, x: np.ndarray):
+        """x: float64 [p, n]."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        p, n = x.shape
+        self._check(self.lib.urlgpu_set_continuous(self._h, x.ctypes.data, n, p))
+        self.p = p
+
+    def set_continuous_device(self, dev_ptr: int, n: int, p: int):
+        self._check(self.lib.urlgpu_set_continuous_device(self._h, C.c_void_p(dev_ptr), n, p))
+        self.p = p
+
+    def gram(self) -> np.ndarray:
+        g = np.zeros((self.p, self.p), dtype=np.float64)
+        self._check(self.lib.urlgpu_get_gram(self._h, g.ctypes.data))
+        return g
+
+    def set_gram(self, g: np.ndarray, n_total: int):
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        self._check(self.lib.urlgpu_set_gram(self._h, g.ctypes.data, n_total, g.shape[0]))
+        self.p = g.shape[0]
+
+    def set_stream(self, stream_ptr: int | None):
+        self._check(self.lib.urlgpu_set_stream(self._h, C.c_void_p(stream_ptr or 0)))
+
+    def synchronize(self):
+        self._check(self.lib.urlgpu_synchronize(self._h))
+
+    # scoring -----------------------------------------------------------------------------
+    def score_variable(self, variable: int, neighbors: int, max_parents: int, score_type: int = BIC,
+                       lam: float = 0.0, flags: int = KEEP_ALL) -> Result:
+        words = mask_words_for(self.p)
+        nb = mask_to_words(neighbors, words)
+        h = C.c_void_p()
+        self._check(self.lib.urlgpu_score_variable(self._h, variable, nb.ctypes.data, words, max_parents, score_type,
+                                                   float(lam), flags, C.byref(h)))
+        return Result(self, h, words)
+
+    def score_one(self, variable: int, parents: int, score_type: int = BIC, lam: float = 0.0):
+        """ScoringFunction::calculateScore -> (float32 score, float64 pre-rounding value)."""
+        words = mask_words_for(self.p)
+        pm = mask_to_words(parents, words)
+        s, v = C.c_float(), C.c_double()
+        self._check(self.lib.urlgpu_score_one(self._h, variable, pm.ctypes.data, words, score_type, float(lam),
+                                              C.byref(s), C.byref(v)))
+        return np.float32(s.value), v.value
+
+    def contingency(self, variable: int, parents: int, n_cells: int) -> np.ndarray:
+        words = mask_words_for(self.p)
+        pm = mask_to_words(parents, words)
+        out = np.zeros(n_cells, dtype=np.int32)
+        self._check(self.lib.urlgpu_contingency(self._h, variable, pm.ctypes.data, words, out.ctypes.data, n_cells))
+        return out
+
+    def prune(self, masks: np.ndarray, scores: np.ndarray) -> np.ndarray:
+        masks = np.ascontiguousarray(masks, dtype=np.uint64)
+        if masks.ndim == 1:
+            masks = masks.reshape(-1, 1)
+        scores = np.ascontiguousarray(scores, dtype=np.float32)
+        keep = np.zeros(len(scores), dtype=np.uint8)
+        self._check(self.lib.urlgpu_prune(self._h, masks.ctypes.data, scores.ctypes.data, len(scores), masks.shape[1],
+                                          keep.ctypes.data))
+        return keep.astype(bool)
+
+    # measurement -------------------------------------------------------------------------
+    def stats(self) -> dict:
+        st = Stats()
+        self._check(self.lib.urlgpu_stats_get(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def reset_stats(self):
+        self._check(self.lib.urlgpu_stats_reset(self._h))
+
+    def enable_timing(self, on: bool = True):
+        self._check(self.lib.urlgpu_stats_enable_timing(self._h, int(on)))
+
+
+from . import datagen  # noqa: E402
+
+
+def device_count() -> int:
+    return load_library().urlgpu_device_count()

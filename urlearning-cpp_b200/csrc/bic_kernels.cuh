@@ -1,0 +1,246 @@
+// bic_kernels.cuh — K1: discrete BIC counting + log-likelihood (sm_100a).
+//
+// Replaces ADTree::makeContab (ad_tree/ad_tree.cpp:95-164), LogLikelihoodCalculator::calculate
+// (scoring_function/log_likelihood_calculator.cpp:22-77) and BICScoringFunction::calculateScore
+// (scoring_function/bic_scoring_function.cpp:32-76) of the reference.
+//
+// Data layout: codes column-major uint8 [p][n_stride], n_stride = n rounded up to 16 so every column starts
+// 16-byte aligned and rows are read with 128-bit loads.  A contingency table of (v, S) is a dense int32 array
+// indexed  x_v + r_v * paIdx,  paIdx = mixed radix over the parents in ascending variable index, lowest
+// index least significant (log_likelihood_calculator.cpp:61-73).
+//
+// Arithmetic contract: qlog[c] = (int64) ilogi[c] * 2^23 where ilogi[c] = (float)(c*ln c) is the
+// reference's own float table (log_likelihood_calculator.h:30-38) built on the host with glibc log.  The
+// log-likelihood  sum_cells ilogi[n_ijk] - sum_j ilogi[n_ij]  is accumulated as an exact int64 (every float
+// table entry is a multiple of 2^-23), so the result is independent of summation order, thread count and
+// GPU count.  It is rounded ONCE to float32, then  score -= tVal * base  in float32 without contraction
+// (bic_scoring_function.cpp:73).
+#pragma once
+#include "common.cuh"
+
+namespace urlgpu {
+
+struct BicData {
+    const uint8_t *codes;   // [p][n_stride]
+    int64_t n, n_stride;
+    const long long *qlog;  // [n+2]
+    float base;             // (float)(ln(N)/2)
+};
+
+// Per-variable candidate description (kernel argument, by value).
+struct CandInfo {
+    int c;                          // number of candidates (v excluded)
+    int v;                          // the child variable
+    int rv;                         // its cardinality
+    int max_parents;
+    int var[kMaxDenseCand];         // candidate -> variable index (ascending)
+    int card[kMaxDenseCand];
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// K6a: classify every compact mask with popcount <= max_parents by table size and append it to a tier list.
+// tier 0: cells <= t0 (small shared-memory tables), tier 1: cells <= t1 (one CTA per SM), tier 2: global.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void bic_classify_kernel(CandInfo ci, uint64_t n_masks, uint32_t t0, uint32_t t1, uint64_t cell_limit,
+                                    uint32_t *list0, uint32_t *list1, uint32_t *list2,
+                                    unsigned long long *counters /*[4]: n0,n1,n2,too_large*/) {
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int tier = -1;
+    if (m < n_masks && __popcll(m) <= ci.max_parents) {
+        uint64_t cells = ci.rv;
+        for (int i = 0; i < ci.c; i++)
+            if ((m >> i) & 1) { cells *= (uint64_t)ci.card[i]; if (cells > cell_limit) cells = cell_limit + 1; }
+        tier = cells <= t0 ? 0 : cells <= t1 ? 1 : cells <= cell_limit ? 2 : 3;
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const unsigned b = __ballot_sync(0xffffffffu, tier == t);
+        if (b == 0) continue;
+        unsigned long long basepos = 0;
+        const int leader = __ffs(b) - 1;
+        if (lane == leader) basepos = atomicAdd(&counters[t], (unsigned long long)__popc(b));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (tier == t && t < 3) {
+            const unsigned long long pos = basepos + __popc(b & ((1u << lane) - 1));
+            (t == 0 ? list0 : t == 1 ? list1 : list2)[pos] = (uint32_t)m;
+        }
+    }
+}
+
+// column list of one set, built by one thread into shared memory
+struct SetCols {
+    const uint8_t *col[kMaxCols];
+    uint32_t stride[kMaxCols];
+    int ncols;
+    uint32_t cells;
+    float tval;
+};
+
+__device__ __forceinline__ void build_cols(const BicData &d, const CandInfo &ci, uint32_t mask, SetCols &sc) {
+    // child first with stride 1, then the parents in ascending variable index
+    sc.col[0] = d.codes + (int64_t)ci.v * d.n_stride;
+    sc.stride[0] = 1;
+    uint32_t base = (uint32_t)ci.rv;
+    int nc = 1;
+    float pen = (float)(ci.rv - 1); // bic_scoring_function.cpp:21
+    for (int i = 0; i < ci.c; i++)
+        if ((mask >> i) & 1) {
+            sc.col[nc] = d.codes + (int64_t)ci.var[i] * d.n_stride;
+            sc.stride[nc] = base;
+            base *= (uint32_t)ci.card[i];
+            pen = __fmul_rn(pen, (float)ci.card[i]); // :25, float product, ascending variable order
+            nc++;
+        }
+    sc.ncols = nc;
+    sc.cells = base;
+    sc.tval = pen;
+}
+
+// accumulate the mixed-radix index of 16 consecutive rows
+__device__ __forceinline__ void accum16(uint4 w, uint32_t s, uint32_t (&idx)[16]) {
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        idx[4 * q + 0] += (ws[q] & 0xffu) * s;
+        idx[4 * q + 1] += ((ws[q] >> 8) & 0xffu) * s;
+        idx[4 * q + 2] += ((ws[q] >> 16) & 0xffu) * s;
+        idx[4 * q + 3] += (ws[q] >> 24) * s;
+    }
+}
+
+// stream rows [row0,row1) (row0 multiple of 16) of one set into `hist` (shared or global int32 table)
+template <typename HistPtr>
+__device__ __forceinline__ void count_rows(const SetCols &sc, int64_t row0, int64_t row1, HistPtr hist, int tid, int nthreads) {
+    const int64_t full_end = row0 + ((row1 - row0) / 16) * 16;
+    const int ncols = sc.ncols;
+    for (int64_t r = row0 + (int64_t)tid * 16; r < full_end; r += (int64_t)nthreads * 16) {
+        uint32_t idx[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) idx[i] = 0;
+        int c = 0;
+        for (; c + 1 < ncols; c += 2) { // two loads in flight
+            const uint4 w0 = ld_stream_u4(reinterpret_cast<const uint4 *>(sc.col[c] + r));
+            const uint4 w1 = ld_stream_u4(reinterpret_cast<const uint4 *>(sc.col[c + 1] + r));
+            accum16(w0, sc.stride[c], idx);
+            accum16(w1, sc.stride[c + 1], idx);
+        }
+        if (c < ncols) accum16(ld_stream_u4(reinterpret_cast<const uint4 *>(sc.col[c] + r)), sc.stride[c], idx);
+#pragma unroll
+        for (int i = 0; i < 16; i++) atomicAdd(&hist[idx[i]], 1);
+    }
+    // ragged tail (< 16 rows)
+    for (int64_t r = full_end + tid; r < row1; r += nthreads) {
+        uint32_t idx = 0;
+        for (int c = 0; c < ncols; c++) idx += (uint32_t)sc.col[c][r] * sc.stride[c];
+        atomicAdd(&hist[idx], 1);
+    }
+}
+
+// sum_cells q[n_ijk] - sum_j q[n_ij] over parent configurations [j0,j1)
+template <typename HistPtr>
+__device__ __forceinline__ long long score_configs(HistPtr hist, int rv, int64_t j0, int64_t j1, const long long *__restrict__ qlog,
+                                                   int tid, int nthreads) {
+    long long acc = 0;
+    for (int64_t j = j0 + tid; j < j1; j += nthreads) {
+        const int64_t b = j * rv;
+        int nij = 0;
+        for (int k = 0; k < rv; k++) {
+            const int cnt = hist[b + k];
+            nij += cnt;
+            if (cnt > 1) acc += __ldg(&qlog[cnt]); // q[0] = q[1] = 0
+        }
+        if (nij > 1) acc -= __ldg(&qlog[nij]);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float bic_finalize(long long acc, float tval, float base) {
+    // acc * 2^-23 is exact in FP64 (|acc| < 2^53); one rounding to float32, then the float32 penalty
+    const float ll = __double2float_rn(__ll2double_rn(acc) * (1.0 / 8388608.0));
+    return __fsub_rn(ll, __fmul_rn(tval, base)); // bic_scoring_function.cpp:73, no FMA contraction
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 (shared-memory tier): one CTA per parent set; whole table in shared memory.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void bic_count_smem_kernel(BicData d, CandInfo ci, const uint32_t *__restrict__ work, float *__restrict__ scores,
+                                      long long *__restrict__ ll_fixed /*optional, dense by mask*/) {
+    extern __shared__ __align__(16) int hist[];
+    __shared__ SetCols sc;
+    __shared__ long long red[32];
+    const uint32_t mask = work[blockIdx.x];
+    if (threadIdx.x == 0) build_cols(d, ci, mask, sc);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < sc.cells; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    count_rows(sc, 0, d.n, hist, threadIdx.x, blockDim.x);
+    __syncthreads();
+    long long acc = score_configs(hist, ci.rv, 0, sc.cells / ci.rv, d.qlog, threadIdx.x, blockDim.x);
+    acc = block_sum_ll(acc, red);
+    if (threadIdx.x == 0) {
+        scores[mask] = bic_finalize(acc, sc.tval, d.base);
+        if (ll_fixed) ll_fixed[mask] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 (global tier): tables live in an L2-resident scratch buffer; grid = (set in batch, row slice).
+// ---------------------------------------------------------------------------------------------------------
+struct GlobalSet {
+    uint32_t mask;
+    uint32_t cells;
+    uint64_t table_off; // in int32 elements
+};
+
+__global__ void bic_count_global_kernel(BicData d, CandInfo ci, const GlobalSet *__restrict__ sets, int *__restrict__ tables,
+                                        int64_t rows_per_slice) {
+    __shared__ SetCols sc;
+    const GlobalSet gs = sets[blockIdx.x];
+    if (threadIdx.x == 0) build_cols(d, ci, gs.mask, sc);
+    __syncthreads();
+    const int64_t row0 = (int64_t)blockIdx.y * rows_per_slice;
+    int64_t row1 = row0 + rows_per_slice;
+    if (row1 > d.n) row1 = d.n;
+    if (row0 >= row1) return;
+    count_rows(sc, row0, row1, tables + gs.table_off, threadIdx.x, blockDim.x);
+}
+
+__global__ void bic_score_tables_kernel(BicData d, CandInfo ci, const GlobalSet *__restrict__ sets, const int *__restrict__ tables,
+                                        long long *__restrict__ acc_out /*[batch]*/, int64_t configs_per_chunk) {
+    __shared__ long long red[32];
+    const GlobalSet gs = sets[blockIdx.x];
+    const int64_t nconf = gs.cells / ci.rv;
+    const int64_t j0 = (int64_t)blockIdx.y * configs_per_chunk;
+    if (j0 >= nconf) return;
+    int64_t j1 = j0 + configs_per_chunk;
+    if (j1 > nconf) j1 = nconf;
+    long long acc = score_configs(tables + gs.table_off, ci.rv, j0, j1, d.qlog, threadIdx.x, blockDim.x);
+    acc = block_sum_ll(acc, red);
+    if (threadIdx.x == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[blockIdx.x]), (unsigned long long)acc);
+}
+
+__global__ void bic_finalize_kernel(BicData d, CandInfo ci, const GlobalSet *__restrict__ sets, const long long *__restrict__ acc, int nsets,
+                                    float *__restrict__ scores, long long *__restrict__ ll_fixed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsets) return;
+    const uint32_t mask = sets[i].mask;
+    float pen = (float)(ci.rv - 1);
+    for (int b = 0; b < ci.c; b++)
+        if ((mask >> b) & 1) pen = __fmul_rn(pen, (float)ci.card[b]);
+    scores[mask] = bic_finalize(acc[i], pen, d.base);
+    if (ll_fixed) ll_fixed[mask] = acc[i];
+}
+
+// store rule of the caller: empty set stored iff score < 1, others iff score < 0 (score_calculator.cpp:59,111)
+__global__ void bic_store_rule_kernel(float *__restrict__ scores, uint64_t n_masks, int max_parents) {
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_masks) return;
+    if (__popcll(m) > max_parents) return; // already sentinel
+    const float s = scores[m];
+    if (is_sentinel(s)) return;
+    const bool stored = (m == 0) ? (s < 1.0f) : (s < 0.0f);
+    if (!stored) scores[m] = sentinel();
+}
+
+} // namespace urlgpu

@@ -1,0 +1,315 @@
+// cbic_kernels.cuh — K2 (standardise + FP64 Gram), K3 (per-set residual variance + score), K4 (acceptance DP)
+// for the continuous "cBIC" score (sm_100a).
+//
+// Replaces BIC_OLS_Function's constructor (scoring_function/BIC_OLS.cpp:30-123), calculateScoreAndBeta
+// (:277-389, incl. the mlpack LinearRegression Train/ComputeError it calls) and calculateScore +
+// find_best_subset_score (:125-276) of the reference.
+//
+// The reference refits an OLS on n rows for every parent set (O(k^2 n) per set).  Here the data is reduced ONCE
+// to the Gram matrix G = Z^T Z of the standardised columns; the residual sum of squares of regressing z_v on
+// z_S is the Schur complement  RSS = G_vv - g_Sv^T G_SS^-1 g_Sv.  Candidate sets are walked as a binary
+// decision tree over the compact candidate bits (highest bit first); including a candidate is one symmetric
+// rank-1 "sweep" of the Schur complement restricted to the still-undecided candidates, so a set whose lowest
+// member is bit j costs j(j+1)/2 FMAs and on average ~4 FMAs per set, instead of a k^3/3 factorisation.
+#pragma once
+#include "common.cuh"
+
+namespace urlgpu {
+
+// ------------------------------------------------------------------------------------------------ K2
+// Fixed-order reductions: every partial is produced by a fixed (block, thread) -> row mapping and the partials
+// are combined sequentially, so the result does not depend on scheduling.
+
+constexpr int kRedBlocks = 256;
+constexpr int kRedThreads = 256;
+
+// out[col*kRedBlocks + b] = sum over this block's rows of f(x - shift[col])   (mode 0: x-shift, mode 1: (x-shift)^2)
+__global__ void col_partial_kernel(const double *__restrict__ x, int64_t n, int64_t stride, const double *__restrict__ shift, int mode,
+                                   double *__restrict__ out) {
+    __shared__ double sh[kRedThreads];
+    const int col = blockIdx.y;
+    const double s = shift ? shift[col] : 0.0;
+    const double *xc = x + (int64_t)col * stride;
+    double acc = 0;
+    for (int64_t r = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; r < n; r += (int64_t)kRedBlocks * kRedThreads) {
+        const double t = xc[r] - s;
+        acc += mode ? t * t : t;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[col * kRedBlocks + blockIdx.x] = sh[0];
+}
+
+// sequential combine of the kRedBlocks partials of each column
+__global__ void col_combine_kernel(const double *__restrict__ partial, int p, double *__restrict__ out) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= p) return;
+    double acc = 0;
+    for (int b = 0; b < kRedBlocks; b++) acc += partial[col * kRedBlocks + b];
+    out[col] = acc;
+}
+
+// mean = sum/n ; after centring: m2 = mean of centred column, var = (acc2 - acc3^2/n)/(n-1) (Armadillo op_var), dev = sqrt(var)
+__global__ void mean_kernel(const double *__restrict__ sum, int p, double n, double *__restrict__ mean) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < p) mean[col] = sum[col] / n;
+}
+__global__ void dev_kernel(const double *__restrict__ acc2, const double *__restrict__ acc3, int p, double n, double *__restrict__ dev) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < p) dev[col] = sqrt((acc2[col] - acc3[col] * acc3[col] / n) / (n - 1.0));
+}
+// z = (x - mean) / dev   (BIC_OLS.cpp:76-77)
+__global__ void standardise_kernel(const double *__restrict__ x, int64_t n, int64_t stride, const double *__restrict__ mean,
+                                   const double *__restrict__ dev, double *__restrict__ z) {
+    const int col = blockIdx.y;
+    const double m = mean[col], d = dev[col];
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        z[(int64_t)col * stride + r] = __ddiv_rn(x[(int64_t)col * stride + r] - m, d);
+}
+
+// Gram partials: CTA (tile_a, tile_b, slice) accumulates a 32x32 block of Z^T Z over its row slice.
+// Rows are staged through shared memory in chunks of 32; each thread owns 4 entries of the tile.
+constexpr int kGramTile = 32;
+constexpr int kGramRows = 64;
+__global__ void gram_partial_kernel(const double *__restrict__ z, int64_t n, int64_t stride, int p, int64_t rows_per_slice,
+                                    double *__restrict__ partial /*[slices][p][p]*/) {
+    __shared__ double sa[kGramTile][kGramRows + 1];
+    __shared__ double sb[kGramTile][kGramRows + 1];
+    const int ta = blockIdx.x, tb = blockIdx.y;
+    if (tb < ta) return; // symmetric: upper tiles only
+    const int slice = blockIdx.z;
+    const int64_t r0 = (int64_t)slice * rows_per_slice;
+    int64_t r1 = r0 + rows_per_slice;
+    if (r1 > n) r1 = n;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; // 16x16 threads, 2x2 entries each
+    double acc[2][2] = {{0, 0}, {0, 0}};
+    for (int64_t rb = r0; rb < r1; rb += kGramRows) {
+        for (int i = threadIdx.x; i < kGramTile * kGramRows; i += blockDim.x) {
+            const int var = i / kGramRows, rr = i % kGramRows;
+            const int64_t r = rb + rr;
+            const int va = ta * kGramTile + var, vb = tb * kGramTile + var;
+            sa[var][rr] = (va < p && r < r1) ? z[(int64_t)va * stride + r] : 0.0;
+            sb[var][rr] = (vb < p && r < r1) ? z[(int64_t)vb * stride + r] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int rr = 0; rr < kGramRows; rr++) {
+            const double a0 = sa[ty][rr], a1 = sa[ty + 16][rr];
+            const double b0 = sb[tx][rr], b1 = sb[tx + 16][rr];
+            acc[0][0] = fma(a0, b0, acc[0][0]);
+            acc[0][1] = fma(a0, b1, acc[0][1]);
+            acc[1][0] = fma(a1, b0, acc[1][0]);
+            acc[1][1] = fma(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+    double *out = partial + (int64_t)slice * p * p;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int a = ta * kGramTile + ty + 16 * i, b = tb * kGramTile + tx + 16 * j;
+            if (a < p && b < p) out[a * p + b] = acc[i][j];
+        }
+}
+// G[a][b] = sum over slices in slice order (fixed order); mirror to the lower triangle
+__global__ void gram_combine_kernel(const double *__restrict__ partial, int p, int slices, double *__restrict__ g) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p * p) return;
+    const int a = idx / p, b = idx % p;
+    if (b < a) return;
+    if ((a / kGramTile) > (b / kGramTile)) return;
+    double acc = 0;
+    for (int s = 0; s < slices; s++) acc += partial[(int64_t)s * p * p + a * p + b];
+    g[a * p + b] = acc;
+    g[b * p + a] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+
+struct CbicParams {
+    int c;            // candidates
+    int J;            // low bits handled by one thread of the DFS kernel
+    int max_parents;
+    double n;         // row count (num_err, BIC_OLS.cpp:348)
+    double lam_logn;  // lambda*log(n)  (:366, evaluated left to right)
+};
+
+// packed lower-triangular index, element order (v, cand0, cand1, ...)
+__host__ __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }
+
+// Level A: one warp per prefix P (the high c-J candidate bits).  Starting from the (c+1)x(c+1) sub-Gram, walk the
+// high candidates from the top: an included one is swept out (Schur complement), either way it is then dropped.
+// Output: roots[e * n_prefix + P] for the (J+1)(J+2)/2 packed entries e of the remaining matrix.
+__global__ void cbic_roots_kernel(const double *__restrict__ subgram /*packed (c+1)(c+2)/2*/, CbicParams prm, uint32_t n_prefix,
+                                  double *__restrict__ roots) {
+    extern __shared__ double smat[]; // [warps][tri size]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t P = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int tsz = (prm.c + 1) * (prm.c + 2) / 2;
+    double *A = smat + warp * tsz;
+    if (P >= n_prefix) return;
+    if (__popc(P) > prm.max_parents) return; // whole subtree unscored
+    for (int e = lane; e < tsz; e += 32) A[e] = subgram[e];
+    __syncwarp();
+    for (int cand = prm.c - 1; cand >= prm.J; cand--) {
+        if ((P >> (cand - prm.J)) & 1) {
+            const int piv = cand + 1; // position in (v, c0, c1, ...)
+            const double inv = 1.0 / A[tri(piv, piv)];
+            for (int a = 0; a < piv; a++) {
+                const double f = -A[tri(piv, a)] * inv;
+                for (int b = lane; b <= a; b += 32) A[tri(a, b)] = fma(f, A[tri(piv, b)], A[tri(a, b)]);
+            }
+            __syncwarp();
+        }
+    }
+    const int outsz = (prm.J + 1) * (prm.J + 2) / 2;
+    for (int e = lane; e < outsz; e += 32) roots[(size_t)e * n_prefix + P] = A[e];
+}
+
+// the_score of one set from its RSS (BIC_OLS.cpp:302-305,366): k == 0 -> 0.0
+__device__ __forceinline__ float cbic_the_score(double rss, int k, const CbicParams &prm) {
+    if (k == 0) return 0.0f;
+    const double ts = prm.n * log(rss / prm.n) + prm.lam_logn * (double)k;
+    return (float)ts;
+}
+
+// Level B: template-recursive DFS over the J low candidate bits.  A has (j+1)(j+2)/2 packed entries over
+// (v, cand0..cand_{j-1}).  Low masks are emitted in ascending order (exclude branch first).  Levels above
+// kInlineLevel are real calls with their matrices on the thread's stack (touched once per 2^j sets); the bottom
+// levels are fully inlined so their matrices live in registers.
+constexpr int kInlineLevel = 4;
+
+__device__ __forceinline__ void cbic_emit(double rss, uint32_t low, int k, const CbicParams &prm, float *__restrict__ out,
+                                          double *__restrict__ out64) {
+    out[low] = cbic_the_score(rss, k, prm);
+    if (out64) out64[low] = (k == 0) ? 0.0 : prm.n * log(rss / prm.n) + prm.lam_logn * (double)k;
+}
+
+template <int j>
+__device__ __forceinline__ void cbic_sweep(const double *A, double *B) {
+    const double inv = 1.0 / A[tri(j, j)];
+#pragma unroll
+    for (int a = 0; a < j; a++) {
+        const double f = -A[tri(j, a)] * inv;
+#pragma unroll
+        for (int b = 0; b <= a; b++) B[tri(a, b)] = fma(f, A[tri(j, b)], A[tri(a, b)]);
+    }
+}
+
+template <int j>
+__device__ __forceinline__ void cbic_dfs_inl(const double *A, uint32_t low, int k, const CbicParams &prm, float *__restrict__ out,
+                                             double *__restrict__ out64) {
+    if constexpr (j == 0) {
+        cbic_emit(A[0], low, k, prm, out, out64);
+    } else {
+        cbic_dfs_inl<j - 1>(A, low, k, prm, out, out64); // candidate j-1 excluded: leading principal submatrix
+        if (k < prm.max_parents) {
+            double B[j * (j + 1) / 2];
+            cbic_sweep<j>(A, B);
+            cbic_dfs_inl<j - 1>(B, low | (1u << (j - 1)), k + 1, prm, out, out64);
+        } else {
+            for (uint32_t m = 0; m < (1u << (j - 1)); m++) out[low | (1u << (j - 1)) | m] = sentinel();
+        }
+    }
+}
+
+template <int j>
+__device__ __noinline__ void cbic_dfs_call(const double *A, uint32_t low, int k, const CbicParams &prm, float *__restrict__ out,
+                                           double *__restrict__ out64) {
+    if constexpr (j <= kInlineLevel) {
+        cbic_dfs_inl<j>(A, low, k, prm, out, out64);
+    } else {
+        cbic_dfs_call<j - 1>(A, low, k, prm, out, out64);
+        if (k < prm.max_parents) {
+            double B[j * (j + 1) / 2];
+            cbic_sweep<j>(A, B);
+            cbic_dfs_call<j - 1>(B, low | (1u << (j - 1)), k + 1, prm, out, out64);
+        } else {
+            for (uint32_t m = 0; m < (1u << (j - 1)); m++) out[low | (1u << (j - 1)) | m] = sentinel();
+        }
+    }
+}
+
+template <int J>
+__global__ void cbic_dfs_kernel(const double *__restrict__ roots, CbicParams prm, uint32_t n_prefix, float *__restrict__ ts_out,
+                                double *__restrict__ ts64_out) {
+    const uint32_t P = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P >= n_prefix) return;
+    float *out = ts_out + ((size_t)P << J);
+    double *out64 = ts64_out ? ts64_out + ((size_t)P << J) : nullptr;
+    const int k0 = __popc(P);
+    if (k0 > prm.max_parents) {
+        for (uint32_t m = 0; m < (1u << J); m++) out[m] = sentinel();
+        return;
+    }
+    double A[(J + 1) * (J + 2) / 2];
+#pragma unroll
+    for (int e = 0; e < (J + 1) * (J + 2) / 2; e++) A[e] = roots[(size_t)e * n_prefix + P];
+    cbic_dfs_call<J>(A, 0u, k0, prm, out, out64);
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+// Acceptance DP of the shipped `score` for cBIC ("clean" recursion), one launch per layer:
+//   ts >  0            -> stored by the caller, val = -ts           (BIC_OLS.cpp:213-224, score_calculator.cpp:111-113)
+//   ts == 0            -> not stored
+//   ts <  0 (or NaN)   -> stored iff F(S) < -ts                     (BIC_OLS.cpp:233-249)
+//   F(S) = max(0, max_{i in S, S\i != {}} g(S\i)),  g(T) = stored(T) ? val(T) : F(T)   (BIC_OLS.cpp:125-172)
+// In: table[mask] = the_score (float) or sentinel (not scored).  Out: table[mask] = stored value or sentinel,
+// gtab[mask] = g.
+__global__ void cbic_accept_layer_kernel(float *__restrict__ table, float *__restrict__ gtab, int c, int layer, uint64_t n_masks) {
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_masks || __popcll(m) != layer) return;
+    const float ts = table[m];
+    if (is_sentinel(ts)) return;
+    if (layer == 0) { table[m] = -ts; gtab[m] = 0.0f; return; } // empty set: -0.0f stored (<1), never consulted
+    if (ts > 0.0f) { table[m] = -ts; gtab[m] = -ts; return; }
+    float F = 0.0f;
+    if (layer > 1) {
+        for (uint64_t b = m; b; b &= b - 1) {
+            const float g = gtab[m ^ (b & (~b + 1))];
+            if (g > F) F = g;
+        }
+    }
+    if (ts == 0.0f) { table[m] = sentinel(); gtab[m] = F; return; }
+    const float val = -ts;
+    if (F >= val) { table[m] = sentinel(); gtab[m] = F; } // BIC_OLS.cpp:234 (NaN compares false -> stored)
+    else { table[m] = val; gtab[m] = val; }
+}
+// URLGPU_CBIC_NO_ACCEPT: store -the_score for every scored set
+__global__ void cbic_negate_kernel(float *__restrict__ table, uint64_t n_masks) {
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_masks) return;
+    const float ts = table[m];
+    if (!is_sentinel(ts)) table[m] = -ts;
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+// Subset-dominance prune (ScoreCalculator::prune, score_calculator.cpp:150-197) as a layer-synchronous DP on the
+// dense table:  M(S) = max(val'(S), max_i M(S\i)),  keep S iff stored and val(S) > max_i M(S\i)  (ties: the
+// subset, having the smaller mask, sorts first and wins — compareSecond :137-148).
+__global__ void prune_layer_kernel(float *__restrict__ table, float *__restrict__ mtab, int layer, uint64_t n_masks) {
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_masks || __popcll(m) != layer) return;
+    float best = -INFINITY;
+    for (uint64_t b = m; b; b &= b - 1) best = fmaxf(best, mtab[m ^ (b & (~b + 1))]);
+    const float v = table[m];
+    const bool stored = !is_sentinel(v);
+    if (stored && layer > 0 && !(v > best)) table[m] = sentinel();
+    mtab[m] = stored ? fmaxf(best, v) : best;
+}
+
+// result compaction helpers --------------------------------------------------------------------------------
+__global__ void count_stored_kernel(const float *__restrict__ table, uint64_t n_masks, unsigned long long *__restrict__ count) {
+    uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c = 0;
+    for (; m < n_masks; m += (uint64_t)gridDim.x * blockDim.x) c += !is_sentinel(table[m]);
+    c = (unsigned long long)warp_sum_ll((long long)c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+} // namespace urlgpu

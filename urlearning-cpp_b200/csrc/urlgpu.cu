@@ -1,0 +1,899 @@
+// urlgpu.cu — C ABI (include/urlgpu.h) and host-side orchestration of the sm_100a kernels.
+//
+// One context owns one device and one stream.  Per-variable results are dense tables indexed by the COMPACT
+// parent-set mask (bit i = i-th candidate of the variable in ascending variable index, the child itself
+// removed — score_calculator.cpp:65-74,100), which makes subset look-ups (accept / prune DPs) a single XOR.
+#include "../../include/urlgpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include "bic_kernels.cuh"
+#include "cbic_kernels.cuh"
+
+using namespace urlgpu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum Family { F_COUNT = 0, F_CUBE, F_CBIC, F_ACCEPT, F_PRUNE, F_GRAM, F_OTHER, F_N };
+
+struct EvPair { cudaEvent_t a, b; int fam; };
+
+} // namespace
+
+struct urlgpu_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+
+    // discrete data
+    int64_t n = 0, n_stride = 0;
+    int p = 0;
+    std::vector<int32_t> card;
+    uint8_t *d_codes = nullptr;
+    long long *d_qlog = nullptr;
+    float base = 0.f;
+    bool have_discrete = false;
+
+    // continuous data
+    int64_t cn = 0;
+    int cp = 0;
+    double *d_z = nullptr;
+    std::vector<double> h_gram;
+    bool have_gram = false;
+
+    // scratch
+    int *d_tables = nullptr; size_t tables_cap = 0;          // int32 elements
+    void *d_misc = nullptr; size_t misc_cap = 0;
+
+    // stats
+    urlgpu_stats st{};
+    bool timing = false;
+    std::vector<EvPair> pending;
+    std::vector<cudaEvent_t> free_events;
+
+    int fail(int code, const std::string &m) { err = m; return code; }
+    int cuda_fail(cudaError_t e, const char *what, int line) {
+        err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what + " (urlgpu.cu:" + std::to_string(line) + ")";
+        return URLGPU_ERR_CUDA;
+    }
+};
+
+#define CK(call)                                                            \
+    do {                                                                    \
+        cudaError_t e_ = (call);                                            \
+        if (e_ != cudaSuccess) return ctx->cuda_fail(e_, #call, __LINE__);  \
+    } while (0)
+
+namespace {
+
+struct DevBuf { // RAII device allocation
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { if (p) { cudaFree(p); p = nullptr; } return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
+cudaEvent_t get_event(urlgpu_ctx *ctx) {
+    if (!ctx->free_events.empty()) { cudaEvent_t e = ctx->free_events.back(); ctx->free_events.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void fold_events(urlgpu_ctx *ctx) {
+    if (ctx->pending.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &ep : ctx->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
+            double *dst = ep.fam == F_COUNT ? &ctx->st.ms_count : ep.fam == F_CUBE ? &ctx->st.ms_cube : ep.fam == F_CBIC ? &ctx->st.ms_cbic
+                        : ep.fam == F_ACCEPT ? &ctx->st.ms_accept : ep.fam == F_PRUNE ? &ctx->st.ms_prune : ep.fam == F_GRAM ? &ctx->st.ms_gram : nullptr;
+            if (dst) *dst += ms;
+        }
+        ctx->free_events.push_back(ep.a);
+        ctx->free_events.push_back(ep.b);
+    }
+    ctx->pending.clear();
+}
+
+// Brackets a group of launches of one kernel family with CUDA events on the context's stream.
+struct Region {
+    urlgpu_ctx *ctx; int fam; EvPair ep{};
+    bool on;
+    Region(urlgpu_ctx *c, int f, uint64_t launches) : ctx(c), fam(f), on(c->timing) {
+        c->st.launches_total += launches;
+        uint64_t *cnt = f == F_COUNT ? &c->st.launches_count : f == F_CUBE ? &c->st.launches_cube : f == F_CBIC ? &c->st.launches_cbic
+                      : f == F_ACCEPT ? &c->st.launches_accept : f == F_PRUNE ? &c->st.launches_prune : &c->st.launches_other;
+        *cnt += launches;
+        if (on) { ep.a = get_event(c); ep.b = get_event(c); ep.fam = f; cudaEventRecord(ep.a, c->stream); }
+    }
+    ~Region() {
+        if (on) {
+            cudaEventRecord(ep.b, ctx->stream);
+            ctx->pending.push_back(ep);
+            if (ctx->pending.size() > 4096) fold_events(ctx);
+        }
+    }
+};
+
+inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// binomial sums (host)
+uint64_t family_size(int c, int K) {
+    uint64_t total = 0, b = 1;
+    for (int l = 0; l <= K && l <= c; l++) {
+        total += b;
+        b = b * (uint64_t)(c - l) / (uint64_t)(l + 1);
+    }
+    return total;
+}
+
+} // namespace
+
+struct urlgpu_result {
+    urlgpu_ctx *ctx = nullptr;
+    int variable = 0, c = 0, max_parents = 0, mask_words = 1;
+    std::vector<int> cand;          // compact bit -> variable index
+    float *d_table = nullptr;       // 2^c floats
+    uint64_t n_masks = 0, n_scored = 0;
+    bool counted = false; uint64_t n_stored = 0;
+    bool compacted = false;
+    std::vector<uint32_t> h_masks;  // canonical order
+    std::vector<float> h_scores;
+};
+
+// ============================================================================================ context
+
+extern "C" int urlgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
+    if (!out) return URLGPU_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_error = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                         "); urlgpu has no CPU fallback";
+        return URLGPU_ERR_CUDA;
+    }
+    if (device_id < 0 || device_id >= ndev) { g_create_error = "device_id out of range"; return URLGPU_ERR_ARG; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return URLGPU_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_error = "device " + std::to_string(device_id) + " (" + prop.name + ", sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                         ") is not a Blackwell sm_100 device; this library carries sm_100a code only";
+        return URLGPU_ERR_CUDA;
+    }
+    auto *ctx = new urlgpu_ctx();
+    ctx->device = device_id;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete ctx;
+        return URLGPU_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaFuncSetAttribute(bic_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 2048);
+    *out = ctx;
+    return URLGPU_OK;
+}
+
+static void free_discrete(urlgpu_ctx *ctx) {
+    if (ctx->d_codes) cudaFree(ctx->d_codes);
+    if (ctx->d_qlog) cudaFree(ctx->d_qlog);
+    ctx->d_codes = nullptr; ctx->d_qlog = nullptr; ctx->have_discrete = false;
+}
+static void free_continuous(urlgpu_ctx *ctx) {
+    if (ctx->d_z) cudaFree(ctx->d_z);
+    ctx->d_z = nullptr; ctx->have_gram = false;
+}
+
+extern "C" int urlgpu_destroy(urlgpu_ctx *ctx) {
+    if (!ctx) return URLGPU_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    fold_events(ctx);
+    for (auto e : ctx->free_events) cudaEventDestroy(e);
+    free_discrete(ctx);
+    free_continuous(ctx);
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->d_misc) cudaFree(ctx->d_misc);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return URLGPU_OK;
+}
+
+extern "C" const char *urlgpu_last_error(urlgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int urlgpu_set_stream(urlgpu_ctx *ctx, void *s) {
+    if (!ctx) return URLGPU_ERR_ARG;
+    fold_events(ctx);
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_synchronize(urlgpu_ctx *ctx) {
+    if (!ctx) return URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_stats_reset(urlgpu_ctx *ctx) {
+    if (!ctx) return URLGPU_ERR_ARG;
+    fold_events(ctx);
+    ctx->st = urlgpu_stats{};
+    return URLGPU_OK;
+}
+extern "C" int urlgpu_stats_get(urlgpu_ctx *ctx, urlgpu_stats *out) {
+    if (!ctx || !out) return URLGPU_ERR_ARG;
+    fold_events(ctx);
+    *out = ctx->st;
+    return URLGPU_OK;
+}
+extern "C" int urlgpu_stats_enable_timing(urlgpu_ctx *ctx, int on) {
+    if (!ctx) return URLGPU_ERR_ARG;
+    fold_events(ctx);
+    ctx->timing = on != 0;
+    return URLGPU_OK;
+}
+
+// ============================================================================================ data upload
+
+static int set_discrete_common(urlgpu_ctx *ctx, const uint8_t *src, bool src_on_device, int64_t n, int p, const int32_t *cardinality) {
+    if (!ctx || !src || !cardinality || n < 1 || p < 1) return ctx ? ctx->fail(URLGPU_ERR_ARG, "set_discrete: bad arguments") : URLGPU_ERR_ARG;
+    if (n > (int64_t)2000000000) return ctx->fail(URLGPU_ERR_LIMIT, "set_discrete: more than 2e9 records");
+    CK(cudaSetDevice(ctx->device));
+    free_discrete(ctx);
+    for (int i = 0; i < p; i++)
+        if (cardinality[i] < 1 || cardinality[i] > 256) return ctx->fail(URLGPU_ERR_ARG, "set_discrete: cardinality must be in 1..256");
+    ctx->n = n; ctx->p = p;
+    ctx->n_stride = (n + 15) / 16 * 16;
+    ctx->card.assign(cardinality, cardinality + p);
+    CK(cudaMalloc(&ctx->d_codes, (size_t)ctx->n_stride * p));
+    CK(cudaMemsetAsync(ctx->d_codes, 0, (size_t)ctx->n_stride * p, ctx->stream));
+    CK(cudaMemcpy2DAsync(ctx->d_codes, (size_t)ctx->n_stride, src, (size_t)n, (size_t)n, (size_t)p,
+                         src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    // the reference's float table ilogi[i] = (float)(i*log(i)) (log_likelihood_calculator.h:30-38), as exact
+    // int64 multiples of 2^-23.  Built on the host with libm's log so it is the same table the reference builds.
+    std::vector<long long> q((size_t)n + 2);
+    q[0] = 0;
+    for (int64_t i = 1; i < n + 2; i++) {
+        const float l = (float)((int)i * std::log((double)(int)i));
+        q[i] = (long long)std::ldexp((double)l, 23);
+    }
+    CK(cudaMalloc(&ctx->d_qlog, q.size() * sizeof(long long)));
+    CK(cudaMemcpyAsync(ctx->d_qlog, q.data(), q.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // q goes out of scope
+    ctx->base = (float)(std::log((double)(int)n) / 2); // bic_scoring_function.cpp:13
+    ctx->have_discrete = true;
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_set_discrete(urlgpu_ctx *ctx, const uint8_t *codes, int64_t n, int p, const int32_t *cardinality) {
+    return set_discrete_common(ctx, codes, false, n, p, cardinality);
+}
+extern "C" int urlgpu_set_discrete_device(urlgpu_ctx *ctx, const uint8_t *d_codes, int64_t n, int p, const int32_t *cardinality) {
+    return set_discrete_common(ctx, d_codes, true, n, p, cardinality);
+}
+
+static int set_continuous_common(urlgpu_ctx *ctx, const double *src, bool src_on_device, int64_t n, int p) {
+    if (!ctx || !src || n < 2 || p < 1) return ctx ? ctx->fail(URLGPU_ERR_ARG, "set_continuous: bad arguments") : URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    free_continuous(ctx);
+    ctx->cn = n; ctx->cp = p;
+    cudaStream_t s = ctx->stream;
+    DevBuf x, part, sums, mean, acc2, acc3, dev, gpart, g;
+    const size_t bytes = (size_t)n * p * sizeof(double);
+    CK(x.alloc(bytes));
+    CK(cudaMalloc(&ctx->d_z, bytes));
+    CK(cudaMemcpyAsync(x.p, src, bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    CK(part.alloc((size_t)p * kRedBlocks * sizeof(double)));
+    CK(sums.alloc(p * sizeof(double))); CK(mean.alloc(p * sizeof(double)));
+    CK(acc2.alloc(p * sizeof(double))); CK(acc3.alloc(p * sizeof(double))); CK(dev.alloc(p * sizeof(double)));
+    {
+        Region rg(ctx, F_GRAM, 12);
+        const dim3 rgrid(kRedBlocks, p);
+        const unsigned pb = blocks_for(p, 128);
+        // mean_x = sum/n  (BIC_OLS.cpp:69)
+        col_partial_kernel<<<rgrid, kRedThreads, 0, s>>>(x.as<double>(), n, n, nullptr, 0, part.as<double>());
+        col_combine_kernel<<<pb, 128, 0, s>>>(part.as<double>(), p, sums.as<double>());
+        mean_kernel<<<pb, 128, 0, s>>>(sums.as<double>(), p, (double)n, mean.as<double>());
+        // dev_x = sqrt(var(x - mean_x)), Armadillo two-pass variance with N-1 (BIC_OLS.cpp:70-71)
+        col_partial_kernel<<<rgrid, kRedThreads, 0, s>>>(x.as<double>(), n, n, mean.as<double>(), 1, part.as<double>());
+        col_combine_kernel<<<pb, 128, 0, s>>>(part.as<double>(), p, acc2.as<double>());
+        col_partial_kernel<<<rgrid, kRedThreads, 0, s>>>(x.as<double>(), n, n, mean.as<double>(), 0, part.as<double>());
+        col_combine_kernel<<<pb, 128, 0, s>>>(part.as<double>(), p, acc3.as<double>());
+        dev_kernel<<<pb, 128, 0, s>>>(acc2.as<double>(), acc3.as<double>(), p, (double)n, dev.as<double>());
+        standardise_kernel<<<dim3(ctx->sm_count * 2, p), 256, 0, s>>>(x.as<double>(), n, n, mean.as<double>(), dev.as<double>(), ctx->d_z);
+        // Gram
+        const int tiles = (p + kGramTile - 1) / kGramTile;
+        int slices = (int)std::min<int64_t>(512, std::max<int64_t>(1, n / 4096));
+        int64_t rps = (n + slices - 1) / slices;
+        rps = (rps + kGramRows - 1) / kGramRows * kGramRows;
+        slices = (int)((n + rps - 1) / rps);
+        CK(gpart.alloc((size_t)slices * p * p * sizeof(double)));
+        CK(g.alloc((size_t)p * p * sizeof(double)));
+        gram_partial_kernel<<<dim3(tiles, tiles, slices), 256, 0, s>>>(ctx->d_z, n, n, p, rps, gpart.as<double>());
+        gram_combine_kernel<<<blocks_for((uint64_t)p * p, 256), 256, 0, s>>>(gpart.as<double>(), p, slices, g.as<double>());
+    }
+    ctx->h_gram.resize((size_t)p * p);
+    CK(cudaMemcpyAsync(ctx->h_gram.data(), g.p, (size_t)p * p * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    ctx->have_gram = true;
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_set_continuous(urlgpu_ctx *ctx, const double *x, int64_t n, int p) { return set_continuous_common(ctx, x, false, n, p); }
+extern "C" int urlgpu_set_continuous_device(urlgpu_ctx *ctx, const double *x, int64_t n, int p) { return set_continuous_common(ctx, x, true, n, p); }
+
+extern "C" int urlgpu_get_gram(urlgpu_ctx *ctx, double *g) {
+    if (!ctx || !g) return URLGPU_ERR_ARG;
+    if (!ctx->have_gram) return ctx->fail(URLGPU_ERR_ARG, "get_gram: no continuous data set");
+    memcpy(g, ctx->h_gram.data(), ctx->h_gram.size() * sizeof(double));
+    return URLGPU_OK;
+}
+extern "C" int urlgpu_set_gram(urlgpu_ctx *ctx, const double *g, int64_t n_total, int p) {
+    if (!ctx || !g || p < 1 || n_total < 2) return ctx ? ctx->fail(URLGPU_ERR_ARG, "set_gram: bad arguments") : URLGPU_ERR_ARG;
+    free_continuous(ctx);
+    ctx->cn = n_total; ctx->cp = p;
+    ctx->h_gram.assign(g, g + (size_t)p * p);
+    ctx->have_gram = true;
+    return URLGPU_OK;
+}
+
+// ============================================================================================ scoring
+
+static int candidates_from_mask(urlgpu_ctx *ctx, int p, int variable, const uint64_t *neighbors, int mask_words, std::vector<int> &cand) {
+    if (mask_words < 1 || (int64_t)mask_words * 64 < p) return ctx->fail(URLGPU_ERR_ARG, "mask_words too small for the variable count");
+    cand.clear();
+    for (int i = 0; i < p; i++)
+        if (i != variable && ((neighbors[i >> 6] >> (i & 63)) & 1)) cand.push_back(i);
+    for (int w = 0; w < mask_words; w++)
+        for (int b = 0; b < 64; b++)
+            if (w * 64 + b >= p && ((neighbors[w] >> b) & 1)) return ctx->fail(URLGPU_ERR_ARG, "mask names a variable >= p");
+    return URLGPU_OK;
+}
+
+static int ensure_tables(urlgpu_ctx *ctx, size_t elems) {
+    if (ctx->tables_cap >= elems) return URLGPU_OK;
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    ctx->d_tables = nullptr; ctx->tables_cap = 0;
+    CK(cudaMalloc(&ctx->d_tables, elems * sizeof(int)));
+    ctx->tables_cap = elems;
+    return URLGPU_OK;
+}
+
+namespace {
+constexpr uint32_t kTier0Cells = 12 * 1024;                 // 48 KB of shared memory, several CTAs per SM
+constexpr uint64_t kCellLimit = (uint64_t)1 << 30;          // 4 GB table
+constexpr size_t kBatchTableElems = (size_t)12 << 20;       // 48 MB of tables per batch: stays L2 resident
+}
+
+static CandInfo make_candinfo(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K) {
+    CandInfo ci{};
+    ci.c = (int)cand.size(); ci.v = variable; ci.rv = ctx->card[variable]; ci.max_parents = K;
+    for (int i = 0; i < ci.c; i++) { ci.var[i] = cand[i]; ci.card[i] = ctx->card[cand[i]]; }
+    return ci;
+}
+
+// Score the listed compact masks (device list for the shared-memory tiers, host list for the global tier)
+static int bic_run_global_tier(urlgpu_ctx *ctx, const BicData &bd, const CandInfo &ci, const std::vector<uint32_t> &masks,
+                               float *d_table, long long *d_llfixed, int *keep_tables_of_first /*optional host out*/, int64_t keep_cells) {
+    if (masks.empty()) return URLGPU_OK;
+    cudaStream_t s = ctx->stream;
+    std::vector<GlobalSet> sets(masks.size());
+    size_t max_cells = 0;
+    for (size_t i = 0; i < masks.size(); i++) {
+        uint64_t cells = ci.rv;
+        for (int b = 0; b < ci.c; b++) if ((masks[i] >> b) & 1) cells *= (uint64_t)ci.card[b];
+        sets[i].mask = masks[i]; sets[i].cells = (uint32_t)cells; sets[i].table_off = 0;
+        max_cells = std::max<size_t>(max_cells, cells);
+    }
+    int rc = ensure_tables(ctx, std::max(kBatchTableElems, max_cells));
+    if (rc) return rc;
+    DevBuf dsets, dacc;
+    CK(dsets.alloc(sets.size() * sizeof(GlobalSet)));
+    CK(dacc.alloc(sets.size() * sizeof(long long)));
+    CK(cudaMemsetAsync(dacc.p, 0, sets.size() * sizeof(long long), s));
+    // batches
+    size_t i0 = 0;
+    std::vector<std::pair<size_t, size_t>> batches;
+    while (i0 < sets.size()) {
+        size_t used = 0, i1 = i0;
+        while (i1 < sets.size() && (i1 == i0 || used + sets[i1].cells <= ctx->tables_cap) && i1 - i0 < 65535) {
+            sets[i1].table_off = used;
+            used += (sets[i1].cells + 3) / 4 * 4;
+            i1++;
+        }
+        batches.push_back({i0, i1});
+        i0 = i1;
+    }
+    CK(cudaMemcpyAsync(dsets.p, sets.data(), sets.size() * sizeof(GlobalSet), cudaMemcpyHostToDevice, s));
+    const int threads = 256;
+    for (auto &bt : batches) {
+        const size_t B = bt.second - bt.first;
+        size_t used = sets[bt.second - 1].table_off + sets[bt.second - 1].cells;
+        Region rg(ctx, F_COUNT, 3);
+        CK(cudaMemsetAsync(ctx->d_tables, 0, used * sizeof(int), s));
+        // row slices so that the batch fills the machine (B*R CTAs ~ 8 per SM)
+        int64_t R = std::max<int64_t>(1, (int64_t)(ctx->sm_count * 8 + B - 1) / (int64_t)B);
+        int64_t rps = (bd.n + R - 1) / R;
+        rps = std::max<int64_t>((rps + 15) / 16 * 16, 16 * threads);
+        R = (bd.n + rps - 1) / rps;
+        bic_count_global_kernel<<<dim3((unsigned)B, (unsigned)R), threads, 0, s>>>(bd, ci, dsets.as<GlobalSet>() + bt.first, ctx->d_tables, rps);
+        uint32_t maxc = 0;
+        for (size_t i = bt.first; i < bt.second; i++) maxc = std::max(maxc, sets[i].cells);
+        int64_t nconf = maxc / ci.rv;
+        int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((nconf + threads * 4 - 1) / (threads * 4), (ctx->sm_count * 8 + (int64_t)B - 1) / (int64_t)B));
+        int64_t cpc = (nconf + chunks - 1) / chunks;
+        bic_score_tables_kernel<<<dim3((unsigned)B, (unsigned)chunks), threads, 0, s>>>(bd, ci, dsets.as<GlobalSet>() + bt.first, ctx->d_tables,
+                                                                                    dacc.as<long long>() + bt.first, cpc);
+        if (keep_tables_of_first && bt.first == 0) {
+            CK(cudaMemcpyAsync(keep_tables_of_first, ctx->d_tables, (size_t)keep_cells * sizeof(int), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+    }
+    if (d_table) {
+        Region rg(ctx, F_OTHER, 1);
+        bic_finalize_kernel<<<blocks_for(sets.size(), 256), 256, 0, s>>>(bd, ci, dsets.as<GlobalSet>(), dacc.as<long long>(), (int)sets.size(), d_table,
+                                                                         d_llfixed);
+    }
+    CK(cudaStreamSynchronize(s)); // dsets/dacc are freed on return
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
+                            uint64_t *n_scored) {
+    cudaStream_t s = ctx->stream;
+    const int c = (int)cand.size();
+    const uint64_t n_masks = (uint64_t)1 << c;
+    const uint64_t fam = family_size(c, K);
+    *n_scored = fam;
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+    CandInfo ci = make_candinfo(ctx, variable, cand, K);
+    const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
+
+    DevBuf lists, counters;
+    CK(lists.alloc(3 * fam * sizeof(uint32_t)));
+    CK(counters.alloc(4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), s));
+    uint32_t *l0 = lists.as<uint32_t>(), *l1 = l0 + fam, *l2 = l1 + fam;
+    {
+        Region rg(ctx, F_OTHER, 1);
+        bic_classify_kernel<<<blocks_for(n_masks, 256), 256, 0, s>>>(ci, n_masks, kTier0Cells, tier1_cells, kCellLimit, l0, l1, l2,
+                                                                    counters.as<unsigned long long>());
+    }
+    unsigned long long hc[4];
+    CK(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (hc[3]) return ctx->fail(URLGPU_ERR_LIMIT, "a contingency table of this family has more than 2^30 cells");
+    if (hc[0]) {
+        Region rg(ctx, F_COUNT, 1);
+        const int threads = ctx->n >= 65536 ? 256 : 128;
+        bic_count_smem_kernel<<<(unsigned)hc[0], threads, kTier0Cells * sizeof(int), s>>>(bd, ci, l0, d_table, d_llfixed);
+    }
+    if (hc[1]) {
+        Region rg(ctx, F_COUNT, 1);
+        bic_count_smem_kernel<<<(unsigned)hc[1], 1024, (size_t)tier1_cells * sizeof(int), s>>>(bd, ci, l1, d_table, d_llfixed);
+    }
+    if (hc[2]) {
+        std::vector<uint32_t> m2(hc[2]);
+        CK(cudaMemcpyAsync(m2.data(), l2, hc[2] * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        std::sort(m2.begin(), m2.end());
+        int rc = bic_run_global_tier(ctx, bd, ci, m2, d_table, d_llfixed, nullptr, 0);
+        if (rc) return rc;
+    }
+    // algorithmic bytes: n*(k+1) per set
+    {
+        double bytes = 0, b = 1;
+        for (int l = 0; l <= K && l <= c; l++) { bytes += b * (double)ctx->n * (l + 1); b = b * (c - l) / (l + 1); }
+        ctx->st.algorithmic_bytes += bytes;
+        ctx->st.sets_scored += fam;
+    }
+    CK(cudaStreamSynchronize(s)); // lists/counters are freed on return
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+template <int J>
+static void launch_cbic_dfs(const double *roots, const CbicParams &prm, uint32_t n_prefix, float *ts, double *ts64, cudaStream_t s) {
+    const int threads = 128;
+    cbic_dfs_kernel<J><<<blocks_for(n_prefix, threads), threads, 0, s>>>(roots, prm, n_prefix, ts, ts64);
+}
+
+static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, double lambda, float *d_table, double *d_ts64,
+                             uint64_t *n_scored) {
+    cudaStream_t s = ctx->stream;
+    const int c = (int)cand.size();
+    const int p = ctx->cp;
+    *n_scored = family_size(c, K);
+    // packed sub-Gram over (v, cand0, cand1, ...)
+    std::vector<int> order(1, variable);
+    order.insert(order.end(), cand.begin(), cand.end());
+    std::vector<double> sub((size_t)(c + 1) * (c + 2) / 2);
+    for (int a = 0; a <= c; a++)
+        for (int b = 0; b <= a; b++) sub[tri(a, b)] = ctx->h_gram[(size_t)order[a] * p + order[b]];
+    CbicParams prm{};
+    prm.c = c;
+    prm.J = std::max(std::min(c, 3), std::min(11, c - 10));
+    prm.max_parents = K;
+    prm.n = (double)(int)ctx->cn;
+    prm.lam_logn = lambda * std::log((double)(int)ctx->cn);
+    const uint32_t n_prefix = 1u << (c - prm.J);
+    const int outsz = (prm.J + 1) * (prm.J + 2) / 2;
+    DevBuf dsub, droots;
+    CK(dsub.alloc(sub.size() * sizeof(double)));
+    CK(droots.alloc((size_t)outsz * n_prefix * sizeof(double)));
+    CK(cudaMemcpyAsync(dsub.p, sub.data(), sub.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    {
+        Region rg(ctx, F_CBIC, 2);
+        const int warps = 8;
+        const size_t smem = (size_t)warps * sub.size() * sizeof(double);
+        cbic_roots_kernel<<<blocks_for(n_prefix, warps), warps * 32, smem, s>>>(dsub.as<double>(), prm, n_prefix, droots.as<double>());
+        switch (prm.J) {
+#define URLGPU_CASE(JJ) case JJ: launch_cbic_dfs<JJ>(droots.as<double>(), prm, n_prefix, d_table, d_ts64, s); break;
+            URLGPU_CASE(0) URLGPU_CASE(1) URLGPU_CASE(2) URLGPU_CASE(3) URLGPU_CASE(4) URLGPU_CASE(5) URLGPU_CASE(6) URLGPU_CASE(7)
+            URLGPU_CASE(8) URLGPU_CASE(9) URLGPU_CASE(10) URLGPU_CASE(11)
+#undef URLGPU_CASE
+        default: return ctx->fail(URLGPU_ERR_INTERNAL, "bad J");
+        }
+    }
+    {
+        double flops = 0, b = 1;
+        for (int l = 0; l <= K && l <= c; l++) { flops += b * ((double)l * l * l / 3.0 + 2.0 * l * l + 2.0 * l); b = b * (c - l) / (l + 1); }
+        ctx->st.algorithmic_flops += flops;
+        ctx->st.sets_scored += *n_scored;
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+static int run_accept(urlgpu_ctx *ctx, float *d_table, int c, int K) {
+    cudaStream_t s = ctx->stream;
+    const uint64_t n_masks = (uint64_t)1 << c;
+    DevBuf g;
+    CK(g.alloc(n_masks * sizeof(float)));
+    {
+        Region rg(ctx, F_ACCEPT, std::min(c, K) + 1);
+        for (int layer = 0; layer <= K && layer <= c; layer++)
+            cbic_accept_layer_kernel<<<blocks_for(n_masks, 256), 256, 0, s>>>(d_table, g.as<float>(), c, layer, n_masks);
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+static int run_prune(urlgpu_ctx *ctx, float *d_table, int c, int K) {
+    cudaStream_t s = ctx->stream;
+    const uint64_t n_masks = (uint64_t)1 << c;
+    DevBuf m;
+    CK(m.alloc(n_masks * sizeof(float)));
+    {
+        Region rg(ctx, F_PRUNE, std::min(c, K) + 1);
+        for (int layer = 0; layer <= K && layer <= c; layer++)
+            prune_layer_kernel<<<blocks_for(n_masks, 256), 256, 0, s>>>(d_table, m.as<float>(), layer, n_masks);
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type,
+                                     double lambda, unsigned filter_flags, urlgpu_result **out) {
+    if (!ctx || !neighbors || !out) return ctx ? ctx->fail(URLGPU_ERR_ARG, "score_variable: null argument") : URLGPU_ERR_ARG;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    const bool bic = score_type == URLGPU_BIC;
+    if (!bic && score_type != URLGPU_CBIC) return ctx->fail(URLGPU_ERR_ARG, "score_variable: unknown score type");
+    if (bic && !ctx->have_discrete) return ctx->fail(URLGPU_ERR_ARG, "score_variable: BIC needs urlgpu_set_discrete first");
+    if (!bic && !ctx->have_gram) return ctx->fail(URLGPU_ERR_ARG, "score_variable: cBIC needs urlgpu_set_continuous first");
+    const int p = bic ? ctx->p : ctx->cp;
+    if (variable < 0 || variable >= p) return ctx->fail(URLGPU_ERR_ARG, "score_variable: variable out of range");
+    std::vector<int> cand;
+    int rc = candidates_from_mask(ctx, p, variable, neighbors, mask_words, cand);
+    if (rc) return rc;
+    const int c = (int)cand.size();
+    if (c > kMaxDenseCand)
+        return ctx->fail(URLGPU_ERR_LIMIT, "score_variable: " + std::to_string(c) + " candidate parents; this build handles at most " +
+                                               std::to_string(kMaxDenseCand) + " (dense 2^c score table)");
+    int K = std::max(0, std::min(max_parents, c));
+    auto *res = new urlgpu_result();
+    res->ctx = ctx; res->variable = variable; res->c = c; res->max_parents = K; res->mask_words = mask_words; res->cand = cand;
+    res->n_masks = (uint64_t)1 << c;
+    cudaError_t e = cudaMalloc(&res->d_table, res->n_masks * sizeof(float));
+    if (e != cudaSuccess) { delete res; return ctx->cuda_fail(e, "cudaMalloc(score table)", __LINE__); }
+    cudaStream_t s = ctx->stream;
+    auto cleanup = [&](int code) { cudaFree(res->d_table); delete res; return code; };
+    fill_u32_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), res->n_masks, kSentinelBits);
+    if (bic) {
+        rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored);
+        if (rc) return cleanup(rc);
+        Region rg(ctx, F_OTHER, 1);
+        bic_store_rule_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(res->d_table, res->n_masks, K);
+    } else {
+        rc = cbic_score_family(ctx, variable, cand, K, lambda, res->d_table, nullptr, &res->n_scored);
+        if (rc) return cleanup(rc);
+        if (filter_flags & URLGPU_CBIC_NO_ACCEPT) {
+            Region rg(ctx, F_OTHER, 1);
+            cbic_negate_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(res->d_table, res->n_masks);
+        } else {
+            rc = run_accept(ctx, res->d_table, c, K);
+            if (rc) return cleanup(rc);
+        }
+    }
+    if (filter_flags & URLGPU_PRUNE_DOMINATED) {
+        rc = run_prune(ctx, res->d_table, c, K);
+        if (rc) return cleanup(rc);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cleanup(ctx->cuda_fail(e, "score_variable", __LINE__));
+    *out = res;
+    return URLGPU_OK;
+}
+
+// ============================================================================================ results
+
+namespace {
+struct StoredInLayer {
+    const float *table; int layer;
+    __host__ __device__ bool operator()(const uint32_t &m) const {
+#ifdef __CUDA_ARCH__
+        return __popc(m) == layer && !is_sentinel(table[m]);
+#else
+        return false;
+#endif
+    }
+};
+__global__ void gather_scores_kernel(const float *__restrict__ table, const uint32_t *__restrict__ masks, uint64_t n, float *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = table[masks[i]];
+}
+} // namespace
+
+static int result_count_impl(urlgpu_result *res) {
+    urlgpu_ctx *ctx = res->ctx;
+    if (res->counted) return URLGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf cnt;
+    CK(cnt.alloc(sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), ctx->stream));
+    count_stored_kernel<<<std::min<unsigned>(blocks_for(res->n_masks, 256), 4096), 256, 0, ctx->stream>>>(res->d_table, res->n_masks,
+                                                                                                       cnt.as<unsigned long long>());
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, cnt.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    res->n_stored = h; res->counted = true;
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_result_count(urlgpu_result *res, uint64_t *n) {
+    if (!res || !n) return URLGPU_ERR_ARG;
+    int rc = result_count_impl(res);
+    if (rc) return rc;
+    *n = res->n_stored;
+    return URLGPU_OK;
+}
+extern "C" int urlgpu_result_scored(urlgpu_result *res, uint64_t *n) {
+    if (!res || !n) return URLGPU_ERR_ARG;
+    *n = res->n_scored;
+    return URLGPU_OK;
+}
+
+// compaction into canonical order: layer by layer, masks ascending within a layer (stable select)
+static int result_compact(urlgpu_result *res) {
+    urlgpu_ctx *ctx = res->ctx;
+    if (res->compacted) return URLGPU_OK;
+    int rc = result_count_impl(res);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    const uint64_t total = res->n_stored;
+    res->h_masks.resize(total); res->h_scores.resize(total);
+    if (total) {
+        DevBuf dmasks, dvals, dnum, tmp;
+        CK(dmasks.alloc(total * sizeof(uint32_t)));
+        CK(dvals.alloc(total * sizeof(float)));
+        CK(dnum.alloc(sizeof(unsigned long long)));
+        thrust::counting_iterator<uint32_t> it(0);
+        size_t tmp_bytes = 0;
+        StoredInLayer pred{res->d_table, 0};
+        cub::DeviceSelect::If(nullptr, tmp_bytes, it, dmasks.as<uint32_t>(), dnum.as<unsigned long long>(), (int64_t)res->n_masks, pred, s);
+        CK(tmp.alloc(tmp_bytes));
+        uint64_t off = 0;
+        for (int layer = 0; layer <= res->max_parents && off < total; layer++) {
+            pred.layer = layer;
+            CK(cub::DeviceSelect::If(tmp.p, tmp_bytes, it, dmasks.as<uint32_t>() + off, dnum.as<unsigned long long>(), (int64_t)res->n_masks, pred, s));
+            unsigned long long h = 0;
+            CK(cudaMemcpyAsync(&h, dnum.p, sizeof h, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            off += h;
+        }
+        if (off != total) return ctx->fail(URLGPU_ERR_INTERNAL, "result compaction lost entries");
+        gather_scores_kernel<<<blocks_for(total, 256), 256, 0, s>>>(res->d_table, dmasks.as<uint32_t>(), total, dvals.as<float>());
+        CK(cudaMemcpyAsync(res->h_masks.data(), dmasks.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(res->h_scores.data(), dvals.p, total * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+    }
+    res->compacted = true;
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_result_fetch(urlgpu_result *res, uint64_t offset, uint64_t n, uint64_t *masks, float *scores) {
+    if (!res) return URLGPU_ERR_ARG;
+    urlgpu_ctx *ctx = res->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int rc = result_compact(res);
+    if (rc) return rc;
+    if (offset + n > res->h_masks.size()) return ctx->fail(URLGPU_ERR_ARG, "result_fetch: range exceeds the stored count");
+    for (uint64_t i = 0; i < n; i++) {
+        const uint32_t cm = res->h_masks[offset + i];
+        if (masks) {
+            uint64_t *dst = masks + i * (uint64_t)res->mask_words;
+            for (int w = 0; w < res->mask_words; w++) dst[w] = 0;
+            for (int b = 0; b < res->c; b++)
+                if ((cm >> b) & 1) dst[res->cand[b] >> 6] |= (uint64_t)1 << (res->cand[b] & 63);
+        }
+        if (scores) scores[i] = res->h_scores[offset + i];
+    }
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_result_free(urlgpu_result *res) {
+    if (!res) return URLGPU_OK;
+    cudaSetDevice(res->ctx->device);
+    if (res->d_table) cudaFree(res->d_table);
+    delete res;
+    return URLGPU_OK;
+}
+
+// ============================================================================================ single set / counts / prune
+
+static int compact_of(urlgpu_ctx *ctx, int p, int variable, const uint64_t *parents, int mask_words, std::vector<int> &cand) {
+    int rc = candidates_from_mask(ctx, p, variable, parents, mask_words, cand);
+    if (rc) return rc;
+    if ((int)cand.size() > kMaxDenseCand) return ctx->fail(URLGPU_ERR_LIMIT, "more than 30 parents in one set");
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *parents, int mask_words, int score_type, double lambda, float *score,
+                                double *value64) {
+    if (!ctx || !parents || !score) return ctx ? ctx->fail(URLGPU_ERR_ARG, "score_one: null argument") : URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const bool bic = score_type == URLGPU_BIC;
+    if (bic && !ctx->have_discrete) return ctx->fail(URLGPU_ERR_ARG, "score_one: BIC needs urlgpu_set_discrete first");
+    if (!bic && !ctx->have_gram) return ctx->fail(URLGPU_ERR_ARG, "score_one: cBIC needs urlgpu_set_continuous first");
+    const int p = bic ? ctx->p : ctx->cp;
+    if (variable < 0 || variable >= p) return ctx->fail(URLGPU_ERR_ARG, "score_one: variable out of range");
+    std::vector<int> cand;
+    int rc = compact_of(ctx, p, variable, parents, mask_words, cand);
+    if (rc) return rc;
+    // the set itself is the whole candidate list: its compact mask is all ones
+    const int c = (int)cand.size();
+    const uint64_t n_masks = (uint64_t)1 << c;
+    const uint32_t full = (uint32_t)(n_masks - 1);
+    cudaStream_t s = ctx->stream;
+    DevBuf tab, aux;
+    CK(tab.alloc(n_masks * sizeof(float)));
+    if (bic) {
+        CK(aux.alloc(n_masks * sizeof(long long)));
+        BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+        CandInfo ci = make_candinfo(ctx, variable, cand, c);
+        uint64_t cells = ci.rv;
+        for (int b = 0; b < c; b++) { cells *= (uint64_t)ci.card[b]; if (cells > kCellLimit) return ctx->fail(URLGPU_ERR_LIMIT, "contingency table exceeds 2^30 cells"); }
+        std::vector<uint32_t> one(1, full);
+        rc = bic_run_global_tier(ctx, bd, ci, one, tab.as<float>(), aux.as<long long>(), nullptr, 0);
+        if (rc) return rc;
+        long long fx = 0;
+        CK(cudaMemcpyAsync(score, tab.as<float>() + full, sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&fx, aux.as<long long>() + full, sizeof fx, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (value64) *value64 = std::ldexp((double)fx, -23);
+    } else {
+        CK(aux.alloc(n_masks * sizeof(double)));
+        uint64_t ns;
+        rc = cbic_score_family(ctx, variable, cand, c, lambda, tab.as<float>(), aux.as<double>(), &ns);
+        if (rc) return rc;
+        float ts = 0;
+        double ts64 = 0;
+        CK(cudaMemcpyAsync(&ts, tab.as<float>() + full, sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&ts64, aux.as<double>() + full, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        *score = -ts; // BIC_OLS.cpp:223,245,275
+        if (value64) *value64 = ts64;
+    }
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_contingency(urlgpu_ctx *ctx, int variable, const uint64_t *parents, int mask_words, int32_t *counts, int64_t n_cells) {
+    if (!ctx || !parents || !counts) return ctx ? ctx->fail(URLGPU_ERR_ARG, "contingency: null argument") : URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_discrete) return ctx->fail(URLGPU_ERR_ARG, "contingency: needs urlgpu_set_discrete first");
+    if (variable < 0 || variable >= ctx->p) return ctx->fail(URLGPU_ERR_ARG, "contingency: variable out of range");
+    std::vector<int> cand;
+    int rc = compact_of(ctx, ctx->p, variable, parents, mask_words, cand);
+    if (rc) return rc;
+    const int c = (int)cand.size();
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+    CandInfo ci = make_candinfo(ctx, variable, cand, c);
+    uint64_t cells = ci.rv;
+    for (int b = 0; b < c; b++) { cells *= (uint64_t)ci.card[b]; if (cells > kCellLimit) return ctx->fail(URLGPU_ERR_LIMIT, "contingency table exceeds 2^30 cells"); }
+    if ((int64_t)cells != n_cells) return ctx->fail(URLGPU_ERR_ARG, "contingency: n_cells must be r_v * prod r_pa = " + std::to_string(cells));
+    std::vector<uint32_t> one(1, (uint32_t)(((uint64_t)1 << c) - 1));
+    return bic_run_global_tier(ctx, bd, ci, one, nullptr, nullptr, counts, n_cells);
+}
+
+extern "C" int urlgpu_prune(urlgpu_ctx *ctx, const uint64_t *masks, const float *scores, uint64_t n, int mask_words, uint8_t *keep) {
+    if (!ctx || !masks || !scores || !keep || mask_words < 1) return ctx ? ctx->fail(URLGPU_ERR_ARG, "prune: bad argument") : URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    // compact the union of all masks to <= 30 bits
+    std::vector<uint64_t> uni(mask_words, 0);
+    for (uint64_t i = 0; i < n; i++)
+        for (int w = 0; w < mask_words; w++) uni[w] |= masks[i * mask_words + w];
+    std::vector<int> vars;
+    for (int w = 0; w < mask_words; w++)
+        for (int b = 0; b < 64; b++) if ((uni[w] >> b) & 1) vars.push_back(w * 64 + b);
+    const int c = (int)vars.size();
+    if (c > kMaxDenseCand) return ctx->fail(URLGPU_ERR_LIMIT, "prune: masks span more than 30 distinct variables");
+    std::vector<int> pos(mask_words * 64, -1);
+    for (int i = 0; i < c; i++) pos[vars[i]] = i;
+    const uint64_t n_masks = (uint64_t)1 << c;
+    std::vector<uint32_t> cm(n);
+    int K = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t m = 0;
+        for (int j = 0; j < c; j++) if ((masks[i * mask_words + (vars[j] >> 6)] >> (vars[j] & 63)) & 1) m |= 1u << j;
+        cm[i] = m;
+        K = std::max(K, __builtin_popcount(m));
+    }
+    cudaStream_t s = ctx->stream;
+    DevBuf tab, dm, dv, dout;
+    CK(tab.alloc(n_masks * sizeof(float)));
+    CK(dm.alloc(n * sizeof(uint32_t))); CK(dv.alloc(n * sizeof(float))); CK(dout.alloc(n * sizeof(float)));
+    fill_u32_kernel<<<blocks_for(n_masks, 256), 256, 0, s>>>(tab.as<uint32_t>(), n_masks, kSentinelBits);
+    // scatter on the host side of a staging table would need 2^c floats; scatter on the device instead
+    CK(cudaMemcpyAsync(dm.p, cm.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dv.p, scores, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    extern __global__ void urlgpu_scatter_kernel(float *, const uint32_t *, const float *, uint64_t);
+    urlgpu_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(tab.as<float>(), dm.as<uint32_t>(), dv.as<float>(), n);
+    int rc = run_prune(ctx, tab.as<float>(), c, K);
+    if (rc) return rc;
+    gather_scores_kernel<<<blocks_for(n, 256), 256, 0, s>>>(tab.as<float>(), dm.as<uint32_t>(), n, dout.as<float>());
+    std::vector<float> out(n);
+    CK(cudaMemcpyAsync(out.data(), dout.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t bits;
+        memcpy(&bits, &out[i], 4);
+        keep[i] = bits != kSentinelBits;
+    }
+    return URLGPU_OK;
+}
+
+__global__ void urlgpu_scatter_kernel(float *table, const uint32_t *masks, const float *vals, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) table[masks[i]] = vals[i];
+}

@@ -1,0 +1,209 @@
+// score_main.cpp — the `score` binary: same command line and .pss output as the reference's
+// urlearning/score/score_main.cpp:209-403, with the inner scoring loop replaced by liburlgpu (B200).
+//
+// Differences, all documented in DESIGN.md: only -f BIC and -f cBIC are offered (the path this engine
+// accelerates); .pss lines are written in canonical (|S|, mask) order instead of boost::unordered_map order;
+// pruning is opt-in through --prune because the reference's call is commented out (score_main.cpp:166-171);
+// -t selects the number of worker threads, thread t driving device t % (visible devices); an unreadable
+// skeleton file is an error; the AD-tree options (-m) are accepted and ignored.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <thread>
+
+#include "gpu_scoring.hpp"
+
+using namespace urlhost;
+
+namespace {
+
+struct Options {
+    std::string inputFile, outputFile, constraintsFile, skeletonFile, sf = "BIC";
+    char delimiter = ',';
+    double lambda = 0.5;
+    int rMin = 5, maxParents = 0, threadCount = 1, runningTime = -1, which = 1;
+    float ess = 1.0f;
+    bool hasHeader = false, doNotPrune = false, prune = false, deCampos = false, adaptive = false, quiet = false;
+};
+
+void usage(const char *argv0) {
+    std::cout << "Compute the scores for a csv file.  Example usage: " << argv0 << " iris.csv iris.pss\n"
+              << "  --input arg                The input file. First positional argument.\n"
+              << "  --output arg               The output file. Second positional argument.\n"
+              << "  -d [ --delimiter ] arg (=,) The delimiter of the input file.\n"
+              << "  -l [ --lambda ] arg        The lambda in cBIC.\n"
+              << "  -k [ --skeleton ] arg      The file specifying the skeleton superstructure\n"
+              << "  -f [ --function ] arg (=BIC) The scoring function to use (BIC | cBIC).\n"
+              << "  -p [ --maxParents ] arg (=0) The maximum number of parents for any variable. A value less than 1 means no limit.\n"
+              << "  -t [ --threads ] arg (=1)  Worker threads; thread t drives GPU t mod (visible GPUs).\n"
+              << "  -s [ --hasHeader ]         The first line of the input file gives the variable names.\n"
+              << "  -o [ --doNotPrune ]        Accepted for compatibility (the reference ignores it).\n"
+              << "  --prune                    Apply ScoreCalculator::prune (subset dominance) before writing.\n"
+              << "  -m, -e, -r, -w, -c, -a, --enableDeCamposPruning   accepted for compatibility.\n"
+              << "  -h [ --help ]              Show this help message.\n";
+}
+
+std::string lexicalFloat(float f) { char b[64]; snprintf(b, sizeof b, "%.9g", (double)f); return b; } // boost::lexical_cast<std::string>(float)
+
+bool parse(int argc, char **argv, Options &o) {
+    std::vector<std::string> pos;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto takes = [&](const char *shortn, const char *longn, std::string &dst) -> bool {
+            std::string l = std::string("--") + longn;
+            if (a == shortn || a == l) {
+                if (i + 1 >= argc) throw std::runtime_error("the required argument for option '" + l + "' is missing");
+                dst = argv[++i];
+                return true;
+            }
+            if (a.rfind(l + "=", 0) == 0) { dst = a.substr(l.size() + 1); return true; }
+            if (shortn[0] && a.size() > 2 && a.rfind(shortn, 0) == 0 && a[1] != '-') { dst = a.substr(2); return true; }
+            return false;
+        };
+        std::string v;
+        if (a == "-h" || a == "--help") return false;
+        else if (takes("", "input", v)) o.inputFile = v;
+        else if (takes("", "output", v)) o.outputFile = v;
+        else if (takes("-d", "delimiter", v)) o.delimiter = v.empty() ? ',' : v[0];
+        else if (takes("-l", "lambda", v)) o.lambda = atof(v.c_str());
+        else if (takes("-w", "scoreType", v)) o.which = atoi(v.c_str());
+        else if (takes("-c", "constraints", v)) o.constraintsFile = v;
+        else if (takes("-k", "skeleton", v)) o.skeletonFile = v;
+        else if (takes("-m", "rMin", v)) o.rMin = atoi(v.c_str());
+        else if (takes("-f", "function", v)) o.sf = v;
+        else if (takes("-e", "ess", v)) o.ess = (float)atof(v.c_str());
+        else if (takes("-p", "maxParents", v)) o.maxParents = atoi(v.c_str());
+        else if (takes("-t", "threads", v)) o.threadCount = atoi(v.c_str());
+        else if (takes("-r", "time", v)) o.runningTime = atoi(v.c_str());
+        else if (a == "-a" || a == "--adaptive") o.adaptive = true;
+        else if (a == "-s" || a == "--hasHeader") o.hasHeader = true;
+        else if (a == "-o" || a == "--doNotPrune") o.doNotPrune = true;
+        else if (a == "--prune") o.prune = true;
+        else if (a == "--quiet") o.quiet = true;
+        else if (a == "--enableDeCamposPruning") o.deCampos = true;
+        else if (a.size() > 1 && a[0] == '-') throw std::runtime_error("unrecognised option '" + a + "'");
+        else pos.push_back(a);
+    }
+    if (o.inputFile.empty() && pos.size() > 0) o.inputFile = pos[0];
+    if (o.outputFile.empty() && pos.size() > 1) o.outputFile = pos[1];
+    if (o.inputFile.empty()) throw std::runtime_error("the option '--input' is required but missing");
+    if (o.outputFile.empty()) throw std::runtime_error("the option '--output' is required but missing");
+    return true;
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    const auto t0 = std::chrono::steady_clock::now();
+    Options o;
+    try {
+        if (argc == 1 || !parse(argc, argv, o)) { usage(argv[0]); return 0; }
+        if (o.threadCount < 1) o.threadCount = 1;
+        if (!o.constraintsFile.empty()) throw std::runtime_error("constraints files (-c) are not supported by the GPU score path");
+        if (o.runningTime > 0) fprintf(stderr, "warning: -r (per-variable time limit) is ignored by the GPU score path\n");
+
+        printf("URLearning, Score Calculator (urlgpu / B200)\n");
+        printf("Input file: '%s'\n", o.inputFile.c_str());
+        printf("Output file: '%s'\n", o.outputFile.c_str());
+        printf("Delimiter: '%c'\n", o.delimiter);
+        printf("Scoring function: '%s'\n", o.sf.c_str());
+        printf("Maximum parents: '%d'\n", o.maxParents);
+        printf("Threads: '%d'\n", o.threadCount);
+        printf("Has header: '%s'\n", o.hasHeader ? "true" : "false");
+        printf("Enable end-of-scoring pruning: '%s'\n", o.prune ? "true" : "False");
+
+        printf("Parsing input file.\n");
+        RecordFile recordFile(o.inputFile, o.delimiter, o.hasHeader);
+        recordFile.read();
+        printf("Initializing data specifications.\n");
+        BayesianNetwork network;
+        network.initialize(recordFile);
+        const int p = network.size();
+        if (p > kVarsetWords * 64) throw std::runtime_error("more than 256 variables");
+
+        std::string sf = o.sf;
+        for (auto &ch : sf) ch = (char)std::tolower((unsigned char)ch); // score_main.cpp:294
+        int maxParents = o.maxParents;
+        if (maxParents > p || maxParents < 1) maxParents = p - 1; // :296-298
+        if (sf == "bic") {
+            int maxParentCount = (int)std::log(2 * recordFile.size() / std::log((double)recordFile.size())); // :301
+            if (maxParentCount < maxParents) maxParents = maxParentCount;
+        } else if (sf != "cbic") {
+            throw std::runtime_error("Invalid scoring function.  The GPU score path offers 'BIC' and 'cBIC'.");
+        }
+
+        printf("Skeleton file %s\n", o.skeletonFile.c_str());
+        Skeleton skeleton;
+        if (!o.skeletonFile.empty()) { // :319-329
+            if (o.skeletonFile.find(".arc") + 4 == o.skeletonFile.size()) skeleton.read_arc_list_file(o.skeletonFile, p);
+            else skeleton.read_matrix_file(o.skeletonFile, p);
+        } else skeleton.set_variable_count(p);
+
+        int ndev = urlgpu_device_count();
+        if (ndev < 1) throw std::runtime_error("urlgpu: no CUDA device available; the score path has no CPU fallback");
+
+        std::vector<std::string> blocks(p);
+        std::vector<uint64_t> scored(p, 0);
+        std::vector<std::string> errors(o.threadCount);
+        auto scoringThread = [&](int thread) { // score_main.cpp:132-207
+            try {
+                scoring::GpuContext gpu(thread % ndev);
+                std::unique_ptr<scoring::ScoringFunction> scoringFunction;
+                if (sf == "bic") scoringFunction.reset(new scoring::GpuBICScoringFunction(gpu, network, recordFile.size()));
+                else scoringFunction.reset(new scoring::GpuBICOLSFunction(gpu, recordFile, o.lambda));
+                scoring::ScoreCalculator scoreCalculator(scoringFunction.get(), maxParents, p, o.prune);
+                for (int variable = 0; variable < p; variable++) {
+                    if (variable % o.threadCount != thread) continue; // :137
+                    scoring::FloatMap sc;
+                    // also include neighbors' neighbors (:145-153)
+                    Varset orig = skeleton.get_neighbors(variable), nb = orig;
+                    for (int j = 0; j < p; j++)
+                        if (orig.get(j) && j != variable) nb = nb | skeleton.get_neighbors(j);
+                    scoreCalculator.calculateScores(variable, sc, nb);
+                    scored[variable] = scoreCalculator.lastScored;
+                    if (!o.quiet)
+                        printf("Thread: %d, Variable: %d, Size %s pruning: %d, neighbor cardinality %d/%d\n", thread, variable,
+                               o.prune ? "after" : "before", (int)sc.size(), orig.cardinality(), nb.cardinality());
+                    std::string &out = blocks[variable];
+                    char buf[64];
+                    out += "VAR " + network.get(variable).name + "\n";                                   // :177
+                    out += "META arity=" + std::to_string(network.getCardinality(variable)) + "\n";      // :178
+                    for (size_t i = 0; i < sc.size(); i++) {
+                        snprintf(buf, sizeof buf, "%f ", sc.values[i]);                                    // :191
+                        out += buf;
+                        for (int q = 0; q < p; q++)
+                            if (sc.keys[i].get(q)) { out += network.get(q).name; out += " "; }             // :193-197
+                        out += "\n";
+                    }
+                    out += "\n";
+                }
+            } catch (const std::exception &e) { errors[thread] = e.what(); }
+        };
+        const auto t1 = std::chrono::steady_clock::now();
+        std::vector<std::thread> threads;
+        for (int t = 0; t < o.threadCount; t++) threads.emplace_back(scoringThread, t); // :372-380
+        for (auto &t : threads) t.join();
+        for (auto &e : errors) if (!e.empty()) throw std::runtime_error(e);
+        const auto t2 = std::chrono::steady_clock::now();
+
+        std::ofstream out(o.outputFile, std::ios_base::out | std::ios_base::binary);
+        if (!out.good()) throw std::runtime_error("Could not open the output file: '" + o.outputFile + "'");
+        out << "META pss_version = 0.1\nMETA input_file=" << o.inputFile << "\nMETA num_records=" << recordFile.size() << "\n"; // :387
+        out << "META parent_limit=" << maxParents << "\nMETA score_type=" << sf << "\nMETA ess=" << lexicalFloat(o.ess) << "\n\n"; // :388
+        for (int v = 0; v < p; v++) out << blocks[v];
+        out.close();
+        const auto t3 = std::chrono::steady_clock::now();
+        uint64_t total = 0;
+        for (auto s : scored) total += s;
+        auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+        printf("Scored %llu parent sets in %.3f s (%.3e sets/s); parse %.3f s, write %.3f s, total %.3f s wall\n", (unsigned long long)total,
+               sec(t1, t2), total / std::max(1e-9, sec(t1, t2)), sec(t0, t1), sec(t2, t3), sec(t0, t3));
+    } catch (const std::exception &e) {
+        fprintf(stderr, "score: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
