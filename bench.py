@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — parent-set local scores per second on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+Workload (default): BASELINE.json configs[3] — synthetic discrete BN p=60, n=1M, arity<=4, generating-graph skeleton
+(stand-in for MMPC), `-p 12` (effective BIC cap 11), BIC + ScoreCache pruning.  It is the configuration the metric's
+roofline target is quoted on and the largest discrete one that fits a single GPU; configs[0..2] are parity-test
+cases (tests/), configs[4] needs 8 GPUs and wide masks.  `--workload cbic` runs configs[2]
+(linear-Gaussian p=30, n=100k, cBIC lambda=2, exhaustive) instead.
+
+A step = one pass of the hot path over every variable this rank owns (variables striped v % N as the reference
+stripes its threads, score_main.cpp:136-139): score every candidate parent set, apply the store rule and the
+subset-dominance prune, results left on the device.  `value` = sets scored by all ranks / max-over-ranks device
+time.  `e2e` repeats the same through the public API with HOST buffers: the H2D copy of the data from pinned
+memory and the D2H fetch of every variable's surviving (mask, score) list are inside the timed region.
+
+--impl reference times the CPU oracle's restatement of the reference path (oracle/, or oracle/_ref when the
+reference's own sources were compiled) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "parent-set local scores/sec"
+UNIT = "sets/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            pk = json.load(f)
+        return float(pk.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.reasons = set()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nme, val in zip(names, f[2:6]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------- workloads
+
+def make_bic_workload(pkg):
+    p, n = 60, 1_000_000
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=p, n=n, seed=4)
+    K = pkg.effective_max_parents(12, p, n, True)
+    nbs = [pkg.two_hop_neighbors(edges, p, v) for v in range(p)]
+    return dict(kind="bic", p=p, n=n, codes=codes, card=card, edges=edges, K=K, nbs=nbs,
+                name="configs[3]: synthetic discrete BN p=60 n=1e6 arity<=4 seed=4, generating-graph skeleton (2-hop), -p 12 -> cap 11, BIC + prune")
+
+
+def make_cbic_workload(pkg):
+    p, n = 30, 100_000
+    x, _ = pkg.datagen.linear_gaussian_sem(p=p, n=n, seed=3)
+    nbs = [(1 << p) - 1] * p
+    return dict(kind="cbic", p=p, n=n, x=x, K=p - 1, nbs=nbs, lam=2.0,
+                name="configs[2]: synthetic linear-Gaussian SEM p=30 n=1e5 seed=3, cBIC lambda=2, all-ones skeleton (2^29 sets/variable), accept + prune")
+
+
+def family_size(c, K):
+    from math import comb
+    return sum(comb(c, l) for l in range(0, min(c, K) + 1))
+
+
+def my_variables(wl, rank, world):
+    return [v for v in range(wl["p"]) if v % world == rank]
+
+
+def sets_of(wl, v):
+    c = bin(wl["nbs"][v] & ~(1 << v)).count("1")
+    return family_size(c, wl["K"])
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+
+def run_gpu(args):
+    import torch
+    pkg = importlib.import_module("urlearning-cpp_b200")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    eng = pkg.Engine(local)  # raises if the CUDA library or the device is missing: no fallback
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    # ---- inputs: rank 0 generates, NCCL broadcast to every GPU (the path's one exchange step) ----
+    wl = (make_bic_workload if args.workload == "bic" else make_cbic_workload)(pkg) if rank == 0 else None
+    if world > 1:
+        box = [None if wl is None else {k: v for k, v in wl.items() if k not in ("codes", "x")}]
+        dist.broadcast_object_list(box, src=0)
+        meta = box[0]
+        if meta["kind"] == "bic":
+            d = torch.empty((meta["p"], meta["n"]), dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                d.copy_(torch.from_numpy(wl["codes"]))
+            dist.broadcast(d, src=0)
+            if rank != 0:
+                wl = dict(meta)
+            wl["dev"] = d
+        else:
+            # the rows are only needed for the Gram: rank 0 forms it, the p*p Gram is broadcast
+            wl = wl if rank == 0 else dict(meta)
+    is_bic = wl["kind"] == "bic"
+    flags = pkg.PRUNE_DOMINATED
+    stype = pkg.BIC if is_bic else pkg.CBIC
+    lam = wl.get("lam", 0.0)
+
+    pinned = None
+    if is_bic:
+        if "dev" in wl:
+            eng.set_discrete_device(wl["dev"].data_ptr(), wl["n"], wl["p"], wl["card"])
+        else:
+            pinned = torch.from_numpy(wl["codes"]).pin_memory()
+            eng.set_discrete(pinned.numpy(), wl["card"])
+    else:
+        if rank == 0:
+            pinned = torch.from_numpy(wl["x"]).pin_memory()
+            eng.set_continuous(pinned.numpy())
+            g = torch.from_numpy(eng.gram()).cuda()
+        else:
+            g = torch.empty((wl["p"], wl["p"]), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.broadcast(g, src=0)
+            if rank != 0:
+                eng.set_gram(g.cpu().numpy(), wl["n"])
+
+    mine = my_variables(wl, rank, world)
+    sets_mine = sum(sets_of(wl, v) for v in mine)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step(fetch=False):
+        flush.fill_(1)  # L2 flush between steps (inside the timed region: ~40 us of a multi-second step)
+        stored = 0
+        for v in mine:
+            res = eng.score_variable(v, wl["nbs"][v], wl["K"], stype, lam=lam, flags=flags)
+            if fetch:
+                m, s = res.fetch()
+                stored += len(s)
+            res.free()
+        return stored
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, **kw):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = 0
+        for _ in range(nsteps):
+            out += step(**kw)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.reset_stats()
+    eng.enable_timing(True)
+    ms, _ = timed(args.steps)
+    st = eng.stats()
+    eng.enable_timing(False)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    total_sets = sets_mine
+    if world > 1:
+        t = torch.tensor([sets_mine], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        total_sets = int(t.item())
+    value = total_sets * args.steps / (ms / 1e3)
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region (every rank uploads its own copy of the data) ----
+    e2e = None
+    if is_bic or world == 1:
+        if is_bic and pinned is None:
+            pinned = wl["dev"].cpu().pin_memory()
+        host = pinned.numpy()
+
+        def e2e_step():
+            if is_bic:
+                eng.set_discrete(host, wl["card"])
+            else:
+                eng.set_continuous(host)
+            return step(fetch=True)
+
+        e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        stored = 0
+        nst = max(1, min(args.steps, 3))
+        for _ in range(nst):
+            stored += e2e_step()
+        e1.record(stream)
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ems], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        h2d = (wl["n"] * wl["p"]) * (1 if is_bic else 8)
+        e2e = {"value": total_sets * nst / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(12 * stored // nst), "steps": nst, "ms_per_step": ems / nst}
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        fam = {"count": st["ms_count"], "cube": st["ms_cube"], "cbic": st["ms_cbic"], "accept": st["ms_accept"], "prune": st["ms_prune"]}
+        dom = max(fam, key=fam.get)
+        if is_bic:
+            k1_ms = st["ms_count"] + st["ms_cube"]
+            k1_launches = st["launches_count"] + st["launches_cube"]
+            achieved = st["algorithmic_bytes"] / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else None
+            roofline = {"bound": "hbm", "kernel": "K1 bic count+cube (families count,cube)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_step": st["algorithmic_bytes"] / args.steps, "kernel_ms_per_step": k1_ms / args.steps,
+                        "launches_per_step": k1_launches / args.steps, "share_of_step": k1_ms / ms, "family_ms": fam}
+        else:
+            k3_ms = st["ms_cbic"]
+            achieved = st["algorithmic_flops"] / (k3_ms / 1e3) / 1e12 if k3_ms > 0 else None
+            roofline = {"bound": "fp64", "kernel": "K3 cbic sweep DFS", "achieved": achieved, "peak": 37.0, "unit": "TFLOP/s",
+                        "frac": achieved / 37.0 if achieved else None, "traffic": None,
+                        "peak_source": "nominal B200 FP64 (no measured FP64 entry in MEASURED_PEAKS.json)",
+                        "algorithmic_flops_per_step": st["algorithmic_flops"] / args.steps, "kernel_ms_per_step": k3_ms / args.steps,
+                        "share_of_step": k3_ms / ms, "family_ms": fam}
+        cpu = cpu_baseline(wl, args) if world == 1 and not args.no_cpu_baseline else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "int32 counts / int64 fixed-point log-likelihood -> f32" if is_bic else "f64 -> f32",
+                "data": "synthetic (seeded numpy generator, urlearning-cpp_b200/datagen.py)",
+                "config": {"workload": wl["name"], "sets_per_step": total_sets, "parallelism": f"variables striped v % {world}",
+                           "l2": "flushed between steps (256 MB write)", "dominant_family": dom},
+                "e2e": e2e, "gpu_launches": int(st["launches_total"]), "clocks": sampler.summary(), "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------- CPU arms
+
+def cpu_sample(wl, budget_s, threads, seed=0):
+    """Time the oracle on a bounded sample: sets drawn uniformly from the whole workload's candidate families."""
+    import oracle_lib as orc
+    rng = np.random.default_rng(seed)
+    p = wl["p"]
+    fam = np.array([sets_of(wl, v) for v in range(p)], dtype=np.float64)
+    t_used, n_done = 0.0, 0
+    batch = 4 * threads
+    z = None
+    if wl["kind"] == "cbic":
+        z = orc.standardise(wl["x"])
+    while t_used < budget_s:
+        v = int(rng.choice(p, p=fam / fam.sum()))
+        cand = [i for i in range(p) if i != v and (wl["nbs"][v] >> i) & 1]
+        masks = []
+        for _ in range(batch):
+            # uniform over the family: pick a layer with probability C(c,l)/family, then a uniform l-subset
+            from math import comb
+            w = np.array([comb(len(cand), l) for l in range(min(len(cand), wl["K"]) + 1)], dtype=np.float64)
+            l = int(rng.choice(len(w), p=w / w.sum()))
+            masks.append(sum(1 << int(i) for i in rng.choice(cand, size=l, replace=False)) if l else 0)
+        t0 = time.perf_counter()
+        if wl["kind"] == "bic":
+            orc.bic_score_many(wl["codes"], wl["card"], v, np.array(masks, dtype=np.uint64), 0, threads)
+        else:
+            import concurrent.futures as cf
+            with cf.ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL
+                list(ex.map(lambda m: orc.cbic_residual(z, v, int(m), wl["lam"]), masks))
+        t_used += time.perf_counter() - t0
+        n_done += batch
+    return n_done / t_used, n_done, t_used
+
+
+def cpu_baseline(wl, args):
+    threads = os.cpu_count() or 1
+    rate, n_done, t_used = cpu_sample(wl, args.cpu_seconds, threads)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_done} parent sets drawn uniformly from the workload's candidate families, {t_used:.1f} s, "
+                      "oracle direct counting / per-set OLS refit (the reference's algorithmic structure), no pruning"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = importlib.import_module("urlearning-cpp_b200")
+    wl = (make_bic_workload if args.workload == "bic" else make_cbic_workload)(pkg)
+    threads = os.cpu_count() or 1
+    per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup):
+        cpu_sample(wl, per_step, threads, seed=100 + i)
+    done, used = 0, 0.0
+    for i in range(args.steps):
+        r, n_done, t_used = cpu_sample(wl, per_step, threads, seed=i)
+        done += n_done
+        used += t_used
+    value = done / used
+    total_sets = sum(sets_of(wl, v) for v in range(wl["p"]))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": used / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32 counts -> f32" if wl["kind"] == "bic" else "f64 -> f32",
+            "data": "synthetic (seeded numpy generator, urlearning-cpp_b200/datagen.py)",
+            "config": {"workload": wl["name"], "sets_per_step": total_sets,
+                       "note": "each step = a bounded uniform sample of the workload's parent sets on the host cores"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{done} sampled parent sets in {used:.1f} s over {args.steps} steps"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="urlgpu", choices=["urlgpu", "reference"])
+    ap.add_argument("--workload", default="bic", choices=["bic", "cbic"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,22 @@ def engine(pkg):
     eng.close()
 
 
+@pytest.fixture(scope="session", params=["cube", "direct"])
+def bic_engine(pkg, request):
+    """BIC engines for both K1 strategies: 'cube' (count roots, marginalise the rest; default) and 'direct' (count every set)."""
+    old = os.environ.get("URLGPU_BIC_MODE")
+    os.environ["URLGPU_BIC_MODE"] = request.param
+    try:
+        eng = pkg.Engine(0)
+    finally:
+        if old is None:
+            os.environ.pop("URLGPU_BIC_MODE", None)
+        else:
+            os.environ["URLGPU_BIC_MODE"] = old
+    yield eng
+    eng.close()
+
+
 DATA = os.path.join(ROOT, "tests", "data")
 
 

@@ -29,7 +29,8 @@ def _check_variable(pkg, orc, eng, codes, card, edges, v, K, flags=0):
     return len(order)
 
 
-def test_hepatitis_all_variables(pkg, orc, engine, data_dir):
+def test_hepatitis_all_variables(pkg, orc, bic_engine, data_dir):
+    engine = bic_engine
     t = orc.Table(os.path.join(data_dir, "hepatitis.clean.csv"), has_header=True)
     codes = t.codes()
     engine.set_discrete(codes, t.card)
@@ -58,7 +59,8 @@ def test_contingency_counts_ragged_rows(pkg, orc, engine):
 
 
 @pytest.mark.parametrize("n", [1, 15, 16, 17, 4097])
-def test_tiny_and_edge_row_counts(pkg, orc, engine, n):
+def test_tiny_and_edge_row_counts(pkg, orc, bic_engine, n):
+    engine = bic_engine
     codes, card, edges, _ = pkg.datagen.discrete_bn(p=6, n=max(n, 2), seed=n, arities=(2, 3))
     codes = codes[:, :n].copy()
     if n < 3:  # N=1: log(1)=0 -> the reference's BIC parent cap divides by zero; use N=2 instead
@@ -71,7 +73,8 @@ def test_tiny_and_edge_row_counts(pkg, orc, engine, n):
         _check_variable(pkg, orc, engine, codes, card, None, v, 5)
 
 
-def test_all_tiers_arity4(pkg, orc, engine):
+def test_all_tiers_arity4(pkg, orc, bic_engine):
+    engine = bic_engine
     """tables from 4 cells to 4^10 = 1M cells: small shared tier, one-CTA-per-SM shared tier and the global tier"""
     codes, card, edges, _ = pkg.datagen.discrete_bn(p=11, n=20011, seed=5, arities=(4,), window=10, max_indegree=3)
     engine.set_discrete(codes, card)
@@ -79,7 +82,8 @@ def test_all_tiers_arity4(pkg, orc, engine):
         _check_variable(pkg, orc, engine, codes, card, None, v, 9)
 
 
-def test_skeleton_two_hop_and_prune(pkg, orc, engine):
+def test_skeleton_two_hop_and_prune(pkg, orc, bic_engine):
+    engine = bic_engine
     codes, card, edges, _ = pkg.datagen.discrete_bn(p=24, n=30000, seed=7, window=3, max_indegree=2)
     engine.set_discrete(codes, card)
     K = pkg.effective_max_parents(12, 24, 30000, True)
@@ -88,7 +92,8 @@ def test_skeleton_two_hop_and_prune(pkg, orc, engine):
         _check_variable(pkg, orc, engine, codes, card, edges, v, K, flags=pkg.PRUNE_DOMINATED)
 
 
-def test_row_permutation_invariance_and_counts_sum(pkg, orc, engine):
+def test_row_permutation_invariance_and_counts_sum(pkg, orc, bic_engine):
+    engine = bic_engine
     codes, card, edges, _ = pkg.datagen.discrete_bn(p=10, n=50000, seed=9)
     perm = np.random.default_rng(1).permutation(50000)
     engine.set_discrete(codes, card)

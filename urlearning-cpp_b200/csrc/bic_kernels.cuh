@@ -165,7 +165,9 @@ __device__ __forceinline__ float bic_finalize(long long acc, float tval, float b
 // K1 (shared-memory tier): one CTA per parent set; whole table in shared memory.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void bic_count_smem_kernel(BicData d, CandInfo ci, const uint32_t *__restrict__ work, float *__restrict__ scores,
-                                      long long *__restrict__ ll_fixed /*optional, dense by mask*/) {
+                                      long long *__restrict__ ll_fixed /*optional, dense by mask*/,
+                                      const uint64_t *__restrict__ table_offs /*optional, per work item*/, int *__restrict__ tables_out,
+                                      long long *__restrict__ acc_out /*optional, per work item*/) {
     extern __shared__ __align__(16) int hist[];
     __shared__ SetCols sc;
     __shared__ long long red[32];
@@ -176,11 +178,17 @@ __global__ void bic_count_smem_kernel(BicData d, CandInfo ci, const uint32_t *__
     __syncthreads();
     count_rows(sc, 0, d.n, hist, threadIdx.x, blockDim.x);
     __syncthreads();
+    if (table_offs) { // cube roots: the table is the parent of marginalised children
+        int *dst = tables_out + table_offs[blockIdx.x];
+        for (uint32_t i = threadIdx.x; i < sc.cells; i += blockDim.x) dst[i] = hist[i];
+    }
+    if (!scores && !acc_out) return;
     long long acc = score_configs(hist, ci.rv, 0, sc.cells / ci.rv, d.qlog, threadIdx.x, blockDim.x);
     acc = block_sum_ll(acc, red);
     if (threadIdx.x == 0) {
-        scores[mask] = bic_finalize(acc, sc.tval, d.base);
+        if (scores) scores[mask] = bic_finalize(acc, sc.tval, d.base);
         if (ll_fixed) ll_fixed[mask] = acc;
+        if (acc_out) acc_out[blockIdx.x] = acc;
     }
 }
 
@@ -241,6 +249,125 @@ __global__ void bic_store_rule_kernel(float *__restrict__ scores, uint64_t n_mas
     if (is_sentinel(s)) return;
     const bool stored = (m == 0) ? (s < 1.0f) : (s < 0.0f);
     if (!stored) scores[m] = sentinel();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 "cube": derive a child table by summing one parent digit out, and score it in the same pass.
+//
+// The candidate family of a variable is closed under taking subsets, so only the ROOT tables (the largest
+// sets) are counted from the rows; every other table is the marginal of a table one variable larger:
+//   child[x_v + rv*(lo + hi*Bc)] = sum_{a<r} parent[x_v + rv*(lo + (hi*r + a)*Bc)]
+// where the dropped digit has stride Bc (in parent-configuration units) and arity r.  Each parent cell is read
+// exactly once, each child cell written once: a pure streaming pass (HBM/L2 bound), no atomics on the tables.
+// The log-likelihood terms of the child are accumulated on the fly (exact int64, see the file header).
+// ---------------------------------------------------------------------------------------------------------
+struct CubePair {
+    uint64_t parent_off, child_off;   // int32 elements
+    uint32_t child_configs;           // child cells / rv
+    uint32_t Bc;                      // stride of the dropped digit, in configurations
+    uint32_t r;                       // arity of the dropped digit
+    uint32_t chunk0;                  // first block of this pair
+};
+
+constexpr int kCubeThreads = 256;
+constexpr int kCubeConfigsPerBlock = 2048;
+
+template <int RV>
+__device__ __forceinline__ void load_cfg(const int *__restrict__ p, int (&v)[RV]) {
+    if constexpr (RV == 4) { const int4 t = *reinterpret_cast<const int4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (RV == 2) { const int2 t = *reinterpret_cast<const int2 *>(p); v[0] = t.x; v[1] = t.y; }
+    else {
+#pragma unroll
+        for (int k = 0; k < RV; k++) v[k] = p[k];
+    }
+}
+template <int RV>
+__device__ __forceinline__ void store_cfg(int *__restrict__ p, const int (&v)[RV]) {
+    if constexpr (RV == 4) *reinterpret_cast<int4 *>(p) = make_int4(v[0], v[1], v[2], v[3]);
+    else if constexpr (RV == 2) *reinterpret_cast<int2 *>(p) = make_int2(v[0], v[1]);
+    else {
+#pragma unroll
+        for (int k = 0; k < RV; k++) p[k] = v[k];
+    }
+}
+
+// RV > 0: compile-time child arity (2,3,4); RV == 0: generic arity rv_dyn
+template <int RV>
+__global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePair *__restrict__ pairs, int npairs, const int *__restrict__ parent_tab,
+                                                                   int *__restrict__ child_tab, int rv_dyn, const long long *__restrict__ qlog,
+                                                                   long long *__restrict__ acc_out /*null: no scoring*/) {
+    __shared__ long long red[32];
+    __shared__ int s_pair;
+    if (threadIdx.x == 0) { // binary search: last pair with chunk0 <= blockIdx.x
+        int lo = 0, hi = npairs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (pairs[mid].chunk0 <= blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        s_pair = lo;
+    }
+    __syncthreads();
+    const int pi = s_pair;
+    const CubePair pr = pairs[pi];
+    const int rv = RV > 0 ? RV : rv_dyn;
+    const uint32_t j0 = (blockIdx.x - pr.chunk0) * kCubeConfigsPerBlock;
+    const uint32_t j1 = min(j0 + (uint32_t)kCubeConfigsPerBlock, pr.child_configs);
+    const int *__restrict__ P = parent_tab + pr.parent_off;
+    int *__restrict__ Cc = child_tab + pr.child_off;
+    long long acc = 0;
+    for (uint32_t j = j0 + threadIdx.x; j < j1; j += kCubeThreads) {
+        const uint32_t hi = j / pr.Bc, lo = j - hi * pr.Bc;
+        const uint64_t pc0 = (uint64_t)lo + (uint64_t)hi * pr.r * pr.Bc;
+        if constexpr (RV > 0) {
+            int cnt[RV];
+#pragma unroll
+            for (int k = 0; k < RV; k++) cnt[k] = 0;
+            for (uint32_t a = 0; a < pr.r; a++) {
+                int t[RV];
+                load_cfg<RV>(P + (pc0 + (uint64_t)a * pr.Bc) * RV, t);
+#pragma unroll
+                for (int k = 0; k < RV; k++) cnt[k] += t[k];
+            }
+            store_cfg<RV>(Cc + (uint64_t)j * RV, cnt);
+            if (acc_out) {
+                int nij = 0;
+#pragma unroll
+                for (int k = 0; k < RV; k++) {
+                    nij += cnt[k];
+                    if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
+                }
+                if (nij > 1) acc -= __ldg(&qlog[nij]);
+            }
+        } else {
+            int nij = 0;
+            for (int k = 0; k < rv; k++) {
+                int cnt = 0;
+                for (uint32_t a = 0; a < pr.r; a++) cnt += P[(pc0 + (uint64_t)a * pr.Bc) * rv + k];
+                Cc[(uint64_t)j * rv + k] = cnt;
+                nij += cnt;
+                if (acc_out && cnt > 1) acc += __ldg(&qlog[cnt]);
+            }
+            if (acc_out && nij > 1) acc -= __ldg(&qlog[nij]);
+        }
+    }
+    if (acc_out) {
+        acc = block_sum_ll(acc, red);
+        if (threadIdx.x == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[pi]), (unsigned long long)acc);
+    }
+}
+
+// scores[res_mask] from the exact accumulators; tVal multiplied in ascending variable order (result-order CandInfo)
+__global__ void cube_finalize_kernel(BicData d, CandInfo ci_res, const uint32_t *__restrict__ res_masks, const long long *__restrict__ acc, int nsets,
+                                     float *__restrict__ scores, long long *__restrict__ ll_fixed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsets) return;
+    const uint32_t mask = res_masks[i];
+    float pen = (float)(ci_res.rv - 1);
+    for (int b = 0; b < ci_res.c; b++)
+        if ((mask >> b) & 1) pen = __fmul_rn(pen, (float)ci_res.card[b]);
+    scores[mask] = bic_finalize(acc[i], pen, d.base);
+    if (ll_fixed) ll_fixed[mask] = acc[i];
 }
 
 } // namespace urlgpu

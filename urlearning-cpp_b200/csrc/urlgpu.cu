@@ -56,6 +56,8 @@ struct urlgpu_ctx {
     // scratch
     int *d_tables = nullptr; size_t tables_cap = 0;          // int32 elements
     void *d_misc = nullptr; size_t misc_cap = 0;
+    int *d_cubeA = nullptr, *d_cubeB = nullptr; size_t cubeA_cap = 0, cubeB_cap = 0; // ping-pong layer buffers of the cube path
+    int bic_mode = 0; // 0 = cube (default), 1 = direct counting of every set (URLGPU_BIC_MODE=direct)
 
     // stats
     urlgpu_stats st{};
@@ -191,6 +193,7 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
         return URLGPU_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *m = getenv("URLGPU_BIC_MODE")) ctx->bic_mode = strcmp(m, "direct") == 0 ? 1 : 0;
     cudaFuncSetAttribute(bic_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 2048);
     *out = ctx;
     return URLGPU_OK;
@@ -216,6 +219,8 @@ extern "C" int urlgpu_destroy(urlgpu_ctx *ctx) {
     free_continuous(ctx);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_misc) cudaFree(ctx->d_misc);
+    if (ctx->d_cubeA) cudaFree(ctx->d_cubeA);
+    if (ctx->d_cubeB) cudaFree(ctx->d_cubeB);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return URLGPU_OK;
@@ -463,8 +468,8 @@ static int bic_run_global_tier(urlgpu_ctx *ctx, const BicData &bd, const CandInf
     return URLGPU_OK;
 }
 
-static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                            uint64_t *n_scored) {
+static int bic_score_family_direct(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
+                                   uint64_t *n_scored) {
     cudaStream_t s = ctx->stream;
     const int c = (int)cand.size();
     const uint64_t n_masks = (uint64_t)1 << c;
@@ -491,11 +496,11 @@ static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int
     if (hc[0]) {
         Region rg(ctx, F_COUNT, 1);
         const int threads = ctx->n >= 65536 ? 256 : 128;
-        bic_count_smem_kernel<<<(unsigned)hc[0], threads, kTier0Cells * sizeof(int), s>>>(bd, ci, l0, d_table, d_llfixed);
+        bic_count_smem_kernel<<<(unsigned)hc[0], threads, kTier0Cells * sizeof(int), s>>>(bd, ci, l0, d_table, d_llfixed, nullptr, nullptr, nullptr);
     }
     if (hc[1]) {
         Region rg(ctx, F_COUNT, 1);
-        bic_count_smem_kernel<<<(unsigned)hc[1], 1024, (size_t)tier1_cells * sizeof(int), s>>>(bd, ci, l1, d_table, d_llfixed);
+        bic_count_smem_kernel<<<(unsigned)hc[1], 1024, (size_t)tier1_cells * sizeof(int), s>>>(bd, ci, l1, d_table, d_llfixed, nullptr, nullptr, nullptr);
     }
     if (hc[2]) {
         std::vector<uint32_t> m2(hc[2]);
@@ -515,6 +520,280 @@ static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int
     CK(cudaStreamSynchronize(s)); // lists/counters are freed on return
     CK(cudaGetLastError());
     return URLGPU_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Cube path: count only the root tables from the rows, derive every other table of the family by summing one
+// digit out of a table one variable larger (cube_derive_kernel).  Candidates are re-ordered by ascending arity
+// ("cube bits"); the parent of a set is the set plus its lowest missing cube bit, so the digit that is summed
+// out always has the smallest arity available and sits right after the child digit.  Layers above max_parents
+// exist only as ancestors (they contain the lowest cube bits), which cuts the number of row-counting passes:
+// with c=16, K=11 the 4368 sets of layer 11 are derived from 1365 roots of layer 12.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+struct CubeSet {
+    uint32_t cube_mask, res_mask;
+    uint64_t cells, off;
+    int parent;       // index in the layer above
+    uint32_t Bc, r;
+};
+inline uint32_t gosper_next(uint32_t v) {
+    const uint32_t t = (v | (v - 1)) + 1;
+    return t | ((((t & (~t + 1)) / (v & (~v + 1))) >> 1) - 1);
+}
+} // namespace
+
+static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
+                                 uint64_t *n_scored, bool *used) {
+    *used = false;
+    cudaStream_t s = ctx->stream;
+    const int c = (int)cand.size();
+    const int Kc = std::min(K, c);
+    const int rv = ctx->card[variable];
+    const uint64_t n = (uint64_t)ctx->n;
+    if (c == 0) return URLGPU_OK; // only the empty set: the direct path handles it
+    // cube order: ascending arity, ties by variable index
+    std::vector<int> perm(c);
+    for (int i = 0; i < c; i++) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return ctx->card[cand[a]] < ctx->card[cand[b]]; });
+    std::vector<int> cube_vars(c);
+    std::vector<uint64_t> ccard(c), prefix(c + 1, 1);
+    for (int i = 0; i < c; i++) { cube_vars[i] = cand[perm[i]]; ccard[i] = (uint64_t)ctx->card[cube_vars[i]]; }
+    for (int i = 0; i < c; i++) prefix[i + 1] = std::min<uint64_t>(prefix[i] * ccard[i], (uint64_t)1 << 40);
+    CandInfo ci_cube = make_candinfo(ctx, variable, cube_vars, K);
+    CandInfo ci_res = make_candinfo(ctx, variable, cand, K);
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+    const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
+
+    // ---- enumerate layers 0..Lmax (layers above Kc: only sets containing the lowest l-Kc cube bits) ----
+    const int Lmax = std::min(Kc + 2, c);
+    std::vector<std::vector<CubeSet>> layers(Lmax + 1);
+    auto make_set = [&](uint32_t cm) {
+        CubeSet cs{};
+        cs.cube_mask = cm;
+        uint64_t cells = (uint64_t)rv;
+        uint32_t rm = 0;
+        for (int i = 0; i < c; i++)
+            if ((cm >> i) & 1) { cells = std::min<uint64_t>(cells * ccard[i], kCellLimit + 1); rm |= 1u << perm[i]; }
+        cs.cells = cells; cs.res_mask = rm; cs.parent = -1;
+        return cs;
+    };
+    for (int l = 0; l <= Lmax; l++) {
+        const int j = std::max(0, l - Kc);      // forced low bits
+        const int free_bits = c - j, pick = l - j;
+        const uint32_t lowmask = (j ? ((1u << j) - 1) : 0);
+        auto &L = layers[l];
+        if (pick == 0) { L.push_back(make_set(lowmask)); continue; }
+        uint32_t v = (1u << pick) - 1;
+        const uint64_t lim = (uint64_t)1 << free_bits;
+        while ((uint64_t)v < lim) {
+            L.push_back(make_set((v << j) | lowmask));
+            if (pick == free_bits) break;
+            v = gosper_next(v);
+        }
+    }
+    // ---- choose the root layer by a simple cost model (seconds) ----
+    auto root_cost = [&](const CubeSet &cs, int l) {
+        if (cs.cells > kCellLimit) return 1e30;
+        if (cs.cells <= tier1_cells) return (double)n * (l + 1) / 6e12 + 2e-7;
+        return (double)n / 1.8e11 + (double)cs.cells * 4.0 / 2.5e12;
+    };
+    auto derive_cost = [&](const CubeSet &cs, int /*l*/, uint64_t rdrop) { return (double)cs.cells * 4.0 * (double)(rdrop + 1) / 5e12 + 1e-7; };
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const double mem_budget = (double)free_b * 0.7 + (double)(ctx->cubeA_cap + ctx->cubeB_cap) * 4.0;
+    std::vector<double> layer_cells(Lmax + 1, 0.0);
+    for (int l = 0; l <= Lmax; l++)
+        for (auto &cs : layers[l]) layer_cells[l] += (double)((cs.cells + 3) / 4 * 4);
+    int Lstar = -1;
+    double best = 1e300;
+    for (int Ls = Kc; Ls <= Lmax; Ls++) {
+        double cost = 0, maxl = 0;
+        for (auto &cs : layers[Ls]) cost += root_cost(cs, Ls);
+        if (cost >= 1e29) continue; // a root table above the 2^30-cell limit
+        for (int l = Kc; l < Ls; l++)
+            for (auto &cs : layers[l]) {
+                const int z = __builtin_ctz(~cs.cube_mask);
+                cost += derive_cost(cs, l, ccard[z]);
+            }
+        for (int l = 0; l <= Ls; l++) maxl = std::max(maxl, layer_cells[l]);
+        if (2.0 * maxl * 4.0 > mem_budget) continue;
+        if (cost < best) { best = cost; Lstar = Ls; }
+    }
+    if (Lstar < 0) return URLGPU_OK; // does not fit: caller falls back to the direct path
+    // ---- offsets and parent links ----
+    size_t max_layer = 0;
+    for (int l = 0; l <= Lstar; l++) {
+        uint64_t off = 0;
+        for (auto &cs : layers[l]) { cs.off = off; off += (cs.cells + 3) / 4 * 4; }
+        max_layer = std::max<size_t>(max_layer, off);
+        if (l < Lstar) {
+            auto &P = layers[l + 1];
+            for (auto &cs : layers[l]) {
+                const int z = __builtin_ctz(~cs.cube_mask); // lowest missing cube bit (< c because l < Lstar <= c)
+                const uint32_t pm = cs.cube_mask | (1u << z);
+                auto it = std::lower_bound(P.begin(), P.end(), pm, [](const CubeSet &a, uint32_t m) { return a.cube_mask < m; });
+                if (it == P.end() || it->cube_mask != pm) return ctx->fail(URLGPU_ERR_INTERNAL, "cube: parent set missing");
+                cs.parent = (int)(it - P.begin());
+                cs.Bc = (uint32_t)prefix[z];
+                cs.r = (uint32_t)ccard[z];
+            }
+        }
+    }
+    if (ctx->cubeA_cap < max_layer) { if (ctx->d_cubeA) cudaFree(ctx->d_cubeA); ctx->d_cubeA = nullptr; ctx->cubeA_cap = 0; CK(cudaMalloc(&ctx->d_cubeA, max_layer * sizeof(int))); ctx->cubeA_cap = max_layer; }
+    if (ctx->cubeB_cap < max_layer) { if (ctx->d_cubeB) cudaFree(ctx->d_cubeB); ctx->d_cubeB = nullptr; ctx->cubeB_cap = 0; CK(cudaMalloc(&ctx->d_cubeB, max_layer * sizeof(int))); ctx->cubeB_cap = max_layer; }
+    int *bufP = ctx->d_cubeA, *bufC = ctx->d_cubeB;
+
+    size_t max_sets = 0;
+    for (int l = 0; l <= Lstar; l++) max_sets = std::max(max_sets, layers[l].size());
+    DevBuf dacc, dres, dpairs, dwork, doffs, dgsets;
+    CK(dacc.alloc(max_sets * sizeof(long long)));
+    CK(dres.alloc(max_sets * sizeof(uint32_t)));
+    CK(dpairs.alloc(max_sets * sizeof(CubePair)));
+    std::vector<uint32_t> hres;
+    auto finalize_layer = [&](int l) -> int {
+        auto &L = layers[l];
+        hres.resize(L.size());
+        for (size_t i = 0; i < L.size(); i++) hres[i] = L[i].res_mask;
+        CK(cudaMemcpyAsync(dres.p, hres.data(), L.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        Region rg(ctx, F_OTHER, 1);
+        cube_finalize_kernel<<<blocks_for(L.size(), 256), 256, 0, s>>>(bd, ci_res, dres.as<uint32_t>(), dacc.as<long long>(), (int)L.size(), d_table, d_llfixed);
+        CK(cudaStreamSynchronize(s)); // hres is reused by the next layer
+        return URLGPU_OK;
+    };
+
+    // ---- roots: counted from the rows ----
+    {
+        auto &R = layers[Lstar];
+        const bool score_roots = Lstar <= Kc;
+        CK(cudaMemsetAsync(dacc.p, 0, R.size() * sizeof(long long), s));
+        std::vector<uint32_t> small_m; std::vector<uint64_t> small_off; std::vector<size_t> small_idx;
+        std::vector<GlobalSet> big; std::vector<size_t> big_idx;
+        for (size_t i = 0; i < R.size(); i++) {
+            if (R[i].cells <= tier1_cells) { small_m.push_back(R[i].cube_mask); small_off.push_back(R[i].off); small_idx.push_back(i); }
+            else { big.push_back(GlobalSet{R[i].cube_mask, (uint32_t)R[i].cells, R[i].off}); big_idx.push_back(i); }
+        }
+        // acc of roots is indexed by position in R: small roots are scattered through an index-ordered launch, so
+        // split the accumulator ranges: [0, small) in launch order then copy back by index on the host if scoring.
+        DevBuf dacc_small, dacc_big;
+        if (!small_m.empty()) {
+            CK(dwork.alloc(small_m.size() * sizeof(uint32_t)));
+            CK(doffs.alloc(small_off.size() * sizeof(uint64_t)));
+            CK(dacc_small.alloc(small_m.size() * sizeof(long long)));
+            CK(cudaMemcpyAsync(dwork.p, small_m.data(), small_m.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(doffs.p, small_off.data(), small_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+            // two launches by table size so that small tables get several CTAs per SM
+            std::vector<size_t> order(small_m.size());
+            Region rg(ctx, F_COUNT, 1);
+            uint32_t maxc = 0;
+            for (size_t i : small_idx) maxc = std::max<uint32_t>(maxc, (uint32_t)R[i].cells);
+            const bool tiny = maxc <= kTier0Cells;
+            const int threads = tiny ? (ctx->n >= 65536 ? 256 : 128) : 1024;
+            const size_t smem = (tiny ? (size_t)kTier0Cells : (size_t)tier1_cells) * sizeof(int);
+            bic_count_smem_kernel<<<(unsigned)small_m.size(), threads, smem, s>>>(bd, ci_cube, dwork.as<uint32_t>(), nullptr, nullptr, doffs.as<uint64_t>(), bufP,
+                                                                               score_roots ? dacc_small.as<long long>() : nullptr);
+        }
+        if (!big.empty()) {
+            CK(dgsets.alloc(big.size() * sizeof(GlobalSet)));
+            CK(dacc_big.alloc(big.size() * sizeof(long long)));
+            CK(cudaMemsetAsync(dacc_big.p, 0, big.size() * sizeof(long long), s));
+            CK(cudaMemcpyAsync(dgsets.p, big.data(), big.size() * sizeof(GlobalSet), cudaMemcpyHostToDevice, s));
+            const int threads = 256;
+            size_t i0 = 0;
+            while (i0 < big.size()) { // batches whose tables (contiguous in bufP) stay L2 resident
+                size_t i1 = i0;
+                uint64_t bytes = 0;
+                while (i1 < big.size() && (i1 == i0 || bytes + big[i1].cells * 4 <= kBatchTableElems * 4) && i1 - i0 < 65535) { bytes += (big[i1].cells + 3) / 4 * 16; i1++; }
+                const size_t B = i1 - i0;
+                Region rg(ctx, F_COUNT, 2 + (score_roots ? 1 : 0));
+                for (size_t i = i0; i < i1; i++) CK(cudaMemsetAsync(bufP + big[i].table_off, 0, big[i].cells * sizeof(int), s));
+                int64_t Rr = std::max<int64_t>(1, (int64_t)(ctx->sm_count * 8 + B - 1) / (int64_t)B);
+                int64_t rps = (bd.n + Rr - 1) / Rr;
+                rps = std::max<int64_t>((rps + 15) / 16 * 16, 16 * threads);
+                Rr = (bd.n + rps - 1) / rps;
+                bic_count_global_kernel<<<dim3((unsigned)B, (unsigned)Rr), threads, 0, s>>>(bd, ci_cube, dgsets.as<GlobalSet>() + i0, bufP, rps);
+                if (score_roots) {
+                    uint32_t maxc = 0;
+                    for (size_t i = i0; i < i1; i++) maxc = std::max(maxc, big[i].cells);
+                    const int64_t nconf = maxc / rv;
+                    const int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((nconf + threads * 4 - 1) / (threads * 4), (ctx->sm_count * 8 + (int64_t)B - 1) / (int64_t)B));
+                    const int64_t cpc = (nconf + chunks - 1) / chunks;
+                    bic_score_tables_kernel<<<dim3((unsigned)B, (unsigned)chunks), threads, 0, s>>>(bd, ci_cube, dgsets.as<GlobalSet>() + i0, bufP,
+                                                                                                dacc_big.as<long long>() + i0, cpc);
+                }
+                i0 = i1;
+            }
+        }
+        if (score_roots) { // gather the two accumulator arrays into layer order
+            std::vector<long long> ha(R.size(), 0), hs(small_m.size()), hb(big.size());
+            if (!hs.empty()) CK(cudaMemcpyAsync(hs.data(), dacc_small.p, hs.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+            if (!hb.empty()) CK(cudaMemcpyAsync(hb.data(), dacc_big.p, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            for (size_t i = 0; i < hs.size(); i++) ha[small_idx[i]] = hs[i];
+            for (size_t i = 0; i < hb.size(); i++) ha[big_idx[i]] = hb[i];
+            CK(cudaMemcpyAsync(dacc.p, ha.data(), ha.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+            int rc = finalize_layer(Lstar);
+            if (rc) return rc;
+        }
+        CK(cudaStreamSynchronize(s)); // small_m / big go out of scope
+    }
+    // ---- derived layers ----
+    std::vector<CubePair> hp;
+    for (int l = Lstar - 1; l >= 0; l--) {
+        auto &L = layers[l];
+        auto &P = layers[l + 1];
+        hp.resize(L.size());
+        uint64_t chunk = 0;
+        for (size_t i = 0; i < L.size(); i++) {
+            const CubeSet &cs = L[i];
+            CubePair pr{};
+            pr.parent_off = P[cs.parent].off; pr.child_off = cs.off;
+            pr.child_configs = (uint32_t)(cs.cells / rv);
+            pr.Bc = cs.Bc; pr.r = cs.r; pr.chunk0 = (uint32_t)chunk;
+            chunk += (pr.child_configs + kCubeConfigsPerBlock - 1) / kCubeConfigsPerBlock;
+            hp[i] = pr;
+        }
+        if (chunk > 0x7fffffffull) return ctx->fail(URLGPU_ERR_LIMIT, "cube: too many blocks in one layer");
+        const bool score = l <= Kc;
+        CK(cudaMemcpyAsync(dpairs.p, hp.data(), hp.size() * sizeof(CubePair), cudaMemcpyHostToDevice, s));
+        if (score) CK(cudaMemsetAsync(dacc.p, 0, L.size() * sizeof(long long), s));
+        {
+            Region rg(ctx, F_CUBE, 1);
+            long long *accp = score ? dacc.as<long long>() : nullptr;
+            const unsigned grid = (unsigned)chunk;
+            switch (rv) {
+            case 2: cube_derive_kernel<2><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), bufP, bufC, rv, ctx->d_qlog, accp); break;
+            case 3: cube_derive_kernel<3><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), bufP, bufC, rv, ctx->d_qlog, accp); break;
+            case 4: cube_derive_kernel<4><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), bufP, bufC, rv, ctx->d_qlog, accp); break;
+            default: cube_derive_kernel<0><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), bufP, bufC, rv, ctx->d_qlog, accp); break;
+            }
+        }
+        CK(cudaStreamSynchronize(s)); // hp is reused
+        if (score) { int rc = finalize_layer(l); if (rc) return rc; }
+        std::swap(bufP, bufC);
+    }
+    CK(cudaGetLastError());
+    *n_scored = family_size(c, K);
+    {
+        double bytes = 0, b = 1;
+        for (int l = 0; l <= K && l <= c; l++) { bytes += b * (double)ctx->n * (l + 1); b = b * (c - l) / (l + 1); }
+        ctx->st.algorithmic_bytes += bytes;
+        ctx->st.sets_scored += *n_scored;
+    }
+    *used = true;
+    return URLGPU_OK;
+}
+
+static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
+                            uint64_t *n_scored) {
+    if (ctx->bic_mode != 1) {
+        bool used = false;
+        int rc = bic_score_family_cube(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used);
+        if (rc || used) return rc;
+    }
+    return bic_score_family_direct(ctx, variable, cand, K, d_table, d_llfixed, n_scored);
 }
 
 template <int J>
