@@ -22,6 +22,6 @@ for v in vars_:
     eng.synchronize()
     dt = time.time() - t0
     st = eng.stats()
-    print(f"v={v} c={c} K={K} sets={res.scored()} wall={dt*1e3:.1f} ms  count_ms={st['ms_count']:.1f} launches={st['launches_total']} "
+    print(f"v={v} c={c} K={K} sets={res.scored()} wall={dt*1e3:.1f} ms  count_ms={st["ms_count"]:.1f} cube_ms={st["ms_cube"]:.1f} prune_ms={st["ms_prune"]:.1f} launches={st['launches_total']} "
           f"sets/s={res.scored()/dt:.3e} alg_GB/s={st['algorithmic_bytes']/dt/1e9:.1f}")
     res.free()

@@ -294,7 +294,7 @@ class Engine:
         self._check(self.lib.urlgpu_stats_enable_timing(self._h, int(on)))
 
 
-from . import datagen  # noqa: E402
+from . import datagen, pss  # noqa: E402
 
 
 def device_count() -> int:

@@ -6,6 +6,7 @@
 #include "../../include/urlgpu.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -548,6 +549,10 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                                  uint64_t *n_scored, bool *used) {
     *used = false;
     cudaStream_t s = ctx->stream;
+    static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto T0 = tnow();
     const int c = (int)cand.size();
     const int Kc = std::min(K, c);
     const int rv = ctx->card[variable];
@@ -644,6 +649,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     if (ctx->cubeA_cap < max_layer) { if (ctx->d_cubeA) cudaFree(ctx->d_cubeA); ctx->d_cubeA = nullptr; ctx->cubeA_cap = 0; CK(cudaMalloc(&ctx->d_cubeA, max_layer * sizeof(int))); ctx->cubeA_cap = max_layer; }
     if (ctx->cubeB_cap < max_layer) { if (ctx->d_cubeB) cudaFree(ctx->d_cubeB); ctx->d_cubeB = nullptr; ctx->cubeB_cap = 0; CK(cudaMalloc(&ctx->d_cubeB, max_layer * sizeof(int))); ctx->cubeB_cap = max_layer; }
     int *bufP = ctx->d_cubeA, *bufC = ctx->d_cubeB;
+    const auto T1 = tnow();
 
     size_t max_sets = 0;
     for (int l = 0; l <= Lstar; l++) max_sets = std::max(max_sets, layers[l].size());
@@ -739,6 +745,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         }
         CK(cudaStreamSynchronize(s)); // small_m / big go out of scope
     }
+    const auto T2 = tnow();
     // ---- derived layers ----
     std::vector<CubePair> hp;
     for (int l = Lstar - 1; l >= 0; l--) {
@@ -775,6 +782,8 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         std::swap(bufP, bufC);
     }
     CK(cudaGetLastError());
+    if (dbg) fprintf(stderr, "[urlgpu cube] v=%d c=%d K=%d L*=%d roots=%zu plan+alloc %.2f ms, roots %.2f ms, derive %.2f ms\n", variable, c, K, Lstar,
+                     layers[Lstar].size(), tms(T0, T1), tms(T1, T2), tms(T2, tnow()));
     *n_scored = family_size(c, K);
     {
         double bytes = 0, b = 1;
@@ -884,6 +893,9 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
                                      double lambda, unsigned filter_flags, urlgpu_result **out) {
     if (!ctx || !neighbors || !out) return ctx ? ctx->fail(URLGPU_ERR_ARG, "score_variable: null argument") : URLGPU_ERR_ARG;
     *out = nullptr;
+    static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
+    const auto T0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     CK(cudaSetDevice(ctx->device));
     const bool bic = score_type == URLGPU_BIC;
     if (!bic && score_type != URLGPU_CBIC) return ctx->fail(URLGPU_ERR_ARG, "score_variable: unknown score type");
@@ -907,6 +919,7 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     cudaStream_t s = ctx->stream;
     auto cleanup = [&](int code) { cudaFree(res->d_table); delete res; return code; };
     fill_u32_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), res->n_masks, kSentinelBits);
+    const double t_alloc = since(T0);
     if (bic) {
         rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored);
         if (rc) return cleanup(rc);
@@ -923,10 +936,12 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
             if (rc) return cleanup(rc);
         }
     }
+    const double t_score = since(T0);
     if (filter_flags & URLGPU_PRUNE_DOMINATED) {
         rc = run_prune(ctx, res->d_table, c, K);
         if (rc) return cleanup(rc);
     }
+    if (dbg) fprintf(stderr, "[urlgpu score_variable] v=%d alloc %.2f ms, score %.2f ms, prune %.2f ms\n", variable, t_alloc, t_score - t_alloc, since(T0) - t_score);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cleanup(ctx->cuda_fail(e, "score_variable", __LINE__));
     *out = res;
@@ -1042,8 +1057,11 @@ extern "C" int urlgpu_result_fetch(urlgpu_result *res, uint64_t offset, uint64_t
 
 extern "C" int urlgpu_result_free(urlgpu_result *res) {
     if (!res) return URLGPU_OK;
+    static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
+    const auto T0 = std::chrono::steady_clock::now();
     cudaSetDevice(res->ctx->device);
     if (res->d_table) cudaFree(res->d_table);
+    if (dbg) fprintf(stderr, "[urlgpu result_free] %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
     delete res;
     return URLGPU_OK;
 }
