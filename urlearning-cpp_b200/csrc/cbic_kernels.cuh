@@ -253,33 +253,16 @@ __global__ void cbic_dfs_kernel(const double *__restrict__ roots, CbicParams prm
     cbic_dfs_call<J>(A, 0u, k0, prm, out, out64);
 }
 
-// ------------------------------------------------------------------------------------------------ K4
-// Acceptance DP of the shipped `score` for cBIC ("clean" recursion), one launch per layer:
+// ------------------------------------------------------------------------------------------------ K4 / K5 rules
+// K4 — acceptance DP of the shipped `score` for cBIC ("clean" recursion), layers ascending:
 //   ts >  0            -> stored by the caller, val = -ts           (BIC_OLS.cpp:213-224, score_calculator.cpp:111-113)
 //   ts == 0            -> not stored
 //   ts <  0 (or NaN)   -> stored iff F(S) < -ts                     (BIC_OLS.cpp:233-249)
 //   F(S) = max(0, max_{i in S, S\i != {}} g(S\i)),  g(T) = stored(T) ? val(T) : F(T)   (BIC_OLS.cpp:125-172)
-// In: table[mask] = the_score (float) or sentinel (not scored).  Out: table[mask] = stored value or sentinel,
-// gtab[mask] = g.
-__global__ void cbic_accept_layer_kernel(float *__restrict__ table, float *__restrict__ gtab, int c, int layer, uint64_t n_masks) {
-    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= n_masks || __popcll(m) != layer) return;
-    const float ts = table[m];
-    if (is_sentinel(ts)) return;
-    if (layer == 0) { table[m] = -ts; gtab[m] = 0.0f; return; } // empty set: -0.0f stored (<1), never consulted
-    if (ts > 0.0f) { table[m] = -ts; gtab[m] = -ts; return; }
-    float F = 0.0f;
-    if (layer > 1) {
-        for (uint64_t b = m; b; b &= b - 1) {
-            const float g = gtab[m ^ (b & (~b + 1))];
-            if (g > F) F = g;
-        }
-    }
-    if (ts == 0.0f) { table[m] = sentinel(); gtab[m] = F; return; }
-    const float val = -ts;
-    if (F >= val) { table[m] = sentinel(); gtab[m] = F; } // BIC_OLS.cpp:234 (NaN compares false -> stored)
-    else { table[m] = val; gtab[m] = val; }
-}
+//   In: table[mask] = the_score (float) or sentinel (not scored).  Out: table[mask] = stored value or sentinel.
+// K5 — subset-dominance prune (ScoreCalculator::prune, score_calculator.cpp:150-197) as a DP on the dense table:
+//   M(S) = max(val'(S), max_i M(S\i)),  keep S iff stored and val(S) > max_i M(S\i)  (ties: the subset, having
+//   the smaller mask, sorts first and wins — compareSecond :137-148).  The empty set is always kept.
 // URLGPU_CBIC_NO_ACCEPT: store -the_score for every scored set
 __global__ void cbic_negate_kernel(float *__restrict__ table, uint64_t n_masks) {
     const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -288,19 +271,81 @@ __global__ void cbic_negate_kernel(float *__restrict__ table, uint64_t n_masks) 
     if (!is_sentinel(ts)) table[m] = -ts;
 }
 
-// ------------------------------------------------------------------------------------------------ K5
-// Subset-dominance prune (ScoreCalculator::prune, score_calculator.cpp:150-197) as a layer-synchronous DP on the
-// dense table:  M(S) = max(val'(S), max_i M(S\i)),  keep S iff stored and val(S) > max_i M(S\i)  (ties: the
-// subset, having the smaller mask, sorts first and wins — compareSecond :137-148).
-__global__ void prune_layer_kernel(float *__restrict__ table, float *__restrict__ mtab, int layer, uint64_t n_masks) {
-    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= n_masks || __popcll(m) != layer) return;
-    float best = -INFINITY;
-    for (uint64_t b = m; b; b &= b - 1) best = fmaxf(best, mtab[m ^ (b & (~b + 1))]);
-    const float v = table[m];
-    const bool stored = !is_sentinel(v);
-    if (stored && layer > 0 && !(v > best)) table[m] = sentinel();
-    mtab[m] = stored ? fmaxf(best, v) : best;
+// ------------------------------------------------------------------------------------------------ K4/K5, segment form
+// The layer-by-layer kernels above scan all 2^c masks once per layer.  The segment form walks the table ONCE:
+// a mask is split into (H, low) with `lb` low bits; one CTA owns the 2^lb-entry segment of a high part H.
+// A set depends only on sets one element smaller: (H, low\b) — same segment, lower popcount — and (H\hb, low) —
+// the same offset in the segments of H's sub-masks.  Launching the high parts in order of popcount(H) makes
+// every dependency segment final, so a CTA (1) folds the popcount(H) dependency segments into one max array with
+// coalesced reads, (2) runs the within-segment DP over popcount sub-layers in shared memory, (3) writes the
+// segment back.  Traffic: (3 + popcount(H)) * 2^lb * 4 B per segment instead of ~c full-table scans.
+constexpr int kSegMaxLb = 11;
+
+struct SegLists {
+    const uint32_t *high_sorted;  // all 2^hb high masks sorted by (popcount, value)
+    const uint16_t *low_sorted;   // all 2^lb low masks sorted by (popcount, value)
+    int low_off[kSegMaxLb + 2];   // start of each popcount class in low_sorted
+};
+
+// MODE 0: cBIC acceptance (see cbic_accept_layer_kernel), aux = gtab.  MODE 1: subset-dominance prune, aux = mtab.
+template <int MODE>
+__global__ void __launch_bounds__(256) segment_dp_kernel(float *__restrict__ table, float *__restrict__ aux, SegLists sl, int high_begin, int lb, int a /*popcount of the high parts of this launch*/,
+                                                         int max_parents) {
+    __shared__ float s_val[1 << kSegMaxLb];
+    __shared__ float s_aux[1 << kSegMaxLb];
+    __shared__ float s_dep[1 << kSegMaxLb];
+    const uint32_t H = sl.high_sorted[high_begin + blockIdx.x];
+    const uint32_t seg = 1u << lb;
+    const size_t base = (size_t)H << lb;
+    const float neutral = MODE == 0 ? 0.0f : -INFINITY;
+    for (uint32_t i = threadIdx.x; i < seg; i += blockDim.x) {
+        s_val[i] = table[base + i];
+        s_aux[i] = neutral;
+        float d = neutral;
+        for (uint32_t hb = H; hb; hb &= hb - 1) {
+            const float g = aux[((size_t)(H ^ (hb & (~hb + 1))) << lb) + i];
+            d = MODE == 0 ? (g > d ? g : d) : fmaxf(d, g);
+        }
+        s_dep[i] = d;
+    }
+    __syncthreads();
+    for (int j = 0; j <= lb; j++) {
+        const int layer = a + j;
+        if (layer <= max_parents) {
+            for (int idx = sl.low_off[j] + threadIdx.x; idx < sl.low_off[j + 1]; idx += blockDim.x) {
+                const uint32_t low = sl.low_sorted[idx];
+                const float v = s_val[low];
+                if (MODE == 0) {
+                    if (is_sentinel(v)) continue;
+                    if (layer == 0) { s_val[low] = -v; s_aux[low] = 0.0f; continue; }
+                    if (v > 0.0f) { s_val[low] = -v; s_aux[low] = -v; continue; }
+                    float F = 0.0f;
+                    if (layer > 1) {
+                        F = s_dep[low] > F ? s_dep[low] : F;
+                        for (uint32_t b = low; b; b &= b - 1) {
+                            const float g = s_aux[low ^ (b & (~b + 1))];
+                            if (g > F) F = g;
+                        }
+                    }
+                    if (v == 0.0f) { s_val[low] = sentinel(); s_aux[low] = F; continue; }
+                    const float val = -v;
+                    if (F >= val) { s_val[low] = sentinel(); s_aux[low] = F; }
+                    else { s_val[low] = val; s_aux[low] = val; }
+                } else {
+                    float best = s_dep[low];
+                    for (uint32_t b = low; b; b &= b - 1) best = fmaxf(best, s_aux[low ^ (b & (~b + 1))]);
+                    const bool stored = !is_sentinel(v);
+                    if (stored && layer > 0 && !(v > best)) s_val[low] = sentinel();
+                    s_aux[low] = stored ? fmaxf(best, v) : best;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < seg; i += blockDim.x) {
+        table[base + i] = s_val[i];
+        aux[base + i] = s_aux[i];
+    }
 }
 
 // result compaction helpers --------------------------------------------------------------------------------

@@ -58,6 +58,8 @@ struct urlgpu_ctx {
     int *d_tables = nullptr; size_t tables_cap = 0;          // int32 elements
     void *d_misc = nullptr; size_t misc_cap = 0;
     int *d_cubeA = nullptr, *d_cubeB = nullptr; size_t cubeA_cap = 0, cubeB_cap = 0; // ping-pong layer buffers of the cube path
+    uint32_t *d_high_sorted = nullptr; int high_bits = -1; std::vector<int> high_off;   // segment DP lists (accept / prune)
+    uint16_t *d_low_sorted = nullptr; int low_bits = -1; std::vector<int> low_off;
     int bic_mode = 0; // 0 = cube (default), 1 = direct counting of every set (URLGPU_BIC_MODE=direct)
 
     // stats
@@ -221,6 +223,8 @@ extern "C" int urlgpu_destroy(urlgpu_ctx *ctx) {
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_misc) cudaFree(ctx->d_misc);
     if (ctx->d_cubeA) cudaFree(ctx->d_cubeA);
+    if (ctx->d_high_sorted) cudaFree(ctx->d_high_sorted);
+    if (ctx->d_low_sorted) cudaFree(ctx->d_low_sorted);
     if (ctx->d_cubeB) cudaFree(ctx->d_cubeB);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -859,35 +863,65 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
     return URLGPU_OK;
 }
 
-static int run_accept(urlgpu_ctx *ctx, float *d_table, int c, int K) {
-    cudaStream_t s = ctx->stream;
-    const uint64_t n_masks = (uint64_t)1 << c;
-    DevBuf g;
-    CK(g.alloc(n_masks * sizeof(float)));
-    {
-        Region rg(ctx, F_ACCEPT, std::min(c, K) + 1);
-        for (int layer = 0; layer <= K && layer <= c; layer++)
-            cbic_accept_layer_kernel<<<blocks_for(n_masks, 256), 256, 0, s>>>(d_table, g.as<float>(), c, layer, n_masks);
+// popcount-sorted lists of the high and low mask parts, cached per (hb, lb)
+static int ensure_seg_lists(urlgpu_ctx *ctx, int hb, int lb) {
+    auto build = [](int bits, std::vector<uint32_t> &sorted, std::vector<int> &off) {
+        const uint32_t n = 1u << bits;
+        sorted.resize(n);
+        off.assign(bits + 2, 0);
+        for (uint32_t m = 0; m < n; m++) off[__builtin_popcount(m) + 1]++;
+        for (int i = 0; i <= bits; i++) off[i + 1] += off[i];
+        std::vector<int> pos(off.begin(), off.end() - 1);
+        for (uint32_t m = 0; m < n; m++) sorted[pos[__builtin_popcount(m)]++] = m;
+    };
+    if (ctx->high_bits != hb) {
+        std::vector<uint32_t> sorted;
+        build(hb, sorted, ctx->high_off);
+        if (ctx->d_high_sorted) cudaFree(ctx->d_high_sorted);
+        ctx->d_high_sorted = nullptr; ctx->high_bits = -1;
+        CK(cudaMalloc(&ctx->d_high_sorted, sorted.size() * sizeof(uint32_t)));
+        CK(cudaMemcpy(ctx->d_high_sorted, sorted.data(), sorted.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        ctx->high_bits = hb;
     }
-    CK(cudaStreamSynchronize(s));
-    CK(cudaGetLastError());
+    if (ctx->low_bits != lb) {
+        std::vector<uint32_t> sorted;
+        build(lb, sorted, ctx->low_off);
+        std::vector<uint16_t> s16(sorted.begin(), sorted.end());
+        if (ctx->d_low_sorted) cudaFree(ctx->d_low_sorted);
+        ctx->d_low_sorted = nullptr; ctx->low_bits = -1;
+        CK(cudaMalloc(&ctx->d_low_sorted, s16.size() * sizeof(uint16_t)));
+        CK(cudaMemcpy(ctx->d_low_sorted, s16.data(), s16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        ctx->low_bits = lb;
+    }
     return URLGPU_OK;
 }
 
-static int run_prune(urlgpu_ctx *ctx, float *d_table, int c, int K) {
+// MODE 0 = cBIC acceptance DP (K4), MODE 1 = subset-dominance prune (K5); one launch per popcount of the high part
+template <int MODE>
+static int run_segment_dp(urlgpu_ctx *ctx, float *d_table, int c, int K) {
     cudaStream_t s = ctx->stream;
     const uint64_t n_masks = (uint64_t)1 << c;
-    DevBuf m;
-    CK(m.alloc(n_masks * sizeof(float)));
+    const int lb = std::min(c, kSegMaxLb), hb = c - lb;
+    int rc = ensure_seg_lists(ctx, hb, lb);
+    if (rc) return rc;
+    DevBuf aux;
+    CK(aux.alloc(n_masks * sizeof(float)));
+    SegLists sl{};
+    sl.high_sorted = ctx->d_high_sorted; sl.low_sorted = ctx->d_low_sorted;
+    for (int i = 0; i <= lb + 1; i++) sl.low_off[i] = ctx->low_off[i];
     {
-        Region rg(ctx, F_PRUNE, std::min(c, K) + 1);
-        for (int layer = 0; layer <= K && layer <= c; layer++)
-            prune_layer_kernel<<<blocks_for(n_masks, 256), 256, 0, s>>>(d_table, m.as<float>(), layer, n_masks);
+        Region rg(ctx, MODE == 0 ? F_ACCEPT : F_PRUNE, std::min(hb, K) + 1);
+        for (int a = 0; a <= hb && a <= K; a++) {
+            const int begin = ctx->high_off[a], count = ctx->high_off[a + 1] - begin;
+            segment_dp_kernel<MODE><<<count, 256, 0, s>>>(d_table, aux.as<float>(), sl, begin, lb, a, K);
+        }
     }
-    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(s)); // aux is freed on return
     CK(cudaGetLastError());
     return URLGPU_OK;
 }
+static int run_accept(urlgpu_ctx *ctx, float *d_table, int c, int K) { return run_segment_dp<0>(ctx, d_table, c, K); }
+static int run_prune(urlgpu_ctx *ctx, float *d_table, int c, int K) { return run_segment_dp<1>(ctx, d_table, c, K); }
 
 extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type,
                                      double lambda, unsigned filter_flags, urlgpu_result **out) {
