@@ -62,6 +62,10 @@ struct urlgpu_ctx {
     uint16_t *d_low_sorted = nullptr; int low_bits = -1; std::vector<int> low_off;
     int bic_mode = 0; // 0 = cube (default), 1 = direct counting of every set (URLGPU_BIC_MODE=direct)
 
+    // caching device allocator: cudaMalloc/cudaFree of multi-GB tables cost tens of ms each
+    struct PoolBlock { void *p; size_t bytes; bool used; };
+    std::vector<PoolBlock> pool;
+
     // stats
     urlgpu_stats st{};
     bool timing = false;
@@ -83,10 +87,47 @@ struct urlgpu_ctx {
 
 namespace {
 
-struct DevBuf { // RAII device allocation
+cudaError_t pool_alloc(urlgpu_ctx *ctx, void **out, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 256);
+    int best = -1;
+    for (size_t i = 0; i < ctx->pool.size(); i++) {
+        auto &b = ctx->pool[i];
+        if (!b.used && b.bytes >= bytes && b.bytes <= bytes * 2 + (1 << 20) && (best < 0 || b.bytes < ctx->pool[best].bytes)) best = (int)i;
+    }
+    if (best >= 0) { ctx->pool[best].used = true; *out = ctx->pool[best].p; return cudaSuccess; }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) { // release every cached block and retry once
+        cudaGetLastError();
+        for (size_t i = 0; i < ctx->pool.size();) {
+            if (!ctx->pool[i].used) { cudaFree(ctx->pool[i].p); ctx->pool.erase(ctx->pool.begin() + i); } else i++;
+        }
+        e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    ctx->pool.push_back({*out, bytes, true});
+    return cudaSuccess;
+}
+void pool_free(urlgpu_ctx *ctx, void *p) {
+    if (!p) return;
+    for (size_t i = 0; i < ctx->pool.size(); i++)
+        if (ctx->pool[i].p == p) {
+            if (ctx->pool[i].bytes > ((size_t)4 << 30)) { cudaFree(p); ctx->pool.erase(ctx->pool.begin() + i); } // do not hoard huge blocks
+            else ctx->pool[i].used = false;
+            return;
+        }
+    cudaFree(p);
+}
+void pool_destroy(urlgpu_ctx *ctx) {
+    for (auto &b : ctx->pool) cudaFree(b.p);
+    ctx->pool.clear();
+}
+
+struct DevBuf { // RAII device allocation from the context's pool (stream-ordered use: callers sync before release)
+    urlgpu_ctx *ctx;
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { if (p) { cudaFree(p); p = nullptr; } return cudaMalloc(&p, bytes ? bytes : 1); }
+    explicit DevBuf(urlgpu_ctx *c) : ctx(c) {}
+    ~DevBuf() { pool_free(ctx, p); }
+    cudaError_t alloc(size_t bytes) { pool_free(ctx, p); p = nullptr; return pool_alloc(ctx, &p, bytes); }
     template <typename T> T *as() { return static_cast<T *>(p); }
 };
 
@@ -226,6 +267,7 @@ extern "C" int urlgpu_destroy(urlgpu_ctx *ctx) {
     if (ctx->d_high_sorted) cudaFree(ctx->d_high_sorted);
     if (ctx->d_low_sorted) cudaFree(ctx->d_low_sorted);
     if (ctx->d_cubeB) cudaFree(ctx->d_cubeB);
+    pool_destroy(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return URLGPU_OK;
@@ -311,7 +353,7 @@ static int set_continuous_common(urlgpu_ctx *ctx, const double *src, bool src_on
     free_continuous(ctx);
     ctx->cn = n; ctx->cp = p;
     cudaStream_t s = ctx->stream;
-    DevBuf x, part, sums, mean, acc2, acc3, dev, gpart, g;
+    DevBuf x(ctx), part(ctx), sums(ctx), mean(ctx), acc2(ctx), acc3(ctx), dev(ctx), gpart(ctx), g(ctx);
     const size_t bytes = (size_t)n * p * sizeof(double);
     CK(x.alloc(bytes));
     CK(cudaMalloc(&ctx->d_z, bytes));
@@ -421,7 +463,7 @@ static int bic_run_global_tier(urlgpu_ctx *ctx, const BicData &bd, const CandInf
     }
     int rc = ensure_tables(ctx, std::max(kBatchTableElems, max_cells));
     if (rc) return rc;
-    DevBuf dsets, dacc;
+    DevBuf dsets(ctx), dacc(ctx);
     CK(dsets.alloc(sets.size() * sizeof(GlobalSet)));
     CK(dacc.alloc(sets.size() * sizeof(long long)));
     CK(cudaMemsetAsync(dacc.p, 0, sets.size() * sizeof(long long), s));
@@ -484,7 +526,7 @@ static int bic_score_family_direct(urlgpu_ctx *ctx, int variable, const std::vec
     CandInfo ci = make_candinfo(ctx, variable, cand, K);
     const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
 
-    DevBuf lists, counters;
+    DevBuf lists(ctx), counters(ctx);
     CK(lists.alloc(3 * fam * sizeof(uint32_t)));
     CK(counters.alloc(4 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), s));
@@ -657,7 +699,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
 
     size_t max_sets = 0;
     for (int l = 0; l <= Lstar; l++) max_sets = std::max(max_sets, layers[l].size());
-    DevBuf dacc, dres, dpairs, dwork, doffs, dgsets;
+    DevBuf dacc(ctx), dres(ctx), dpairs(ctx), dwork(ctx), doffs(ctx), dgsets(ctx);
     CK(dacc.alloc(max_sets * sizeof(long long)));
     CK(dres.alloc(max_sets * sizeof(uint32_t)));
     CK(dpairs.alloc(max_sets * sizeof(CubePair)));
@@ -686,7 +728,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         }
         // acc of roots is indexed by position in R: small roots are scattered through an index-ordered launch, so
         // split the accumulator ranges: [0, small) in launch order then copy back by index on the host if scoring.
-        DevBuf dacc_small, dacc_big;
+        DevBuf dacc_small(ctx), dacc_big(ctx);
         if (!small_m.empty()) {
             CK(dwork.alloc(small_m.size() * sizeof(uint32_t)));
             CK(doffs.alloc(small_off.size() * sizeof(uint64_t)));
@@ -835,7 +877,7 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
     prm.lam_logn = lambda * std::log((double)(int)ctx->cn);
     const uint32_t n_prefix = 1u << (c - prm.J);
     const int outsz = (prm.J + 1) * (prm.J + 2) / 2;
-    DevBuf dsub, droots;
+    DevBuf dsub(ctx), droots(ctx);
     CK(dsub.alloc(sub.size() * sizeof(double)));
     CK(droots.alloc((size_t)outsz * n_prefix * sizeof(double)));
     CK(cudaMemcpyAsync(dsub.p, sub.data(), sub.size() * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -904,7 +946,7 @@ static int run_segment_dp(urlgpu_ctx *ctx, float *d_table, int c, int K) {
     const int lb = std::min(c, kSegMaxLb), hb = c - lb;
     int rc = ensure_seg_lists(ctx, hb, lb);
     if (rc) return rc;
-    DevBuf aux;
+    DevBuf aux(ctx);
     CK(aux.alloc(n_masks * sizeof(float)));
     SegLists sl{};
     sl.high_sorted = ctx->d_high_sorted; sl.low_sorted = ctx->d_low_sorted;
@@ -948,10 +990,10 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     auto *res = new urlgpu_result();
     res->ctx = ctx; res->variable = variable; res->c = c; res->max_parents = K; res->mask_words = mask_words; res->cand = cand;
     res->n_masks = (uint64_t)1 << c;
-    cudaError_t e = cudaMalloc(&res->d_table, res->n_masks * sizeof(float));
+    cudaError_t e = pool_alloc(ctx, reinterpret_cast<void **>(&res->d_table), res->n_masks * sizeof(float));
     if (e != cudaSuccess) { delete res; return ctx->cuda_fail(e, "cudaMalloc(score table)", __LINE__); }
     cudaStream_t s = ctx->stream;
-    auto cleanup = [&](int code) { cudaFree(res->d_table); delete res; return code; };
+    auto cleanup = [&](int code) { pool_free(ctx, res->d_table); delete res; return code; };
     fill_u32_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), res->n_masks, kSentinelBits);
     const double t_alloc = since(T0);
     if (bic) {
@@ -1005,7 +1047,7 @@ static int result_count_impl(urlgpu_result *res) {
     urlgpu_ctx *ctx = res->ctx;
     if (res->counted) return URLGPU_OK;
     CK(cudaSetDevice(ctx->device));
-    DevBuf cnt;
+    DevBuf cnt(ctx);
     CK(cnt.alloc(sizeof(unsigned long long)));
     CK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), ctx->stream));
     count_stored_kernel<<<std::min<unsigned>(blocks_for(res->n_masks, 256), 4096), 256, 0, ctx->stream>>>(res->d_table, res->n_masks,
@@ -1040,7 +1082,7 @@ static int result_compact(urlgpu_result *res) {
     const uint64_t total = res->n_stored;
     res->h_masks.resize(total); res->h_scores.resize(total);
     if (total) {
-        DevBuf dmasks, dvals, dnum, tmp;
+        DevBuf dmasks(ctx), dvals(ctx), dnum(ctx), tmp(ctx);
         CK(dmasks.alloc(total * sizeof(uint32_t)));
         CK(dvals.alloc(total * sizeof(float)));
         CK(dnum.alloc(sizeof(unsigned long long)));
@@ -1094,7 +1136,7 @@ extern "C" int urlgpu_result_free(urlgpu_result *res) {
     static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
     const auto T0 = std::chrono::steady_clock::now();
     cudaSetDevice(res->ctx->device);
-    if (res->d_table) cudaFree(res->d_table);
+    if (res->d_table) { cudaStreamSynchronize(res->ctx->stream); pool_free(res->ctx, res->d_table); }
     if (dbg) fprintf(stderr, "[urlgpu result_free] %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
     delete res;
     return URLGPU_OK;
@@ -1126,7 +1168,7 @@ extern "C" int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *p
     const uint64_t n_masks = (uint64_t)1 << c;
     const uint32_t full = (uint32_t)(n_masks - 1);
     cudaStream_t s = ctx->stream;
-    DevBuf tab, aux;
+    DevBuf tab(ctx), aux(ctx);
     CK(tab.alloc(n_masks * sizeof(float)));
     if (bic) {
         CK(aux.alloc(n_masks * sizeof(long long)));
@@ -1200,7 +1242,7 @@ extern "C" int urlgpu_prune(urlgpu_ctx *ctx, const uint64_t *masks, const float 
         K = std::max(K, __builtin_popcount(m));
     }
     cudaStream_t s = ctx->stream;
-    DevBuf tab, dm, dv, dout;
+    DevBuf tab(ctx), dm(ctx), dv(ctx), dout(ctx);
     CK(tab.alloc(n_masks * sizeof(float)));
     CK(dm.alloc(n * sizeof(uint32_t))); CK(dv.alloc(n * sizeof(float))); CK(dout.alloc(n * sizeof(float)));
     fill_u32_kernel<<<blocks_for(n_masks, 256), 256, 0, s>>>(tab.as<uint32_t>(), n_masks, kSentinelBits);
