@@ -188,7 +188,9 @@ extern "C" int orc_read_skeleton(const char *path, int p, uint64_t *edges) {
         if (first) { first = false; if ((int)tok.size() != p) return fail("skeleton matrix width != variable count"); }
         int col = 0;
         for (auto &s : tok) {
-            if (s == "TRUE" || std::fabs(atof(s.c_str())) > 0.05) { /* skeleton.cpp:91 */
+            /* skeleton.cpp:91 writes `abs(atof(x)) > 0.05` with no using-directive in scope, so GCC binds ::abs(int): the
+             * value is truncated first and only |x| >= 1 (or "TRUE") makes an edge.  Pinned by oracle/_ref. */
+            if (s == "TRUE" || std::abs((int)atof(s.c_str())) > 0.05) {
                 if (!add_edge(row, col)) return fail("skeleton matrix entry out of range (row " + std::to_string(row) + ")");
             }
             col++;

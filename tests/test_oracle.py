@@ -53,9 +53,11 @@ def test_skeleton_readers(orc, tmp_path, data_dir):
     edges, init = orc.read_skeleton(os.path.join(data_dir, "skeleton4_ones.csv"), 4)
     assert init and edges == [15] * 4
     m = tmp_path / "m.csv"
-    m.write_text("0,TRUE,0,0\n0,0,0.06,0\n0,0,0,0.04\n0,0,0,0\n")
+    m.write_text("0,TRUE,0,0\n0,0,1,0\n0,0,0,0.9\n0,0,0,0\n")
     edges, init = orc.read_skeleton(str(m), 4)
-    assert edges == [0b0010, 0b0101, 0b0010, 0]  # symmetrised, |x| > 0.05 (skeleton.cpp:91)
+    # symmetrised; `abs(atof(x)) > 0.05` binds ::abs(int) in the reference as compiled by GCC, so 0.9 is NOT an edge
+    # (skeleton.cpp:91; pinned against the reference's own code in test_ref_pin.py)
+    assert edges == [0b0010, 0b0101, 0b0010, 0]
     assert orc.two_hop(edges, 4, True, 0) == 0b0111  # N(0) | N(1)
     assert orc.two_hop(edges, 4, True, 3) == 0
     assert orc.two_hop(edges, 4, False, 3) == 0b1111  # uninitialised skeleton: all ones (skeleton.hpp:57-60)

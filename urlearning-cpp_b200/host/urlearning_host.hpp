@@ -132,7 +132,8 @@ public:
             if (first) { first = false; if ((int)tok.size() != p) throw std::runtime_error("Skeleton matrix width differs from the variable count"); }
             int col = 0;
             for (auto &s : tok) {
-                if (s == "TRUE" || std::fabs(atof(s.c_str())) > 0.05) add_edge(row, col); // skeleton.cpp:91
+                // skeleton.cpp:91 `abs(atof(x)) > 0.05` binds ::abs(int) under GCC: x is truncated, so |x| >= 1 or "TRUE"
+                if (s == "TRUE" || std::abs((int)atof(s.c_str())) > 0.05) add_edge(row, col);
                 col++;
             }
             row++; // blank lines count as rows (skeleton.cpp:84-99)
