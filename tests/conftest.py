@@ -33,9 +33,11 @@ def engine(pkg):
     eng.close()
 
 
-@pytest.fixture(scope="session", params=["cube", "direct"])
+@pytest.fixture(scope="session", params=["slice", "cube", "direct"])
 def bic_engine(pkg, request):
-    """BIC engines for both K1 strategies: 'cube' (count roots, marginalise the rest; default) and 'direct' (count every set)."""
+    """BIC engines for the three K1 strategies: 'slice' (default: roots counted in shared-memory slices, subtrees derived on
+    chip; falls back to cube), 'cube' (roots counted into global tables, the rest marginalised through HBM) and 'direct'
+    (every set counted from the rows)."""
     old = os.environ.get("URLGPU_BIC_MODE")
     os.environ["URLGPU_BIC_MODE"] = request.param
     try:

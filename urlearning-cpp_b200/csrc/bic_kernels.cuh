@@ -268,6 +268,8 @@ struct CubePair {
     uint32_t Bc;                      // stride of the dropped digit, in configurations
     uint32_t r;                       // arity of the dropped digit
     uint32_t chunk0;                  // first block of this pair
+    uint32_t acc_index;               // accumulator of the child (its position in the layer)
+    uint32_t leaf;                    // the child has no children of its own (cube bit 0 clear): its table is not written
 };
 
 constexpr int kCubeThreads = 256;
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
 #pragma unroll
                 for (int k = 0; k < RV; k++) cnt[k] += t[k];
             }
-            store_cfg<RV>(Cc + (uint64_t)j * RV, cnt);
+            if (!pr.leaf) store_cfg<RV>(Cc + (uint64_t)j * RV, cnt);
             if (acc_out) {
                 int nij = 0;
 #pragma unroll
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
             for (int k = 0; k < rv; k++) {
                 int cnt = 0;
                 for (uint32_t a = 0; a < pr.r; a++) cnt += P[(pc0 + (uint64_t)a * pr.Bc) * rv + k];
-                Cc[(uint64_t)j * rv + k] = cnt;
+                if (!pr.leaf) Cc[(uint64_t)j * rv + k] = cnt;
                 nij += cnt;
                 if (acc_out && cnt > 1) acc += __ldg(&qlog[cnt]);
             }
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
     }
     if (acc_out) {
         acc = block_sum_ll(acc, red);
-        if (threadIdx.x == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[pi]), (unsigned long long)acc);
+        if (threadIdx.x == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[pr.acc_index]), (unsigned long long)acc);
     }
 }
 

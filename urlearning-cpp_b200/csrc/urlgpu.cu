@@ -17,6 +17,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include "bic_kernels.cuh"
+#include "slice_kernels.cuh"
 #include "cbic_kernels.cuh"
 
 using namespace urlgpu;
@@ -60,7 +61,8 @@ struct urlgpu_ctx {
     int *d_cubeA = nullptr, *d_cubeB = nullptr; size_t cubeA_cap = 0, cubeB_cap = 0; // ping-pong layer buffers of the cube path
     uint32_t *d_high_sorted = nullptr; int high_bits = -1; std::vector<int> high_off;   // segment DP lists (accept / prune)
     uint16_t *d_low_sorted = nullptr; int low_bits = -1; std::vector<int> low_off;
-    int bic_mode = 0; // 0 = cube (default), 1 = direct counting of every set (URLGPU_BIC_MODE=direct)
+    bool use_slice_count = true; // cube path: count big roots in shared-memory slices (URLGPU_SLICE_COUNT=0 disables)
+    int bic_mode = 2; // 2 = cube (default), 0 = slice (experimental: whole subtrees on chip), 1 = direct counting of every set (URLGPU_BIC_MODE=cube|slice|direct)
 
     // caching device allocator: cudaMalloc/cudaFree of multi-GB tables cost tens of ms each
     struct PoolBlock { void *p; size_t bytes; bool used; };
@@ -237,8 +239,11 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
         return URLGPU_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
-    if (const char *m = getenv("URLGPU_BIC_MODE")) ctx->bic_mode = strcmp(m, "direct") == 0 ? 1 : 0;
+    if (const char *m = getenv("URLGPU_SLICE_COUNT")) ctx->use_slice_count = atoi(m) != 0;
+    if (const char *m = getenv("URLGPU_BIC_MODE")) ctx->bic_mode = strcmp(m, "direct") == 0 ? 1 : strcmp(m, "slice") == 0 ? 0 : 2;
     cudaFuncSetAttribute(bic_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 2048);
+    cudaFuncSetAttribute(bic_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024 * 4 + 16 * (1 << kSliceMaxRun));
+    cudaFuncSetAttribute(bic_slice_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024 * 4);
     *out = ctx;
     return URLGPU_OK;
 }
@@ -591,8 +596,57 @@ inline uint32_t gosper_next(uint32_t v) {
 }
 } // namespace
 
+
+// Bucketed copy of the (child + candidate) columns of one variable: rows grouped by the joint value of the top
+// `dmax` cube digits, plus the row offset of every prefix (slice_kernels.cuh).
+namespace {
+struct SliceBuckets {
+    DevBuf keys, hist, off, cursor, sorted;
+    SliceVar sv{};
+    bool ready = false;
+    explicit SliceBuckets(urlgpu_ctx *ctx) : keys(ctx), hist(ctx), off(ctx), cursor(ctx), sorted(ctx) {}
+};
+} // namespace
+
+static int slice_prepare(urlgpu_ctx *ctx, const BicData &bd, const CandInfo &ci_cube, const std::vector<uint64_t> &ccard, int K, SliceBuckets &sb) {
+    if (sb.ready) return URLGPU_OK;
+    cudaStream_t s = ctx->stream;
+    const int c = ci_cube.c;
+    const uint64_t n = (uint64_t)ctx->n;
+    int dmax = 0;
+    uint64_t Pd = 1;
+    while (dmax < c && dmax < kSliceMaxDepth && Pd * ccard[c - 1 - dmax] <= 65536) { Pd *= ccard[c - 1 - dmax]; dmax++; }
+    SliceVar &sv = sb.sv;
+    sv.c = c; sv.rv = ci_cube.rv; sv.max_parents = K; sv.dmax = dmax; sv.P_dmax = (uint32_t)Pd;
+    for (int i = 0; i < c; i++) sv.card[i] = (int)ccard[i];
+    CK(sb.off.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+    if (dmax > 0) {
+        CK(sb.keys.alloc(n * sizeof(uint32_t)));
+        CK(sb.hist.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+        CK(sb.cursor.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+        CK(sb.sorted.alloc((size_t)(c + 1) * ctx->n_stride));
+        CK(cudaMemsetAsync(sb.hist.p, 0, ((size_t)Pd + 1) * sizeof(uint32_t), s));
+        Region rg(ctx, F_COUNT, 3);
+        slice_key_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, dmax, sb.keys.as<uint32_t>(), sb.hist.as<uint32_t>());
+        slice_scan_kernel<<<1, 1024, 0, s>>>(sb.hist.as<uint32_t>(), (uint32_t)Pd, sb.off.as<uint32_t>(), sb.cursor.as<uint32_t>());
+        slice_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, sb.keys.as<uint32_t>(), sb.cursor.as<uint32_t>(), sb.sorted.as<uint8_t>());
+        for (int i = 0; i <= c; i++) sv.cols[i] = sb.sorted.as<uint8_t>() + (size_t)i * ctx->n_stride;
+    } else {
+        const uint32_t h[2] = {0, (uint32_t)n};
+        CK(cudaMemcpyAsync(sb.off.p, h, sizeof h, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        sv.cols[0] = ctx->d_codes + (size_t)ci_cube.v * ctx->n_stride;
+        for (int i = 0; i < c; i++) sv.cols[i + 1] = ctx->d_codes + (size_t)ci_cube.var[i] * ctx->n_stride;
+    }
+    sv.prefix_off = sb.off.as<uint32_t>();
+    sb.ready = true;
+    return URLGPU_OK;
+}
+
+// `only_roots` (optional): restrict the work to the sub-forest below these root sets of layer `roots_layer`
+// (cube masks); the slice path hands over the roots it cannot slice.
 static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                                 uint64_t *n_scored, bool *used) {
+                                 uint64_t *n_scored, bool *used, const std::vector<uint32_t> *only_roots = nullptr, int roots_layer = -1) {
     *used = false;
     cudaStream_t s = ctx->stream;
     static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
@@ -618,7 +672,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
 
     // ---- enumerate layers 0..Lmax (layers above Kc: only sets containing the lowest l-Kc cube bits) ----
-    const int Lmax = std::min(Kc + 2, c);
+    const int Lmax = only_roots ? roots_layer : std::min(Kc + 2, c);
     std::vector<std::vector<CubeSet>> layers(Lmax + 1);
     auto make_set = [&](uint32_t cm) {
         CubeSet cs{};
@@ -630,7 +684,14 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         cs.cells = cells; cs.res_mask = rm; cs.parent = -1;
         return cs;
     };
-    for (int l = 0; l <= Lmax; l++) {
+    if (only_roots) { // the sub-forest of the given roots: root P, run = trailing ones of P, descendants P ^ D
+        for (uint32_t P : *only_roots) {
+            const int z = std::min(c, (int)__builtin_ctz(~P));
+            for (uint32_t D = 0; D < (1u << z); D++) layers[Lmax - __builtin_popcount(D)].push_back(make_set(P ^ D));
+        }
+        for (auto &L : layers) std::sort(L.begin(), L.end(), [](const CubeSet &a, const CubeSet &b) { return a.cube_mask < b.cube_mask; });
+    }
+    for (int l = 0; l <= Lmax && !only_roots; l++) {
         const int j = std::max(0, l - Kc);      // forced low bits
         const int free_bits = c - j, pick = l - j;
         const uint32_t lowmask = (j ? ((1u << j) - 1) : 0);
@@ -648,7 +709,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     auto root_cost = [&](const CubeSet &cs, int l) {
         if (cs.cells > kCellLimit) return 1e30;
         if (cs.cells <= tier1_cells) return (double)n * (l + 1) / 6e12 + 2e-7;
-        return (double)n / 1.8e11 + (double)cs.cells * 4.0 / 2.5e12;
+        return 6.5e-6 + (double)cs.cells * 1.95e-12; // fitted to the slice-count kernel on B200 (n = 1e6)
     };
     auto derive_cost = [&](const CubeSet &cs, int /*l*/, uint64_t rdrop) { return (double)cs.cells * 4.0 * (double)(rdrop + 1) / 5e12 + 1e-7; };
     size_t free_b = 0, total_b = 0;
@@ -659,7 +720,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         for (auto &cs : layers[l]) layer_cells[l] += (double)((cs.cells + 3) / 4 * 4);
     int Lstar = -1;
     double best = 1e300;
-    for (int Ls = Kc; Ls <= Lmax; Ls++) {
+    for (int Ls = only_roots ? Lmax : Kc; Ls <= Lmax; Ls++) {
         double cost = 0, maxl = 0;
         for (auto &cs : layers[Ls]) cost += root_cost(cs, Ls);
         if (cost >= 1e29) continue; // a root table above the 2^30-cell limit
@@ -752,30 +813,77 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             CK(cudaMemsetAsync(dacc_big.p, 0, big.size() * sizeof(long long), s));
             CK(cudaMemcpyAsync(dgsets.p, big.data(), big.size() * sizeof(GlobalSet), cudaMemcpyHostToDevice, s));
             const int threads = 256;
+            // (1) roots whose table can be cut along its top digits are counted in shared-memory slices of the
+            //     bucketed rows and written out once (bic_slice_count_kernel); (2) the rest use global RED atomics.
+            std::vector<SliceCountRoot> scr;
+            std::vector<char> sliced(big.size(), 0);
+            uint64_t sc_chunk = 0;
+            const uint32_t sc_budget = 52 * 1024; // 208 KB of table per CTA, one 1024-thread CTA per SM
+            if (ctx->n >= 65536 && ctx->use_slice_count) {
+                int dmax = 0;
+                uint64_t Pd = 1;
+                while (dmax < c && dmax < kSliceMaxDepth && Pd * ccard[c - 1 - dmax] <= 65536) { Pd *= ccard[c - 1 - dmax]; dmax++; }
+                for (size_t i = 0; i < big.size(); i++) {
+                    const uint32_t P = big[i].mask;
+                    uint64_t slices = 1, depth_prod = 1;
+                    int depth = 0;
+                    bool reached = false;
+                    for (int b = c - 1; b >= 0 && depth < dmax; b--) {
+                        depth++;
+                        depth_prod *= ccard[b];
+                        if ((P >> b) & 1) { slices *= ccard[b]; if (big[i].cells / slices <= sc_budget) { reached = true; break; } }
+                    }
+                    if (!reached || slices > 65535) continue;
+                    const uint64_t segs = depth_prod / slices;
+                    if (segs > (uint64_t)kSliceMaxSeg || (segs > 1 && n / depth_prod < 24)) continue;
+                    SliceCountRoot r{};
+                    r.mask = P; r.chunk0 = (uint32_t)sc_chunk; r.table_off = big[i].table_off; r.nslices = (uint16_t)slices; r.depth = (uint8_t)depth;
+                    sc_chunk += slices;
+                    scr.push_back(r);
+                    sliced[i] = 1;
+                }
+                if (sc_chunk < 128 || sc_chunk > 0x7fffffffull) { scr.clear(); std::fill(sliced.begin(), sliced.end(), 0); sc_chunk = 0; }
+            }
+            DevBuf dscr(ctx);
+            SliceBuckets sb(ctx);
+            if (!scr.empty()) {
+                int rc2 = slice_prepare(ctx, bd, ci_cube, ccard, K, sb);
+                if (rc2) return rc2;
+                CK(dscr.alloc(scr.size() * sizeof(SliceCountRoot)));
+                CK(cudaMemcpyAsync(dscr.p, scr.data(), scr.size() * sizeof(SliceCountRoot), cudaMemcpyHostToDevice, s));
+                Region rg(ctx, F_COUNT, 1);
+                bic_slice_count_kernel<<<(unsigned)sc_chunk, kSliceCountThreads, (size_t)sc_budget * sizeof(int), s>>>(sb.sv, dscr.as<SliceCountRoot>(), (int)scr.size(), bufP);
+            }
             size_t i0 = 0;
-            while (i0 < big.size()) { // batches whose tables (contiguous in bufP) stay L2 resident
+            while (i0 < big.size()) { // RED batches whose tables stay L2 resident; sliced roots only need scoring
                 size_t i1 = i0;
                 uint64_t bytes = 0;
-                while (i1 < big.size() && (i1 == i0 || bytes + big[i1].cells * 4 <= kBatchTableElems * 4) && i1 - i0 < 65535) { bytes += (big[i1].cells + 3) / 4 * 16; i1++; }
+                while (i1 < big.size() && (i1 == i0 || bytes + big[i1].cells * 4 <= kBatchTableElems * 4) && i1 - i0 < 65535 && sliced[i1] == sliced[i0]) { bytes += (big[i1].cells + 3) / 4 * 16; i1++; }
                 const size_t B = i1 - i0;
-                Region rg(ctx, F_COUNT, 2 + (score_roots ? 1 : 0));
-                for (size_t i = i0; i < i1; i++) CK(cudaMemsetAsync(bufP + big[i].table_off, 0, big[i].cells * sizeof(int), s));
-                int64_t Rr = std::max<int64_t>(1, (int64_t)(ctx->sm_count * 8 + B - 1) / (int64_t)B);
-                int64_t rps = (bd.n + Rr - 1) / Rr;
-                rps = std::max<int64_t>((rps + 15) / 16 * 16, 16 * threads);
-                Rr = (bd.n + rps - 1) / rps;
-                bic_count_global_kernel<<<dim3((unsigned)B, (unsigned)Rr), threads, 0, s>>>(bd, ci_cube, dgsets.as<GlobalSet>() + i0, bufP, rps);
-                if (score_roots) {
-                    uint32_t maxc = 0;
-                    for (size_t i = i0; i < i1; i++) maxc = std::max(maxc, big[i].cells);
-                    const int64_t nconf = maxc / rv;
-                    const int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((nconf + threads * 4 - 1) / (threads * 4), (ctx->sm_count * 8 + (int64_t)B - 1) / (int64_t)B));
-                    const int64_t cpc = (nconf + chunks - 1) / chunks;
-                    bic_score_tables_kernel<<<dim3((unsigned)B, (unsigned)chunks), threads, 0, s>>>(bd, ci_cube, dgsets.as<GlobalSet>() + i0, bufP,
-                                                                                                dacc_big.as<long long>() + i0, cpc);
+                const bool red = !sliced[i0];
+                if (red || score_roots) {
+                    Region rg(ctx, F_COUNT, (red ? 2 : 0) + (score_roots ? 1 : 0));
+                    if (red) {
+                        for (size_t i = i0; i < i1; i++) CK(cudaMemsetAsync(bufP + big[i].table_off, 0, big[i].cells * sizeof(int), s));
+                        int64_t Rr = std::max<int64_t>(1, (int64_t)(ctx->sm_count * 8 + B - 1) / (int64_t)B);
+                        int64_t rps = (bd.n + Rr - 1) / Rr;
+                        rps = std::max<int64_t>((rps + 15) / 16 * 16, 16 * threads);
+                        Rr = (bd.n + rps - 1) / rps;
+                        bic_count_global_kernel<<<dim3((unsigned)B, (unsigned)Rr), threads, 0, s>>>(bd, ci_cube, dgsets.as<GlobalSet>() + i0, bufP, rps);
+                    }
+                    if (score_roots) {
+                        uint32_t maxc = 0;
+                        for (size_t i = i0; i < i1; i++) maxc = std::max(maxc, big[i].cells);
+                        const int64_t nconf = maxc / rv;
+                        const int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((nconf + threads * 4 - 1) / (threads * 4), (ctx->sm_count * 8 + (int64_t)B - 1) / (int64_t)B));
+                        const int64_t cpc = (nconf + chunks - 1) / chunks;
+                        bic_score_tables_kernel<<<dim3((unsigned)B, (unsigned)chunks), threads, 0, s>>>(bd, ci_cube, dgsets.as<GlobalSet>() + i0, bufP,
+                                                                                                    dacc_big.as<long long>() + i0, cpc);
+                    }
                 }
                 i0 = i1;
             }
+            CK(cudaStreamSynchronize(s)); // scr / sb are released here
         }
         if (score_roots) { // gather the two accumulator arrays into layer order
             std::vector<long long> ha(R.size(), 0), hs(small_m.size()), hb(big.size());
@@ -793,20 +901,32 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     }
     const auto T2 = tnow();
     // ---- derived layers ----
+    // Pairs are emitted grouped by PARENT: blocks are dispatched in launch order, so the children of one parent run
+    // back to back and all but the first read the parent table from L2 (126 MB) instead of HBM.
     std::vector<CubePair> hp;
     for (int l = Lstar - 1; l >= 0; l--) {
         auto &L = layers[l];
         auto &P = layers[l + 1];
+        if (L.empty()) break; // sub-forest mode: runs shorter than the layer count leave the lower layers empty
+        std::vector<uint32_t> first(P.size() + 1, 0), order(L.size());
+        for (auto &cs : L) first[cs.parent + 1]++;
+        for (size_t i = 0; i < P.size(); i++) first[i + 1] += first[i];
+        {
+            std::vector<uint32_t> pos(first.begin(), first.end() - 1);
+            for (size_t i = 0; i < L.size(); i++) order[pos[L[i].parent]++] = (uint32_t)i;
+        }
         hp.resize(L.size());
         uint64_t chunk = 0;
-        for (size_t i = 0; i < L.size(); i++) {
-            const CubeSet &cs = L[i];
+        for (size_t k = 0; k < order.size(); k++) {
+            const CubeSet &cs = L[order[k]];
             CubePair pr{};
             pr.parent_off = P[cs.parent].off; pr.child_off = cs.off;
             pr.child_configs = (uint32_t)(cs.cells / rv);
             pr.Bc = cs.Bc; pr.r = cs.r; pr.chunk0 = (uint32_t)chunk;
+            pr.acc_index = order[k];
+            pr.leaf = (cs.cube_mask & 1u) == 0; // lowest missing bit is 0: nothing is derived from this set
             chunk += (pr.child_configs + kCubeConfigsPerBlock - 1) / kCubeConfigsPerBlock;
-            hp[i] = pr;
+            hp[k] = pr;
         }
         if (chunk > 0x7fffffffull) return ctx->fail(URLGPU_ERR_LIMIT, "cube: too many blocks in one layer");
         const bool score = l <= Kc;
@@ -831,7 +951,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     if (dbg) fprintf(stderr, "[urlgpu cube] v=%d c=%d K=%d L*=%d roots=%zu plan+alloc %.2f ms, roots %.2f ms, derive %.2f ms\n", variable, c, K, Lstar,
                      layers[Lstar].size(), tms(T0, T1), tms(T1, T2), tms(T2, tnow()));
     *n_scored = family_size(c, K);
-    {
+    if (!only_roots) {
         double bytes = 0, b = 1;
         for (int l = 0; l <= K && l <= c; l++) { bytes += b * (double)ctx->n * (l + 1); b = b * (c - l) / (l + 1); }
         ctx->st.algorithmic_bytes += bytes;
@@ -841,14 +961,174 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     return URLGPU_OK;
 }
 
+static int bic_score_family_slice(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
+                                  uint64_t *n_scored, bool *used);
+
 static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
                             uint64_t *n_scored) {
+    if (ctx->bic_mode == 0) {
+        bool used = false;
+        int rc = bic_score_family_slice(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used);
+        if (rc || used) return rc;
+    }
     if (ctx->bic_mode != 1) {
         bool used = false;
         int rc = bic_score_family_cube(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used);
         if (rc || used) return rc;
     }
     return bic_score_family_direct(ctx, variable, cand, K, d_table, d_llfixed, n_scored);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Slice path (slice_kernels.cuh): roots counted in shared-memory slices of bucketed rows, subtrees derived on chip.
+// Roots that cannot be sliced (run too long, table not separable within the bucketed prefix depth, segments too
+// short) are handed to the cube path as a sub-forest.
+// ------------------------------------------------------------------------------------------------------------
+static int bic_score_family_slice(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
+                                  uint64_t *n_scored, bool *used) {
+    *used = false;
+    cudaStream_t s = ctx->stream;
+    const int c = (int)cand.size();
+    if (c == 0) return URLGPU_OK;
+    const int Kc = std::min(K, c);
+    const int rv = ctx->card[variable];
+    const uint64_t n = (uint64_t)ctx->n;
+    std::vector<int> perm(c);
+    for (int i = 0; i < c; i++) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return ctx->card[cand[a]] < ctx->card[cand[b]]; });
+    std::vector<int> cube_vars(c);
+    std::vector<uint64_t> ccard(c);
+    for (int i = 0; i < c; i++) { cube_vars[i] = cand[perm[i]]; ccard[i] = (uint64_t)ctx->card[cube_vars[i]]; }
+    CandInfo ci_cube = make_candinfo(ctx, variable, cube_vars, K);
+    CandInfo ci_res = make_candinfo(ctx, variable, cand, K);
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+
+    const int Lstar = std::min(Kc + 1, c);
+    const int jforced = Lstar - Kc;                       // 0 or 1 forced low bits
+    // bucketing depth: top digits whose joint arity stays <= 65536
+    int dmax = 0;
+    uint64_t Pd = 1;
+    while (dmax < c && dmax < kSliceMaxDepth && Pd * ccard[c - 1 - dmax] <= 65536) { Pd *= ccard[c - 1 - dmax]; dmax++; }
+    const uint32_t budget = 24 * 1024;                    // table cells per CTA (96 KB): two CTAs per SM
+    const size_t smem = (size_t)budget * 4 + ((size_t)4 + 4 + 8) * (1u << kSliceMaxRun);
+
+    std::vector<SliceRoot> sroots;
+    std::vector<uint32_t> groots;
+    uint64_t chunk = 0, acc_total = 0;
+    {
+        const int free_bits = c - jforced, pick = Lstar - jforced;
+        const uint32_t lowmask = jforced ? ((1u << jforced) - 1) : 0;
+        uint32_t v = pick ? (1u << pick) - 1 : 0;
+        const uint64_t lim = (uint64_t)1 << free_bits;
+        while (true) {
+            const uint32_t P = (v << jforced) | lowmask;
+            const int z = std::min(c, (int)__builtin_ctz(~P));
+            bool ok = z <= kSliceMaxRun;
+            uint64_t cells = (uint64_t)rv, runprod = 1, runplus = 1;
+            for (int i = 0; i < c; i++) if ((P >> i) & 1) cells = std::min<uint64_t>(cells * ccard[i], (uint64_t)1 << 50);
+            for (int i = 0; i < z; i++) { runprod *= ccard[i]; runplus *= ccard[i] + 1; }
+            if (cells > ((uint64_t)1 << 40)) ok = false;
+            uint64_t slices = 1, depth_prod = 1;
+            int depth = 0;
+            if (ok) {
+                const uint64_t total = cells / runprod * runplus;      // all 2^z tables of the un-sliced root
+                if (total > budget) {
+                    bool reached = false;
+                    for (int b = c - 1; b > z && depth < dmax; b--) {
+                        depth++;
+                        depth_prod *= ccard[b];
+                        if ((P >> b) & 1) slices *= ccard[b];
+                        if ((P >> b) & 1 && total / slices <= budget) { reached = true; break; }
+                    }
+                    ok = reached && slices <= 65535;
+                    if (ok) {
+                        const uint64_t segs = depth_prod / slices;
+                        if (segs > 1 && (n / depth_prod < 24 || segs > (uint64_t)kSliceMaxSeg)) ok = false;
+                    }
+                }
+            }
+            if (ok) {
+                SliceRoot sr{};
+                sr.mask = P; sr.chunk0 = (uint32_t)chunk; sr.acc_off = (uint32_t)acc_total;
+                sr.nslices = (uint16_t)slices; sr.depth = (uint8_t)depth; sr.z = (uint8_t)z;
+                chunk += slices; acc_total += (uint64_t)1 << z;
+                sroots.push_back(sr);
+            } else groots.push_back(P);
+            if (pick == 0 || pick == free_bits) break;
+            v = gosper_next(v);
+            if ((uint64_t)v >= lim) break;
+        }
+    }
+    if (chunk > 0x7fffffffull || acc_total > 0xffffffffull) return URLGPU_OK;   // let the cube path handle it
+    if (chunk < 64 && n > 200000) { // too few CTAs to fill the machine: the cube path counts such roots with many CTAs
+        for (auto &sr : sroots) groots.push_back(sr.mask);
+        sroots.clear(); chunk = 0; acc_total = 0;
+    }
+    static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
+    if (dbg) fprintf(stderr, "[urlgpu slice] v=%d c=%d K=%d L*=%d dmax=%d slice roots=%zu (%llu CTAs) global roots=%zu\n", variable, c, K, Lstar, dmax, sroots.size(),
+                     (unsigned long long)chunk, groots.size());
+    if (!sroots.empty()) {
+        DevBuf dkeys(ctx), dhist(ctx), doff(ctx), dcursor(ctx), dsorted(ctx), droots(ctx), dacc(ctx), dperm(ctx);
+        SliceVar sv{};
+        sv.c = c; sv.rv = rv; sv.max_parents = K; sv.dmax = dmax; sv.P_dmax = (uint32_t)Pd;
+        for (int i = 0; i < c; i++) sv.card[i] = (int)ccard[i];
+        CK(doff.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+        if (dmax > 0) {
+            CK(dkeys.alloc(n * sizeof(uint32_t)));
+            CK(dhist.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+            CK(dcursor.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+            CK(dsorted.alloc((size_t)(c + 1) * ctx->n_stride));
+            CK(cudaMemsetAsync(dhist.p, 0, ((size_t)Pd + 1) * sizeof(uint32_t), s));
+            Region rg(ctx, F_COUNT, 3);
+            slice_key_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, dmax, dkeys.as<uint32_t>(), dhist.as<uint32_t>());
+            slice_scan_kernel<<<1, 1024, 0, s>>>(dhist.as<uint32_t>(), (uint32_t)Pd, doff.as<uint32_t>(), dcursor.as<uint32_t>());
+            slice_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, dkeys.as<uint32_t>(), dcursor.as<uint32_t>(), dsorted.as<uint8_t>());
+            for (int i = 0; i <= c; i++) sv.cols[i] = dsorted.as<uint8_t>() + (size_t)i * ctx->n_stride;
+        } else {
+            const uint32_t h[2] = {0, (uint32_t)n};
+            CK(cudaMemcpyAsync(doff.p, h, sizeof h, cudaMemcpyHostToDevice, s));
+            sv.cols[0] = ctx->d_codes + (size_t)variable * ctx->n_stride;
+            for (int i = 0; i < c; i++) sv.cols[i + 1] = ctx->d_codes + (size_t)cube_vars[i] * ctx->n_stride;
+        }
+        sv.prefix_off = doff.as<uint32_t>();
+        CK(droots.alloc(sroots.size() * sizeof(SliceRoot)));
+        CK(dacc.alloc(acc_total * sizeof(long long)));
+        CK(dperm.alloc(kMaxDenseCand));
+        uint8_t hperm[kMaxDenseCand] = {0};
+        for (int i = 0; i < c; i++) hperm[i] = (uint8_t)perm[i];
+        CK(cudaMemcpyAsync(droots.p, sroots.data(), sroots.size() * sizeof(SliceRoot), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dperm.p, hperm, kMaxDenseCand, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(dacc.p, 0, acc_total * sizeof(long long), s));
+        {
+            Region rg(ctx, F_COUNT, 1);
+            bic_slice_kernel<<<(unsigned)chunk, kSliceThreads, smem, s>>>(sv, droots.as<SliceRoot>(), (int)sroots.size(), ctx->d_qlog, dacc.as<long long>(), budget);
+        }
+        {
+            Region rg(ctx, F_OTHER, 1);
+            slice_finalize_kernel<<<blocks_for(acc_total, 256), 256, 0, s>>>(bd, ci_res, droots.as<SliceRoot>(), (int)sroots.size(), dperm.as<uint8_t>(), dacc.as<long long>(),
+                                                                          (uint32_t)acc_total, d_table, d_llfixed);
+        }
+        CK(cudaStreamSynchronize(s)); // host arrays and pooled buffers go out of scope
+        CK(cudaGetLastError());
+    }
+    if (!groots.empty()) {
+        bool cu = false;
+        uint64_t dummy = 0;
+        std::sort(groots.begin(), groots.end());
+        int rc = bic_score_family_cube(ctx, variable, cand, K, d_table, d_llfixed, &dummy, &cu, &groots, Lstar);
+        if (rc) return rc;
+        if (!cu) return ctx->fail(URLGPU_ERR_LIMIT, "slice path: the cube sub-forest does not fit in device memory");
+    }
+    *n_scored = family_size(c, K);
+    {
+        double bytes = 0, b = 1;
+        for (int l = 0; l <= K && l <= c; l++) { bytes += b * (double)ctx->n * (l + 1); b = b * (c - l) / (l + 1); }
+        ctx->st.algorithmic_bytes += bytes;
+        ctx->st.sets_scored += *n_scored;
+    }
+    *used = true;
+    return URLGPU_OK;
 }
 
 template <int J>
