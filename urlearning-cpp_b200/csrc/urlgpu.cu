@@ -64,6 +64,12 @@ struct urlgpu_ctx {
     bool use_slice_count = true; // cube path: count big roots in shared-memory slices (URLGPU_SLICE_COUNT=0 disables)
     int bic_mode = 2; // 2 = cube (default), 0 = slice (experimental: whole subtrees on chip), 1 = direct counting of every set (URLGPU_BIC_MODE=cube|slice|direct)
 
+    // pinned staging arena for host->device descriptor uploads (pageable cudaMemcpyAsync would sync the stream)
+    // two arenas used alternately per call, each guarded by an event recorded when its call has been enqueued, so the
+    // host can plan and upload call k+1 while the GPU still executes call k
+    char *h_stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0}; size_t stage_used = 0;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr}; int stage_cur = 0;
+
     // caching device allocator: cudaMalloc/cudaFree of multi-GB tables cost tens of ms each
     struct PoolBlock { void *p; size_t bytes; bool used; };
     std::vector<PoolBlock> pool;
@@ -273,6 +279,7 @@ extern "C" int urlgpu_destroy(urlgpu_ctx *ctx) {
     if (ctx->d_low_sorted) cudaFree(ctx->d_low_sorted);
     if (ctx->d_cubeB) cudaFree(ctx->d_cubeB);
     pool_destroy(ctx);
+    for (int k = 0; k < 2; k++) { if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]); if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return URLGPU_OK;
@@ -597,6 +604,45 @@ inline uint32_t gosper_next(uint32_t v) {
 } // namespace
 
 
+// Truly asynchronous H2D upload of a host array: the bytes are copied into one of the context's two pinned arenas
+// (bump allocated) and sent with cudaMemcpyAsync.  stage_begin() switches to the other arena and waits only for the
+// call that used it two calls ago; stage_end() marks the end of the current call.
+static int stage_begin(urlgpu_ctx *ctx) {
+    ctx->stage_cur ^= 1;
+    const int k = ctx->stage_cur;
+    if (!ctx->stage_ev[k]) CK(cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(ctx->stage_ev[k]));
+    ctx->stage_used = 0;
+    return URLGPU_OK;
+}
+static int stage_end(urlgpu_ctx *ctx) {
+    const int k = ctx->stage_cur;
+    if (ctx->stage_ev[k]) CK(cudaEventRecord(ctx->stage_ev[k], ctx->stream));
+    return URLGPU_OK;
+}
+static int h2d_async(urlgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return URLGPU_OK;
+    const int k = ctx->stage_cur;
+    const size_t need = (ctx->stage_used + 255) / 256 * 256 + bytes;
+    if (need > ctx->stage_cap[k]) {
+        // the arena is full: drain the stream (pending copies read from it), then grow
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (bytes > ctx->stage_cap[k]) {
+            if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
+            ctx->h_stage[k] = nullptr; ctx->stage_cap[k] = 0;
+            const size_t cap = std::max<size_t>(bytes * 2, (size_t)32 << 20);
+            CK(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_stage[k]), cap, cudaHostAllocDefault));
+            ctx->stage_cap[k] = cap;
+        }
+        ctx->stage_used = 0;
+    }
+    const size_t off = (ctx->stage_used + 255) / 256 * 256;
+    memcpy(ctx->h_stage[k] + off, src, bytes);
+    ctx->stage_used = off + bytes;
+    CK(cudaMemcpyAsync(dst, ctx->h_stage[k] + off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return URLGPU_OK;
+}
+
 // Bucketed copy of the (child + candidate) columns of one variable: rows grouped by the joint value of the top
 // `dmax` cube digits, plus the row offset of every prefix (slice_kernels.cuh).
 namespace {
@@ -649,6 +695,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                                  uint64_t *n_scored, bool *used, const std::vector<uint32_t> *only_roots = nullptr, int roots_layer = -1) {
     *used = false;
     cudaStream_t s = ctx->stream;
+    { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
     static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
     auto tnow = [] { return std::chrono::steady_clock::now(); };
     auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
@@ -674,14 +721,28 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     // ---- enumerate layers 0..Lmax (layers above Kc: only sets containing the lowest l-Kc cube bits) ----
     const int Lmax = only_roots ? roots_layer : std::min(Kc + 2, c);
     std::vector<std::vector<CubeSet>> layers(Lmax + 1);
+    // per-byte lookup tables: cells factor and result-order mask of every 8-bit group of cube bits
+    std::vector<uint64_t> cellsT(4 * 256, 1);
+    std::vector<uint32_t> resT(4 * 256, 0);
+    for (int g = 0; g < 4; g++)
+        for (int m = 0; m < 256; m++) {
+            uint64_t f = 1; uint32_t rm = 0;
+            for (int b = 0; b < 8; b++) {
+                const int i = g * 8 + b;
+                if (i < c && ((m >> b) & 1)) { f *= ccard[i]; rm |= 1u << perm[i]; }
+            }
+            cellsT[g * 256 + m] = f; resT[g * 256 + m] = rm;
+        }
     auto make_set = [&](uint32_t cm) {
         CubeSet cs{};
         cs.cube_mask = cm;
-        uint64_t cells = (uint64_t)rv;
-        uint32_t rm = 0;
-        for (int i = 0; i < c; i++)
-            if ((cm >> i) & 1) { cells = std::min<uint64_t>(cells * ccard[i], kCellLimit + 1); rm |= 1u << perm[i]; }
-        cs.cells = cells; cs.res_mask = rm; cs.parent = -1;
+        const uint32_t b0 = cm & 255, b1 = (cm >> 8) & 255, b2 = (cm >> 16) & 255, b3 = cm >> 24;
+        __uint128_t cells = (__uint128_t)rv * cellsT[b0] * cellsT[256 + b1];
+        cells = std::min<__uint128_t>(cells, kCellLimit + 1) * cellsT[512 + b2];
+        cells = std::min<__uint128_t>(cells, kCellLimit + 1) * cellsT[768 + b3];
+        cs.cells = (uint64_t)std::min<__uint128_t>(cells, kCellLimit + 1);
+        cs.res_mask = resT[b0] | resT[256 + b1] | resT[512 + b2] | resT[768 + b3];
+        cs.parent = -1;
         return cs;
     };
     if (only_roots) { // the sub-forest of the given roots: root P, run = trailing ones of P, descendants P ^ D
@@ -769,10 +830,9 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         auto &L = layers[l];
         hres.resize(L.size());
         for (size_t i = 0; i < L.size(); i++) hres[i] = L[i].res_mask;
-        CK(cudaMemcpyAsync(dres.p, hres.data(), L.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        { int rc_ = h2d_async(ctx, dres.p, hres.data(), L.size() * sizeof(uint32_t)); if (rc_) return rc_; }
         Region rg(ctx, F_OTHER, 1);
         cube_finalize_kernel<<<blocks_for(L.size(), 256), 256, 0, s>>>(bd, ci_res, dres.as<uint32_t>(), dacc.as<long long>(), (int)L.size(), d_table, d_llfixed);
-        CK(cudaStreamSynchronize(s)); // hres is reused by the next layer
         return URLGPU_OK;
     };
 
@@ -794,8 +854,8 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             CK(dwork.alloc(small_m.size() * sizeof(uint32_t)));
             CK(doffs.alloc(small_off.size() * sizeof(uint64_t)));
             CK(dacc_small.alloc(small_m.size() * sizeof(long long)));
-            CK(cudaMemcpyAsync(dwork.p, small_m.data(), small_m.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(doffs.p, small_off.data(), small_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+            { int rc_ = h2d_async(ctx, dwork.p, small_m.data(), small_m.size() * sizeof(uint32_t)); if (rc_) return rc_; }
+            { int rc_ = h2d_async(ctx, doffs.p, small_off.data(), small_off.size() * sizeof(uint64_t)); if (rc_) return rc_; }
             // two launches by table size so that small tables get several CTAs per SM
             std::vector<size_t> order(small_m.size());
             Region rg(ctx, F_COUNT, 1);
@@ -811,7 +871,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             CK(dgsets.alloc(big.size() * sizeof(GlobalSet)));
             CK(dacc_big.alloc(big.size() * sizeof(long long)));
             CK(cudaMemsetAsync(dacc_big.p, 0, big.size() * sizeof(long long), s));
-            CK(cudaMemcpyAsync(dgsets.p, big.data(), big.size() * sizeof(GlobalSet), cudaMemcpyHostToDevice, s));
+            { int rc_ = h2d_async(ctx, dgsets.p, big.data(), big.size() * sizeof(GlobalSet)); if (rc_) return rc_; }
             const int threads = 256;
             // (1) roots whose table can be cut along its top digits are counted in shared-memory slices of the
             //     bucketed rows and written out once (bic_slice_count_kernel); (2) the rest use global RED atomics.
@@ -850,7 +910,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 int rc2 = slice_prepare(ctx, bd, ci_cube, ccard, K, sb);
                 if (rc2) return rc2;
                 CK(dscr.alloc(scr.size() * sizeof(SliceCountRoot)));
-                CK(cudaMemcpyAsync(dscr.p, scr.data(), scr.size() * sizeof(SliceCountRoot), cudaMemcpyHostToDevice, s));
+                { int rc_ = h2d_async(ctx, dscr.p, scr.data(), scr.size() * sizeof(SliceCountRoot)); if (rc_) return rc_; }
                 Region rg(ctx, F_COUNT, 1);
                 bic_slice_count_kernel<<<(unsigned)sc_chunk, kSliceCountThreads, (size_t)sc_budget * sizeof(int), s>>>(sb.sv, dscr.as<SliceCountRoot>(), (int)scr.size(), bufP);
             }
@@ -883,7 +943,6 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 }
                 i0 = i1;
             }
-            CK(cudaStreamSynchronize(s)); // scr / sb are released here
         }
         if (score_roots) { // gather the two accumulator arrays into layer order
             std::vector<long long> ha(R.size(), 0), hs(small_m.size()), hb(big.size());
@@ -892,12 +951,11 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             CK(cudaStreamSynchronize(s));
             for (size_t i = 0; i < hs.size(); i++) ha[small_idx[i]] = hs[i];
             for (size_t i = 0; i < hb.size(); i++) ha[big_idx[i]] = hb[i];
-            CK(cudaMemcpyAsync(dacc.p, ha.data(), ha.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
+            { int rc_ = h2d_async(ctx, dacc.p, ha.data(), ha.size() * sizeof(long long)); if (rc_) return rc_; }
             CK(cudaStreamSynchronize(s));
             int rc = finalize_layer(Lstar);
             if (rc) return rc;
         }
-        CK(cudaStreamSynchronize(s)); // small_m / big go out of scope
     }
     const auto T2 = tnow();
     // ---- derived layers ----
@@ -930,7 +988,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         }
         if (chunk > 0x7fffffffull) return ctx->fail(URLGPU_ERR_LIMIT, "cube: too many blocks in one layer");
         const bool score = l <= Kc;
-        CK(cudaMemcpyAsync(dpairs.p, hp.data(), hp.size() * sizeof(CubePair), cudaMemcpyHostToDevice, s));
+        { int rc_ = h2d_async(ctx, dpairs.p, hp.data(), hp.size() * sizeof(CubePair)); if (rc_) return rc_; }
         if (score) CK(cudaMemsetAsync(dacc.p, 0, L.size() * sizeof(long long), s));
         {
             Region rg(ctx, F_CUBE, 1);
@@ -943,11 +1001,11 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             default: cube_derive_kernel<0><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), bufP, bufC, rv, ctx->d_qlog, accp); break;
             }
         }
-        CK(cudaStreamSynchronize(s)); // hp is reused
         if (score) { int rc = finalize_layer(l); if (rc) return rc; }
         std::swap(bufP, bufC);
     }
     CK(cudaGetLastError());
+    { int rc_ = stage_end(ctx); if (rc_) return rc_; }
     if (dbg) fprintf(stderr, "[urlgpu cube] v=%d c=%d K=%d L*=%d roots=%zu plan+alloc %.2f ms, roots %.2f ms, derive %.2f ms\n", variable, c, K, Lstar,
                      layers[Lstar].size(), tms(T0, T1), tms(T1, T2), tms(T2, tnow()));
     *n_scored = family_size(c, K);
@@ -1238,7 +1296,6 @@ static int run_segment_dp(urlgpu_ctx *ctx, float *d_table, int c, int K) {
             segment_dp_kernel<MODE><<<count, 256, 0, s>>>(d_table, aux.as<float>(), sl, begin, lb, a, K);
         }
     }
-    CK(cudaStreamSynchronize(s)); // aux is freed on return
     CK(cudaGetLastError());
     return URLGPU_OK;
 }
@@ -1416,7 +1473,7 @@ extern "C" int urlgpu_result_free(urlgpu_result *res) {
     static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
     const auto T0 = std::chrono::steady_clock::now();
     cudaSetDevice(res->ctx->device);
-    if (res->d_table) { cudaStreamSynchronize(res->ctx->stream); pool_free(res->ctx, res->d_table); }
+    if (res->d_table) pool_free(res->ctx, res->d_table); // stream-ordered reuse: no sync needed
     if (dbg) fprintf(stderr, "[urlgpu result_free] %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
     delete res;
     return URLGPU_OK;
