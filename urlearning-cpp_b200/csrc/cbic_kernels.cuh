@@ -137,6 +137,7 @@ struct CbicParams {
     int max_parents;
     double n;         // row count (num_err, BIC_OLS.cpp:348)
     double lam_logn;  // lambda*log(n)  (:366, evaluated left to right)
+    double log_n;     // log(n)
 };
 
 // packed lower-triangular index, element order (v, cand0, cand1, ...)
@@ -171,24 +172,19 @@ __global__ void cbic_roots_kernel(const double *__restrict__ subgram /*packed (c
     for (int e = lane; e < outsz; e += 32) roots[(size_t)e * n_prefix + P] = A[e];
 }
 
-// the_score of one set from its RSS (BIC_OLS.cpp:302-305,366): k == 0 -> 0.0
-__device__ __forceinline__ float cbic_the_score(double rss, int k, const CbicParams &prm) {
-    if (k == 0) return 0.0f;
-    const double ts = prm.n * log(rss / prm.n) + prm.lam_logn * (double)k;
-    return (float)ts;
+// the_score of one set from its RSS (BIC_OLS.cpp:302-305,366): k == 0 -> 0.0.
+// n*log(RSS/n) is evaluated as n*(log(RSS) - log(n)) with log(n) hoisted: one FP64 division less per set.
+__device__ __forceinline__ double cbic_the_score64(double rss, int k, const CbicParams &prm) {
+    if (k == 0) return 0.0;
+    return prm.n * (log(rss) - prm.log_n) + prm.lam_logn * (double)k;
 }
 
 // Level B: template-recursive DFS over the J low candidate bits.  A has (j+1)(j+2)/2 packed entries over
 // (v, cand0..cand_{j-1}).  Low masks are emitted in ascending order (exclude branch first).  Levels above
 // kInlineLevel are real calls with their matrices on the thread's stack (touched once per 2^j sets); the bottom
-// levels are fully inlined so their matrices live in registers.
+// levels are fully inlined so their matrices live in registers, and the scores of the 8 sets below a level-3 node are
+// collected in registers and written as one full 32-byte sector (two 128-bit stores).
 constexpr int kInlineLevel = 4;
-
-__device__ __forceinline__ void cbic_emit(double rss, uint32_t low, int k, const CbicParams &prm, float *__restrict__ out,
-                                          double *__restrict__ out64) {
-    out[low] = cbic_the_score(rss, k, prm);
-    if (out64) out64[low] = (k == 0) ? 0.0 : prm.n * log(rss / prm.n) + prm.lam_logn * (double)k;
-}
 
 template <int j>
 __device__ __forceinline__ void cbic_sweep(const double *A, double *B) {
@@ -201,11 +197,39 @@ __device__ __forceinline__ void cbic_sweep(const double *A, double *B) {
     }
 }
 
+// bottom three levels: LOCAL = the low mask bits decided so far (compile time -> buf[] stays in registers)
+template <int j, uint32_t LOCAL>
+__device__ __forceinline__ void cbic_dfs_buf(const double *A, uint32_t low, int k, const CbicParams &prm, float (&buf)[8], double *__restrict__ out64) {
+    if constexpr (j == 0) {
+        const double ts = cbic_the_score64(A[0], k, prm);
+        buf[LOCAL] = (float)ts;
+        if (out64) out64[low | LOCAL] = ts;
+    } else {
+        cbic_dfs_buf<j - 1, LOCAL>(A, low, k, prm, buf, out64);
+        if (k < prm.max_parents) {
+            double B[j * (j + 1) / 2];
+            cbic_sweep<j>(A, B);
+            cbic_dfs_buf<j - 1, (LOCAL | (1u << (j - 1)))>(B, low, k + 1, prm, buf, out64);
+        } else {
+#pragma unroll
+            for (uint32_t m = 0; m < (1u << (j - 1)); m++) buf[LOCAL | (1u << (j - 1)) | m] = sentinel();
+        }
+    }
+}
+
 template <int j>
 __device__ __forceinline__ void cbic_dfs_inl(const double *A, uint32_t low, int k, const CbicParams &prm, float *__restrict__ out,
                                              double *__restrict__ out64) {
-    if constexpr (j == 0) {
-        cbic_emit(A[0], low, k, prm, out, out64);
+    if constexpr (j == 3) {
+        float buf[8];
+        cbic_dfs_buf<3, 0u>(A, low, k, prm, buf, out64);
+        float4 *o4 = reinterpret_cast<float4 *>(out + low); // low is a multiple of 8 here
+        o4[0] = make_float4(buf[0], buf[1], buf[2], buf[3]);
+        o4[1] = make_float4(buf[4], buf[5], buf[6], buf[7]);
+    } else if constexpr (j == 0) {
+        const double ts = cbic_the_score64(A[0], k, prm);
+        out[low] = (float)ts;
+        if (out64) out64[low] = ts;
     } else {
         cbic_dfs_inl<j - 1>(A, low, k, prm, out, out64); // candidate j-1 excluded: leading principal submatrix
         if (k < prm.max_parents) {
@@ -346,15 +370,6 @@ __global__ void __launch_bounds__(256) segment_dp_kernel(float *__restrict__ tab
         table[base + i] = s_val[i];
         aux[base + i] = s_aux[i];
     }
-}
-
-// result compaction helpers --------------------------------------------------------------------------------
-__global__ void count_stored_kernel(const float *__restrict__ table, uint64_t n_masks, unsigned long long *__restrict__ count) {
-    uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long c = 0;
-    for (; m < n_masks; m += (uint64_t)gridDim.x * blockDim.x) c += !is_sentinel(table[m]);
-    c = (unsigned long long)warp_sum_ll((long long)c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
 
 } // namespace urlgpu

@@ -202,7 +202,7 @@ struct urlgpu_result {
     std::vector<int> cand;          // compact bit -> variable index
     float *d_table = nullptr;       // 2^c floats
     uint64_t n_masks = 0, n_scored = 0;
-    bool counted = false; uint64_t n_stored = 0;
+    bool counted = false; uint64_t n_stored = 0; uint64_t layer_count[32] = {0};
     bool compacted = false;
     std::vector<uint32_t> h_masks;  // canonical order
     std::vector<float> h_scores;
@@ -1213,6 +1213,7 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
     prm.max_parents = K;
     prm.n = (double)(int)ctx->cn;
     prm.lam_logn = lambda * std::log((double)(int)ctx->cn);
+    prm.log_n = std::log((double)(int)ctx->cn);
     const uint32_t n_prefix = 1u << (c - prm.J);
     const int outsz = (prm.J + 1) * (prm.J + 2) / 2;
     DevBuf dsub(ctx), droots(ctx);
@@ -1380,19 +1381,33 @@ __global__ void gather_scores_kernel(const float *__restrict__ table, const uint
 }
 } // namespace
 
+namespace {
+__global__ void count_by_layer_kernel(const float *__restrict__ table, uint64_t n_masks, unsigned long long *__restrict__ counts /*[32]*/) {
+    __shared__ unsigned int sh[32];
+    if (threadIdx.x < 32) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < n_masks; m += (uint64_t)gridDim.x * blockDim.x)
+        if (!is_sentinel(table[m])) atomicAdd(&sh[__popcll(m)], 1u);
+    __syncthreads();
+    if (threadIdx.x < 32 && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+} // namespace
+
+// stored entries per layer (one kernel, one D2H)
 static int result_count_impl(urlgpu_result *res) {
     urlgpu_ctx *ctx = res->ctx;
     if (res->counted) return URLGPU_OK;
     CK(cudaSetDevice(ctx->device));
     DevBuf cnt(ctx);
-    CK(cnt.alloc(sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), ctx->stream));
-    count_stored_kernel<<<std::min<unsigned>(blocks_for(res->n_masks, 256), 4096), 256, 0, ctx->stream>>>(res->d_table, res->n_masks,
-                                                                                                       cnt.as<unsigned long long>());
-    unsigned long long h = 0;
-    CK(cudaMemcpyAsync(&h, cnt.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cnt.alloc(32 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(cnt.p, 0, 32 * sizeof(unsigned long long), ctx->stream));
+    count_by_layer_kernel<<<std::min<unsigned>(blocks_for(res->n_masks, 256), 2048), 256, 0, ctx->stream>>>(res->d_table, res->n_masks, cnt.as<unsigned long long>());
+    unsigned long long h[32];
+    CK(cudaMemcpyAsync(h, cnt.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    res->n_stored = h; res->counted = true;
+    res->n_stored = 0;
+    for (int l = 0; l < 32; l++) { res->layer_count[l] = h[l]; res->n_stored += h[l]; }
+    res->counted = true;
     return URLGPU_OK;
 }
 
@@ -1409,7 +1424,8 @@ extern "C" int urlgpu_result_scored(urlgpu_result *res, uint64_t *n) {
     return URLGPU_OK;
 }
 
-// compaction into canonical order: layer by layer, masks ascending within a layer (stable select)
+// compaction into canonical order: layer by layer, masks ascending within a layer (order-preserving select into the
+// layer's known output range; no host round trip between layers)
 static int result_compact(urlgpu_result *res) {
     urlgpu_ctx *ctx = res->ctx;
     if (res->compacted) return URLGPU_OK;
@@ -1429,15 +1445,12 @@ static int result_compact(urlgpu_result *res) {
         cub::DeviceSelect::If(nullptr, tmp_bytes, it, dmasks.as<uint32_t>(), dnum.as<unsigned long long>(), (int64_t)res->n_masks, pred, s);
         CK(tmp.alloc(tmp_bytes));
         uint64_t off = 0;
-        for (int layer = 0; layer <= res->max_parents && off < total; layer++) {
+        for (int layer = 0; layer < 32; layer++) {
+            if (!res->layer_count[layer]) continue;
             pred.layer = layer;
             CK(cub::DeviceSelect::If(tmp.p, tmp_bytes, it, dmasks.as<uint32_t>() + off, dnum.as<unsigned long long>(), (int64_t)res->n_masks, pred, s));
-            unsigned long long h = 0;
-            CK(cudaMemcpyAsync(&h, dnum.p, sizeof h, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            off += h;
+            off += res->layer_count[layer];
         }
-        if (off != total) return ctx->fail(URLGPU_ERR_INTERNAL, "result compaction lost entries");
         gather_scores_kernel<<<blocks_for(total, 256), 256, 0, s>>>(res->d_table, dmasks.as<uint32_t>(), total, dvals.as<float>());
         CK(cudaMemcpyAsync(res->h_masks.data(), dmasks.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(res->h_scores.data(), dvals.p, total * sizeof(float), cudaMemcpyDeviceToHost, s));
