@@ -297,6 +297,128 @@ def run_gpu(args):
     eng.close()
 
 
+
+# ---------------------------------------------------------------------------------------------- config 5 (optional workload)
+
+def run_gpu_cbic5(args):
+    """BASELINE configs[4]: linear-Gaussian p=200, n=1e7, skeleton degree <= 16, cBIC lambda=2, rows sharded across the
+    ranks.  Step = sharded standardise + FP64 Gram (DMMA) + two all-gathers + Gram all-gather, then every owned
+    variable's family (2-hop neighbourhood, explicit -p 4: the reference's default p-1 over the 2-hop set is
+    astronomically large and p=200 does not fit its 64-bit varset) with accept + prune."""
+    import torch
+    pkg = importlib.import_module("urlearning-cpp_b200")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    p, n_total, K, lam = 200, args.n5, 4, 2.0
+    n_local = n_total // world
+    n_total = n_local * world
+    # same DAG and weights on every rank (seeded), rank-specific noise; generated on the device
+    rng = np.random.default_rng(5)
+    window, indeg = 7, 3
+    parents, weights = [], []
+    for i in range(p):
+        cands = np.arange(max(0, i - window), i)
+        k = min(indeg, len(cands))
+        pa = sorted(rng.choice(cands, size=k, replace=False).tolist()) if k else []
+        parents.append(pa)
+        weights.append([float(rng.uniform(0.5, 1.5) * rng.choice([-1.0, 1.0])) for _ in pa])
+    edges = [0] * p
+    for i in range(p):
+        for j in parents[i]:
+            edges[i] |= 1 << j
+            edges[j] |= 1 << i
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1000 + rank)
+    x = torch.randn((p, n_local), dtype=torch.float64, device="cuda", generator=gen)
+    for i in range(p):
+        for j, w in zip(parents[i], weights[i]):
+            x[i] += w * x[j]
+    nbs = [pkg.two_hop_neighbors(edges, p, v) for v in range(p)]
+    cmax = max(bin(nb & ~(1 << v)).count("1") for v, nb in enumerate(nbs))
+    eng = pkg.Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    mine = [v for v in range(p) if v % world == rank]
+    sets_total = sum(family_size(bin(nbs[v] & ~(1 << v)).count("1"), K) for v in range(p))
+
+    def allsum(a):
+        if world == 1:
+            return a
+        t = torch.from_numpy(a).cuda()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        out = parts[0].clone()
+        for q in parts[1:]:   # fixed rank order: identical result on every rank and for every run
+            out += q
+        return out.cpu().numpy()
+
+    def step():
+        eng.shard_begin(x.data_ptr(), n_local, p)
+        s1, _ = eng.shard_moments(None)
+        mean = allsum(s1) / n_total
+        a1, a2 = eng.shard_moments(mean)
+        S1, S2 = allsum(a1), allsum(a2)
+        dev = np.sqrt((S2 - S1 * S1 / n_total) / (n_total - 1.0))
+        eng.shard_finish(mean, dev, n_total)
+        g = allsum(eng.gram())
+        eng.set_gram(g, n_total)
+        for v in mine:
+            res = eng.score_variable(v, nbs[v], K, pkg.CBIC, lam=lam, flags=pkg.PRUNE_DOMINATED)
+            res.free()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.reset_stats()
+    eng.enable_timing(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    st = eng.stats()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if rank == 0:
+        gram_tf = st["gram_flops"] / (st["ms_gram"] / 1e3) / 1e12 if st["ms_gram"] > 0 else None
+        line = {"metric": METRIC, "value": sets_total * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64 -> f32", "data": "synthetic (seeded, generated on the device with torch)",
+                "config": {"workload": f"configs[4]: linear-Gaussian p=200 n={n_total} (rows sharded over {world} GPU(s)), skeleton degree<=16 "
+                                       f"(window {window}, in-degree {indeg}), 2-hop candidates (max {cmax}), explicit -p {K}, cBIC lambda=2, accept + prune",
+                           "sets_per_step": sets_total, "parallelism": f"rows sharded n/{world} for the Gram, variables striped v % {world}"},
+                "e2e": None, "gpu_launches": int(st["launches_total"]), "clocks": sampler.summary(),
+                "roofline": {"bound": "fp64", "kernel": "K2 gram_partial_kernel (DMMA m8n8k4.f64) incl. standardise + moments", "achieved": gram_tf,
+                             "peak": 37.0, "unit": "TFLOP/s", "frac": gram_tf / 37.0 if gram_tf else None, "traffic": None,
+                             "peak_source": "nominal B200 FP64 (no measured FP64 entry in MEASURED_PEAKS.json)",
+                             "gram_ms_per_step_rank0": st["ms_gram"] / args.steps, "gram_flops_per_step_rank0": st["gram_flops"] / args.steps,
+                             "family_ms": {"gram": st["ms_gram"], "cbic": st["ms_cbic"], "accept": st["ms_accept"], "prune": st["ms_prune"]}},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
 # ---------------------------------------------------------------------------------------------- CPU arms
 
 def cpu_sample(wl, budget_s, threads, seed=0):
@@ -375,12 +497,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="urlgpu", choices=["urlgpu", "reference"])
-    ap.add_argument("--workload", default="bic", choices=["bic", "cbic"])
+    ap.add_argument("--workload", default="bic", choices=["bic", "cbic", "cbic5"])
+    ap.add_argument("--n5", type=int, default=10_000_000, help="total rows of the cbic5 workload")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cbic5":
+        run_gpu_cbic5(args)
     else:
         run_gpu(args)
 

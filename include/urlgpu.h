@@ -71,6 +71,16 @@ int urlgpu_set_discrete_device(urlgpu_ctx *ctx, const uint8_t *d_codes_colmajor,
 /* raw continuous data; the engine centres, scales by the sample std (N-1) and forms G = Z^T Z in FP64 */
 int urlgpu_set_continuous(urlgpu_ctx *ctx, const double *x_colmajor, int64_t n, int p);
 int urlgpu_set_continuous_device(urlgpu_ctx *ctx, const double *d_x_colmajor, int64_t n, int p);
+/* Row-sharded protocol for data larger than one GPU (config 5: p=200, n=1e7, 8 GPUs).  Every rank holds n_local rows:
+ *   urlgpu_shard_begin(rows)                         attach this rank's rows (on_device=1: x is a device pointer, used in place)
+ *   urlgpu_shard_moments(NULL, s1, NULL)             -> all ranks sum s1 in rank order -> mean = S1/n_total
+ *   urlgpu_shard_moments(mean, s1, s2)               -> all ranks sum -> dev = sqrt((S2 - S1^2/n_total)/(n_total-1))
+ *   urlgpu_shard_finish(mean, dev, n_total)          standardise + partial Gram of the local rows
+ *   urlgpu_get_gram / (all-gather, sum in rank order) / urlgpu_set_gram(G, n_total, p)
+ * urlgpu_set_continuous is exactly this sequence with one shard.  The exchange steps carry p or p*p doubles. */
+int urlgpu_shard_begin(urlgpu_ctx *ctx, const double *x_colmajor, int64_t n_local, int p, int on_device);
+int urlgpu_shard_moments(urlgpu_ctx *ctx, const double *shift /* p or NULL */, double *sum1 /* p or NULL */, double *sum2 /* p or NULL */);
+int urlgpu_shard_finish(urlgpu_ctx *ctx, const double *mean, const double *dev, int64_t n_total);
 /* The Gram G = Z^T Z (p*p, symmetric) can be exported (oracle-side recomputation, multi-GPU broadcast) and
  * installed without the raw data (a rank that only scores needs G and n, not the rows). */
 int urlgpu_get_gram(urlgpu_ctx *ctx, double *gram_rowmajor /* p*p */);
@@ -114,6 +124,7 @@ typedef struct urlgpu_stats {
     uint64_t sets_scored;
     double algorithmic_bytes;  /* BIC: sum over scored sets of n*(|S|+1) */
     double algorithmic_flops;  /* cBIC: sum over scored sets of k^3/3+2k^2+2k */
+    double gram_flops;         /* K2: 2*n*p^2 per Gram formed */
 } urlgpu_stats;
 int urlgpu_stats_reset(urlgpu_ctx *ctx);
 int urlgpu_stats_get(urlgpu_ctx *ctx, urlgpu_stats *out);

@@ -29,7 +29,7 @@ KEEP_ALL, PRUNE_DOMINATED, CBIC_NO_ACCEPT = 0, 2, 4
 ABI_SYMBOLS = [
     "urlgpu_create", "urlgpu_destroy", "urlgpu_last_error", "urlgpu_device_count", "urlgpu_set_stream",
     "urlgpu_synchronize", "urlgpu_set_discrete", "urlgpu_set_discrete_device", "urlgpu_set_continuous",
-    "urlgpu_set_continuous_device", "urlgpu_get_gram", "urlgpu_set_gram", "urlgpu_score_variable",
+    "urlgpu_set_continuous_device", "urlgpu_shard_begin", "urlgpu_shard_moments", "urlgpu_shard_finish", "urlgpu_get_gram", "urlgpu_set_gram", "urlgpu_score_variable",
     "urlgpu_result_count", "urlgpu_result_scored", "urlgpu_result_fetch", "urlgpu_result_free",
     "urlgpu_score_one", "urlgpu_contingency", "urlgpu_prune", "urlgpu_stats_reset", "urlgpu_stats_get",
     "urlgpu_stats_enable_timing",
@@ -47,7 +47,7 @@ class Stats(C.Structure):
         ("launches_other", C.c_uint64),
         ("ms_count", C.c_double), ("ms_cube", C.c_double), ("ms_cbic", C.c_double), ("ms_accept", C.c_double),
         ("ms_prune", C.c_double), ("ms_gram", C.c_double),
-        ("sets_scored", C.c_uint64), ("algorithmic_bytes", C.c_double), ("algorithmic_flops", C.c_double),
+        ("sets_scored", C.c_uint64), ("algorithmic_bytes", C.c_double), ("algorithmic_flops", C.c_double), ("gram_flops", C.c_double),
     ]
 
     def as_dict(self):
@@ -79,6 +79,9 @@ def load_library():
     lib.urlgpu_set_discrete_device.argtypes = [vp, vp, i64, i32, vp]
     lib.urlgpu_set_continuous.argtypes = [vp, vp, i64, i32]
     lib.urlgpu_set_continuous_device.argtypes = [vp, vp, i64, i32]
+    lib.urlgpu_shard_begin.argtypes = [vp, vp, i64, i32, i32]
+    lib.urlgpu_shard_moments.argtypes = [vp, vp, vp, vp]
+    lib.urlgpu_shard_finish.argtypes = [vp, vp, vp, i64]
     lib.urlgpu_get_gram.argtypes = [vp, vp]
     lib.urlgpu_set_gram.argtypes = [vp, vp, i64, i32]
     lib.urlgpu_score_variable.argtypes = [vp, i32, vp, i32, i32, i32, C.c_double, C.c_uint, P(vp)]
@@ -228,6 +231,31 @@ class Engine:
     def set_continuous_device(self, dev_ptr: int, n: int, p: int):
         self._check(self.lib.urlgpu_set_continuous_device(self._h, C.c_void_p(dev_ptr), n, p))
         self.p = p
+
+    # row-sharded protocol (include/urlgpu.h): moments and the partial Gram of this rank's rows
+    def shard_begin(self, x, n_local: int | None = None, p: int | None = None):
+        """x: float64 [p, n_local] numpy array (copied) or a device pointer (int) used in place."""
+        if isinstance(x, int):
+            self._check(self.lib.urlgpu_shard_begin(self._h, C.c_void_p(x), n_local, p, 1))
+            self.p = p
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            self._keep = [x]
+            self._check(self.lib.urlgpu_shard_begin(self._h, x.ctypes.data, x.shape[1], x.shape[0], 0))
+            self.p = x.shape[0]
+
+    def shard_moments(self, shift=None):
+        s1 = np.zeros(self.p)
+        s2 = np.zeros(self.p)
+        sh = None if shift is None else np.ascontiguousarray(shift, dtype=np.float64)
+        self._check(self.lib.urlgpu_shard_moments(self._h, None if sh is None else sh.ctypes.data, s1.ctypes.data, s2.ctypes.data))
+        return s1, s2
+
+    def shard_finish(self, mean, dev, n_total: int):
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        dev = np.ascontiguousarray(dev, dtype=np.float64)
+        self._check(self.lib.urlgpu_shard_finish(self._h, mean.ctypes.data, dev.ctypes.data, n_total))
+        self._keep = []
 
     def gram(self) -> np.ndarray:
         g = np.zeros((self.p, self.p), dtype=np.float64)

@@ -71,50 +71,83 @@ __global__ void standardise_kernel(const double *__restrict__ x, int64_t n, int6
         z[(int64_t)col * stride + r] = __ddiv_rn(x[(int64_t)col * stride + r] - m, d);
 }
 
-// Gram partials: CTA (tile_a, tile_b, slice) accumulates a 32x32 block of Z^T Z over its row slice.
-// Rows are staged through shared memory in chunks of 32; each thread owns 4 entries of the tile.
+// Gram partials on the FP64 tensor pipe (DMMA): G = Z^T Z is the only dense contraction of the path.
+// tcgen05/wgmma have no f64 kind, so this is mma.sync.m8n8k4.f64 (SASS DMMA).  Z is variable-major ([p][n], records
+// contiguous), which is exactly the fragment layout of both operands: lane l holds Z[a0 + l/4][r0 + l%4] for A (row
+// major, 8 variables x 4 records) and Z[b0 + l/4][r0 + l%4] for B (column major, 4 records x 8 variables), so
+// fragments are loaded straight from global/L2 as 32-byte runs, no shared-memory staging.  One warp owns a 32x32
+// block of G (4x4 MMA tiles, 32 FP64 accumulators per lane); the 4 warps of a CTA split the CTA's row slice and are
+// combined in fixed order.  Grid = (upper-triangular tile pair, row slice) with the tile pair fastest, so the CTAs
+// running together work on the same rows and Z is fetched from HBM once (L2 serves the p/32-fold reuse).
 constexpr int kGramTile = 32;
-constexpr int kGramRows = 64;
-__global__ void gram_partial_kernel(const double *__restrict__ z, int64_t n, int64_t stride, int p, int64_t rows_per_slice,
-                                    double *__restrict__ partial /*[slices][p][p]*/) {
-    __shared__ double sa[kGramTile][kGramRows + 1];
-    __shared__ double sb[kGramTile][kGramRows + 1];
-    const int ta = blockIdx.x, tb = blockIdx.y;
-    if (tb < ta) return; // symmetric: upper tiles only
-    const int slice = blockIdx.z;
-    const int64_t r0 = (int64_t)slice * rows_per_slice;
-    int64_t r1 = r0 + rows_per_slice;
-    if (r1 > n) r1 = n;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; // 16x16 threads, 2x2 entries each
-    double acc[2][2] = {{0, 0}, {0, 0}};
-    for (int64_t rb = r0; rb < r1; rb += kGramRows) {
-        for (int i = threadIdx.x; i < kGramTile * kGramRows; i += blockDim.x) {
-            const int var = i / kGramRows, rr = i % kGramRows;
-            const int64_t r = rb + rr;
-            const int va = ta * kGramTile + var, vb = tb * kGramTile + var;
-            sa[var][rr] = (va < p && r < r1) ? z[(int64_t)va * stride + r] : 0.0;
-            sb[var][rr] = (vb < p && r < r1) ? z[(int64_t)vb * stride + r] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int rr = 0; rr < kGramRows; rr++) {
-            const double a0 = sa[ty][rr], a1 = sa[ty + 16][rr];
-            const double b0 = sb[tx][rr], b1 = sb[tx + 16][rr];
-            acc[0][0] = fma(a0, b0, acc[0][0]);
-            acc[0][1] = fma(a0, b1, acc[0][1]);
-            acc[1][0] = fma(a1, b0, acc[1][0]);
-            acc[1][1] = fma(a1, b1, acc[1][1]);
-        }
-        __syncthreads();
+constexpr int kGramWarps = 4;
+
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kGramWarps * 32) gram_partial_kernel(const double *__restrict__ z, int64_t n, int64_t stride, int p, int64_t rows_per_slice, int tiles,
+                                                                      double *__restrict__ partial /*[slices][p][p]*/) {
+    __shared__ double red[kGramWarps][32][33];
+    // blockIdx.x enumerates the upper-triangular tile pairs (ta <= tb)
+    int ta = 0, rem = blockIdx.x;
+    while (rem >= tiles - ta) { rem -= tiles - ta; ta++; }
+    const int tb = ta + rem;
+    const int slice = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t s0 = (int64_t)slice * rows_per_slice;
+    const int64_t s1 = min(s0 + rows_per_slice, n);
+    // each warp takes a contiguous quarter of the slice (multiple of 4 rows)
+    const int64_t per = ((s1 - s0 + kGramWarps - 1) / kGramWarps + 3) / 4 * 4;
+    const int64_t r0 = min(s0 + warp * per, s1), r1 = min(r0 + per, s1);
+    const int vrow = lane >> 2, kk = lane & 3;
+    const double *pa[4], *pb[4];
+    bool va[4], vb[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int a = ta * kGramTile + t * 8 + vrow, b = tb * kGramTile + t * 8 + vrow;
+        va[t] = a < p; vb[t] = b < p;
+        pa[t] = z + (int64_t)(va[t] ? a : 0) * stride + kk;
+        pb[t] = z + (int64_t)(vb[t] ? b : 0) * stride + kk;
     }
-    double *out = partial + (int64_t)slice * p * p;
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int a = ta * kGramTile + ty + 16 * i, b = tb * kGramTile + tx + 16 * j;
-            if (a < p && b < p) out[a * p + b] = acc[i][j];
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int64_t r = r0; r < r1; r += 4) {
+        const bool in = r + kk < r1;
+        double fa[4], fb[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            fa[t] = (in && va[t]) ? __ldg(pa[t] + r) : 0.0;
+            fb[t] = (in && vb[t]) ? __ldg(pb[t] + r) : 0.0;
         }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+    }
+    // C fragment: lane holds C[row = lane/4][col = (lane%4)*2 + {0,1}] of each 8x8 tile
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            red[warp][i * 8 + vrow][j * 8 + kk * 2 + 0] = acc[i][j][0];
+            red[warp][i * 8 + vrow][j * 8 + kk * 2 + 1] = acc[i][j][1];
+        }
+    __syncthreads();
+    double *out = partial + (int64_t)slice * p * p;
+    for (int e = threadIdx.x; e < kGramTile * kGramTile; e += blockDim.x) {
+        const int i = e / kGramTile, j = e % kGramTile;
+        const int a = ta * kGramTile + i, b = tb * kGramTile + j;
+        if (a < p && b < p) {
+            double sum = red[0][i][j];
+#pragma unroll
+            for (int w = 1; w < kGramWarps; w++) sum += red[w][i][j]; // fixed order
+            out[a * p + b] = sum;
+        }
+    }
 }
 // G[a][b] = sum over slices in slice order (fixed order); mirror to the lower triangle
 __global__ void gram_combine_kernel(const double *__restrict__ partial, int p, int slices, double *__restrict__ g) {

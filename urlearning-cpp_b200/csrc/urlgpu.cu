@@ -52,6 +52,8 @@ struct urlgpu_ctx {
     int64_t cn = 0;
     int cp = 0;
     double *d_z = nullptr;
+    double *d_zcache = nullptr; size_t zcache_cap = 0;
+    double *d_x = nullptr; const double *d_x_view = nullptr; int64_t shard_n = 0; bool borrow_device_x = false; // attached raw rows (sharded protocol)
     std::vector<double> h_gram;
     bool have_gram = false;
 
@@ -261,6 +263,8 @@ static void free_discrete(urlgpu_ctx *ctx) {
 }
 static void free_continuous(urlgpu_ctx *ctx) {
     if (ctx->d_z) cudaFree(ctx->d_z);
+    if (ctx->d_x) cudaFree(ctx->d_x);
+    ctx->d_x = nullptr; ctx->d_x_view = nullptr;
     ctx->d_z = nullptr; ctx->have_gram = false;
 }
 
@@ -273,6 +277,7 @@ extern "C" int urlgpu_destroy(urlgpu_ctx *ctx) {
     free_discrete(ctx);
     free_continuous(ctx);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->d_zcache) cudaFree(ctx->d_zcache);
     if (ctx->d_misc) cudaFree(ctx->d_misc);
     if (ctx->d_cubeA) cudaFree(ctx->d_cubeA);
     if (ctx->d_high_sorted) cudaFree(ctx->d_high_sorted);
@@ -359,56 +364,125 @@ extern "C" int urlgpu_set_discrete_device(urlgpu_ctx *ctx, const uint8_t *d_code
     return set_discrete_common(ctx, d_codes, true, n, p, cardinality);
 }
 
-static int set_continuous_common(urlgpu_ctx *ctx, const double *src, bool src_on_device, int64_t n, int p) {
-    if (!ctx || !src || n < 2 || p < 1) return ctx ? ctx->fail(URLGPU_ERR_ARG, "set_continuous: bad arguments") : URLGPU_ERR_ARG;
+// ---- continuous data: the pieces below are the single-GPU urlgpu_set_continuous and, called separately, the
+// row-sharded multi-GPU protocol (urlgpu_shard_begin / _moments / _finish, see include/urlgpu.h) ----
+
+static int shard_begin_impl(urlgpu_ctx *ctx, const double *src, bool src_on_device, int64_t n_local, int p) {
+    if (!ctx || !src || n_local < 1 || p < 1) return ctx ? ctx->fail(URLGPU_ERR_ARG, "continuous data: bad arguments") : URLGPU_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     free_continuous(ctx);
-    ctx->cn = n; ctx->cp = p;
+    if (ctx->d_x) { cudaFree(ctx->d_x); ctx->d_x = nullptr; }
+    ctx->shard_n = n_local; ctx->cp = p;
+    const size_t bytes = (size_t)n_local * p * sizeof(double);
+    if (src_on_device && ctx->borrow_device_x) ctx->d_x_view = src; // no copy: the caller keeps the buffer alive until shard_finish
+    else {
+        CK(cudaMalloc(&ctx->d_x, bytes));
+        CK(cudaMemcpyAsync(ctx->d_x, src, bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+        ctx->d_x_view = ctx->d_x;
+    }
+    return URLGPU_OK;
+}
+
+// sum1[c] = sum_r (x[c][r] - shift[c]), sum2[c] = sum_r (x[c][r] - shift[c])^2 over the attached rows (fixed order)
+static int shard_moments_impl(urlgpu_ctx *ctx, const double *shift_host, double *sum1, double *sum2) {
+    if (!ctx || !ctx->d_x_view) return ctx ? ctx->fail(URLGPU_ERR_ARG, "shard_moments: call urlgpu_shard_begin first") : URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    DevBuf x(ctx), part(ctx), sums(ctx), mean(ctx), acc2(ctx), acc3(ctx), dev(ctx), gpart(ctx), g(ctx);
-    const size_t bytes = (size_t)n * p * sizeof(double);
-    CK(x.alloc(bytes));
-    CK(cudaMalloc(&ctx->d_z, bytes));
-    CK(cudaMemcpyAsync(x.p, src, bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    const int p = ctx->cp;
+    const int64_t n = ctx->shard_n;
+    DevBuf part(ctx), out(ctx), shift(ctx);
     CK(part.alloc((size_t)p * kRedBlocks * sizeof(double)));
-    CK(sums.alloc(p * sizeof(double))); CK(mean.alloc(p * sizeof(double)));
-    CK(acc2.alloc(p * sizeof(double))); CK(acc3.alloc(p * sizeof(double))); CK(dev.alloc(p * sizeof(double)));
+    CK(out.alloc((size_t)2 * p * sizeof(double)));
+    if (shift_host) {
+        CK(shift.alloc(p * sizeof(double)));
+        CK(cudaMemcpyAsync(shift.p, shift_host, p * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
     {
-        Region rg(ctx, F_GRAM, 12);
+        Region rg(ctx, F_GRAM, 4);
         const dim3 rgrid(kRedBlocks, p);
         const unsigned pb = blocks_for(p, 128);
-        // mean_x = sum/n  (BIC_OLS.cpp:69)
-        col_partial_kernel<<<rgrid, kRedThreads, 0, s>>>(x.as<double>(), n, n, nullptr, 0, part.as<double>());
-        col_combine_kernel<<<pb, 128, 0, s>>>(part.as<double>(), p, sums.as<double>());
-        mean_kernel<<<pb, 128, 0, s>>>(sums.as<double>(), p, (double)n, mean.as<double>());
-        // dev_x = sqrt(var(x - mean_x)), Armadillo two-pass variance with N-1 (BIC_OLS.cpp:70-71)
-        col_partial_kernel<<<rgrid, kRedThreads, 0, s>>>(x.as<double>(), n, n, mean.as<double>(), 1, part.as<double>());
-        col_combine_kernel<<<pb, 128, 0, s>>>(part.as<double>(), p, acc2.as<double>());
-        col_partial_kernel<<<rgrid, kRedThreads, 0, s>>>(x.as<double>(), n, n, mean.as<double>(), 0, part.as<double>());
-        col_combine_kernel<<<pb, 128, 0, s>>>(part.as<double>(), p, acc3.as<double>());
-        dev_kernel<<<pb, 128, 0, s>>>(acc2.as<double>(), acc3.as<double>(), p, (double)n, dev.as<double>());
-        standardise_kernel<<<dim3(ctx->sm_count * 2, p), 256, 0, s>>>(x.as<double>(), n, n, mean.as<double>(), dev.as<double>(), ctx->d_z);
-        // Gram
+        for (int mode = 0; mode < 2; mode++) {
+            if ((mode == 0 && !sum1) || (mode == 1 && !sum2)) continue;
+            col_partial_kernel<<<rgrid, kRedThreads, 0, s>>>(ctx->d_x_view, n, n, shift_host ? shift.as<double>() : nullptr, mode, part.as<double>());
+            col_combine_kernel<<<pb, 128, 0, s>>>(part.as<double>(), p, out.as<double>() + (size_t)mode * p);
+        }
+    }
+    if (sum1) CK(cudaMemcpyAsync(sum1, out.as<double>(), p * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (sum2) CK(cudaMemcpyAsync(sum2, out.as<double>() + p, p * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+// z = (x - mean)/dev on the attached rows (BIC_OLS.cpp:76-77), partial Gram of these rows; n_total = rows of the whole data set
+static int shard_finish_impl(urlgpu_ctx *ctx, const double *mean_host, const double *dev_host, int64_t n_total, bool keep_z) {
+    if (!ctx || !ctx->d_x_view || !mean_host || !dev_host) return ctx ? ctx->fail(URLGPU_ERR_ARG, "shard_finish: call urlgpu_shard_begin first") : URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int p = ctx->cp;
+    const int64_t n = ctx->shard_n;
+    DevBuf md(ctx), gpart(ctx), g(ctx);
+    CK(md.alloc((size_t)2 * p * sizeof(double)));
+    CK(cudaMemcpyAsync(md.p, mean_host, p * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(md.as<double>() + p, dev_host, p * sizeof(double), cudaMemcpyHostToDevice, s));
+    // standardise in place when the engine owns the copy, else into a fresh buffer
+    double *zbuf = ctx->d_x;
+    const bool borrowed = zbuf == nullptr;
+    if (borrowed) { // caller's device buffer is left untouched: standardise into a cached scratch buffer
+        const size_t need = (size_t)n * p * sizeof(double);
+        if (ctx->zcache_cap < need) { if (ctx->d_zcache) cudaFree(ctx->d_zcache); ctx->d_zcache = nullptr; ctx->zcache_cap = 0; CK(cudaMalloc(&ctx->d_zcache, need)); ctx->zcache_cap = need; }
+        zbuf = ctx->d_zcache;
+    }
+    {
+        Region rg(ctx, F_GRAM, 3);
+        standardise_kernel<<<dim3(ctx->sm_count * 2, p), 256, 0, s>>>(ctx->d_x_view, n, n, md.as<double>(), md.as<double>() + p, zbuf);
         const int tiles = (p + kGramTile - 1) / kGramTile;
-        int slices = (int)std::min<int64_t>(512, std::max<int64_t>(1, n / 4096));
-        int64_t rps = (n + slices - 1) / slices;
-        rps = (rps + kGramRows - 1) / kGramRows * kGramRows;
-        slices = (int)((n + rps - 1) / rps);
+        // row slices: all p columns of one slice stay L2 resident (<= ~48 MB) so every tile pair re-reads them from L2
+        int64_t rps = std::max<int64_t>(4096, std::min<int64_t>(((int64_t)48 << 20) / ((int64_t)p * 8), 65536));
+        rps = rps / 16 * 16;
+        const int slices = (int)((n + rps - 1) / rps);
         CK(gpart.alloc((size_t)slices * p * p * sizeof(double)));
         CK(g.alloc((size_t)p * p * sizeof(double)));
-        gram_partial_kernel<<<dim3(tiles, tiles, slices), 256, 0, s>>>(ctx->d_z, n, n, p, rps, gpart.as<double>());
+        gram_partial_kernel<<<dim3(tiles * (tiles + 1) / 2, slices), kGramWarps * 32, 0, s>>>(zbuf, n, n, p, rps, tiles, gpart.as<double>());
         gram_combine_kernel<<<blocks_for((uint64_t)p * p, 256), 256, 0, s>>>(gpart.as<double>(), p, slices, g.as<double>());
+        ctx->st.gram_flops += 2.0 * (double)n * p * p;
     }
     ctx->h_gram.resize((size_t)p * p);
     CK(cudaMemcpyAsync(ctx->h_gram.data(), g.p, (size_t)p * p * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    if (!borrowed) { if (keep_z) ctx->d_z = zbuf; else cudaFree(zbuf); }
+    ctx->d_x = nullptr; ctx->d_x_view = nullptr;
+    ctx->cn = n_total;
     ctx->have_gram = true;
     return URLGPU_OK;
 }
 
+static int set_continuous_common(urlgpu_ctx *ctx, const double *src, bool src_on_device, int64_t n, int p) {
+    if (!ctx || !src || n < 2 || p < 1) return ctx ? ctx->fail(URLGPU_ERR_ARG, "set_continuous: bad arguments") : URLGPU_ERR_ARG;
+    ctx->borrow_device_x = false;
+    int rc = shard_begin_impl(ctx, src, src_on_device, n, p);
+    if (rc) return rc;
+    std::vector<double> s1(p), s2(p), mean(p), dev(p);
+    // mean_x = sum/n (BIC_OLS.cpp:69); dev_x = sqrt(var(x - mean_x)), Armadillo's variance with N-1 (:70-71)
+    rc = shard_moments_impl(ctx, nullptr, s1.data(), nullptr);
+    if (rc) return rc;
+    for (int c = 0; c < p; c++) mean[c] = s1[c] / (double)n;
+    rc = shard_moments_impl(ctx, mean.data(), s1.data(), s2.data());
+    if (rc) return rc;
+    for (int c = 0; c < p; c++) dev[c] = std::sqrt((s2[c] - s1[c] * s1[c] / (double)n) / ((double)n - 1.0));
+    return shard_finish_impl(ctx, mean.data(), dev.data(), n, false);
+}
+
 extern "C" int urlgpu_set_continuous(urlgpu_ctx *ctx, const double *x, int64_t n, int p) { return set_continuous_common(ctx, x, false, n, p); }
 extern "C" int urlgpu_set_continuous_device(urlgpu_ctx *ctx, const double *x, int64_t n, int p) { return set_continuous_common(ctx, x, true, n, p); }
+
+extern "C" int urlgpu_shard_begin(urlgpu_ctx *ctx, const double *x_colmajor, int64_t n_local, int p, int on_device) {
+    if (ctx) ctx->borrow_device_x = on_device != 0;
+    return shard_begin_impl(ctx, x_colmajor, on_device != 0, n_local, p);
+}
+extern "C" int urlgpu_shard_moments(urlgpu_ctx *ctx, const double *shift, double *sum1, double *sum2) { return shard_moments_impl(ctx, shift, sum1, sum2); }
+extern "C" int urlgpu_shard_finish(urlgpu_ctx *ctx, const double *mean, const double *dev, int64_t n_total) { return shard_finish_impl(ctx, mean, dev, n_total, false); }
 
 extern "C" int urlgpu_get_gram(urlgpu_ctx *ctx, double *g) {
     if (!ctx || !g) return URLGPU_ERR_ARG;
