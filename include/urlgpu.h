@@ -114,7 +114,7 @@ int urlgpu_prune(urlgpu_ctx *ctx, const uint64_t *masks, const float *scores, ui
  * accumulated since the last reset. */
 typedef struct urlgpu_stats {
     uint64_t launches_total;
-    uint64_t launches_count;   /* K1 row-count kernels */
+    uint64_t launches_count;   /* K1 row-count / row-bucketing kernels */
     uint64_t launches_cube;    /* K1 marginalise+score kernels */
     uint64_t launches_cbic;    /* K3 */
     uint64_t launches_accept;  /* K4 */
@@ -125,6 +125,8 @@ typedef struct urlgpu_stats {
     double algorithmic_bytes;  /* BIC: sum over scored sets of n*(|S|+1) */
     double algorithmic_flops;  /* cBIC: sum over scored sets of k^3/3+2k^2+2k */
     double gram_flops;         /* K2: 2*n*p^2 per Gram formed */
+    uint64_t launches_tree;    /* K1 on-chip count + marginalise + score kernel */
+    double ms_tree;
 } urlgpu_stats;
 int urlgpu_stats_reset(urlgpu_ctx *ctx);
 int urlgpu_stats_get(urlgpu_ctx *ctx, urlgpu_stats *out);

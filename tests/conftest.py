@@ -33,11 +33,12 @@ def engine(pkg):
     eng.close()
 
 
-@pytest.fixture(scope="session", params=["slice", "cube", "direct"])
+@pytest.fixture(scope="session", params=["tree", "cube", "direct", "auto"])
 def bic_engine(pkg, request):
-    """BIC engines for the three K1 strategies: 'slice' (default: roots counted in shared-memory slices, subtrees derived on
-    chip; falls back to cube), 'cube' (roots counted into global tables, the rest marginalised through HBM) and 'direct'
-    (every set counted from the rows)."""
+    """BIC engines for the K1 strategies: 'tree' (tables counted in shared-memory slices of bucketed packed rows, subtrees
+    marginalised on chip; falls back to cube when a family cannot be laid out that way), 'cube' (roots counted into global
+    tables, the rest marginalised through HBM), 'direct' (every set counted from the rows) and 'auto' (the default: tree
+    for n >= 32768, else cube)."""
     old = os.environ.get("URLGPU_BIC_MODE")
     os.environ["URLGPU_BIC_MODE"] = request.param
     try:

@@ -82,6 +82,31 @@ def test_all_tiers_arity4(pkg, orc, bic_engine):
         _check_variable(pkg, orc, engine, codes, card, None, v, 9)
 
 
+@pytest.mark.parametrize("budget,run,unit", [(1024, 2, 64), (3072, 6, 256), (12288, 6, 1024), (24576, 8, 2048), (4096, 3, 256)])
+def test_tree_path_slicing_variants(pkg, orc, budget, run, unit):
+    """the on-chip tree path under different slice budgets / run limits: deep slicing with many row segments, single-unit
+    slices, long runs; every variant must reproduce the oracle bit for bit"""
+    keys = {"URLGPU_BIC_MODE": "tree", "URLGPU_TREE_BUDGET": str(budget), "URLGPU_TREE_RUN": str(run), "URLGPU_TREE_UNIT": str(unit)}
+    old = {k: os.environ.get(k) for k in keys}
+    os.environ.update(keys)
+    try:
+        eng = pkg.Engine(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=14, n=40009, seed=21, arities=(2, 3, 4), window=6, max_indegree=3)
+    eng.set_discrete(codes, card)
+    eng.reset_stats()
+    for v, K in ((0, 13), (6, 8), (13, 5), (9, 1), (3, 0)):
+        _check_variable(pkg, orc, eng, codes, card, None, v, K)
+    _check_variable(pkg, orc, eng, codes, card, edges, 7, 6, flags=pkg.PRUNE_DOMINATED)
+    assert eng.stats()["launches_tree"] >= 3  # the tree kernel really ran (no silent fall-back to the cube path)
+    eng.close()
+
+
 def test_skeleton_two_hop_and_prune(pkg, orc, bic_engine):
     engine = bic_engine
     codes, card, edges, _ = pkg.datagen.discrete_bn(p=24, n=30000, seed=7, window=3, max_indegree=2)

@@ -13,15 +13,16 @@ eng = pkg.Engine(0)
 eng.set_discrete(codes, card)
 K = pkg.effective_max_parents(12, p, n, True)
 eng.enable_timing(True)
-for v in vars_:
-    nb = pkg.two_hop_neighbors(edges, p, v)
-    c = bin(nb & ~(1 << v)).count("1")
-    eng.reset_stats()
-    t0 = time.time()
-    res = eng.score_variable(v, nb, K, pkg.BIC)
-    eng.synchronize()
-    dt = time.time() - t0
-    st = eng.stats()
-    print(f"v={v} c={c} K={K} sets={res.scored()} wall={dt*1e3:.1f} ms  count_ms={st["ms_count"]:.1f} cube_ms={st["ms_cube"]:.1f} prune_ms={st["ms_prune"]:.1f} launches={st['launches_total']} "
-          f"sets/s={res.scored()/dt:.3e} alg_GB/s={st['algorithmic_bytes']/dt/1e9:.1f}")
-    res.free()
+for rep in range(2):
+    for v in vars_:
+        nb = pkg.two_hop_neighbors(edges, p, v)
+        c = bin(nb & ~(1 << v)).count("1")
+        eng.reset_stats()
+        t0 = time.time()
+        res = eng.score_variable(v, nb, K, pkg.BIC)
+        eng.synchronize()
+        dt = time.time() - t0
+        st = eng.stats()
+        print(f"v={v} c={c} K={K} sets={res.scored()} wall={dt*1e3:.1f} ms  count_ms={st['ms_count']:.2f} cube_ms={st['ms_cube']:.2f} tree_ms={st['ms_tree']:.2f} "
+              f"launches={st['launches_total']} sets/s={res.scored()/dt:.3e} alg_GB/s={st['algorithmic_bytes']/dt/1e9:.1f}")
+        res.free()

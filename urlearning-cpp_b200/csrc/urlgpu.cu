@@ -14,10 +14,12 @@
 #include <vector>
 
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
 #include "bic_kernels.cuh"
 #include "slice_kernels.cuh"
+#include "tree_kernels.cuh"
 #include "cbic_kernels.cuh"
 
 using namespace urlgpu;
@@ -26,7 +28,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum Family { F_COUNT = 0, F_CUBE, F_CBIC, F_ACCEPT, F_PRUNE, F_GRAM, F_OTHER, F_N };
+enum Family { F_COUNT = 0, F_CUBE, F_CBIC, F_ACCEPT, F_PRUNE, F_GRAM, F_TREE, F_OTHER, F_N };
 
 struct EvPair { cudaEvent_t a, b; int fam; };
 
@@ -64,7 +66,12 @@ struct urlgpu_ctx {
     uint32_t *d_high_sorted = nullptr; int high_bits = -1; std::vector<int> high_off;   // segment DP lists (accept / prune)
     uint16_t *d_low_sorted = nullptr; int low_bits = -1; std::vector<int> low_off;
     bool use_slice_count = true; // cube path: count big roots in shared-memory slices (URLGPU_SLICE_COUNT=0 disables)
-    int bic_mode = 2; // 2 = cube (default), 0 = slice (experimental: whole subtrees on chip), 1 = direct counting of every set (URLGPU_BIC_MODE=cube|slice|direct)
+    // K1 strategy (URLGPU_BIC_MODE=auto|tree|cube|direct): 3 = auto (tree when n >= 32768, else cube), 0 = tree (tables counted and
+    // marginalised in shared memory), 2 = cube (tables marginalised through HBM), 1 = direct counting of every set
+    int bic_mode = 3;
+    uint32_t tree_budget = 12 * 1024;   // cells of a slice table (URLGPU_TREE_BUDGET); the warps' stacks get the same
+    int tree_run = 6;                   // run limit t (URLGPU_TREE_RUN)
+    uint32_t tree_unit_cap = 1024;      // largest unit table r_v * prod_{i<t} r_i (URLGPU_TREE_UNIT)
 
     // pinned staging arena for host->device descriptor uploads (pageable cudaMemcpyAsync would sync the stream)
     // two arenas used alternately per call, each guarded by an event recorded when its call has been enqueued, so the
@@ -155,7 +162,8 @@ void fold_events(urlgpu_ctx *ctx) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
             double *dst = ep.fam == F_COUNT ? &ctx->st.ms_count : ep.fam == F_CUBE ? &ctx->st.ms_cube : ep.fam == F_CBIC ? &ctx->st.ms_cbic
-                        : ep.fam == F_ACCEPT ? &ctx->st.ms_accept : ep.fam == F_PRUNE ? &ctx->st.ms_prune : ep.fam == F_GRAM ? &ctx->st.ms_gram : nullptr;
+                        : ep.fam == F_ACCEPT ? &ctx->st.ms_accept : ep.fam == F_PRUNE ? &ctx->st.ms_prune : ep.fam == F_GRAM ? &ctx->st.ms_gram
+                        : ep.fam == F_TREE ? &ctx->st.ms_tree : nullptr;
             if (dst) *dst += ms;
         }
         ctx->free_events.push_back(ep.a);
@@ -171,7 +179,8 @@ struct Region {
     Region(urlgpu_ctx *c, int f, uint64_t launches) : ctx(c), fam(f), on(c->timing) {
         c->st.launches_total += launches;
         uint64_t *cnt = f == F_COUNT ? &c->st.launches_count : f == F_CUBE ? &c->st.launches_cube : f == F_CBIC ? &c->st.launches_cbic
-                      : f == F_ACCEPT ? &c->st.launches_accept : f == F_PRUNE ? &c->st.launches_prune : &c->st.launches_other;
+                      : f == F_ACCEPT ? &c->st.launches_accept : f == F_PRUNE ? &c->st.launches_prune : f == F_TREE ? &c->st.launches_tree
+                      : &c->st.launches_other;
         *cnt += launches;
         if (on) { ep.a = get_event(c); ep.b = get_event(c); ep.fam = f; cudaEventRecord(ep.a, c->stream); }
     }
@@ -248,9 +257,16 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
     }
     ctx->stream = ctx->own_stream;
     if (const char *m = getenv("URLGPU_SLICE_COUNT")) ctx->use_slice_count = atoi(m) != 0;
-    if (const char *m = getenv("URLGPU_BIC_MODE")) ctx->bic_mode = strcmp(m, "direct") == 0 ? 1 : strcmp(m, "slice") == 0 ? 0 : 2;
+    if (const char *m = getenv("URLGPU_BIC_MODE"))
+        ctx->bic_mode = strcmp(m, "direct") == 0 ? 1 : strcmp(m, "tree") == 0 ? 0 : strcmp(m, "cube") == 0 ? 2 : 3;
+    if (const char *m = getenv("URLGPU_TREE_BUDGET")) ctx->tree_budget = (uint32_t)std::max(1024, std::min(atoi(m), 26 * 1024)) / 4 * 4;
+    if (const char *m = getenv("URLGPU_TREE_RUN")) ctx->tree_run = std::max(1, std::min(atoi(m), kTreeMaxRun));
+    if (const char *m = getenv("URLGPU_TREE_UNIT")) ctx->tree_unit_cap = (uint32_t)std::max(16, atoi(m));
     cudaFuncSetAttribute(bic_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 2048);
-    cudaFuncSetAttribute(bic_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024 * 4 + 16 * (1 << kSliceMaxRun));
+    cudaFuncSetAttribute(bic_tree_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ctx->tree_budget * sizeof(int)));
+    cudaFuncSetAttribute(bic_tree_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ctx->tree_budget * sizeof(int)));
+    cudaFuncSetAttribute(bic_tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ctx->tree_budget * sizeof(int)));
+    cudaFuncSetAttribute(bic_tree_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ctx->tree_budget * sizeof(int)));
     cudaFuncSetAttribute(bic_slice_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024 * 4);
     *out = ctx;
     return URLGPU_OK;
@@ -1093,14 +1109,15 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     return URLGPU_OK;
 }
 
-static int bic_score_family_slice(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                                  uint64_t *n_scored, bool *used);
+static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
+                                 uint64_t *n_scored, bool *used);
 
 static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
                             uint64_t *n_scored) {
-    if (ctx->bic_mode == 0) {
+    // mode 0 = tree (forced), 3 = auto: tree for data sets large enough to fill the machine, else cube
+    if (ctx->bic_mode == 0 || (ctx->bic_mode == 3 && ctx->n >= 32768)) {
         bool used = false;
-        int rc = bic_score_family_slice(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used);
+        int rc = bic_score_family_tree(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used);
         if (rc || used) return rc;
     }
     if (ctx->bic_mode != 1) {
@@ -1113,16 +1130,26 @@ static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int
 
 
 // ------------------------------------------------------------------------------------------------------------
-// Slice path (slice_kernels.cuh): roots counted in shared-memory slices of bucketed rows, subtrees derived on chip.
-// Roots that cannot be sliced (run too long, table not separable within the bucketed prefix depth, segments too
-// short) are handed to the cube path as a sub-forest.
+// Tree path (tree_kernels.cuh): every contingency table is counted or marginalised in shared memory; nothing but
+// the bucketed packed rows (L2 resident) and the per-set accumulators is read from or written to device memory.
+// Returns with *used = false (nothing launched) when the family cannot be laid out this way: packed row wider
+// than 64 bits, first candidate's arity too large for a run, or a root table that cannot be cut into slices
+// that fit the shared-memory budget.  The caller then takes the cube path.
 // ------------------------------------------------------------------------------------------------------------
-static int bic_score_family_slice(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                                  uint64_t *n_scored, bool *used) {
+template <int RV>
+static void launch_tree(const TreeVar &tv, const TreeRoot *roots, const uint32_t *map, const long long *qlog, long long *acc, uint32_t budget, unsigned grid,
+                        size_t smem, cudaStream_t s) {
+    bic_tree_kernel<RV><<<grid, kTreeThreads, smem, s>>>(tv, roots, map, qlog, acc, budget, budget);
+}
+
+static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
+                                 uint64_t *n_scored, bool *used) {
     *used = false;
     cudaStream_t s = ctx->stream;
     const int c = (int)cand.size();
     if (c == 0) return URLGPU_OK;
+    static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
+    const auto T0 = std::chrono::steady_clock::now();
     const int Kc = std::min(K, c);
     const int rv = ctx->card[variable];
     const uint64_t n = (uint64_t)ctx->n;
@@ -1132,126 +1159,184 @@ static int bic_score_family_slice(urlgpu_ctx *ctx, int variable, const std::vect
     std::vector<int> cube_vars(c);
     std::vector<uint64_t> ccard(c);
     for (int i = 0; i < c; i++) { cube_vars[i] = cand[perm[i]]; ccard[i] = (uint64_t)ctx->card[cube_vars[i]]; }
+    // ---- packed row layout: uniform field width by the largest arity ----
+    TreeVar tv{};
+    tv.c = c; tv.rv = rv; tv.max_parents = K;
+    {
+        uint64_t maxr = (uint64_t)rv;
+        for (int i = 0; i < c; i++) maxr = std::max(maxr, ccard[i]);
+        tv.w = maxr <= 4 ? 2 : maxr <= 16 ? 4 : 8;
+        if ((c + 1) * tv.w > 64) return URLGPU_OK;
+        for (int i = 0; i < c; i++) tv.card[i] = (uint16_t)ccard[i];
+    }
+    // ---- run limit t: the lowest t digits are the ones summed out on chip ----
+    const uint32_t B = ctx->tree_budget;                      // cells of the slice table; the warps' stacks get the same
+    int t = 0;
+    {
+        uint64_t R = 1;
+        while (t < c && t < ctx->tree_run && (uint64_t)rv * R * ccard[t] <= ctx->tree_unit_cap) { R *= ccard[t]; t++; }
+    }
+    if (t == 0) return URLGPU_OK;
+    tv.t = t;
+    tv.pre[0] = 1;
+    for (int b = 0; b < t; b++) tv.pre[b + 1] = tv.pre[b] * (uint32_t)ccard[b];
+    for (int b = 0; b <= t; b++) tv.magic[b] = tv.pre[b] > 1 ? 0xFFFFFFFFu / tv.pre[b] : 0;
+    const int Lstar = std::min(Kc + 1, c);
+    // ---- bucketed zone: top digits (all above the run) whose joint arity stays <= kTreeMaxBuckets ----
+    int dmax = 0;
+    uint64_t Pd = 1;
+    while (c - 1 - dmax >= t && dmax < kTreeMaxZone && Pd * ccard[c - 1 - dmax] <= kTreeMaxBuckets) { Pd *= ccard[c - 1 - dmax]; dmax++; }
+    tv.dmax = dmax; tv.P_dmax = (uint32_t)Pd;
+    // per-unit stack need (cells) for a run of z digits
+    auto stack_unit = [&](int z) {
+        uint32_t tot = 0;
+        const uint32_t U0 = (uint32_t)rv * tv.pre[z];
+        for (int d = 1; d <= z; d++) tot += (U0 / tv.pre[d] + 3u) & ~3u;
+        return tot;
+    };
+    // ---- roots ----
+    std::vector<TreeRoot> roots;
+    uint64_t covered = 0;
+    bool ok = true;
+    auto binom = [](int a, int b) { if (b < 0 || b > a) return (uint64_t)0; uint64_t r = 1; for (int i = 0; i < b; i++) r = r * (uint64_t)(a - i) / (uint64_t)(i + 1); return r; };
+    auto add_root = [&](uint32_t A, int z) {
+        const int size = __builtin_popcount(A);
+        for (int j = 0; j <= z; j++) if (size - j <= K) covered += binom(z, j);
+        const uint32_t U0 = (uint32_t)rv * tv.pre[z];
+        const uint32_t su = stack_unit(z);
+        uint64_t H = 1;
+        for (int b = z; b < c; b++) if ((A >> b) & 1) { H *= ccard[b]; if (H > ((uint64_t)1 << 40)) H = (uint64_t)1 << 40; }
+        int depth = 0;
+        uint64_t nslices = 1, nseg = 1;
+        if ((uint64_t)kTreeWarps * su > B) { ok = false; return; } // every warp needs stack space for at least one unit
+        auto fits = [&](uint64_t h) { return (uint64_t)U0 * h <= B; };
+        while (!fits(H)) {
+            if (depth == dmax) { ok = false; return; }
+            const int b = c - 1 - depth;
+            depth++;
+            if ((A >> b) & 1) { H /= ccard[b]; nslices *= ccard[b]; } else nseg *= ccard[b];
+            if (nseg > (uint64_t)kTreeMaxSeg) { ok = false; return; }
+        }
+        if (U0 > B || (uint64_t)U0 * H > 65535) { ok = false; return; }
+        // optional deeper cut: keep the rows of one CTA below ~32k so single CTAs do not become the tail
+        while (n / nslices > 32768 && depth < dmax) {
+            int d2 = depth;
+            uint64_t seg2 = nseg;
+            while (d2 < dmax && !((A >> (c - 1 - d2)) & 1)) { seg2 *= ccard[c - 1 - d2]; d2++; }
+            if (d2 == dmax || seg2 > 256) break;
+            const int b = c - 1 - d2;
+            H /= ccard[b]; nslices *= ccard[b]; nseg = seg2; depth = d2 + 1;
+        }
+        if (nslices > 0x3fffffffull) { ok = false; return; }
+        TreeRoot r{};
+        r.mask = A; r.nslices = (uint32_t)nslices; r.H = (uint32_t)H; r.nseg = (uint32_t)nseg;
+        r.z = (uint8_t)z; r.size = (uint8_t)size;
+        // in-slice columns: child, run digits, present digits between the run and the zone (strides < S0 <= 65535)
+        r.fstride[0] = 1;
+        for (int b = 0; b < z; b++) r.fstride[b + 1] = (uint16_t)((uint32_t)rv * tv.pre[b]);
+        uint32_t hs = U0;
+        for (int b = z; b < c - depth; b++)
+            if ((A >> b) & 1) { r.fstride[b + 1] = (uint16_t)hs; hs *= (uint32_t)ccard[b]; }
+        for (int f = 0; f <= c; f++)
+            if (r.fstride[f]) r.gmask |= (uint8_t)(1u << (f * tv.w / 8));
+        uint64_t w = 1;
+        for (int b = c - depth; b < c; b++) {
+            if ((A >> b) & 1) { r.pres_card[r.npres] = (uint16_t)ccard[b]; r.pres_weight[r.npres] = (uint32_t)w; r.npres++; }
+            else { r.abs_card[r.nabs] = (uint16_t)ccard[b]; r.abs_weight[r.nabs] = (uint32_t)w; r.nabs++; }
+            w *= ccard[b];
+        }
+        r.q_stride = (uint32_t)(Pd / w);
+        roots.push_back(r);
+    };
+    auto for_each_subset = [&](int bits, int pick, auto &&fn) { // all `pick`-subsets of `bits` positions, increasing
+        if (pick < 0 || pick > bits) return;
+        if (pick == 0) { fn(0u); return; }
+        uint32_t v = (1u << pick) - 1;
+        const uint64_t lim = (uint64_t)1 << bits;
+        while ((uint64_t)v < lim) {
+            fn(v);
+            if (pick == bits) break;
+            v = gosper_next(v);
+        }
+    };
+    const uint32_t low_t = (1u << t) - 1;
+    for (int i = 0; i <= c - t && t + i <= Lstar && ok; i++)      // (1) sets containing all t low bits
+        for_each_subset(c - t, i, [&](uint32_t hm) { if (ok) add_root(low_t | (hm << t), t); });
+    for (int z = 1; z < t && ok; z++)                              // (2) layer-L* sets whose lowest missing bit is z < t
+        for_each_subset(c - z - 1, Lstar - z, [&](uint32_t hm) { if (ok) add_root(((1u << z) - 1) | (hm << (z + 1)), z); });
+    if (!ok) return URLGPU_OK;
+    if (covered != family_size(c, K)) return ctx->fail(URLGPU_ERR_INTERNAL, "tree: the roots do not cover the family exactly once");
+    // heavy CTAs (few slices = many rows each) first
+    std::stable_sort(roots.begin(), roots.end(), [](const TreeRoot &a, const TreeRoot &b) { return a.nslices < b.nslices; });
+    uint64_t chunk = 0, acc_total = 0;
+    for (auto &r : roots) { r.chunk0 = (uint32_t)chunk; r.acc_off = (uint32_t)acc_total; chunk += r.nslices; acc_total += (uint64_t)1 << r.z; }
+    if (chunk > 0x7fffffffull || acc_total > 0x7fffffffull) return URLGPU_OK;
+    // ---- device side ----
+    { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
     CandInfo ci_cube = make_candinfo(ctx, variable, cube_vars, K);
     CandInfo ci_res = make_candinfo(ctx, variable, cand, K);
     BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
-
-    const int Lstar = std::min(Kc + 1, c);
-    const int jforced = Lstar - Kc;                       // 0 or 1 forced low bits
-    // bucketing depth: top digits whose joint arity stays <= 65536
-    int dmax = 0;
-    uint64_t Pd = 1;
-    while (dmax < c && dmax < kSliceMaxDepth && Pd * ccard[c - 1 - dmax] <= 65536) { Pd *= ccard[c - 1 - dmax]; dmax++; }
-    const uint32_t budget = 24 * 1024;                    // table cells per CTA (96 KB): two CTAs per SM
-    const size_t smem = (size_t)budget * 4 + ((size_t)4 + 4 + 8) * (1u << kSliceMaxRun);
-
-    std::vector<SliceRoot> sroots;
-    std::vector<uint32_t> groots;
-    uint64_t chunk = 0, acc_total = 0;
+    DevBuf dkeys(ctx), dhist(ctx), doff(ctx), dcursor(ctx), drows(ctx), droots(ctx), dmap(ctx), dacc(ctx), dperm(ctx), dtmp(ctx);
+    CK(dkeys.alloc(n * sizeof(uint32_t)));
+    CK(dhist.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+    CK(doff.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+    CK(dcursor.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+    CK(drows.alloc(n * sizeof(unsigned long long)));
+    CK(droots.alloc(roots.size() * sizeof(TreeRoot)));
+    CK(dmap.alloc(chunk * sizeof(uint32_t)));
+    CK(dacc.alloc(acc_total * sizeof(long long)));
+    CK(dperm.alloc(kMaxDenseCand));
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, dhist.as<uint32_t>(), doff.as<uint32_t>(), (int)(Pd + 1), s));
+    CK(dtmp.alloc(tmp_bytes));
+    uint8_t hperm[kMaxDenseCand] = {0};
+    for (int i = 0; i < c; i++) hperm[i] = (uint8_t)perm[i];
+    std::vector<uint16_t> cfgtab((size_t)(t + 1) << t, 0);
+    for (int z = 0; z <= t; z++)
+        for (uint32_t D = 0; D < (1u << z); D++) {
+            uint32_t v = tv.pre[z];
+            for (int i = 0; i < z; i++) if ((D >> i) & 1) v /= (uint32_t)ccard[i];
+            cfgtab[((size_t)z << t) + D] = (uint16_t)v;
+        }
+    DevBuf dcfg(ctx);
+    CK(dcfg.alloc(cfgtab.size() * sizeof(uint16_t)));
+    { int rc_ = h2d_async(ctx, dcfg.p, cfgtab.data(), cfgtab.size() * sizeof(uint16_t)); if (rc_) return rc_; }
+    tv.cfg_tab = dcfg.as<uint16_t>();
+    { int rc_ = h2d_async(ctx, droots.p, roots.data(), roots.size() * sizeof(TreeRoot)); if (rc_) return rc_; }
+    { int rc_ = h2d_async(ctx, dperm.p, hperm, kMaxDenseCand); if (rc_) return rc_; }
+    tv.rows = drows.as<unsigned long long>();
+    tv.prefix_off = doff.as<uint32_t>();
     {
-        const int free_bits = c - jforced, pick = Lstar - jforced;
-        const uint32_t lowmask = jforced ? ((1u << jforced) - 1) : 0;
-        uint32_t v = pick ? (1u << pick) - 1 : 0;
-        const uint64_t lim = (uint64_t)1 << free_bits;
-        while (true) {
-            const uint32_t P = (v << jforced) | lowmask;
-            const int z = std::min(c, (int)__builtin_ctz(~P));
-            bool ok = z <= kSliceMaxRun;
-            uint64_t cells = (uint64_t)rv, runprod = 1, runplus = 1;
-            for (int i = 0; i < c; i++) if ((P >> i) & 1) cells = std::min<uint64_t>(cells * ccard[i], (uint64_t)1 << 50);
-            for (int i = 0; i < z; i++) { runprod *= ccard[i]; runplus *= ccard[i] + 1; }
-            if (cells > ((uint64_t)1 << 40)) ok = false;
-            uint64_t slices = 1, depth_prod = 1;
-            int depth = 0;
-            if (ok) {
-                const uint64_t total = cells / runprod * runplus;      // all 2^z tables of the un-sliced root
-                if (total > budget) {
-                    bool reached = false;
-                    for (int b = c - 1; b > z && depth < dmax; b--) {
-                        depth++;
-                        depth_prod *= ccard[b];
-                        if ((P >> b) & 1) slices *= ccard[b];
-                        if ((P >> b) & 1 && total / slices <= budget) { reached = true; break; }
-                    }
-                    ok = reached && slices <= 65535;
-                    if (ok) {
-                        const uint64_t segs = depth_prod / slices;
-                        if (segs > 1 && (n / depth_prod < 24 || segs > (uint64_t)kSliceMaxSeg)) ok = false;
-                    }
-                }
-            }
-            if (ok) {
-                SliceRoot sr{};
-                sr.mask = P; sr.chunk0 = (uint32_t)chunk; sr.acc_off = (uint32_t)acc_total;
-                sr.nslices = (uint16_t)slices; sr.depth = (uint8_t)depth; sr.z = (uint8_t)z;
-                chunk += slices; acc_total += (uint64_t)1 << z;
-                sroots.push_back(sr);
-            } else groots.push_back(P);
-            if (pick == 0 || pick == free_bits) break;
-            v = gosper_next(v);
-            if ((uint64_t)v >= lim) break;
-        }
-    }
-    if (chunk > 0x7fffffffull || acc_total > 0xffffffffull) return URLGPU_OK;   // let the cube path handle it
-    if (chunk < 64 && n > 200000) { // too few CTAs to fill the machine: the cube path counts such roots with many CTAs
-        for (auto &sr : sroots) groots.push_back(sr.mask);
-        sroots.clear(); chunk = 0; acc_total = 0;
-    }
-    static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
-    if (dbg) fprintf(stderr, "[urlgpu slice] v=%d c=%d K=%d L*=%d dmax=%d slice roots=%zu (%llu CTAs) global roots=%zu\n", variable, c, K, Lstar, dmax, sroots.size(),
-                     (unsigned long long)chunk, groots.size());
-    if (!sroots.empty()) {
-        DevBuf dkeys(ctx), dhist(ctx), doff(ctx), dcursor(ctx), dsorted(ctx), droots(ctx), dacc(ctx), dperm(ctx);
-        SliceVar sv{};
-        sv.c = c; sv.rv = rv; sv.max_parents = K; sv.dmax = dmax; sv.P_dmax = (uint32_t)Pd;
-        for (int i = 0; i < c; i++) sv.card[i] = (int)ccard[i];
-        CK(doff.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
-        if (dmax > 0) {
-            CK(dkeys.alloc(n * sizeof(uint32_t)));
-            CK(dhist.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
-            CK(dcursor.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
-            CK(dsorted.alloc((size_t)(c + 1) * ctx->n_stride));
-            CK(cudaMemsetAsync(dhist.p, 0, ((size_t)Pd + 1) * sizeof(uint32_t), s));
-            Region rg(ctx, F_COUNT, 3);
-            slice_key_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, dmax, dkeys.as<uint32_t>(), dhist.as<uint32_t>());
-            slice_scan_kernel<<<1, 1024, 0, s>>>(dhist.as<uint32_t>(), (uint32_t)Pd, doff.as<uint32_t>(), dcursor.as<uint32_t>());
-            slice_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, dkeys.as<uint32_t>(), dcursor.as<uint32_t>(), dsorted.as<uint8_t>());
-            for (int i = 0; i <= c; i++) sv.cols[i] = dsorted.as<uint8_t>() + (size_t)i * ctx->n_stride;
-        } else {
-            const uint32_t h[2] = {0, (uint32_t)n};
-            CK(cudaMemcpyAsync(doff.p, h, sizeof h, cudaMemcpyHostToDevice, s));
-            sv.cols[0] = ctx->d_codes + (size_t)variable * ctx->n_stride;
-            for (int i = 0; i < c; i++) sv.cols[i + 1] = ctx->d_codes + (size_t)cube_vars[i] * ctx->n_stride;
-        }
-        sv.prefix_off = doff.as<uint32_t>();
-        CK(droots.alloc(sroots.size() * sizeof(SliceRoot)));
-        CK(dacc.alloc(acc_total * sizeof(long long)));
-        CK(dperm.alloc(kMaxDenseCand));
-        uint8_t hperm[kMaxDenseCand] = {0};
-        for (int i = 0; i < c; i++) hperm[i] = (uint8_t)perm[i];
-        CK(cudaMemcpyAsync(droots.p, sroots.data(), sroots.size() * sizeof(SliceRoot), cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(dperm.p, hperm, kMaxDenseCand, cudaMemcpyHostToDevice, s));
+        Region rg(ctx, F_COUNT, 5);
+        CK(cudaMemsetAsync(dhist.p, 0, ((size_t)Pd + 1) * sizeof(uint32_t), s));
+        tree_key_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, dmax, dkeys.as<uint32_t>(), dhist.as<uint32_t>());
+        CK(cub::DeviceScan::ExclusiveSum(dtmp.p, tmp_bytes, dhist.as<uint32_t>(), doff.as<uint32_t>(), (int)(Pd + 1), s));
+        CK(cudaMemcpyAsync(dcursor.p, doff.p, ((size_t)Pd + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        tree_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, tv, dkeys.as<uint32_t>(), dcursor.as<uint32_t>(), drows.as<unsigned long long>());
+        tree_map_kernel<<<blocks_for(chunk, 256), 256, 0, s>>>(droots.as<TreeRoot>(), (int)roots.size(), (uint32_t)chunk, dmap.as<uint32_t>());
         CK(cudaMemsetAsync(dacc.p, 0, acc_total * sizeof(long long), s));
-        {
-            Region rg(ctx, F_COUNT, 1);
-            bic_slice_kernel<<<(unsigned)chunk, kSliceThreads, smem, s>>>(sv, droots.as<SliceRoot>(), (int)sroots.size(), ctx->d_qlog, dacc.as<long long>(), budget);
-        }
-        {
-            Region rg(ctx, F_OTHER, 1);
-            slice_finalize_kernel<<<blocks_for(acc_total, 256), 256, 0, s>>>(bd, ci_res, droots.as<SliceRoot>(), (int)sroots.size(), dperm.as<uint8_t>(), dacc.as<long long>(),
-                                                                          (uint32_t)acc_total, d_table, d_llfixed);
-        }
-        CK(cudaStreamSynchronize(s)); // host arrays and pooled buffers go out of scope
-        CK(cudaGetLastError());
     }
-    if (!groots.empty()) {
-        bool cu = false;
-        uint64_t dummy = 0;
-        std::sort(groots.begin(), groots.end());
-        int rc = bic_score_family_cube(ctx, variable, cand, K, d_table, d_llfixed, &dummy, &cu, &groots, Lstar);
-        if (rc) return rc;
-        if (!cu) return ctx->fail(URLGPU_ERR_LIMIT, "slice path: the cube sub-forest does not fit in device memory");
+    {
+        Region rg(ctx, F_TREE, 1);
+        const size_t smem = (size_t)2 * B * sizeof(int);
+        const unsigned grid = (unsigned)chunk;
+        switch (rv) {
+        case 2: launch_tree<2>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, dacc.as<long long>(), B, grid, smem, s); break;
+        case 3: launch_tree<3>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, dacc.as<long long>(), B, grid, smem, s); break;
+        case 4: launch_tree<4>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, dacc.as<long long>(), B, grid, smem, s); break;
+        default: launch_tree<0>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, dacc.as<long long>(), B, grid, smem, s); break;
+        }
     }
+    {
+        Region rg(ctx, F_OTHER, 1);
+        tree_finalize_kernel<<<blocks_for(acc_total, 256), 256, 0, s>>>(bd, ci_res, droots.as<TreeRoot>(), (int)roots.size(), dperm.as<uint8_t>(), dacc.as<long long>(),
+                                                                     (uint32_t)acc_total, d_table, d_llfixed);
+    }
+    CK(cudaGetLastError());
+    { int rc_ = stage_end(ctx); if (rc_) return rc_; }
+    if (dbg) fprintf(stderr, "[urlgpu tree] v=%d c=%d K=%d L*=%d t=%d dmax=%d buckets=%llu roots=%zu CTAs=%llu host %.2f ms\n", variable, c, K, Lstar, t, dmax,
+                     (unsigned long long)Pd, roots.size(), (unsigned long long)chunk,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
     *n_scored = family_size(c, K);
     {
         double bytes = 0, b = 1;
