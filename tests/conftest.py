@@ -33,12 +33,11 @@ def engine(pkg):
     eng.close()
 
 
-@pytest.fixture(scope="session", params=["tree", "cube", "direct", "auto"])
+@pytest.fixture(scope="session", params=["cube", "tree", "direct"])
 def bic_engine(pkg, request):
-    """BIC engines for the K1 strategies: 'tree' (tables counted in shared-memory slices of bucketed packed rows, subtrees
-    marginalised on chip; falls back to cube when a family cannot be laid out that way), 'cube' (roots counted into global
-    tables, the rest marginalised through HBM), 'direct' (every set counted from the rows) and 'auto' (the default: tree
-    for n >= 32768, else cube)."""
+    """BIC engines for the K1 strategies: 'cube' (the default: roots counted into global tables, the rest marginalised through
+    HBM), 'tree' (tables counted in shared-memory slices of bucketed packed rows, subtrees marginalised on chip; falls back
+    to cube when a family cannot be laid out that way) and 'direct' (every set counted from the rows)."""
     old = os.environ.get("URLGPU_BIC_MODE")
     os.environ["URLGPU_BIC_MODE"] = request.param
     try:

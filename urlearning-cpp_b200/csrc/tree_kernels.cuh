@@ -38,7 +38,6 @@ namespace urlgpu {
 constexpr int kTreeMaxRun = 8;          // t <= 8: at most 256 tables per subtree
 constexpr int kTreeWarps = 8;
 constexpr int kTreeThreads = kTreeWarps * 32;
-constexpr uint32_t kTreeMaxSeg = 1u << 22; // row segments per slice
 constexpr int kTreeMaxZone = 20;        // bucketed top digits
 constexpr uint32_t kTreeMaxBuckets = 1u << 20;
 
@@ -62,7 +61,8 @@ struct TreeRoot {                       // built on the host, one per root
     uint32_t H;                         // units per slice
     uint32_t nseg;                      // row segments per slice
     uint32_t q_stride;                  // buckets per joint value of the zone digits (P_dmax / P_zone)
-    uint8_t z, size, npres, nabs, gmask, pad[3]; // gmask: bytes of the packed row that hold an in-slice field
+    uint8_t z, size, npres, nabs, gmask, ng, pad[2]; // gmask: bytes of the packed row that hold an in-slice field (ng of them)
+    uint8_t glist[8];                   // those bytes, ascending
     uint16_t fstride[32];               // stride of packed field f in the slice table (0: not an in-slice column)
     uint16_t pres_card[kTreeMaxZone];   // present zone digits, lowest first (slice index is mixed radix over them)
     uint32_t pres_weight[kTreeMaxZone]; //   weight of the digit inside the zone prefix index
@@ -153,6 +153,76 @@ __device__ __forceinline__ long long warp_sum_ll_redux(long long v) {
     return ((long long)hi << 24) + (long long)lo;
 }
 
+// ---- count the slice's rows.  The rows are `nseg` contiguous segments of the bucketed rows; they are walked as ONE
+// concatenated range (segbeg/segoff in shared memory): a warp takes 128 consecutive positions per step, lane l the
+// positions l, l+32, l+64, l+96, so every load is coalesced inside a segment and four loads are in flight per lane.
+// NG = number of bytes of the packed word that hold an in-slice field (compile time: the look-ups unroll).
+template <int NG>
+__device__ __forceinline__ void tree_count(const unsigned long long *__restrict__ rows, const uint32_t *segbeg, const uint32_t *segoff, uint32_t nseg,
+                                           uint32_t total, int *tab, const uint16_t *lut, const uint8_t *glist, int warp, int lane) {
+    uint32_t gsh[NG];
+#pragma unroll
+    for (int i = 0; i < NG; i++) gsh[i] = 8u * glist[i];
+    for (uint32_t base = (uint32_t)warp * 128u; base < total; base += kTreeWarps * 128u) {
+        const uint32_t p0 = base + lane;
+        uint32_t seg = 0;
+        if (nseg > 1 && p0 < total) { // last segment with segoff[seg] <= p0
+            uint32_t lo = 0, hi = nseg - 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (segoff[mid] <= p0) lo = mid; else hi = mid - 1;
+            }
+            seg = lo;
+        }
+        unsigned long long w[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t p = p0 + 32u * u;
+            ok[u] = p < total;
+            if (ok[u]) {
+                while (segoff[seg + 1] <= p) seg++; // also skips empty segments
+                w[u] = __ldg(rows + segbeg[seg] + (p - segoff[seg]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (ok[u]) {
+                uint32_t idx = 0;
+#pragma unroll
+                for (int i = 0; i < NG; i++) idx += lut[(gsh[i] << 5) + ((uint32_t)(w[u] >> gsh[i]) & 255u)];
+                atomicAdd(&tab[idx], 1);
+            }
+    }
+}
+
+// slices with more segments than the shared-memory segment tables hold (a root whose present digits all sit below many
+// absent ones): warp `warp` owns segments warp, warp + W, ... and fetches the bounds of 32 of them at once
+template <int NG, typename BoundsFn>
+__device__ __forceinline__ void tree_count_fragmented(const unsigned long long *__restrict__ rows, BoundsFn seg_bounds, uint32_t nseg, int *tab,
+                                                      const uint16_t *lut, const uint8_t *glist, int warp, int lane) {
+    uint32_t gsh[NG];
+#pragma unroll
+    for (int i = 0; i < NG; i++) gsh[i] = 8u * glist[i];
+    for (uint32_t j0 = 0; warp + kTreeWarps * j0 < nseg; j0 += 32) {
+        const uint32_t seg = warp + kTreeWarps * (j0 + lane);
+        uint32_t r0 = 0, r1 = 0;
+        if (seg < nseg) seg_bounds(seg, r0, r1);
+        const uint32_t left = (nseg - warp - kTreeWarps * j0 + kTreeWarps - 1) / kTreeWarps;
+        const int cnt = (int)min(32u, left);
+        for (int k = 0; k < cnt; k++) {
+            const uint32_t b0 = __shfl_sync(0xffffffffu, r0, k), b1 = __shfl_sync(0xffffffffu, r1, k);
+            for (uint32_t g = b0 + lane; g < b1; g += 32) {
+                const unsigned long long w = __ldg(rows + g);
+                uint32_t idx = 0;
+#pragma unroll
+                for (int i = 0; i < NG; i++) idx += lut[(gsh[i] << 5) + ((uint32_t)(w >> gsh[i]) & 255u)];
+                atomicAdd(&tab[idx], 1);
+            }
+        }
+    }
+}
+
 // RV > 0: compile-time child arity (2,3,4); RV == 0: generic
 template <int RV>
 __global__ void __launch_bounds__(kTreeThreads) bic_tree_kernel(TreeVar tv, const TreeRoot *__restrict__ roots, const uint32_t *__restrict__ cta_root,
@@ -200,21 +270,11 @@ __global__ void __launch_bounds__(kTreeThreads) bic_tree_kernel(TreeVar tv, cons
         }
     }
     __syncthreads();
-    // ---- count: one packed row per lane per load.  The slice's rows are `nseg` contiguous segments of the bucketed
-    // rows, one per joint value of the absent zone digits; a warp fetches the bounds of 32 of its segments at once ----
+    // ---- count ----
     {
-        const uint32_t gmask = rt.gmask;
-        auto count_row = [&](unsigned long long w64) {
-            const uint32_t lo = (uint32_t)w64, hi = (uint32_t)(w64 >> 32);
-            uint32_t idx = 0;
-#pragma unroll
-            for (int g = 0; g < 4; g++)
-                if ((gmask >> g) & 1) idx += s_lut[g * 256 + ((lo >> (8 * g)) & 255u)];
-#pragma unroll
-            for (int g = 0; g < 4; g++)
-                if ((gmask >> (4 + g)) & 1) idx += s_lut[(4 + g) * 256 + ((hi >> (8 * g)) & 255u)];
-            atomicAdd(&s_dyn[idx], 1);
-        };
+        uint32_t *s_segbeg = reinterpret_cast<uint32_t *>(s_dyn + table_budget);
+        uint32_t *s_segoff = s_segbeg + (stack_budget - 1) / 2;   // nseg + 1 entries
+        const uint32_t nseg = rt.nseg;
         uint32_t qb = 0;
         {
             uint32_t rem = si;
@@ -226,24 +286,43 @@ __global__ void __launch_bounds__(kTreeThreads) bic_tree_kernel(TreeVar tv, cons
             r0 = __ldg(&tv.prefix_off[(size_t)q * rt.q_stride]);
             r1 = __ldg(&tv.prefix_off[(size_t)(q + 1) * rt.q_stride]);
         };
-        const uint32_t nseg = rt.nseg;
-        if (nseg <= 4) { // few long segments: the whole CTA walks each one
-            for (uint32_t sg = 0; sg < nseg; sg++) {
+        if (nseg + 1 <= (stack_budget - 1) / 2) {
+            for (uint32_t seg = tid; seg < nseg; seg += kTreeThreads) {
                 uint32_t r0, r1;
-                seg_bounds(sg, r0, r1);
-                for (uint32_t g = r0 + tid; g < r1; g += kTreeThreads) count_row(__ldg(tv.rows + g));
+                seg_bounds(seg, r0, r1);
+                s_segbeg[seg] = r0;
+                s_segoff[seg] = r1 - r0; // length for now
             }
-        } else {         // warp `warp` owns segments warp, warp + W, ...
-            for (uint32_t j0 = 0; warp + kTreeWarps * j0 < nseg; j0 += 32) {
-                const uint32_t seg = warp + kTreeWarps * (j0 + lane);
-                uint32_t r0 = 0, r1 = 0;
-                if (seg < nseg) seg_bounds(seg, r0, r1);
-                const uint32_t left = (nseg - warp - kTreeWarps * j0 + kTreeWarps - 1) / kTreeWarps;
-                const int cnt = (int)min(32u, left);
-                for (int k = 0; k < cnt; k++) {
-                    const uint32_t b0 = __shfl_sync(0xffffffffu, r0, k), b1 = __shfl_sync(0xffffffffu, r1, k);
-                    for (uint32_t g = b0 + lane; g < b1; g += 32) count_row(__ldg(tv.rows + g));
+            __syncthreads();
+            if (warp == 0) { // exclusive scan of the segment lengths
+                uint32_t carry = 0;
+                for (uint32_t b0 = 0; b0 < nseg; b0 += 32) {
+                    const uint32_t i = b0 + lane;
+                    const uint32_t len = i < nseg ? s_segoff[i] : 0;
+                    uint32_t x = len;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                    if (i < nseg) s_segoff[i] = carry + x - len;
+                    carry += __shfl_sync(0xffffffffu, x, 31);
                 }
+                if (lane == 0) s_segoff[nseg] = carry;
+            }
+            __syncthreads();
+            const uint32_t total = s_segoff[nseg];
+            switch (rt.ng) {
+#define URLGPU_TREE_COUNT(NG) case NG: tree_count<NG>(tv.rows, s_segbeg, s_segoff, nseg, total, s_dyn, s_lut, rt.glist, warp, lane); break;
+                URLGPU_TREE_COUNT(1) URLGPU_TREE_COUNT(2) URLGPU_TREE_COUNT(3) URLGPU_TREE_COUNT(4)
+                URLGPU_TREE_COUNT(5) URLGPU_TREE_COUNT(6) URLGPU_TREE_COUNT(7) URLGPU_TREE_COUNT(8)
+#undef URLGPU_TREE_COUNT
+            default: break;
+            }
+        } else {
+            switch (rt.ng) {
+#define URLGPU_TREE_COUNT(NG) case NG: tree_count_fragmented<NG>(tv.rows, seg_bounds, nseg, s_dyn, s_lut, rt.glist, warp, lane); break;
+                URLGPU_TREE_COUNT(1) URLGPU_TREE_COUNT(2) URLGPU_TREE_COUNT(3) URLGPU_TREE_COUNT(4)
+                URLGPU_TREE_COUNT(5) URLGPU_TREE_COUNT(6) URLGPU_TREE_COUNT(7) URLGPU_TREE_COUNT(8)
+#undef URLGPU_TREE_COUNT
+            default: break;
             }
         }
     }

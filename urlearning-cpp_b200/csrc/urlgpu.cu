@@ -66,10 +66,11 @@ struct urlgpu_ctx {
     uint32_t *d_high_sorted = nullptr; int high_bits = -1; std::vector<int> high_off;   // segment DP lists (accept / prune)
     uint16_t *d_low_sorted = nullptr; int low_bits = -1; std::vector<int> low_off;
     bool use_slice_count = true; // cube path: count big roots in shared-memory slices (URLGPU_SLICE_COUNT=0 disables)
-    // K1 strategy (URLGPU_BIC_MODE=auto|tree|cube|direct): 3 = auto (tree when n >= 32768, else cube), 0 = tree (tables counted and
-    // marginalised in shared memory), 2 = cube (tables marginalised through HBM), 1 = direct counting of every set
-    int bic_mode = 3;
-    uint32_t tree_budget = 12 * 1024;   // cells of a slice table (URLGPU_TREE_BUDGET); the warps' stacks get the same
+    // K1 strategy (URLGPU_BIC_MODE=cube|tree|direct): 2 = cube (default: roots counted in shared-memory slices, the rest
+    // marginalised through HBM), 0 = tree (every table counted or marginalised in shared memory; measured 0.6-0.9x the cube
+    // path on config 4, instruction bound — kept as an opt-in strategy), 1 = direct counting of every set
+    int bic_mode = 2;
+    uint32_t tree_budget = 8 * 1024;    // cells of a slice table (URLGPU_TREE_BUDGET); the warps' stacks get the same
     int tree_run = 6;                   // run limit t (URLGPU_TREE_RUN)
     uint32_t tree_unit_cap = 1024;      // largest unit table r_v * prod_{i<t} r_i (URLGPU_TREE_UNIT)
 
@@ -258,7 +259,7 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
     ctx->stream = ctx->own_stream;
     if (const char *m = getenv("URLGPU_SLICE_COUNT")) ctx->use_slice_count = atoi(m) != 0;
     if (const char *m = getenv("URLGPU_BIC_MODE"))
-        ctx->bic_mode = strcmp(m, "direct") == 0 ? 1 : strcmp(m, "tree") == 0 ? 0 : strcmp(m, "cube") == 0 ? 2 : 3;
+        ctx->bic_mode = strcmp(m, "direct") == 0 ? 1 : strcmp(m, "tree") == 0 ? 0 : 2;
     if (const char *m = getenv("URLGPU_TREE_BUDGET")) ctx->tree_budget = (uint32_t)std::max(1024, std::min(atoi(m), 26 * 1024)) / 4 * 4;
     if (const char *m = getenv("URLGPU_TREE_RUN")) ctx->tree_run = std::max(1, std::min(atoi(m), kTreeMaxRun));
     if (const char *m = getenv("URLGPU_TREE_UNIT")) ctx->tree_unit_cap = (uint32_t)std::max(16, atoi(m));
@@ -1114,8 +1115,7 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
 
 static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
                             uint64_t *n_scored) {
-    // mode 0 = tree (forced), 3 = auto: tree for data sets large enough to fill the machine, else cube
-    if (ctx->bic_mode == 0 || (ctx->bic_mode == 3 && ctx->n >= 32768)) {
+    if (ctx->bic_mode == 0) {
         bool used = false;
         int rc = bic_score_family_tree(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used);
         if (rc || used) return rc;
@@ -1209,13 +1209,14 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
         int depth = 0;
         uint64_t nslices = 1, nseg = 1;
         if ((uint64_t)kTreeWarps * su > B) { ok = false; return; } // every warp needs stack space for at least one unit
+        const uint64_t max_seg = (uint64_t)1 << 22;                  // beyond (B-1)/2 - 1 segments the kernel takes its fragmented-slice loop
         auto fits = [&](uint64_t h) { return (uint64_t)U0 * h <= B; };
         while (!fits(H)) {
             if (depth == dmax) { ok = false; return; }
             const int b = c - 1 - depth;
             depth++;
             if ((A >> b) & 1) { H /= ccard[b]; nslices *= ccard[b]; } else nseg *= ccard[b];
-            if (nseg > (uint64_t)kTreeMaxSeg) { ok = false; return; }
+            if (nseg > max_seg) { ok = false; return; }
         }
         if (U0 > B || (uint64_t)U0 * H > 65535) { ok = false; return; }
         // optional deeper cut: keep the rows of one CTA below ~32k so single CTAs do not become the tail
@@ -1239,6 +1240,7 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
             if ((A >> b) & 1) { r.fstride[b + 1] = (uint16_t)hs; hs *= (uint32_t)ccard[b]; }
         for (int f = 0; f <= c; f++)
             if (r.fstride[f]) r.gmask |= (uint8_t)(1u << (f * tv.w / 8));
+        for (int g = 0; g < 8; g++) if ((r.gmask >> g) & 1) r.glist[r.ng++] = (uint8_t)g;
         uint64_t w = 1;
         for (int b = c - depth; b < c; b++) {
             if ((A >> b) & 1) { r.pres_card[r.npres] = (uint16_t)ccard[b]; r.pres_weight[r.npres] = (uint32_t)w; r.npres++; }
