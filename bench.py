@@ -46,6 +46,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(kind):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/traffic.json, written from the .ncu-rep by tools/traffic_from_ncu.py); None when absent."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kind)
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -81,20 +91,37 @@ class ClockSampler(threading.Thread):
 
 # ---------------------------------------------------------------------------------------------- workloads
 
-def make_bic_workload(pkg):
-    p, n = 60, 1_000_000
-    codes, card, edges, _ = pkg.datagen.discrete_bn(p=p, n=n, seed=4)
-    K = pkg.effective_max_parents(12, p, n, True)
+BIC_NAME = ("configs[3]: synthetic discrete BN p=60 n=1e6 arity<=4 seed=4, generating-graph skeleton (2-hop), -p 12 -> cap 11, "
+            "BIC + prune")
+
+
+def bic_block(pkg, block):
+    """block 0 is BASELINE configs[3] itself; block b > 0 has the same arities, DAG and skeleton with its own CPTs and rows"""
+    return pkg.datagen.discrete_bn(p=60, n=1_000_000, seed=4, sample_seed=None if block == 0 else 1000 + block)
+
+
+def make_bic_workload(pkg, blocks=1, codes=None, card=None):
+    """`blocks` replicas of the config-4 network side by side in one data set of 60*blocks variables (block-diagonal
+    skeleton).  codes/card may be passed in (multi-GPU: every rank generated one block and they were all-gathered)."""
+    pb, n = 60, 1_000_000
+    if codes is None:
+        parts = [bic_block(pkg, b) for b in range(blocks)]
+        codes = np.concatenate([q[0] for q in parts], axis=0)
+        card = np.concatenate([q[1] for q in parts])
+    _, _, edges0, _ = pkg.datagen.discrete_bn(p=pb, n=2, seed=4)  # the structure only (tiny sample)
+    p = pb * blocks
+    edges = [edges0[i % pb] << (pb * (i // pb)) for i in range(p)]
+    K = pkg.effective_max_parents(12, pb, n, True)
     nbs = [pkg.two_hop_neighbors(edges, p, v) for v in range(p)]
-    return dict(kind="bic", p=p, n=n, codes=codes, card=card, edges=edges, K=K, nbs=nbs,
-                name="configs[3]: synthetic discrete BN p=60 n=1e6 arity<=4 seed=4, generating-graph skeleton (2-hop), -p 12 -> cap 11, BIC + prune")
+    name = BIC_NAME if blocks == 1 else BIC_NAME + f"; weak scaling: {blocks} replicas of that network (own CPTs and rows) as one {p}-variable data set"
+    return dict(kind="bic", p=p, n=n, codes=codes, card=np.asarray(card, dtype=np.int32), edges=edges, K=K, nbs=nbs, name=name, blocks=blocks)
 
 
 def make_cbic_workload(pkg):
     p, n = 30, 100_000
     x, _ = pkg.datagen.linear_gaussian_sem(p=p, n=n, seed=3)
     nbs = [(1 << p) - 1] * p
-    return dict(kind="cbic", p=p, n=n, x=x, K=p - 1, nbs=nbs, lam=2.0,
+    return dict(kind="cbic", p=p, n=n, x=x, K=p - 1, nbs=nbs, lam=2.0, blocks=1,
                 name="configs[2]: synthetic linear-Gaussian SEM p=30 n=1e5 seed=3, cBIC lambda=2, all-ones skeleton (2^29 sets/variable), accept + prune")
 
 
@@ -103,13 +130,19 @@ def family_size(c, K):
     return sum(comb(c, l) for l in range(0, min(c, K) + 1))
 
 
-def my_variables(wl, rank, world):
-    return [v for v in range(wl["p"]) if v % world == rank]
-
-
 def sets_of(wl, v):
     c = bin(wl["nbs"][v] & ~(1 << v)).count("1")
     return family_size(c, wl["K"])
+
+
+def owners_of(pkg, wl, world):
+    """variable -> rank.  BIC: longest-processing-time-first on the predicted table cells (families differ by orders of
+    magnitude); cBIC config 3: every family has the same size, the reference's striping v % N is already balanced."""
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
+    if wl["kind"] != "bic" or world == 1:
+        return [v % world for v in range(wl["p"])]
+    costs = [D.family_cost(wl["card"], v, wl["nbs"][v], wl["K"]) for v in range(wl["p"])]
+    return D.assign_lpt(costs, world)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -129,35 +162,54 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     eng = pkg.Engine(local)  # raises if the CUDA library or the device is missing: no fallback
-    stream = torch.cuda.current_stream()
+    # one non-default stream for everything that is timed (the legacy default stream would serialise with the engine's copy stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
+    is_bic = args.workload == "bic"
+    weak = is_bic and args.scaling == "weak"
 
-    # ---- inputs: rank 0 generates, NCCL broadcast to every GPU (the path's one exchange step) ----
-    wl = (make_bic_workload if args.workload == "bic" else make_cbic_workload)(pkg) if rank == 0 else None
-    if world > 1:
-        box = [None if wl is None else {k: v for k, v in wl.items() if k not in ("codes", "x")}]
-        dist.broadcast_object_list(box, src=0)
-        meta = box[0]
-        if meta["kind"] == "bic":
-            d = torch.empty((meta["p"], meta["n"]), dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                d.copy_(torch.from_numpy(wl["codes"]))
-            dist.broadcast(d, src=0)
-            if rank != 0:
-                wl = dict(meta)
-            wl["dev"] = d
+    # ---- inputs.  The exchange step of the path over NCCL/NVLink:
+    #   weak BIC: every rank generates one 60-variable block, the blocks are all-gathered into the 60N-variable data set;
+    #   strong BIC: rank 0 generates configs[3], broadcast;  cBIC: rank 0 forms the Gram, the p*p Gram is broadcast.
+    dev = None
+    if is_bic:
+        if world == 1:
+            wl = make_bic_workload(pkg, 1)
+        elif weak:
+            codes_b, card_b, _, _ = bic_block(pkg, rank)
+            mine_dev = torch.from_numpy(codes_b).cuda()
+            dev = torch.empty((60 * world, codes_b.shape[1]), dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(dev, mine_dev)
+            cards = torch.empty(60 * world, dtype=torch.int32, device="cuda")
+            dist.all_gather_into_tensor(cards, torch.from_numpy(np.asarray(card_b, dtype=np.int32)).cuda())
+            del mine_dev
+            wl = make_bic_workload(pkg, world, codes=False, card=cards.cpu().numpy())
         else:
-            # the rows are only needed for the Gram: rank 0 forms it, the p*p Gram is broadcast
-            wl = wl if rank == 0 else dict(meta)
-    is_bic = wl["kind"] == "bic"
+            wl = make_bic_workload(pkg, 1) if rank == 0 else None
+            box = [None if wl is None else {k: v for k, v in wl.items() if k != "codes"}]
+            dist.broadcast_object_list(box, src=0)
+            dev = torch.empty((box[0]["p"], box[0]["n"]), dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                dev.copy_(torch.from_numpy(wl["codes"]))
+            dist.broadcast(dev, src=0)
+            wl = wl if rank == 0 else dict(box[0])
+    else:
+        wl = make_cbic_workload(pkg) if rank == 0 else None
+        if world > 1:
+            box = [None if wl is None else {k: v for k, v in wl.items() if k != "x"}]
+            dist.broadcast_object_list(box, src=0)
+            wl = wl if rank == 0 else dict(box[0])
     flags = pkg.PRUNE_DOMINATED
     stype = pkg.BIC if is_bic else pkg.CBIC
     lam = wl.get("lam", 0.0)
 
     pinned = None
     if is_bic:
-        if "dev" in wl:
-            eng.set_discrete_device(wl["dev"].data_ptr(), wl["n"], wl["p"], wl["card"])
+        if dev is not None:
+            eng.set_discrete_device(dev.data_ptr(), wl["n"], wl["p"], wl["card"])
+            pinned = dev.cpu().pin_memory()
+            del dev
         else:
             pinned = torch.from_numpy(wl["codes"]).pin_memory()
             eng.set_discrete(pinned.numpy(), wl["card"])
@@ -173,19 +225,32 @@ def run_gpu(args):
             if rank != 0:
                 eng.set_gram(g.cpu().numpy(), wl["n"])
 
-    mine = my_variables(wl, rank, world)
+    owner = owners_of(pkg, wl, world)
+    mine = [v for v in range(wl["p"]) if owner[v] == rank]
+    if is_bic and os.environ.get("BENCH_ORDER") == "big_first":
+        mine.sort(key=lambda v: -sets_of(wl, v))
     sets_mine = sum(sets_of(wl, v) for v in mine)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step(fetch=False):
-        flush.fill_(1)  # L2 flush between steps (inside the timed region: ~40 us of a multi-second step)
+        """one pass of the hot path over this rank's variables.  fetch: read every surviving cache back to the host,
+        software-pipelined one variable deep (v+1 is enqueued before v is read)."""
+        flush.fill_(1)  # L2 flush between steps (inside the timed region: ~40 us of a step of hundreds of ms)
         stored = 0
+        prev = None
         for v in mine:
             res = eng.score_variable(v, wl["nbs"][v], wl["K"], stype, lam=lam, flags=flags)
             if fetch:
-                m, s = res.fetch()
-                stored += len(s)
-            res.free()
+                res.prefetch()
+                if prev is not None:
+                    stored += len(prev.fetch()[1])
+                    prev.free()
+                prev = res
+            else:
+                res.free()
+        if prev is not None:
+            stored += len(prev.fetch()[1])
+            prev.free()
         return stored
 
     def barrier():
@@ -193,21 +258,23 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, **kw):
+    def maxed(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def timed(nsteps, fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         out = 0
         for _ in range(nsteps):
-            out += step(**kw)
+            out += fn()
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, out
+        return maxed(e0.elapsed_time(e1)), out
 
     for _ in range(args.warmup):
         step()
@@ -215,7 +282,7 @@ def run_gpu(args):
     sampler.start()
     eng.reset_stats()
     eng.enable_timing(True)
-    ms, _ = timed(args.steps)
+    ms, _ = timed(args.steps, step)
     st = eng.stats()
     eng.enable_timing(False)
     sampler.stop_flag = True
@@ -228,11 +295,10 @@ def run_gpu(args):
         total_sets = int(t.item())
     value = total_sets * args.steps / (ms / 1e3)
 
-    # ---- e2e: host buffers, H2D + D2H inside the timed region (every rank uploads its own copy of the data) ----
+    # ---- e2e: the public API with HOST buffers: the H2D copy of the data from pinned memory (every rank uploads the
+    # columns of the whole data set) and the D2H fetch of every surviving (mask, score) list are inside the timed region
     e2e = None
     if is_bic or world == 1:
-        if is_bic and pinned is None:
-            pinned = wl["dev"].cpu().pin_memory()
         host = pinned.numpy()
 
         def e2e_step():
@@ -243,50 +309,55 @@ def run_gpu(args):
             return step(fetch=True)
 
         e2e_step()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        stored = 0
         nst = max(1, min(args.steps, 3))
-        for _ in range(nst):
-            stored += e2e_step()
-        e1.record(stream)
-        barrier()
-        ems = e0.elapsed_time(e1)
+        ems, stored = timed(nst, e2e_step)
+        h2d = (wl["n"] * wl["p"]) * (1 if is_bic else 8) * world
         if world > 1:
-            t = torch.tensor([ems], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
-        h2d = (wl["n"] * wl["p"]) * (1 if is_bic else 8)
+            t = torch.tensor([stored], device="cuda", dtype=torch.int64)
+            dist.all_reduce(t)
+            stored = int(t.item())
+        words = pkg.mask_words_for(wl["p"])
         e2e = {"value": total_sets * nst / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(12 * stored // nst), "steps": nst, "ms_per_step": ems / nst}
+               "d2h_bytes_per_step": int((8 * words + 4) * stored // nst), "steps": nst, "ms_per_step": ems / nst}
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        fam = {"count": st["ms_count"], "cube": st["ms_cube"], "cbic": st["ms_cbic"], "accept": st["ms_accept"], "prune": st["ms_prune"]}
+        fam = {"count": st["ms_count"], "cube": st["ms_cube"], "tree": st["ms_tree"], "cbic": st["ms_cbic"], "accept": st["ms_accept"],
+               "prune": st["ms_prune"]}
         dom = max(fam, key=fam.get)
         if is_bic:
-            k1_ms = st["ms_count"] + st["ms_cube"]
-            k1_launches = st["launches_count"] + st["launches_cube"]
+            k1_ms = st["ms_count"] + st["ms_cube"] + st["ms_tree"]
+            k1_launches = st["launches_count"] + st["launches_cube"] + st["launches_tree"]
             achieved = st["algorithmic_bytes"] / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else None
-            roofline = {"bound": "hbm", "kernel": "K1 bic count+cube (families count,cube)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
+            issued = (st["k1_bytes_read"] + st["k1_bytes_written"]) / args.steps
+            roofline = {"bound": "hbm", "kernel": "K1 = bic_slice_count_kernel (root tables from the rows) + cube_derive_kernel (every other table by "
+                                                  "marginalisation, scored in the same pass)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                        "traffic": load_traffic("bic"), "peak_source": peak_src,
                         "algorithmic_bytes_per_step": st["algorithmic_bytes"] / args.steps, "kernel_ms_per_step": k1_ms / args.steps,
-                        "launches_per_step": k1_launches / args.steps, "share_of_step": k1_ms / ms, "family_ms": fam}
+                        "launches_per_step": k1_launches / args.steps, "share_of_step": k1_ms / ms,
+                        "issued_bytes_per_step": issued,
+                        "issued_frac_of_peak": issued / (k1_ms / args.steps / 1e3) / 1e9 / peak if k1_ms > 0 else None,
+                        "note": "algorithmic bytes = sum over scored sets of n*(|S|+1) (SURVEY 8d); the kernels replace most row passes by "
+                                "marginalising tables, so frac > 1 is expected; issued_* = bytes the K1 kernels actually load/store "
+                                "(rank 0, counted by the host plan)",
+                        "family_ms": fam}
         else:
             k3_ms = st["ms_cbic"]
             achieved = st["algorithmic_flops"] / (k3_ms / 1e3) / 1e12 if k3_ms > 0 else None
             roofline = {"bound": "fp64", "kernel": "K3 cbic sweep DFS", "achieved": achieved, "peak": 37.0, "unit": "TFLOP/s",
-                        "frac": achieved / 37.0 if achieved else None, "traffic": None,
+                        "frac": achieved / 37.0 if achieved else None, "traffic": load_traffic("cbic"),
                         "peak_source": "nominal B200 FP64 (no measured FP64 entry in MEASURED_PEAKS.json)",
                         "algorithmic_flops_per_step": st["algorithmic_flops"] / args.steps, "kernel_ms_per_step": k3_ms / args.steps,
                         "share_of_step": k3_ms / ms, "family_ms": fam}
         cpu = cpu_baseline(wl, args) if world == 1 and not args.no_cpu_baseline else None
+        scaling = "weak" if weak else "strong"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "int32 counts / int64 fixed-point log-likelihood -> f32" if is_bic else "f64 -> f32",
                 "data": "synthetic (seeded numpy generator, urlearning-cpp_b200/datagen.py)",
-                "config": {"workload": wl["name"], "sets_per_step": total_sets, "parallelism": f"variables striped v % {world}",
+                "config": {"workload": wl["name"], "sets_per_step": total_sets,
+                           "parallelism": ("variables dealt to ranks by predicted cost (LPT)" if is_bic else "variables striped v % N") + f", N={world}",
                            "l2": "flushed between steps (256 MB write)", "dominant_family": dom},
                 "e2e": e2e, "gpu_launches": int(st["launches_total"]), "clocks": sampler.summary(), "roofline": roofline,
                 "cpu_baseline": cpu}
@@ -467,7 +538,7 @@ def run_reference(args):
     if rank != 0:
         return
     pkg = importlib.import_module("urlearning-cpp_b200")
-    wl = (make_bic_workload if args.workload == "bic" else make_cbic_workload)(pkg)
+    wl = make_bic_workload(pkg, 1) if args.workload == "bic" else make_cbic_workload(pkg)
     threads = os.cpu_count() or 1
     per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup):
@@ -480,7 +551,8 @@ def run_reference(args):
     value = done / used
     total_sets = sum(sets_of(wl, v) for v in range(wl["p"]))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": used / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": used / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak" if (wl["kind"] == "bic" and args.scaling == "weak") else "strong",
             "vs_baseline": None, "dtype": "int32 counts -> f32" if wl["kind"] == "bic" else "f64 -> f32",
             "data": "synthetic (seeded numpy generator, urlearning-cpp_b200/datagen.py)",
             "config": {"workload": wl["name"], "sets_per_step": total_sets,
@@ -498,6 +570,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="urlgpu", choices=["urlgpu", "reference"])
     ap.add_argument("--workload", default="bic", choices=["bic", "cbic", "cbic5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="BIC with N > 1 GPUs: weak = N replicas of the configs[3] network in one 60N-variable data set (per-GPU work "
+                         "fixed); strong = configs[3] itself split over the ranks")
     ap.add_argument("--n5", type=int, default=10_000_000, help="total rows of the cbic5 workload")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

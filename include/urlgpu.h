@@ -92,6 +92,11 @@ int urlgpu_set_gram(urlgpu_ctx *ctx, const double *gram_rowmajor, int64_t n_tota
  * the device until fetched. */
 int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents,
                           int score_type, double lambda, unsigned filter_flags, urlgpu_result **out);
+/* Optional: enqueue the compaction of the stored entries (canonical order) behind the scoring kernels without any host
+ * synchronisation.  A caller that prefetches v, scores v+1 and only then counts/fetches v keeps the GPU busy while the
+ * host reads results (the reference overlaps nothing: scoringThread writes each block when its variable is done,
+ * score_main.cpp:173-205).  count/fetch call it themselves when it was not called. */
+int urlgpu_result_prefetch(urlgpu_result *res);
 int urlgpu_result_count(urlgpu_result *res, uint64_t *n_stored);   /* stored entries (after filters) */
 int urlgpu_result_scored(urlgpu_result *res, uint64_t *n_scored);  /* candidate sets scored */
 /* canonical order: (|S| ascending, mask ascending as an integer).  masks: n*mask_words words. */
@@ -127,6 +132,8 @@ typedef struct urlgpu_stats {
     double gram_flops;         /* K2: 2*n*p^2 per Gram formed */
     uint64_t launches_tree;    /* K1 on-chip count + marginalise + score kernel */
     double ms_tree;
+    double k1_bytes_read;      /* cube path: bytes the K1 kernels load from global memory (rows + parent tables; L2 may absorb re-reads) */
+    double k1_bytes_written;   /* cube path: bytes of contingency tables the K1 kernels store */
 } urlgpu_stats;
 int urlgpu_stats_reset(urlgpu_ctx *ctx);
 int urlgpu_stats_get(urlgpu_ctx *ctx, urlgpu_stats *out);

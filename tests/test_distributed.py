@@ -37,14 +37,16 @@ def _worker(rank, world, port, out_path):
     codes = D.broadcast_tensor(codes, (p, n), torch.uint8, "cpu").numpy()
     card = D.broadcast_tensor(card, (p,), torch.int32, "cpu").numpy()
     K = pkg.effective_max_parents(0, p, n, True)
+    costs = [D.family_cost(card, v, pkg.two_hop_neighbors(None, p, v), K) for v in range(p)]
+    owner = D.assign_lpt(costs, world) if os.environ.get("URLGPU_TEST_LPT") == "1" else None
     local = {}
-    for v in D.stripe(p, rank, world):
+    for v in ([v for v in range(p) if owner[v] == rank] if owner else D.stripe(p, rank, world)):
         nb = pkg.two_hop_neighbors(None, p, v)
         masks = orc.enumerate_sets(v, nb, p, K)
         scores = orc.bic_score_many(codes, card, v, masks, threads=1)
         order = orc.canonical_order(masks)
         local[v] = (masks[order].reshape(-1, 1), scores[order])
-    caches = D.gather_caches(local, p, 1, "cpu")
+    caches = D.gather_caches(local, p, 1, "cpu", owner=owner)
     if rank == 0:
         assert sorted(caches) == list(range(p))
         pkg.pss.write_pss(out_path, "data/hepatitis.clean.csv", n, K, "BIC", meta[0]["names"], card, caches)
@@ -54,11 +56,13 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_pss_identical_to_single_process(tmp_path):
-    out = str(tmp_path / "two_rank.pss")
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
-    assert hashlib.sha256(open(out, "rb").read()).hexdigest() == GOLD["hepatitis_bic"]["sha256"]
+def test_two_rank_gloo_pss_identical_to_single_process(tmp_path, monkeypatch):
+    for k, lpt in enumerate(("0", "1")):  # the reference's striping, then cost-balanced ownership
+        monkeypatch.setenv("URLGPU_TEST_LPT", lpt)
+        out = str(tmp_path / f"two_rank_{lpt}.pss")
+        port = 29500 + ((os.getpid() + 7 * k) % 2000)
+        mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+        assert hashlib.sha256(open(out, "rb").read()).hexdigest() == GOLD["hepatitis_bic"]["sha256"]
 
 
 def test_stripe_matches_reference_rule():
@@ -67,3 +71,37 @@ def test_stripe_matches_reference_rule():
         owned = [D.stripe(60, r, world) for r in range(world)]
         assert sorted(sum(owned, [])) == list(range(60))
         assert all(v % world == r for r in range(world) for v in owned[r])
+
+
+def test_lpt_assignment_is_balanced_and_deterministic():
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
+    pkg = importlib.import_module("urlearning-cpp_b200")
+    rng = np.random.default_rng(0)
+    card = rng.choice([2, 3, 4], size=60)
+    edges = [0] * 60
+    for i in range(60):
+        for j in range(max(0, i - 4), i):
+            if rng.random() < 0.6:
+                edges[i] |= 1 << j
+                edges[j] |= 1 << i
+    costs = [D.family_cost(card, v, pkg.two_hop_neighbors(edges, 60, v), 11) for v in range(60)]
+    assert all(c > 0 for c in costs)
+    for world in (1, 2, 4, 8):
+        owner = D.assign_lpt(costs, world)
+        assert owner == D.assign_lpt(list(costs), world)
+        assert set(owner) <= set(range(world))
+        loads = [sum(c for c, o in zip(costs, owner) if o == r) for r in range(world)]
+        # LPT bound: max load <= mean + largest item
+        assert max(loads) <= sum(costs) / world + max(costs) + 1e-9
+        stripe_loads = [sum(costs[v] for v in D.stripe(60, r, world)) for r in range(world)]
+        assert max(loads) <= max(stripe_loads) + 1e-9
+
+
+def test_family_cost_matches_brute_force():
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
+    import itertools
+    card = [2, 3, 4, 2, 3]
+    nb, v, K = 0b11101, 0, 2
+    cand = [2, 3, 4]
+    want = sum(card[v] * np.prod([card[i] for i in s]) for l in range(K + 1) for s in itertools.combinations(cand, l))
+    assert D.family_cost(card, v, nb, K) == want

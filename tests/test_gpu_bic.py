@@ -146,6 +146,34 @@ def test_score_binary_matches_oracle_pss(pkg, orc, data_dir, tmp_path):
     assert open(out, "rb").read() == open(ref, "rb").read()
 
 
+def test_pipelined_prefetch_matches_plain_fetch(pkg, engine):
+    """prefetch(v) / score(v+1) / fetch(v): the compaction is enqueued behind the scoring kernels and the payload is copied
+    on a second stream while the next variable runs; results must equal the unpipelined ones, in canonical order"""
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=20, n=70001, seed=13, window=4, max_indegree=3)
+    engine.set_discrete(codes, card)
+    K = 6
+    nbs = [pkg.two_hop_neighbors(edges, 20, v) for v in range(20)]
+    plain = []
+    for v in range(20):
+        r = engine.score_variable(v, nbs[v], K, pkg.BIC, flags=pkg.PRUNE_DOMINATED)
+        plain.append(r.fetch())
+        r.free()
+    for rep in range(2):
+        got, prev = [], None
+        for v in range(20):
+            r = engine.score_variable(v, nbs[v], K, pkg.BIC, flags=pkg.PRUNE_DOMINATED).prefetch()
+            if prev is not None:
+                got.append(prev.fetch())
+                prev.free()
+            prev = r
+        got.append(prev.fetch())
+        prev.free()
+        for (m0, s0), (m1, s1) in zip(plain, got):
+            assert np.array_equal(m0, m1) and np.array_equal(s0.view(np.uint32), s1.view(np.uint32))
+            pc = [bin(int(x)).count("1") for x in m1[:, 0]]
+            assert pc == sorted(pc)  # canonical order: layer by layer
+
+
 def test_errors_are_loud(pkg, engine):
     with pytest.raises(pkg.UrlGpuError):
         engine.score_variable(99, 1, 1, pkg.BIC)

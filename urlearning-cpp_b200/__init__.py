@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "urlgpu_create", "urlgpu_destroy", "urlgpu_last_error", "urlgpu_device_count", "urlgpu_set_stream",
     "urlgpu_synchronize", "urlgpu_set_discrete", "urlgpu_set_discrete_device", "urlgpu_set_continuous",
     "urlgpu_set_continuous_device", "urlgpu_shard_begin", "urlgpu_shard_moments", "urlgpu_shard_finish", "urlgpu_get_gram", "urlgpu_set_gram", "urlgpu_score_variable",
-    "urlgpu_result_count", "urlgpu_result_scored", "urlgpu_result_fetch", "urlgpu_result_free",
+    "urlgpu_result_prefetch", "urlgpu_result_count", "urlgpu_result_scored", "urlgpu_result_fetch", "urlgpu_result_free",
     "urlgpu_score_one", "urlgpu_contingency", "urlgpu_prune", "urlgpu_stats_reset", "urlgpu_stats_get",
     "urlgpu_stats_enable_timing",
 ]
@@ -48,7 +48,7 @@ class Stats(C.Structure):
         ("ms_count", C.c_double), ("ms_cube", C.c_double), ("ms_cbic", C.c_double), ("ms_accept", C.c_double),
         ("ms_prune", C.c_double), ("ms_gram", C.c_double),
         ("sets_scored", C.c_uint64), ("algorithmic_bytes", C.c_double), ("algorithmic_flops", C.c_double), ("gram_flops", C.c_double),
-        ("launches_tree", C.c_uint64), ("ms_tree", C.c_double),
+        ("launches_tree", C.c_uint64), ("ms_tree", C.c_double), ("k1_bytes_read", C.c_double), ("k1_bytes_written", C.c_double),
     ]
 
     def as_dict(self):
@@ -86,6 +86,7 @@ def load_library():
     lib.urlgpu_get_gram.argtypes = [vp, vp]
     lib.urlgpu_set_gram.argtypes = [vp, vp, i64, i32]
     lib.urlgpu_score_variable.argtypes = [vp, i32, vp, i32, i32, i32, C.c_double, C.c_uint, P(vp)]
+    lib.urlgpu_result_prefetch.argtypes = [vp]
     lib.urlgpu_result_count.argtypes = [vp, P(u64)]
     lib.urlgpu_result_scored.argtypes = [vp, P(u64)]
     lib.urlgpu_result_fetch.argtypes = [vp, u64, u64, vp, vp]
@@ -149,6 +150,11 @@ class Result:
 
     def __init__(self, eng: "Engine", handle, words: int):
         self._eng, self._h, self.words = eng, handle, words
+
+    def prefetch(self) -> "Result":
+        """enqueue the on-device compaction behind the scoring kernels (no host sync); fetch() then only waits for it"""
+        self._eng._check(self._eng.lib.urlgpu_result_prefetch(self._h))
+        return self
 
     def count(self) -> int:
         n = C.c_uint64()

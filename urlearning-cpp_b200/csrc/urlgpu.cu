@@ -7,15 +7,14 @@
 
 #include <algorithm>
 #include <chrono>
+#include <ctime>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include <cub/device/device_select.cuh>
 #include <cub/device/device_scan.cuh>
-#include <thrust/iterator/counting_iterator.h>
 
 #include "bic_kernels.cuh"
 #include "slice_kernels.cuh"
@@ -37,6 +36,11 @@ struct EvPair { cudaEvent_t a, b; int fam; };
 struct urlgpu_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // device->host copies of fetched results: not ordered behind later scoring work
+    std::vector<unsigned long long *> free_pinned; // 33-counter blocks of pinned host memory (urlgpu_result::h_counts)
+    // scratch of the copy stream (expanded masks of the range being fetched).  NOT from the pool: pool blocks are recycled in
+    // the order of the scoring stream, the copy stream runs concurrently with it
+    uint64_t *d_fetch_wide = nullptr; size_t fetch_wide_cap = 0; int *d_fetch_cand = nullptr;
     std::string err;
     int sm_count = 148;
     size_t smem_optin = 0;
@@ -63,6 +67,7 @@ struct urlgpu_ctx {
     int *d_tables = nullptr; size_t tables_cap = 0;          // int32 elements
     void *d_misc = nullptr; size_t misc_cap = 0;
     int *d_cubeA = nullptr, *d_cubeB = nullptr; size_t cubeA_cap = 0, cubeB_cap = 0; // ping-pong layer buffers of the cube path
+    size_t mem_free_sample = 0;  // free device memory (plus the cube buffers) when the current data set was installed
     uint32_t *d_high_sorted = nullptr; int high_bits = -1; std::vector<int> high_off;   // segment DP lists (accept / prune)
     uint16_t *d_low_sorted = nullptr; int low_bits = -1; std::vector<int> low_off;
     bool use_slice_count = true; // cube path: count big roots in shared-memory slices (URLGPU_SLICE_COUNT=0 disables)
@@ -83,6 +88,10 @@ struct urlgpu_ctx {
     // caching device allocator: cudaMalloc/cudaFree of multi-GB tables cost tens of ms each
     struct PoolBlock { void *p; size_t bytes; bool used; };
     std::vector<PoolBlock> pool;
+
+    // URLGPU_DEBUG_TIMING: wall time the host spends blocked in (0) staging-arena waits, (1) cudaMemGetInfo, (2) cudaMalloc of
+    // pool blocks, (3) pinned-arena copies, (4) arena growth, printed by urlgpu_destroy
+    double dbg_wall[8] = {0}; uint64_t dbg_n[8] = {0};
 
     // stats
     urlgpu_stats st{};
@@ -105,14 +114,32 @@ struct urlgpu_ctx {
 
 namespace {
 
-cudaError_t pool_alloc(urlgpu_ctx *ctx, void **out, size_t bytes) {
+struct DbgTimer {
+    urlgpu_ctx *c; int k; std::chrono::steady_clock::time_point t0;
+    DbgTimer(urlgpu_ctx *ctx, int kind) : c(ctx), k(kind), t0(std::chrono::steady_clock::now()) {}
+    ~DbgTimer() { c->dbg_wall[k] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); c->dbg_n[k]++; }
+};
+
+// size classes: powers of two up to 64 MB, multiples of 64 MB above.  Requests of any size then find a cached block after
+// the first few calls (per-variable tables differ in size from variable to variable; exact-size caching never converged)
+size_t pool_class(size_t bytes) {
     bytes = std::max<size_t>(bytes, 256);
+    const size_t big = (size_t)64 << 20;
+    if (bytes > big) return (bytes + big - 1) / big * big;
+    size_t c = 256;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+
+cudaError_t pool_alloc(urlgpu_ctx *ctx, void **out, size_t bytes) {
+    bytes = pool_class(bytes);
     int best = -1;
     for (size_t i = 0; i < ctx->pool.size(); i++) {
         auto &b = ctx->pool[i];
-        if (!b.used && b.bytes >= bytes && b.bytes <= bytes * 2 + (1 << 20) && (best < 0 || b.bytes < ctx->pool[best].bytes)) best = (int)i;
+        if (!b.used && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 && (best < 0 || b.bytes < ctx->pool[best].bytes)) best = (int)i;
     }
     if (best >= 0) { ctx->pool[best].used = true; *out = ctx->pool[best].p; return cudaSuccess; }
+    DbgTimer dt(ctx, 2);
     cudaError_t e = cudaMalloc(out, bytes);
     if (e != cudaSuccess) { // release every cached block and retry once
         cudaGetLastError();
@@ -214,10 +241,15 @@ struct urlgpu_result {
     std::vector<int> cand;          // compact bit -> variable index
     float *d_table = nullptr;       // 2^c floats
     uint64_t n_masks = 0, n_scored = 0;
-    bool counted = false; uint64_t n_stored = 0; uint64_t layer_count[32] = {0};
-    bool compacted = false;
-    std::vector<uint32_t> h_masks;  // canonical order
-    std::vector<float> h_scores;
+    // compaction into canonical order (|S|, mask): enqueued on the context's stream by urlgpu_result_prefetch, no host sync
+    bool prefetched = false, counted = false;
+    uint32_t *d_masks = nullptr;    // compact masks, canonical order (capacity n_scored)
+    float *d_vals = nullptr;
+    uint32_t *d_segcnt = nullptr;   // [32 layers][segments] stored entries, then their exclusive prefix
+    unsigned long long *d_counts = nullptr;  // [33]: stored entries per layer, total
+    unsigned long long *h_counts = nullptr;  // pinned copy
+    cudaEvent_t ready = nullptr;    // compaction + the copy of the counts have completed
+    uint64_t n_stored = 0; uint64_t layer_count[32] = {0};
 };
 
 // ============================================================================================ context
@@ -251,7 +283,8 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
     ctx->device = device_id;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
         delete ctx;
         return URLGPU_ERR_CUDA;
@@ -290,6 +323,10 @@ extern "C" int urlgpu_destroy(urlgpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     fold_events(ctx);
+    if (getenv("URLGPU_DEBUG_TIMING"))
+        fprintf(stderr, "[urlgpu host waits] arena wait %.1f ms (%llu), cudaMemGetInfo %.1f ms (%llu), pool cudaMalloc %.1f ms (%llu), arena copies %.1f ms (%llu), arena growth %.1f ms (%llu)\n",
+                ctx->dbg_wall[0], (unsigned long long)ctx->dbg_n[0], ctx->dbg_wall[1], (unsigned long long)ctx->dbg_n[1], ctx->dbg_wall[2], (unsigned long long)ctx->dbg_n[2],
+                ctx->dbg_wall[3], (unsigned long long)ctx->dbg_n[3], ctx->dbg_wall[4], (unsigned long long)ctx->dbg_n[4]);
     for (auto e : ctx->free_events) cudaEventDestroy(e);
     free_discrete(ctx);
     free_continuous(ctx);
@@ -302,6 +339,10 @@ extern "C" int urlgpu_destroy(urlgpu_ctx *ctx) {
     if (ctx->d_cubeB) cudaFree(ctx->d_cubeB);
     pool_destroy(ctx);
     for (int k = 0; k < 2; k++) { if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]); if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]); }
+    for (auto *hp : ctx->free_pinned) cudaFreeHost(hp);
+    if (ctx->d_fetch_wide) cudaFree(ctx->d_fetch_wide);
+    if (ctx->d_fetch_cand) cudaFree(ctx->d_fetch_cand);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return URLGPU_OK;
@@ -371,6 +412,7 @@ static int set_discrete_common(urlgpu_ctx *ctx, const uint8_t *src, bool src_on_
     CK(cudaStreamSynchronize(ctx->stream)); // q goes out of scope
     ctx->base = (float)(std::log((double)(int)n) / 2); // bic_scoring_function.cpp:13
     ctx->have_discrete = true;
+    ctx->mem_free_sample = 0;
     return URLGPU_OK;
 }
 
@@ -701,6 +743,7 @@ inline uint32_t gosper_next(uint32_t v) {
 static int stage_begin(urlgpu_ctx *ctx) {
     ctx->stage_cur ^= 1;
     const int k = ctx->stage_cur;
+    DbgTimer dt(ctx, 0);
     if (!ctx->stage_ev[k]) CK(cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming));
     else CK(cudaEventSynchronize(ctx->stage_ev[k]));
     ctx->stage_used = 0;
@@ -716,6 +759,7 @@ static int h2d_async(urlgpu_ctx *ctx, void *dst, const void *src, size_t bytes) 
     const int k = ctx->stage_cur;
     const size_t need = (ctx->stage_used + 255) / 256 * 256 + bytes;
     if (need > ctx->stage_cap[k]) {
+        DbgTimer dt(ctx, 4);
         // the arena is full: drain the stream (pending copies read from it), then grow
         CK(cudaStreamSynchronize(ctx->stream));
         if (bytes > ctx->stage_cap[k]) {
@@ -728,6 +772,7 @@ static int h2d_async(urlgpu_ctx *ctx, void *dst, const void *src, size_t bytes) 
         ctx->stage_used = 0;
     }
     const size_t off = (ctx->stage_used + 255) / 256 * 256;
+    DbgTimer dt(ctx, 3);
     memcpy(ctx->h_stage[k] + off, src, bytes);
     ctx->stage_used = off + bytes;
     CK(cudaMemcpyAsync(dst, ctx->h_stage[k] + off, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -788,6 +833,8 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     cudaStream_t s = ctx->stream;
     { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
     static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
+    auto cpu_ms = [] { timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double C0 = dbg ? cpu_ms() : 0.0;
     auto tnow = [] { return std::chrono::steady_clock::now(); };
     auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto T0 = tnow();
@@ -864,9 +911,14 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         return 6.5e-6 + (double)cs.cells * 1.95e-12; // fitted to the slice-count kernel on B200 (n = 1e6)
     };
     auto derive_cost = [&](const CubeSet &cs, int /*l*/, uint64_t rdrop) { return (double)cs.cells * 4.0 * (double)(rdrop + 1) / 5e12 + 1e-7; };
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    const double mem_budget = (double)free_b * 0.7 + (double)(ctx->cubeA_cap + ctx->cubeB_cap) * 4.0;
+    // free device memory is sampled once per data set: cudaMemGetInfo blocks for ~1.5 ms while the GPU is busy (measured)
+    if (ctx->mem_free_sample == 0) {
+        size_t free_b = 0, total_b = 0;
+        DbgTimer dt(ctx, 1);
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        ctx->mem_free_sample = free_b + (ctx->cubeA_cap + ctx->cubeB_cap) * sizeof(int);
+    }
+    const double mem_budget = (double)ctx->mem_free_sample * 0.7;
     std::vector<double> layer_cells(Lmax + 1, 0.0);
     for (int l = 0; l <= Lmax; l++)
         for (auto &cs : layers[l]) layer_cells[l] += (double)((cs.cells + 3) / 4 * 4);
@@ -909,6 +961,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     if (ctx->cubeB_cap < max_layer) { if (ctx->d_cubeB) cudaFree(ctx->d_cubeB); ctx->d_cubeB = nullptr; ctx->cubeB_cap = 0; CK(cudaMalloc(&ctx->d_cubeB, max_layer * sizeof(int))); ctx->cubeB_cap = max_layer; }
     int *bufP = ctx->d_cubeA, *bufC = ctx->d_cubeB;
     const auto T1 = tnow();
+    const double C1 = dbg ? cpu_ms() : 0.0;
 
     size_t max_sets = 0;
     for (int l = 0; l <= Lstar; l++) max_sets = std::max(max_sets, layers[l].size());
@@ -935,6 +988,8 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         std::vector<uint32_t> small_m; std::vector<uint64_t> small_off; std::vector<size_t> small_idx;
         std::vector<GlobalSet> big; std::vector<size_t> big_idx;
         for (size_t i = 0; i < R.size(); i++) {
+            ctx->st.k1_bytes_written += 4.0 * (double)R[i].cells;                                   // the root table
+            ctx->st.k1_bytes_read += (double)n * (double)(__builtin_popcount(R[i].cube_mask) + 1);  // its columns (L2 resident)
             if (R[i].cells <= tier1_cells) { small_m.push_back(R[i].cube_mask); small_off.push_back(R[i].off); small_idx.push_back(i); }
             else { big.push_back(GlobalSet{R[i].cube_mask, (uint32_t)R[i].cells, R[i].off}); big_idx.push_back(i); }
         }
@@ -1074,6 +1129,8 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             pr.Bc = cs.Bc; pr.r = cs.r; pr.chunk0 = (uint32_t)chunk;
             pr.acc_index = order[k];
             pr.leaf = (cs.cube_mask & 1u) == 0; // lowest missing bit is 0: nothing is derived from this set
+            ctx->st.k1_bytes_read += 4.0 * (double)cs.cells * (double)cs.r;
+            if (!pr.leaf) ctx->st.k1_bytes_written += 4.0 * (double)cs.cells;
             chunk += (pr.child_configs + kCubeConfigsPerBlock - 1) / kCubeConfigsPerBlock;
             hp[k] = pr;
         }
@@ -1097,8 +1154,8 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     }
     CK(cudaGetLastError());
     { int rc_ = stage_end(ctx); if (rc_) return rc_; }
-    if (dbg) fprintf(stderr, "[urlgpu cube] v=%d c=%d K=%d L*=%d roots=%zu plan+alloc %.2f ms, roots %.2f ms, derive %.2f ms\n", variable, c, K, Lstar,
-                     layers[Lstar].size(), tms(T0, T1), tms(T1, T2), tms(T2, tnow()));
+    if (dbg) fprintf(stderr, "[urlgpu cube] v=%d c=%d K=%d L*=%d roots=%zu plan+alloc %.2f ms (cpu %.2f), roots %.2f ms, derive %.2f ms, cpu total %.2f\n", variable, c, K, Lstar,
+                     layers[Lstar].size(), tms(T0, T1), C1 - C0, tms(T1, T2), tms(T2, tnow()), cpu_ms() - C0);
     *n_scored = family_size(c, K);
     if (!only_roots) {
         double bytes = 0, b = 1;
@@ -1524,57 +1581,167 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
 }
 
 // ============================================================================================ results
+//
+// The stored entries of a variable's dense table are compacted ON THE DEVICE into the canonical order (|S| ascending,
+// mask ascending) by three kernels with no host round trip: per-(layer, 2048-mask segment) counts, an exclusive scan
+// per layer plus the layer bases, and an order-preserving write.  urlgpu_result_prefetch enqueues them (and a copy of
+// the 33 counters into pinned memory) on the context's stream right behind the scoring kernels, so a caller that
+// scores variable v+1 before fetching v never stalls the GPU; the payload is then copied on a second stream.
 
 namespace {
-struct StoredInLayer {
-    const float *table; int layer;
-    __host__ __device__ bool operator()(const uint32_t &m) const {
-#ifdef __CUDA_ARCH__
-        return __popc(m) == layer && !is_sentinel(table[m]);
-#else
-        return false;
-#endif
-    }
-};
-__global__ void gather_scores_kernel(const float *__restrict__ table, const uint32_t *__restrict__ masks, uint64_t n, float *__restrict__ out) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = table[masks[i]];
-}
-} // namespace
+constexpr int kCompactSeg = 2048;      // masks per CTA
+constexpr int kCompactThreads = 256;   // 8 consecutive masks per thread
 
-namespace {
-__global__ void count_by_layer_kernel(const float *__restrict__ table, uint64_t n_masks, unsigned long long *__restrict__ counts /*[32]*/) {
+__global__ void __launch_bounds__(kCompactThreads) compact_count_kernel(const float *__restrict__ table, uint64_t n_masks, uint32_t nseg,
+                                                                        uint32_t *__restrict__ segcnt /*[32][nseg]*/) {
     __shared__ unsigned int sh[32];
     if (threadIdx.x < 32) sh[threadIdx.x] = 0;
     __syncthreads();
-    for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < n_masks; m += (uint64_t)gridDim.x * blockDim.x)
-        if (!is_sentinel(table[m])) atomicAdd(&sh[__popcll(m)], 1u);
+    const uint64_t m0 = (uint64_t)blockIdx.x * kCompactSeg + (uint64_t)threadIdx.x * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint64_t m = m0 + k;
+        if (m < n_masks && !is_sentinel(table[m])) atomicAdd(&sh[__popcll(m)], 1u);
+    }
     __syncthreads();
-    if (threadIdx.x < 32 && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+    if (threadIdx.x < 32) segcnt[(size_t)threadIdx.x * nseg + blockIdx.x] = sh[threadIdx.x];
+}
+
+// one CTA per layer: exclusive scan of its segment counts in place; totals to counts[layer]
+__global__ void __launch_bounds__(1024) compact_scan_kernel(uint32_t *__restrict__ segcnt, uint32_t nseg, unsigned long long *__restrict__ counts) {
+    __shared__ unsigned long long part[1024];
+    uint32_t *row = segcnt + (size_t)blockIdx.x * nseg;
+    const uint32_t per = (nseg + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = min(nseg, threadIdx.x * per), e = min(nseg, b + per);
+    unsigned long long sum = 0;
+    for (uint32_t i = b; i < e; i++) sum += row[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (uint32_t i = 0; i < blockDim.x; i++) { const unsigned long long t = part[i]; part[i] = run; run += t; }
+        counts[blockIdx.x] = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (uint32_t i = b; i < e; i++) { const uint32_t t = row[i]; row[i] = (uint32_t)run; run += t; } // a layer holds < 2^32 entries (c <= 30)
+}
+
+__global__ void compact_bases_kernel(unsigned long long *__restrict__ counts /*[33]*/, unsigned long long *__restrict__ bases /*[32]*/) {
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int l = 0; l < 32; l++) { bases[l] = run; run += counts[l]; }
+        counts[32] = run;
+    }
+}
+
+__global__ void __launch_bounds__(kCompactThreads) compact_write_kernel(const float *__restrict__ table, uint64_t n_masks, uint32_t nseg,
+                                                                        const uint32_t *__restrict__ segoff, const unsigned long long *__restrict__ bases,
+                                                                        uint32_t *__restrict__ out_masks, float *__restrict__ out_vals) {
+    __shared__ uint8_t cnt[32][kCompactThreads];   // stored entries of layer l among thread t's 8 masks
+    __shared__ uint16_t excl[32][kCompactThreads]; // exclusive prefix over the threads
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < 32 * kCompactThreads; i += kCompactThreads) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t m0 = (uint64_t)blockIdx.x * kCompactSeg + (uint64_t)t * 8;
+    float v[8];
+    unsigned stored = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint64_t m = m0 + k;
+        v[k] = m < n_masks ? table[m] : sentinel();
+        if (!is_sentinel(v[k])) { stored |= 1u << k; cnt[__popcll(m)][t]++; }
+    }
+    __syncthreads();
+    for (int l = warp; l < 32; l += kCompactThreads / 32) { // warp `warp` scans layers warp, warp + 8, ...
+        unsigned carry = 0;
+        for (int b0 = 0; b0 < kCompactThreads; b0 += 32) {
+            const unsigned c0 = cnt[l][b0 + lane];
+            unsigned x = c0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            excl[l][b0 + lane] = (uint16_t)(carry + x - c0);
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+    }
+    __syncthreads();
+    if (!stored) return;
+    unsigned seen[4] = {0, 0, 0, 0}; // per-layer entries already written by this thread: its 8 masks span <= 4 distinct popcounts
+    const int pc0 = __popcll(m0 >> 3);  // popcount of the shared high part; the low 3 bits add 0..3
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (!((stored >> k) & 1)) continue;
+        const int dl = __popc(k), l = pc0 + dl;
+        const unsigned long long pos = bases[l] + segoff[(size_t)l * nseg + blockIdx.x] + excl[l][t] + seen[dl];
+        seen[dl]++;
+        out_masks[pos] = (uint32_t)(m0 + k);
+        out_vals[pos] = v[k];
+    }
+}
+
+// compact mask -> the caller's multi-word varsets
+__global__ void expand_masks_kernel(const uint32_t *__restrict__ masks, uint64_t n, const int *__restrict__ cand, int c, int words, uint64_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t cm = masks[i];
+    for (int w = 0; w < words; w++) {
+        uint64_t x = 0;
+        for (int b = 0; b < c; b++)
+            if (((cm >> b) & 1) && (cand[b] >> 6) == w) x |= (uint64_t)1 << (cand[b] & 63);
+        out[i * (uint64_t)words + w] = x;
+    }
 }
 } // namespace
 
-// stored entries per layer (one kernel, one D2H)
-static int result_count_impl(urlgpu_result *res) {
+static int result_prefetch_impl(urlgpu_result *res) {
+    urlgpu_ctx *ctx = res->ctx;
+    if (res->prefetched) return URLGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t nseg = (uint32_t)((res->n_masks + kCompactSeg - 1) / kCompactSeg);
+    const uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>(res->n_scored, res->n_masks));
+    CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_masks), cap * sizeof(uint32_t)));
+    CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_vals), cap * sizeof(float)));
+    CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_segcnt), (size_t)32 * nseg * sizeof(uint32_t)));
+    CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_counts), (33 + 32) * sizeof(unsigned long long)));
+    if (!ctx->free_pinned.empty()) { res->h_counts = ctx->free_pinned.back(); ctx->free_pinned.pop_back(); }
+    else CK(cudaHostAlloc(reinterpret_cast<void **>(&res->h_counts), 33 * sizeof(unsigned long long), cudaHostAllocDefault));
+    res->ready = get_event(ctx);
+    {
+        Region rg(ctx, F_OTHER, 4);
+        compact_count_kernel<<<nseg, kCompactThreads, 0, s>>>(res->d_table, res->n_masks, nseg, res->d_segcnt);
+        compact_scan_kernel<<<32, 1024, 0, s>>>(res->d_segcnt, nseg, res->d_counts);
+        compact_bases_kernel<<<1, 32, 0, s>>>(res->d_counts, res->d_counts + 33);
+        compact_write_kernel<<<nseg, kCompactThreads, 0, s>>>(res->d_table, res->n_masks, nseg, res->d_segcnt, res->d_counts + 33, res->d_masks, res->d_vals);
+    }
+    CK(cudaMemcpyAsync(res->h_counts, res->d_counts, 33 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(res->ready, s));
+    CK(cudaGetLastError());
+    res->prefetched = true;
+    return URLGPU_OK;
+}
+
+static int result_wait_counts(urlgpu_result *res) {
     urlgpu_ctx *ctx = res->ctx;
     if (res->counted) return URLGPU_OK;
-    CK(cudaSetDevice(ctx->device));
-    DevBuf cnt(ctx);
-    CK(cnt.alloc(32 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(cnt.p, 0, 32 * sizeof(unsigned long long), ctx->stream));
-    count_by_layer_kernel<<<std::min<unsigned>(blocks_for(res->n_masks, 256), 2048), 256, 0, ctx->stream>>>(res->d_table, res->n_masks, cnt.as<unsigned long long>());
-    unsigned long long h[32];
-    CK(cudaMemcpyAsync(h, cnt.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    res->n_stored = 0;
-    for (int l = 0; l < 32; l++) { res->layer_count[l] = h[l]; res->n_stored += h[l]; }
+    int rc = result_prefetch_impl(res);
+    if (rc) return rc;
+    CK(cudaEventSynchronize(res->ready));
+    res->n_stored = res->h_counts[32];
+    for (int l = 0; l < 32; l++) res->layer_count[l] = res->h_counts[l];
+    if (res->n_stored > std::min<uint64_t>(res->n_scored, res->n_masks)) return ctx->fail(URLGPU_ERR_INTERNAL, "result: more stored entries than scored sets");
     res->counted = true;
     return URLGPU_OK;
 }
 
+extern "C" int urlgpu_result_prefetch(urlgpu_result *res) {
+    if (!res) return URLGPU_ERR_ARG;
+    return result_prefetch_impl(res);
+}
+
 extern "C" int urlgpu_result_count(urlgpu_result *res, uint64_t *n) {
     if (!res || !n) return URLGPU_ERR_ARG;
-    int rc = result_count_impl(res);
+    int rc = result_wait_counts(res);
     if (rc) return rc;
     *n = res->n_stored;
     return URLGPU_OK;
@@ -1585,70 +1752,50 @@ extern "C" int urlgpu_result_scored(urlgpu_result *res, uint64_t *n) {
     return URLGPU_OK;
 }
 
-// compaction into canonical order: layer by layer, masks ascending within a layer (order-preserving select into the
-// layer's known output range; no host round trip between layers)
-static int result_compact(urlgpu_result *res) {
-    urlgpu_ctx *ctx = res->ctx;
-    if (res->compacted) return URLGPU_OK;
-    int rc = result_count_impl(res);
-    if (rc) return rc;
-    cudaStream_t s = ctx->stream;
-    const uint64_t total = res->n_stored;
-    res->h_masks.resize(total); res->h_scores.resize(total);
-    if (total) {
-        DevBuf dmasks(ctx), dvals(ctx), dnum(ctx), tmp(ctx);
-        CK(dmasks.alloc(total * sizeof(uint32_t)));
-        CK(dvals.alloc(total * sizeof(float)));
-        CK(dnum.alloc(sizeof(unsigned long long)));
-        thrust::counting_iterator<uint32_t> it(0);
-        size_t tmp_bytes = 0;
-        StoredInLayer pred{res->d_table, 0};
-        cub::DeviceSelect::If(nullptr, tmp_bytes, it, dmasks.as<uint32_t>(), dnum.as<unsigned long long>(), (int64_t)res->n_masks, pred, s);
-        CK(tmp.alloc(tmp_bytes));
-        uint64_t off = 0;
-        for (int layer = 0; layer < 32; layer++) {
-            if (!res->layer_count[layer]) continue;
-            pred.layer = layer;
-            CK(cub::DeviceSelect::If(tmp.p, tmp_bytes, it, dmasks.as<uint32_t>() + off, dnum.as<unsigned long long>(), (int64_t)res->n_masks, pred, s));
-            off += res->layer_count[layer];
-        }
-        gather_scores_kernel<<<blocks_for(total, 256), 256, 0, s>>>(res->d_table, dmasks.as<uint32_t>(), total, dvals.as<float>());
-        CK(cudaMemcpyAsync(res->h_masks.data(), dmasks.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(res->h_scores.data(), dvals.p, total * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        CK(cudaGetLastError());
-    }
-    res->compacted = true;
-    return URLGPU_OK;
-}
-
 extern "C" int urlgpu_result_fetch(urlgpu_result *res, uint64_t offset, uint64_t n, uint64_t *masks, float *scores) {
     if (!res) return URLGPU_ERR_ARG;
     urlgpu_ctx *ctx = res->ctx;
     CK(cudaSetDevice(ctx->device));
-    int rc = result_compact(res);
+    int rc = result_wait_counts(res);
     if (rc) return rc;
-    if (offset + n > res->h_masks.size()) return ctx->fail(URLGPU_ERR_ARG, "result_fetch: range exceeds the stored count");
-    for (uint64_t i = 0; i < n; i++) {
-        const uint32_t cm = res->h_masks[offset + i];
-        if (masks) {
-            uint64_t *dst = masks + i * (uint64_t)res->mask_words;
-            for (int w = 0; w < res->mask_words; w++) dst[w] = 0;
-            for (int b = 0; b < res->c; b++)
-                if ((cm >> b) & 1) dst[res->cand[b] >> 6] |= (uint64_t)1 << (res->cand[b] & 63);
+    if (offset + n > res->n_stored) return ctx->fail(URLGPU_ERR_ARG, "result_fetch: range exceeds the stored count");
+    if (n == 0) return URLGPU_OK;
+    cudaStream_t cs = ctx->copy_stream; // the compaction has completed (ready event): nothing here waits for later scoring work
+    if (masks) {
+        const size_t need = n * (size_t)res->mask_words * sizeof(uint64_t);
+        if (ctx->fetch_wide_cap < need) {
+            if (ctx->d_fetch_wide) cudaFree(ctx->d_fetch_wide);
+            ctx->d_fetch_wide = nullptr; ctx->fetch_wide_cap = 0;
+            const size_t cap = std::max<size_t>(need + need / 2, (size_t)1 << 20);
+            CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_fetch_wide), cap));
+            ctx->fetch_wide_cap = cap;
         }
-        if (scores) scores[i] = res->h_scores[offset + i];
+        if (!ctx->d_fetch_cand) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_fetch_cand), (kMaxDenseCand + 2) * sizeof(int)));
+        if (!res->cand.empty()) CK(cudaMemcpyAsync(ctx->d_fetch_cand, res->cand.data(), res->cand.size() * sizeof(int), cudaMemcpyHostToDevice, cs));
+        expand_masks_kernel<<<blocks_for(n, 256), 256, 0, cs>>>(res->d_masks + offset, n, ctx->d_fetch_cand, res->c, res->mask_words, ctx->d_fetch_wide);
+        CK(cudaMemcpyAsync(masks, ctx->d_fetch_wide, need, cudaMemcpyDeviceToHost, cs));
     }
+    if (scores) CK(cudaMemcpyAsync(scores, res->d_vals + offset, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CK(cudaStreamSynchronize(cs));
+    CK(cudaGetLastError());
     return URLGPU_OK;
 }
 
 extern "C" int urlgpu_result_free(urlgpu_result *res) {
     if (!res) return URLGPU_OK;
-    static const bool dbg = getenv("URLGPU_DEBUG_TIMING") != nullptr;
-    const auto T0 = std::chrono::steady_clock::now();
-    cudaSetDevice(res->ctx->device);
-    if (res->d_table) pool_free(res->ctx, res->d_table); // stream-ordered reuse: no sync needed
-    if (dbg) fprintf(stderr, "[urlgpu result_free] %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
+    urlgpu_ctx *ctx = res->ctx;
+    cudaSetDevice(ctx->device);
+    // stream-ordered reuse: the pool hands these blocks to later work on the same stream, no sync needed
+    if (res->d_table) pool_free(ctx, res->d_table);
+    if (res->d_masks) pool_free(ctx, res->d_masks);
+    if (res->d_vals) pool_free(ctx, res->d_vals);
+    if (res->d_segcnt) pool_free(ctx, res->d_segcnt);
+    if (res->d_counts) pool_free(ctx, res->d_counts);
+    if (res->h_counts) {
+        if (res->ready) cudaEventSynchronize(res->ready); // the pinned block must not be recycled while its copy is in flight
+        ctx->free_pinned.push_back(res->h_counts);
+    }
+    if (res->ready) ctx->free_events.push_back(res->ready);
     delete res;
     return URLGPU_OK;
 }
@@ -1761,6 +1908,7 @@ extern "C" int urlgpu_prune(urlgpu_ctx *ctx, const uint64_t *masks, const float 
     CK(cudaMemcpyAsync(dm.p, cm.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(dv.p, scores, n * sizeof(float), cudaMemcpyHostToDevice, s));
     extern __global__ void urlgpu_scatter_kernel(float *, const uint32_t *, const float *, uint64_t);
+    extern __global__ void gather_scores_kernel(const float *, const uint32_t *, uint64_t, float *);
     urlgpu_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(tab.as<float>(), dm.as<uint32_t>(), dv.as<float>(), n);
     int rc = run_prune(ctx, tab.as<float>(), c, K);
     if (rc) return rc;
@@ -1775,6 +1923,11 @@ extern "C" int urlgpu_prune(urlgpu_ctx *ctx, const uint64_t *masks, const float 
         keep[i] = bits != kSentinelBits;
     }
     return URLGPU_OK;
+}
+
+__global__ void gather_scores_kernel(const float *__restrict__ table, const uint32_t *__restrict__ masks, uint64_t n, float *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = table[masks[i]];
 }
 
 __global__ void urlgpu_scatter_kernel(float *table, const uint32_t *masks, const float *vals, uint64_t n) {

@@ -9,12 +9,15 @@ import numpy as np
 
 
 def discrete_bn(p: int = 60, n: int = 1_000_000, seed: int = 4, window: int = 4, max_indegree: int = 3,
-                arities=(2, 3, 4), alpha: float = 0.5):
+                arities=(2, 3, 4), alpha: float = 0.5, sample_seed: int | None = None):
     """Config 4: discrete Bayesian network, forward sampled.
 
     Variable i draws up to ``max_indegree`` parents from the ``window`` preceding variables, so the undirected
     generating graph (the skeleton handed to ``score -k``, standing in for MMPC) has degree <= 2*window and the
     2-hop neighbourhood of any variable lies inside [i-2*window, i+2*window].  CPT rows ~ Dirichlet(alpha).
+
+    ``sample_seed``: draw the CPTs and the rows from an independent generator, keeping the arities and the DAG of
+    ``seed`` (replicas of one network structure with their own data: the blocks of bench.py's weak-scaling data set).
 
     Returns (codes uint8 [p, n], card int32 [p], edges list[int] skeleton masks, parents list[list[int]]).
     """
@@ -26,6 +29,8 @@ def discrete_bn(p: int = 60, n: int = 1_000_000, seed: int = 4, window: int = 4,
         cands = np.arange(lo, i)
         k = min(max_indegree, len(cands))
         parents.append(sorted(rng.choice(cands, size=k, replace=False).tolist()) if k else [])
+    if sample_seed is not None:
+        rng = np.random.default_rng(sample_seed)
     codes = np.zeros((p, n), dtype=np.uint8)
     for i in range(p):
         pa = parents[i]

@@ -110,11 +110,29 @@ public:
     // score_calculator.cpp:33-135: every subset of neighbors\{variable} with <= maxParents members, stored under
     // the reference's rule; with prune, score_calculator.cpp:150-197 applied on the device as well.
     void calculateScores(int variable, FloatMap &cache, const varset &neighbors) {
+        Pending pd = beginScores(variable, neighbors);
+        finishScores(pd, cache);
+    }
+
+    // The same call split in two so a driver can keep the GPU busy: beginScores enqueues the scoring kernels and the
+    // on-device compaction of the cache (no host synchronisation); finishScores waits for that variable only and
+    // copies its cache out.  scoringThread calls beginScores(v+1) before finishScores(v).
+    struct Pending { urlgpu_result *res = nullptr; int variable = -1; };
+    Pending beginScores(int variable, const varset &neighbors) {
         urlgpu_ctx *ctx = scoringFunction->context();
-        urlgpu_result *res = nullptr;
+        Pending pd;
+        pd.variable = variable;
         unsigned flags = pruneFlag ? URLGPU_PRUNE_DOMINATED : URLGPU_KEEP_ALL;
         check(ctx, urlgpu_score_variable(ctx, variable, neighbors.w, urlhost::kVarsetWords, maxParents, scoringFunction->scoreType(),
-                                         scoringFunction->getLambda(), flags, &res));
+                                         scoringFunction->getLambda(), flags, &pd.res));
+        int rc = urlgpu_result_prefetch(pd.res);
+        if (rc != URLGPU_OK) { urlgpu_result_free(pd.res); check(ctx, rc); }
+        return pd;
+    }
+    void finishScores(Pending &pd, FloatMap &cache) {
+        urlgpu_ctx *ctx = scoringFunction->context();
+        urlgpu_result *res = pd.res;
+        pd.res = nullptr;
         uint64_t n = 0;
         int rc = urlgpu_result_count(res, &n);
         if (rc == URLGPU_OK) {

@@ -155,15 +155,20 @@ int main(int argc, char **argv) {
                 if (sf == "bic") scoringFunction.reset(new scoring::GpuBICScoringFunction(gpu, network, recordFile.size()));
                 else scoringFunction.reset(new scoring::GpuBICOLSFunction(gpu, recordFile, o.lambda));
                 scoring::ScoreCalculator scoreCalculator(scoringFunction.get(), maxParents, p, o.prune);
-                for (int variable = 0; variable < p; variable++) {
-                    if (variable % o.threadCount != thread) continue; // :137
-                    scoring::FloatMap sc;
-                    // also include neighbors' neighbors (:145-153)
-                    Varset orig = skeleton.get_neighbors(variable), nb = orig;
+                // two-hop candidate mask (:145-153)
+                auto neighbors_of = [&](int variable, Varset &orig) {
+                    orig = skeleton.get_neighbors(variable);
+                    Varset nb = orig;
                     for (int j = 0; j < p; j++)
                         if (orig.get(j) && j != variable) nb = nb | skeleton.get_neighbors(j);
-                    scoreCalculator.calculateScores(variable, sc, nb);
+                    return nb;
+                };
+                auto emit = [&](scoring::ScoreCalculator::Pending &pd) { // the variable's .pss block (:173-203)
+                    const int variable = pd.variable;
+                    scoring::FloatMap sc;
+                    scoreCalculator.finishScores(pd, sc);
                     scored[variable] = scoreCalculator.lastScored;
+                    Varset orig, nb = neighbors_of(variable, orig);
                     if (!o.quiet)
                         printf("Thread: %d, Variable: %d, Size %s pruning: %d, neighbor cardinality %d/%d\n", thread, variable,
                                o.prune ? "after" : "before", (int)sc.size(), orig.cardinality(), nb.cardinality());
@@ -179,7 +184,17 @@ int main(int argc, char **argv) {
                         out += "\n";
                     }
                     out += "\n";
+                };
+                // software pipeline of depth one: variable v+1 is enqueued before v's cache is read back
+                scoring::ScoreCalculator::Pending prev;
+                for (int variable = 0; variable < p; variable++) {
+                    if (variable % o.threadCount != thread) continue; // :137
+                    Varset orig;
+                    scoring::ScoreCalculator::Pending cur = scoreCalculator.beginScores(variable, neighbors_of(variable, orig));
+                    if (prev.res) emit(prev);
+                    prev = cur;
                 }
+                if (prev.res) emit(prev);
             } catch (const std::exception &e) { errors[thread] = e.what(); }
         };
         const auto t1 = std::chrono::steady_clock::now();
