@@ -56,6 +56,13 @@ def load_traffic(kind):
     return None
 
 
+def traffic_fields(kind):
+    t = load_traffic(kind)
+    if not t:
+        return {"traffic": None}
+    return {"traffic": t["dram_bytes_per_launch"], "traffic_detail": {k: t[k] for k in ("kernel", "grid", "launch_us_under_ncu", "dram_gbps_under_ncu", "report")}}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -333,7 +340,7 @@ def run_gpu(args):
             roofline = {"bound": "hbm", "kernel": "K1 = bic_slice_count_kernel (root tables from the rows) + cube_derive_kernel (every other table by "
                                                   "marginalisation, scored in the same pass)",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                        "traffic": load_traffic("bic"), "peak_source": peak_src,
+                        **traffic_fields("bic"), "peak_source": peak_src,
                         "algorithmic_bytes_per_step": st["algorithmic_bytes"] / args.steps, "kernel_ms_per_step": k1_ms / args.steps,
                         "launches_per_step": k1_launches / args.steps, "share_of_step": k1_ms / ms,
                         "issued_bytes_per_step": issued,
@@ -346,7 +353,7 @@ def run_gpu(args):
             k3_ms = st["ms_cbic"]
             achieved = st["algorithmic_flops"] / (k3_ms / 1e3) / 1e12 if k3_ms > 0 else None
             roofline = {"bound": "fp64", "kernel": "K3 cbic sweep DFS", "achieved": achieved, "peak": 37.0, "unit": "TFLOP/s",
-                        "frac": achieved / 37.0 if achieved else None, "traffic": load_traffic("cbic"),
+                        "frac": achieved / 37.0 if achieved else None, **traffic_fields("cbic"),
                         "peak_source": "nominal B200 FP64 (no measured FP64 entry in MEASURED_PEAKS.json)",
                         "algorithmic_flops_per_step": st["algorithmic_flops"] / args.steps, "kernel_ms_per_step": k3_ms / args.steps,
                         "share_of_step": k3_ms / ms, "family_ms": fam}
