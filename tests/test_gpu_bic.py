@@ -107,6 +107,30 @@ def test_tree_path_slicing_variants(pkg, orc, budget, run, unit):
     eng.close()
 
 
+@pytest.mark.parametrize("fuse,budget", [("1", 22528), ("1", 2048), ("0", 22528), ("1", 40000)])
+def test_cube_roots_counted_in_slices_and_fused(pkg, orc, fuse, budget):
+    """the cube path's big roots: counted in shared-memory slices of the packed rows; ancestor-only roots (layer K+1) hand
+    their children straight to the next layer (fused) or, with URLGPU_FUSE_ROOTS=0 / a run that does not fit the slice
+    budget, are written out and marginalised through HBM.  All variants bit-exact against the oracle."""
+    keys = {"URLGPU_BIC_MODE": "cube", "URLGPU_FUSE_ROOTS": fuse, "URLGPU_ROOT_BUDGET": str(budget)}
+    old = {k: os.environ.get(k) for k in keys}
+    os.environ.update(keys)
+    try:
+        eng = pkg.Engine(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=14, n=70003, seed=31, arities=(2, 3, 4), window=6, max_indegree=3)
+    eng.set_discrete(codes, card)
+    for v, K in ((2, 9), (11, 8), (5, 10)):
+        _check_variable(pkg, orc, eng, codes, card, None, v, K)
+    _check_variable(pkg, orc, eng, codes, card, None, 7, 9, flags=pkg.PRUNE_DOMINATED)
+    eng.close()
+
+
 def test_skeleton_two_hop_and_prune(pkg, orc, bic_engine):
     engine = bic_engine
     codes, card, edges, _ = pkg.datagen.discrete_bn(p=24, n=30000, seed=7, window=3, max_indegree=2)

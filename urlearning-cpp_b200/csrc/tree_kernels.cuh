@@ -36,6 +36,7 @@
 namespace urlgpu {
 
 constexpr int kTreeMaxRun = 8;          // t <= 8: at most 256 tables per subtree
+constexpr int kPreMax = 16;             // prefix products of the lowest digits kept in TreeVar (run of the cube path's fused roots)
 constexpr int kTreeWarps = 8;
 constexpr int kTreeThreads = kTreeWarps * 32;
 constexpr int kTreeMaxZone = 20;        // bucketed top digits
@@ -46,8 +47,8 @@ struct TreeVar {                        // per-variable constants (kernel argume
     int w;                              // bits per packed field (2, 4 or 8); field f sits at bit f*w
     uint32_t P_dmax;                    // number of buckets = joint arity of the top dmax digits
     uint16_t card[kMaxDenseCand];       // cube order
-    uint32_t pre[kTreeMaxRun + 1];      // pre[b] = prod_{i<b} card[i]
-    uint32_t magic[kTreeMaxRun + 1];    // floor((2^32-1) / pre[b]) for fast_div
+    uint32_t pre[kPreMax + 1];          // pre[b] = prod_{i<b} card[i] (saturating at 2^31)
+    uint32_t magic[kPreMax + 1];        // floor((2^32-1) / pre[b]) for fast_div
     const unsigned long long *rows;     // [n] packed rows, bucketed
     const uint32_t *prefix_off;         // [P_dmax + 1] first row of every bucket
     const uint16_t *cfg_tab;            // [(t+1) << t]: cfg_tab[(z << t) + D] = pre[z] / prod_{i in D} card[i], D subset of {0..z-1}
@@ -157,13 +158,13 @@ __device__ __forceinline__ long long warp_sum_ll_redux(long long v) {
 // concatenated range (segbeg/segoff in shared memory): a warp takes 128 consecutive positions per step, lane l the
 // positions l, l+32, l+64, l+96, so every load is coalesced inside a segment and four loads are in flight per lane.
 // NG = number of bytes of the packed word that hold an in-slice field (compile time: the look-ups unroll).
-template <int NG>
+template <int NG, int NW = kTreeWarps>
 __device__ __forceinline__ void tree_count(const unsigned long long *__restrict__ rows, const uint32_t *segbeg, const uint32_t *segoff, uint32_t nseg,
                                            uint32_t total, int *tab, const uint16_t *lut, const uint8_t *glist, int warp, int lane) {
     uint32_t gsh[NG];
 #pragma unroll
     for (int i = 0; i < NG; i++) gsh[i] = 8u * glist[i];
-    for (uint32_t base = (uint32_t)warp * 128u; base < total; base += kTreeWarps * 128u) {
+    for (uint32_t base = (uint32_t)warp * 128u; base < total; base += NW * 128u) {
         const uint32_t p0 = base + lane;
         uint32_t seg = 0;
         if (nseg > 1 && p0 < total) { // last segment with segoff[seg] <= p0
@@ -198,17 +199,17 @@ __device__ __forceinline__ void tree_count(const unsigned long long *__restrict_
 
 // slices with more segments than the shared-memory segment tables hold (a root whose present digits all sit below many
 // absent ones): warp `warp` owns segments warp, warp + W, ... and fetches the bounds of 32 of them at once
-template <int NG, typename BoundsFn>
+template <int NG, typename BoundsFn, int NW = kTreeWarps>
 __device__ __forceinline__ void tree_count_fragmented(const unsigned long long *__restrict__ rows, BoundsFn seg_bounds, uint32_t nseg, int *tab,
                                                       const uint16_t *lut, const uint8_t *glist, int warp, int lane) {
     uint32_t gsh[NG];
 #pragma unroll
     for (int i = 0; i < NG; i++) gsh[i] = 8u * glist[i];
-    for (uint32_t j0 = 0; warp + kTreeWarps * j0 < nseg; j0 += 32) {
-        const uint32_t seg = warp + kTreeWarps * (j0 + lane);
+    for (uint32_t j0 = 0; warp + NW * j0 < nseg; j0 += 32) {
+        const uint32_t seg = warp + NW * (j0 + lane);
         uint32_t r0 = 0, r1 = 0;
         if (seg < nseg) seg_bounds(seg, r0, r1);
-        const uint32_t left = (nseg - warp - kTreeWarps * j0 + kTreeWarps - 1) / kTreeWarps;
+        const uint32_t left = (nseg - warp - NW * j0 + NW - 1) / NW;
         const int cnt = (int)min(32u, left);
         for (int k = 0; k < cnt; k++) {
             const uint32_t b0 = __shfl_sync(0xffffffffu, r0, k), b1 = __shfl_sync(0xffffffffu, r1, k);
@@ -402,6 +403,191 @@ __global__ void tree_finalize_kernel(BicData d, CandInfo ci_res, const TreeRoot 
         if ((rm >> b) & 1) pen = __fmul_rn(pen, (float)ci_res.card[b]);
     scores[rm] = bic_finalize(acc[i], pen, d.base);
     if (ll_fixed) ll_fixed[rm] = acc[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Roots of the CUBE path (bic_kernels.cuh) counted with the same machinery: one CTA per (root, slice) histograms the
+// slice in shared memory from the bucketed packed rows, then
+//   * plain root (nchild == 0): the slice is written to its place in the root's dense global table;
+//   * fused root (nchild == z > 0): the root is only an ancestor (layer K+1), so its table is never written.  The
+//     CTA sums each run digit b < z out of the slice (a block-wide pass: the slice holds the whole run), scores
+//     child b = root \ {b} on the fly and writes the child's slice to ITS global table unless b == 0 (nothing is
+//     derived from a set that lacks bit 0).  This removes the write and the z reads of the largest layer of tables.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kRootWarps = 16;
+constexpr int kRootThreads = kRootWarps * 32;
+constexpr int kRootMaxChild = 16;
+
+struct CubeRoot {
+    TreeRoot t;                              // slicing description; t.z = fused run (0 for a plain root), t.acc_off unused
+    unsigned long long table_off;            // plain: the root's table in `tables` (int32 elements)
+    unsigned long long child_off[kRootMaxChild];   // fused: child b's table in `child_tables`
+    uint32_t child_acc[kRootMaxChild];       // and its accumulator
+    uint32_t nchild, pad;
+};
+
+__global__ void root_map_kernel(const CubeRoot *__restrict__ roots, int nroots, uint32_t total, uint32_t *__restrict__ cta_root) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int lo = 0, hi = nroots - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (roots[mid].t.chunk0 <= i) lo = mid; else hi = mid - 1;
+    }
+    cta_root[i] = (uint32_t)lo;
+}
+
+template <int RV>
+__global__ void __launch_bounds__(kRootThreads) bic_root_kernel(TreeVar tv, const CubeRoot *__restrict__ roots, const uint32_t *__restrict__ cta_root,
+                                                                const long long *__restrict__ qlog, int *__restrict__ tables, int *__restrict__ child_tables,
+                                                                long long *__restrict__ acc_out, uint32_t table_budget /*cells*/, uint32_t seg_cap) {
+    extern __shared__ __align__(16) int s_dyn[];              // [table_budget] slice table, then segbeg[seg_cap], segoff[seg_cap + 1]
+    __shared__ CubeRoot cr;
+    __shared__ uint16_t s_lut[8 * 256];
+    __shared__ long long s_red[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rv = RV > 0 ? RV : tv.rv;
+    {
+        const uint32_t ri = cta_root[blockIdx.x];
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(roots + ri);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&cr);
+        for (int i = tid; i < (int)(sizeof(CubeRoot) / 4); i += kRootThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const TreeRoot &rt = cr.t;
+    const int z = rt.z;
+    const uint32_t S0 = rt.H * (uint32_t)rv * tv.pre[z];
+    const uint32_t si = blockIdx.x - rt.chunk0;
+    {
+        int4 *t4 = reinterpret_cast<int4 *>(s_dyn);
+        for (uint32_t i = tid; i < (S0 + 3) / 4; i += kRootThreads) t4[i] = make_int4(0, 0, 0, 0);
+        const int w = tv.w, fpb = 8 / w;
+        const uint32_t fm = (1u << w) - 1u;
+        for (int e = tid; e < 8 * 256; e += kRootThreads) {
+            const int g = e >> 8;
+            if (!((rt.gmask >> g) & 1)) continue;
+            const uint32_t val = e & 255;
+            uint32_t sum = 0;
+            for (int k = 0; k < fpb; k++) sum += ((val >> (k * w)) & fm) * rt.fstride[g * fpb + k];
+            s_lut[e] = (uint16_t)sum;
+        }
+    }
+    // ---- count ----
+    {
+        uint32_t *s_segbeg = reinterpret_cast<uint32_t *>(s_dyn + table_budget);
+        uint32_t *s_segoff = s_segbeg + seg_cap;
+        const uint32_t nseg = rt.nseg;
+        uint32_t qb = 0;
+        {
+            uint32_t rem = si;
+            for (int a = 0; a < rt.npres; a++) { const uint32_t cb = rt.pres_card[a]; qb += (rem % cb) * rt.pres_weight[a]; rem /= cb; }
+        }
+        auto seg_bounds = [&](uint32_t seg, uint32_t &r0, uint32_t &r1) {
+            uint32_t q = qb, rs = seg;
+            for (int a = 0; a < rt.nabs; a++) { const uint32_t cb = rt.abs_card[a]; q += (rs % cb) * rt.abs_weight[a]; rs /= cb; }
+            r0 = __ldg(&tv.prefix_off[(size_t)q * rt.q_stride]);
+            r1 = __ldg(&tv.prefix_off[(size_t)(q + 1) * rt.q_stride]);
+        };
+        if (nseg <= seg_cap) {
+            for (uint32_t seg = tid; seg < nseg; seg += kRootThreads) {
+                uint32_t r0, r1;
+                seg_bounds(seg, r0, r1);
+                s_segbeg[seg] = r0;
+                s_segoff[seg] = r1 - r0;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t carry = 0;
+                for (uint32_t b0 = 0; b0 < nseg; b0 += 32) {
+                    const uint32_t i = b0 + lane;
+                    const uint32_t len = i < nseg ? s_segoff[i] : 0;
+                    uint32_t x = len;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                    if (i < nseg) s_segoff[i] = carry + x - len;
+                    carry += __shfl_sync(0xffffffffu, x, 31);
+                }
+                if (lane == 0) s_segoff[nseg] = carry;
+            }
+            __syncthreads();
+            const uint32_t total = s_segoff[nseg];
+            switch (rt.ng) {
+#define URLGPU_ROOT_COUNT(NG) case NG: tree_count<NG, kRootWarps>(tv.rows, s_segbeg, s_segoff, nseg, total, s_dyn, s_lut, rt.glist, warp, lane); break;
+                URLGPU_ROOT_COUNT(1) URLGPU_ROOT_COUNT(2) URLGPU_ROOT_COUNT(3) URLGPU_ROOT_COUNT(4)
+                URLGPU_ROOT_COUNT(5) URLGPU_ROOT_COUNT(6) URLGPU_ROOT_COUNT(7) URLGPU_ROOT_COUNT(8)
+#undef URLGPU_ROOT_COUNT
+            default: break;
+            }
+        } else {
+            __syncthreads(); // the look-up tables
+            switch (rt.ng) {
+#define URLGPU_ROOT_COUNT(NG) case NG: tree_count_fragmented<NG, decltype(seg_bounds), kRootWarps>(tv.rows, seg_bounds, nseg, s_dyn, s_lut, rt.glist, warp, lane); break;
+                URLGPU_ROOT_COUNT(1) URLGPU_ROOT_COUNT(2) URLGPU_ROOT_COUNT(3) URLGPU_ROOT_COUNT(4)
+                URLGPU_ROOT_COUNT(5) URLGPU_ROOT_COUNT(6) URLGPU_ROOT_COUNT(7) URLGPU_ROOT_COUNT(8)
+#undef URLGPU_ROOT_COUNT
+            default: break;
+            }
+        }
+    }
+    __syncthreads();
+    if (cr.nchild == 0) { // plain root: the slice goes to its place in the dense table (slicing digits are the most significant)
+        const unsigned long long off = cr.table_off + (unsigned long long)si * S0;
+        if ((S0 & 3u) == 0 && (off & 3ull) == 0) {
+            int4 *dst = reinterpret_cast<int4 *>(tables + off);
+            const int4 *src4 = reinterpret_cast<const int4 *>(s_dyn);
+            for (uint32_t i = tid; i < S0 / 4; i += kRootThreads) dst[i] = src4[i];
+        } else {
+            int *dst = tables + off;
+            for (uint32_t i = tid; i < S0; i += kRootThreads) dst[i] = s_dyn[i];
+        }
+        return;
+    }
+    // fused root: children b = 0 .. z-1
+    const uint32_t cfg_src = S0 / (uint32_t)rv;
+    for (int b = 0; b < z; b++) {
+        const uint32_t r = tv.card[b], pre = tv.pre[b], magic = tv.magic[b];
+        const uint32_t cfg_dst = cfg_src / r;
+        int *dst = child_tables + cr.child_off[b] + (unsigned long long)si * (S0 / r);
+        const bool store = b > 0;
+        long long acc = 0;
+        for (uint32_t j = tid; j < cfg_dst; j += kRootThreads) {
+            const uint32_t hi = fast_div(j, pre, magic), lo = j - hi * pre;
+            const uint32_t p0 = lo + hi * r * pre;
+            if constexpr (RV > 0) {
+                int cnt[RV];
+                load_cfg<RV>(s_dyn + (size_t)p0 * RV, cnt);
+                for (uint32_t a = 1; a < r; a++) {
+                    int t[RV];
+                    load_cfg<RV>(s_dyn + (size_t)(p0 + a * pre) * RV, t);
+#pragma unroll
+                    for (int k = 0; k < RV; k++) cnt[k] += t[k];
+                }
+                if (store) store_cfg<RV>(dst + (size_t)j * RV, cnt);
+                int nij = 0;
+#pragma unroll
+                for (int k = 0; k < RV; k++) nij += cnt[k];
+                if (nij > 1) {
+#pragma unroll
+                    for (int k = 0; k < RV; k++)
+                        if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
+                    acc -= __ldg(&qlog[nij]);
+                }
+            } else {
+                int nij = 0;
+                for (int k = 0; k < rv; k++) {
+                    int cnt = 0;
+                    for (uint32_t a = 0; a < r; a++) cnt += s_dyn[(size_t)(p0 + a * pre) * rv + k];
+                    if (store) dst[(size_t)j * rv + k] = cnt;
+                    nij += cnt;
+                    if (cnt > 1) acc += __ldg(&qlog[cnt]);
+                }
+                if (nij > 1) acc -= __ldg(&qlog[nij]);
+            }
+        }
+        acc = block_sum_ll(acc, s_red);
+        if (tid == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[cr.child_acc[b]]), (unsigned long long)acc);
+        __syncthreads(); // s_red is reused by the next child
+    }
 }
 
 } // namespace urlgpu

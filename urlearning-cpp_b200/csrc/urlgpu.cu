@@ -71,6 +71,8 @@ struct urlgpu_ctx {
     uint32_t *d_high_sorted = nullptr; int high_bits = -1; std::vector<int> high_off;   // segment DP lists (accept / prune)
     uint16_t *d_low_sorted = nullptr; int low_bits = -1; std::vector<int> low_off;
     bool use_slice_count = true; // cube path: count big roots in shared-memory slices (URLGPU_SLICE_COUNT=0 disables)
+    bool fuse_roots = true;      // cube path: ancestor-only roots hand their children straight to HBM (URLGPU_FUSE_ROOTS=0 disables)
+    uint32_t root_budget = 22 * 1024; // cells of a root slice (URLGPU_ROOT_BUDGET): 88 KB + segment tables, two 512-thread CTAs per SM
     // K1 strategy (URLGPU_BIC_MODE=cube|tree|direct): 2 = cube (default: roots counted in shared-memory slices, the rest
     // marginalised through HBM), 0 = tree (every table counted or marginalised in shared memory; measured 0.6-0.9x the cube
     // path on config 4, instruction bound — kept as an opt-in strategy), 1 = direct counting of every set
@@ -291,6 +293,15 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
     }
     ctx->stream = ctx->own_stream;
     if (const char *m = getenv("URLGPU_SLICE_COUNT")) ctx->use_slice_count = atoi(m) != 0;
+    if (const char *m = getenv("URLGPU_FUSE_ROOTS")) ctx->fuse_roots = atoi(m) != 0;
+    if (const char *m = getenv("URLGPU_ROOT_BUDGET")) ctx->root_budget = (uint32_t)std::max(1024, std::min(atoi(m), 48 * 1024)) / 4 * 4;
+    {
+        const int smem = (int)((ctx->root_budget + 2 * 2048 + 1) * sizeof(int));
+        cudaFuncSetAttribute(bic_root_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(bic_root_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(bic_root_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(bic_root_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
     if (const char *m = getenv("URLGPU_BIC_MODE"))
         ctx->bic_mode = strcmp(m, "direct") == 0 ? 1 : strcmp(m, "tree") == 0 ? 0 : 2;
     if (const char *m = getenv("URLGPU_TREE_BUDGET")) ctx->tree_budget = (uint32_t)std::max(1024, std::min(atoi(m), 26 * 1024)) / 4 * 4;
@@ -981,6 +992,8 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     };
 
     // ---- roots: counted from the rows ----
+    std::vector<char> fused_root(layers[Lstar].size(), 0); // root tables that never reach HBM: their children come out of the root kernel
+    bool fused_any = false;
     {
         auto &R = layers[Lstar];
         const bool score_roots = Lstar <= Kc;
@@ -1019,46 +1032,141 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             CK(cudaMemsetAsync(dacc_big.p, 0, big.size() * sizeof(long long), s));
             { int rc_ = h2d_async(ctx, dgsets.p, big.data(), big.size() * sizeof(GlobalSet)); if (rc_) return rc_; }
             const int threads = 256;
-            // (1) roots whose table can be cut along its top digits are counted in shared-memory slices of the
-            //     bucketed rows and written out once (bic_slice_count_kernel); (2) the rest use global RED atomics.
-            std::vector<SliceCountRoot> scr;
+            // (1) roots whose table can be cut along its top digits are counted in shared-memory slices of the bucketed
+            //     packed rows (bic_root_kernel, tree_kernels.cuh).  A root that is only an ancestor (layer K+1) and whose
+            //     run of low digits fits one slice is FUSED: its children are marginalised, scored and written by the
+            //     same CTA and the root table never reaches HBM.  (2) The rest use global RED atomics.
             std::vector<char> sliced(big.size(), 0);
-            uint64_t sc_chunk = 0;
-            const uint32_t sc_budget = 52 * 1024; // 208 KB of table per CTA, one 1024-thread CTA per SM
-            if (ctx->n >= 65536 && ctx->use_slice_count) {
+            std::vector<CubeRoot> croots;
+            DevBuf dkeys(ctx), dhist(ctx), doffp(ctx), dcursor(ctx), drows(ctx), dcroots(ctx), dmap(ctx), dtmp(ctx);
+            TreeVar tv{};
+            uint64_t rchunk = 0;
+            const uint32_t RB = ctx->root_budget, seg_cap = 2048;
+            bool packed_ok = ctx->n >= 65536 && ctx->use_slice_count;
+            if (packed_ok) {
+                uint64_t maxr = (uint64_t)rv;
+                for (int i = 0; i < c; i++) maxr = std::max(maxr, ccard[i]);
+                tv.c = c; tv.rv = rv; tv.max_parents = K; tv.t = 0;
+                tv.w = maxr <= 4 ? 2 : maxr <= 16 ? 4 : 8;
+                if ((c + 1) * tv.w > 64) packed_ok = false;
+                for (int i = 0; i < c; i++) tv.card[i] = (uint16_t)ccard[i];
+                tv.pre[0] = 1;
+                for (int b = 0; b < kPreMax; b++) tv.pre[b + 1] = (uint32_t)std::min<uint64_t>((uint64_t)tv.pre[b] * (b < c ? ccard[b] : 1), (uint64_t)1 << 31);
+                for (int b = 0; b <= kPreMax; b++) tv.magic[b] = tv.pre[b] > 1 ? 0xFFFFFFFFu / tv.pre[b] : 0;
+            }
+            if (packed_ok) {
                 int dmax = 0;
                 uint64_t Pd = 1;
-                while (dmax < c && dmax < kSliceMaxDepth && Pd * ccard[c - 1 - dmax] <= 65536) { Pd *= ccard[c - 1 - dmax]; dmax++; }
+                while (dmax < c && dmax < kTreeMaxZone && Pd * ccard[c - 1 - dmax] <= kTreeMaxBuckets) { Pd *= ccard[c - 1 - dmax]; dmax++; }
+                tv.dmax = dmax; tv.P_dmax = (uint32_t)Pd;
+                auto &Lc = layers[Lstar > 0 ? Lstar - 1 : 0];
                 for (size_t i = 0; i < big.size(); i++) {
                     const uint32_t P = big[i].mask;
-                    uint64_t slices = 1, depth_prod = 1;
-                    int depth = 0;
-                    bool reached = false;
-                    for (int b = c - 1; b >= 0 && depth < dmax; b--) {
-                        depth++;
-                        depth_prod *= ccard[b];
-                        if ((P >> b) & 1) { slices *= ccard[b]; if (big[i].cells / slices <= sc_budget) { reached = true; break; } }
+                    const int run = std::min(c, (int)__builtin_ctz(~P));
+                    CubeRoot cr{};
+                    TreeRoot &r = cr.t;
+                    // slicing along the top digits until the slice fits; `zf` low digits must stay inside the slice
+                    auto try_slice = [&](int zf) {
+                        uint64_t H = 1;
+                        for (int b = zf; b < c; b++) if ((P >> b) & 1) { H *= ccard[b]; if (H > ((uint64_t)1 << 40)) H = (uint64_t)1 << 40; }
+                        const uint64_t U0 = (uint64_t)rv * tv.pre[zf];
+                        if (U0 > RB) return false;
+                        int depth = 0;
+                        uint64_t nslices = 1, nseg = 1;
+                        while (U0 * H > RB) {
+                            const int b = c - 1 - depth;
+                            if (depth == dmax || b < zf) return false;
+                            depth++;
+                            if ((P >> b) & 1) { H /= ccard[b]; nslices *= ccard[b]; } else nseg *= ccard[b];
+                            if (nseg > ((uint64_t)1 << 22)) return false;
+                        }
+                        if (nslices > 0x3fffffffull) return false;
+                        r = TreeRoot{};
+                        r.mask = P; r.nslices = (uint32_t)nslices; r.H = (uint32_t)H; r.nseg = (uint32_t)nseg; r.z = (uint8_t)zf;
+                        r.size = (uint8_t)__builtin_popcount(P);
+                        r.fstride[0] = 1;
+                        for (int b = 0; b < zf; b++) r.fstride[b + 1] = (uint16_t)((uint32_t)rv * tv.pre[b]);
+                        uint32_t hs = (uint32_t)U0;
+                        for (int b = zf; b < c - depth; b++)
+                            if ((P >> b) & 1) { r.fstride[b + 1] = (uint16_t)hs; hs *= (uint32_t)ccard[b]; }
+                        for (int f = 0; f <= c; f++)
+                            if (r.fstride[f]) r.gmask |= (uint8_t)(1u << (f * tv.w / 8));
+                        for (int g = 0; g < 8; g++) if ((r.gmask >> g) & 1) r.glist[r.ng++] = (uint8_t)g;
+                        uint64_t w = 1;
+                        for (int b = c - depth; b < c; b++) {
+                            if ((P >> b) & 1) { r.pres_card[r.npres] = (uint16_t)ccard[b]; r.pres_weight[r.npres] = (uint32_t)w; r.npres++; }
+                            else { r.abs_card[r.nabs] = (uint16_t)ccard[b]; r.abs_weight[r.nabs] = (uint32_t)w; r.nabs++; }
+                            w *= ccard[b];
+                        }
+                        r.q_stride = (uint32_t)(Pd / w);
+                        return true;
+                    };
+                    bool fused = false;
+                    if (!score_roots && ctx->fuse_roots && Lstar >= 1 && run >= 1 && run <= kRootMaxChild && run <= kPreMax && try_slice(run)) {
+                        fused = true;
+                        cr.nchild = (uint32_t)run;
+                        for (int b = 0; b < run && fused; b++) {
+                            const uint32_t cm = P & ~(1u << b);
+                            auto it = std::lower_bound(Lc.begin(), Lc.end(), cm, [](const CubeSet &a, uint32_t m) { return a.cube_mask < m; });
+                            if (it == Lc.end() || it->cube_mask != cm) { fused = false; break; }
+                            cr.child_off[b] = it->off;
+                            cr.child_acc[b] = (uint32_t)(it - Lc.begin());
+                        }
                     }
-                    if (!reached || slices > 65535) continue;
-                    const uint64_t segs = depth_prod / slices;
-                    if (segs > (uint64_t)kSliceMaxSeg || (segs > 1 && n / depth_prod < 24)) continue;
-                    SliceCountRoot r{};
-                    r.mask = P; r.chunk0 = (uint32_t)sc_chunk; r.table_off = big[i].table_off; r.nslices = (uint16_t)slices; r.depth = (uint8_t)depth;
-                    sc_chunk += slices;
-                    scr.push_back(r);
+                    if (!fused) {
+                        cr = CubeRoot{};
+                        if (!try_slice(0)) continue; // cannot be cut to the budget: RED path below
+                        cr.table_off = big[i].table_off;
+                    }
+                    r.chunk0 = (uint32_t)rchunk;
+                    rchunk += r.nslices;
+                    croots.push_back(cr);
                     sliced[i] = 1;
+                    if (fused) fused_root[big_idx[i]] = 1;
                 }
-                if (sc_chunk < 128 || sc_chunk > 0x7fffffffull) { scr.clear(); std::fill(sliced.begin(), sliced.end(), 0); sc_chunk = 0; }
+                if (rchunk < 128 || rchunk > 0x7fffffffull) { // too few CTAs to fill the machine
+                    croots.clear(); std::fill(sliced.begin(), sliced.end(), 0); std::fill(fused_root.begin(), fused_root.end(), 0); rchunk = 0;
+                }
             }
-            DevBuf dscr(ctx);
-            SliceBuckets sb(ctx);
-            if (!scr.empty()) {
-                int rc2 = slice_prepare(ctx, bd, ci_cube, ccard, K, sb);
-                if (rc2) return rc2;
-                CK(dscr.alloc(scr.size() * sizeof(SliceCountRoot)));
-                { int rc_ = h2d_async(ctx, dscr.p, scr.data(), scr.size() * sizeof(SliceCountRoot)); if (rc_) return rc_; }
-                Region rg(ctx, F_COUNT, 1);
-                bic_slice_count_kernel<<<(unsigned)sc_chunk, kSliceCountThreads, (size_t)sc_budget * sizeof(int), s>>>(sb.sv, dscr.as<SliceCountRoot>(), (int)scr.size(), bufP);
+            if (!croots.empty()) {
+                bool any_fused = false;
+                for (auto &cr : croots) any_fused |= cr.nchild > 0;
+                if (any_fused) {
+                    fused_any = true;
+                    CK(cudaMemsetAsync(dacc.p, 0, layers[Lstar - 1].size() * sizeof(long long), s)); // the children's accumulators
+                }
+                const uint64_t Pd = tv.P_dmax;
+                CK(dkeys.alloc(n * sizeof(uint32_t)));
+                CK(dhist.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+                CK(doffp.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+                CK(dcursor.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
+                CK(drows.alloc(n * sizeof(unsigned long long)));
+                CK(dcroots.alloc(croots.size() * sizeof(CubeRoot)));
+                CK(dmap.alloc(rchunk * sizeof(uint32_t)));
+                size_t tmp_bytes = 0;
+                CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, dhist.as<uint32_t>(), doffp.as<uint32_t>(), (int)(Pd + 1), s));
+                CK(dtmp.alloc(tmp_bytes));
+                { int rc_ = h2d_async(ctx, dcroots.p, croots.data(), croots.size() * sizeof(CubeRoot)); if (rc_) return rc_; }
+                tv.rows = drows.as<unsigned long long>();
+                tv.prefix_off = doffp.as<uint32_t>();
+                tv.cfg_tab = nullptr;
+                Region rg(ctx, F_COUNT, 6);
+                CK(cudaMemsetAsync(dhist.p, 0, ((size_t)Pd + 1) * sizeof(uint32_t), s));
+                tree_key_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, tv.dmax, dkeys.as<uint32_t>(), dhist.as<uint32_t>());
+                CK(cub::DeviceScan::ExclusiveSum(dtmp.p, tmp_bytes, dhist.as<uint32_t>(), doffp.as<uint32_t>(), (int)(Pd + 1), s));
+                CK(cudaMemcpyAsync(dcursor.p, doffp.p, ((size_t)Pd + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+                tree_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, tv, dkeys.as<uint32_t>(), dcursor.as<uint32_t>(), drows.as<unsigned long long>());
+                root_map_kernel<<<blocks_for(rchunk, 256), 256, 0, s>>>(dcroots.as<CubeRoot>(), (int)croots.size(), (uint32_t)rchunk, dmap.as<uint32_t>());
+                const size_t smem = ((size_t)RB + 2 * seg_cap + 1) * sizeof(int);
+                const unsigned grid = (unsigned)rchunk;
+                switch (rv) {
+#define URLGPU_ROOT(RVV) bic_root_kernel<RVV><<<grid, kRootThreads, smem, s>>>(tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, bufP, bufC, dacc.as<long long>(), RB, seg_cap)
+                case 2: URLGPU_ROOT(2); break;
+                case 3: URLGPU_ROOT(3); break;
+                case 4: URLGPU_ROOT(4); break;
+                default: URLGPU_ROOT(0); break;
+#undef URLGPU_ROOT
+                }
             }
             size_t i0 = 0;
             while (i0 < big.size()) { // RED batches whose tables stay L2 resident; sliced roots only need scoring
@@ -1112,14 +1220,17 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         auto &L = layers[l];
         auto &P = layers[l + 1];
         if (L.empty()) break; // sub-forest mode: runs shorter than the layer count leave the lower layers empty
-        std::vector<uint32_t> first(P.size() + 1, 0), order(L.size());
-        for (auto &cs : L) first[cs.parent + 1]++;
+        const bool top = l == Lstar - 1 && fused_any; // children of fused roots were produced by the root kernel
+        std::vector<uint32_t> first(P.size() + 1, 0), order;
+        auto skip = [&](const CubeSet &cs) { return top && fused_root[cs.parent]; };
+        for (auto &cs : L) if (!skip(cs)) first[cs.parent + 1]++;
         for (size_t i = 0; i < P.size(); i++) first[i + 1] += first[i];
+        order.resize(first[P.size()]);
         {
             std::vector<uint32_t> pos(first.begin(), first.end() - 1);
-            for (size_t i = 0; i < L.size(); i++) order[pos[L[i].parent]++] = (uint32_t)i;
+            for (size_t i = 0; i < L.size(); i++) if (!skip(L[i])) order[pos[L[i].parent]++] = (uint32_t)i;
         }
-        hp.resize(L.size());
+        hp.resize(order.size());
         uint64_t chunk = 0;
         for (size_t k = 0; k < order.size(); k++) {
             const CubeSet &cs = L[order[k]];
@@ -1137,8 +1248,8 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         if (chunk > 0x7fffffffull) return ctx->fail(URLGPU_ERR_LIMIT, "cube: too many blocks in one layer");
         const bool score = l <= Kc;
         { int rc_ = h2d_async(ctx, dpairs.p, hp.data(), hp.size() * sizeof(CubePair)); if (rc_) return rc_; }
-        if (score) CK(cudaMemsetAsync(dacc.p, 0, L.size() * sizeof(long long), s));
-        {
+        if (score && !top) CK(cudaMemsetAsync(dacc.p, 0, L.size() * sizeof(long long), s));
+        if (chunk > 0) {
             Region rg(ctx, F_CUBE, 1);
             long long *accp = score ? dacc.as<long long>() : nullptr;
             const unsigned grid = (unsigned)chunk;
