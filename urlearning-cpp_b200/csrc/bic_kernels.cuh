@@ -318,30 +318,50 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
     const int *__restrict__ P = parent_tab + pr.parent_off;
     int *__restrict__ Cc = child_tab + pr.child_off;
     long long acc = 0;
-    for (uint32_t j = j0 + threadIdx.x; j < j1; j += kCubeThreads) {
-        const uint32_t hi = j / pr.Bc, lo = j - hi * pr.Bc;
-        const uint64_t pc0 = (uint64_t)lo + (uint64_t)hi * pr.r * pr.Bc;
-        if constexpr (RV > 0) {
-            int cnt[RV];
+    if constexpr (RV > 0) {
+        // two configurations per thread and iteration: 2*r independent 128-bit loads in flight before the first add
+        auto score_cfg = [&](const int (&cnt)[RV]) {
+            int nij = 0;
 #pragma unroll
-            for (int k = 0; k < RV; k++) cnt[k] = 0;
-            for (uint32_t a = 0; a < pr.r; a++) {
-                int t[RV];
-                load_cfg<RV>(P + (pc0 + (uint64_t)a * pr.Bc) * RV, t);
+            for (int k = 0; k < RV; k++) nij += cnt[k];
+            if (nij > 1) { // q[0] = q[1] = 0
 #pragma unroll
-                for (int k = 0; k < RV; k++) cnt[k] += t[k];
-            }
-            if (!pr.leaf) store_cfg<RV>(Cc + (uint64_t)j * RV, cnt);
-            if (acc_out) {
-                int nij = 0;
-#pragma unroll
-                for (int k = 0; k < RV; k++) {
-                    nij += cnt[k];
+                for (int k = 0; k < RV; k++)
                     if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
-                }
-                if (nij > 1) acc -= __ldg(&qlog[nij]);
+                acc -= __ldg(&qlog[nij]);
             }
-        } else {
+        };
+        for (uint32_t j = j0 + threadIdx.x; j < j1; j += 2 * kCubeThreads) {
+            const uint32_t jb = j + kCubeThreads;
+            const bool two = jb < j1;
+            const uint32_t hiA = j / pr.Bc, loA = j - hiA * pr.Bc;
+            const uint64_t pcA = (uint64_t)loA + (uint64_t)hiA * pr.r * pr.Bc;
+            const uint32_t jB = two ? jb : j;
+            const uint32_t hiB = jB / pr.Bc, loB = jB - hiB * pr.Bc;
+            const uint64_t pcB = (uint64_t)loB + (uint64_t)hiB * pr.r * pr.Bc;
+            int cntA[RV], cntB[RV];
+            load_cfg<RV>(P + pcA * RV, cntA);
+            load_cfg<RV>(P + pcB * RV, cntB);
+            for (uint32_t a = 1; a < pr.r; a++) {
+                int tA[RV], tB[RV];
+                load_cfg<RV>(P + (pcA + (uint64_t)a * pr.Bc) * RV, tA);
+                load_cfg<RV>(P + (pcB + (uint64_t)a * pr.Bc) * RV, tB);
+#pragma unroll
+                for (int k = 0; k < RV; k++) { cntA[k] += tA[k]; cntB[k] += tB[k]; }
+            }
+            if (!pr.leaf) {
+                store_cfg<RV>(Cc + (uint64_t)j * RV, cntA);
+                if (two) store_cfg<RV>(Cc + (uint64_t)jb * RV, cntB);
+            }
+            if (acc_out) {
+                score_cfg(cntA);
+                if (two) score_cfg(cntB);
+            }
+        }
+    } else {
+        for (uint32_t j = j0 + threadIdx.x; j < j1; j += kCubeThreads) {
+            const uint32_t hi = j / pr.Bc, lo = j - hi * pr.Bc;
+            const uint64_t pc0 = (uint64_t)lo + (uint64_t)hi * pr.r * pr.Bc;
             int nij = 0;
             for (int k = 0; k < rv; k++) {
                 int cnt = 0;

@@ -312,7 +312,6 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
     cudaFuncSetAttribute(bic_tree_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ctx->tree_budget * sizeof(int)));
     cudaFuncSetAttribute(bic_tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ctx->tree_budget * sizeof(int)));
     cudaFuncSetAttribute(bic_tree_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ctx->tree_budget * sizeof(int)));
-    cudaFuncSetAttribute(bic_slice_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024 * 4);
     *out = ctx;
     return URLGPU_OK;
 }
@@ -790,52 +789,6 @@ static int h2d_async(urlgpu_ctx *ctx, void *dst, const void *src, size_t bytes) 
     return URLGPU_OK;
 }
 
-// Bucketed copy of the (child + candidate) columns of one variable: rows grouped by the joint value of the top
-// `dmax` cube digits, plus the row offset of every prefix (slice_kernels.cuh).
-namespace {
-struct SliceBuckets {
-    DevBuf keys, hist, off, cursor, sorted;
-    SliceVar sv{};
-    bool ready = false;
-    explicit SliceBuckets(urlgpu_ctx *ctx) : keys(ctx), hist(ctx), off(ctx), cursor(ctx), sorted(ctx) {}
-};
-} // namespace
-
-static int slice_prepare(urlgpu_ctx *ctx, const BicData &bd, const CandInfo &ci_cube, const std::vector<uint64_t> &ccard, int K, SliceBuckets &sb) {
-    if (sb.ready) return URLGPU_OK;
-    cudaStream_t s = ctx->stream;
-    const int c = ci_cube.c;
-    const uint64_t n = (uint64_t)ctx->n;
-    int dmax = 0;
-    uint64_t Pd = 1;
-    while (dmax < c && dmax < kSliceMaxDepth && Pd * ccard[c - 1 - dmax] <= 65536) { Pd *= ccard[c - 1 - dmax]; dmax++; }
-    SliceVar &sv = sb.sv;
-    sv.c = c; sv.rv = ci_cube.rv; sv.max_parents = K; sv.dmax = dmax; sv.P_dmax = (uint32_t)Pd;
-    for (int i = 0; i < c; i++) sv.card[i] = (int)ccard[i];
-    CK(sb.off.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
-    if (dmax > 0) {
-        CK(sb.keys.alloc(n * sizeof(uint32_t)));
-        CK(sb.hist.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
-        CK(sb.cursor.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
-        CK(sb.sorted.alloc((size_t)(c + 1) * ctx->n_stride));
-        CK(cudaMemsetAsync(sb.hist.p, 0, ((size_t)Pd + 1) * sizeof(uint32_t), s));
-        Region rg(ctx, F_COUNT, 3);
-        slice_key_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, dmax, sb.keys.as<uint32_t>(), sb.hist.as<uint32_t>());
-        slice_scan_kernel<<<1, 1024, 0, s>>>(sb.hist.as<uint32_t>(), (uint32_t)Pd, sb.off.as<uint32_t>(), sb.cursor.as<uint32_t>());
-        slice_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, sb.keys.as<uint32_t>(), sb.cursor.as<uint32_t>(), sb.sorted.as<uint8_t>());
-        for (int i = 0; i <= c; i++) sv.cols[i] = sb.sorted.as<uint8_t>() + (size_t)i * ctx->n_stride;
-    } else {
-        const uint32_t h[2] = {0, (uint32_t)n};
-        CK(cudaMemcpyAsync(sb.off.p, h, sizeof h, cudaMemcpyHostToDevice, s));
-        CK(cudaStreamSynchronize(s));
-        sv.cols[0] = ctx->d_codes + (size_t)ci_cube.v * ctx->n_stride;
-        for (int i = 0; i < c; i++) sv.cols[i + 1] = ctx->d_codes + (size_t)ci_cube.var[i] * ctx->n_stride;
-    }
-    sv.prefix_off = sb.off.as<uint32_t>();
-    sb.ready = true;
-    return URLGPU_OK;
-}
-
 // `only_roots` (optional): restrict the work to the sub-forest below these root sets of layer `roots_layer`
 // (cube masks); the slice path hands over the roots it cannot slice.
 static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
@@ -1001,8 +954,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         std::vector<uint32_t> small_m; std::vector<uint64_t> small_off; std::vector<size_t> small_idx;
         std::vector<GlobalSet> big; std::vector<size_t> big_idx;
         for (size_t i = 0; i < R.size(); i++) {
-            ctx->st.k1_bytes_written += 4.0 * (double)R[i].cells;                                   // the root table
-            ctx->st.k1_bytes_read += (double)n * (double)(__builtin_popcount(R[i].cube_mask) + 1);  // its columns (L2 resident)
+            ctx->st.k1_bytes_read += 8.0 * (double)n;  // one packed row word per record and root (L2 resident)
             if (R[i].cells <= tier1_cells) { small_m.push_back(R[i].cube_mask); small_off.push_back(R[i].off); small_idx.push_back(i); }
             else { big.push_back(GlobalSet{R[i].cube_mask, (uint32_t)R[i].cells, R[i].off}); big_idx.push_back(i); }
         }
@@ -1123,6 +1075,9 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                     croots.push_back(cr);
                     sliced[i] = 1;
                     if (fused) fused_root[big_idx[i]] = 1;
+                    if (fused) { // only the children that have children of their own are stored
+                        for (int b = 1; b < run; b++) ctx->st.k1_bytes_written += 4.0 * (double)big[i].cells / (double)ccard[b];
+                    }
                 }
                 if (rchunk < 128 || rchunk > 0x7fffffffull) { // too few CTAs to fill the machine
                     croots.clear(); std::fill(sliced.begin(), sliced.end(), 0); std::fill(fused_root.begin(), fused_root.end(), 0); rchunk = 0;
@@ -1220,6 +1175,8 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         auto &L = layers[l];
         auto &P = layers[l + 1];
         if (L.empty()) break; // sub-forest mode: runs shorter than the layer count leave the lower layers empty
+        if (l == Lstar - 1)
+            for (size_t i = 0; i < P.size(); i++) if (!fused_root[i]) ctx->st.k1_bytes_written += 4.0 * (double)P[i].cells; // root tables that were written
         const bool top = l == Lstar - 1 && fused_any; // children of fused roots were produced by the root kernel
         std::vector<uint32_t> first(P.size() + 1, 0), order;
         auto skip = [&](const CubeSet &cs) { return top && fused_root[cs.parent]; };
