@@ -168,12 +168,17 @@ def run_gpu(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    eng = pkg.Engine(local)  # raises if the CUDA library or the device is missing: no fallback
-    # one non-default stream for everything that is timed (the legacy default stream would serialise with the engine's copy stream)
+    # T contexts (streams) on this GPU, one host thread each: the reference's `-t T` worker threads (score_main.cpp:372-380)
+    # pointed at one device.  Raises if the CUDA library or the device is missing: no fallback.
+    is_bic = args.workload == "bic"
+    T = max(1, args.threads_per_gpu) if is_bic else 1
+    pool = pkg.EnginePool(local, T)
+    eng = pool.engines[0]
+    # one non-default stream for the timing events and the L2 flush (the legacy default stream would serialise with the engines' streams)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    eng.set_stream(stream.cuda_stream)
-    is_bic = args.workload == "bic"
+    if T == 1:
+        eng.set_stream(stream.cuda_stream)
     weak = is_bic and args.scaling == "weak"
 
     # ---- inputs.  The exchange step of the path over NCCL/NVLink:
@@ -214,12 +219,13 @@ def run_gpu(args):
     pinned = None
     if is_bic:
         if dev is not None:
-            eng.set_discrete_device(dev.data_ptr(), wl["n"], wl["p"], wl["card"])
+            torch.cuda.synchronize()
+            pool.set_discrete_device(dev.data_ptr(), wl["n"], wl["p"], wl["card"])
             pinned = dev.cpu().pin_memory()
             del dev
         else:
             pinned = torch.from_numpy(wl["codes"]).pin_memory()
-            eng.set_discrete(pinned.numpy(), wl["card"])
+            pool.set_discrete(pinned.numpy(), wl["card"])
     else:
         if rank == 0:
             pinned = torch.from_numpy(wl["x"]).pin_memory()
@@ -234,31 +240,20 @@ def run_gpu(args):
 
     owner = owners_of(pkg, wl, world)
     mine = [v for v in range(wl["p"]) if owner[v] == rank]
-    if is_bic and os.environ.get("BENCH_ORDER") == "big_first":
-        mine.sort(key=lambda v: -sets_of(wl, v))
     sets_mine = sum(sets_of(wl, v) for v in mine)
+    items = [(v, wl["nbs"][v]) for v in mine]
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
+    costs = [D.family_cost(wl["card"], v, wl["nbs"][v], wl["K"]) for v in mine] if is_bic else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step(fetch=False):
-        """one pass of the hot path over this rank's variables.  fetch: read every surviving cache back to the host,
-        software-pipelined one variable deep (v+1 is enqueued before v is read)."""
+        """one pass of the hot path over this rank's variables (dealt to the pool's contexts by predicted cost).  fetch: read
+        every surviving cache back to the host, software-pipelined one variable deep (v+1 is enqueued before v is read).
+        Returns after every context has drained, so consecutive steps do not overlap."""
         flush.fill_(1)  # L2 flush between steps (inside the timed region: ~40 us of a step of hundreds of ms)
-        stored = 0
-        prev = None
-        for v in mine:
-            res = eng.score_variable(v, wl["nbs"][v], wl["K"], stype, lam=lam, flags=flags)
-            if fetch:
-                res.prefetch()
-                if prev is not None:
-                    stored += len(prev.fetch()[1])
-                    prev.free()
-                prev = res
-            else:
-                res.free()
-        if prev is not None:
-            stored += len(prev.fetch()[1])
-            prev.free()
-        return stored
+        stream.synchronize()
+        out = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch=fetch, costs=costs)
+        return sum(len(x[1]) for x in out.values()) if fetch else 0
 
     def barrier():
         if world > 1:
@@ -287,11 +282,19 @@ def run_gpu(args):
         step()
     sampler = ClockSampler(local)
     sampler.start()
+    pool.reset_stats()
+    ms, _ = timed(args.steps, step)
+    launches_total = pool.stats()["launches_total"]
+    # per-kernel device time for the roofline: one more pass of the same step on ONE context, so kernels run one at a time
+    # and the library's CUDA events (recorded on the launching stream around every kernel family) do not overlap
     eng.reset_stats()
     eng.enable_timing(True)
-    ms, _ = timed(args.steps, step)
+    flush.fill_(1)
+    stream.synchronize()
+    pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch=False, costs=costs, contexts=1)
     st = eng.stats()
     eng.enable_timing(False)
+    roof_steps = 1
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -310,15 +313,15 @@ def run_gpu(args):
 
         def e2e_step():
             if is_bic:
-                eng.set_discrete(host, wl["card"])
+                pool.set_discrete(host, wl["card"])  # every context uploads its own copy: T x the data set per step
             else:
-                eng.set_continuous(host)
+                pool.set_continuous(host)
             return step(fetch=True)
 
         e2e_step()
         nst = max(1, min(args.steps, 3))
         ems, stored = timed(nst, e2e_step)
-        h2d = (wl["n"] * wl["p"]) * (1 if is_bic else 8) * world
+        h2d = (wl["n"] * wl["p"]) * (1 if is_bic else 8) * world * T
         if world > 1:
             t = torch.tensor([stored], device="cuda", dtype=torch.int64)
             dist.all_reduce(t)
@@ -336,15 +339,17 @@ def run_gpu(args):
             k1_ms = st["ms_count"] + st["ms_cube"] + st["ms_tree"]
             k1_launches = st["launches_count"] + st["launches_cube"] + st["launches_tree"]
             achieved = st["algorithmic_bytes"] / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else None
-            issued = (st["k1_bytes_read"] + st["k1_bytes_written"]) / args.steps
+            issued = (st["k1_bytes_read"] + st["k1_bytes_written"]) / roof_steps
             roofline = {"bound": "hbm", "kernel": "K1 = bic_slice_count_kernel (root tables from the rows) + cube_derive_kernel (every other table by "
                                                   "marginalisation, scored in the same pass)",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                         **traffic_fields("bic"), "peak_source": peak_src,
-                        "algorithmic_bytes_per_step": st["algorithmic_bytes"] / args.steps, "kernel_ms_per_step": k1_ms / args.steps,
-                        "launches_per_step": k1_launches / args.steps, "share_of_step": k1_ms / ms,
+                        "algorithmic_bytes_per_step": st["algorithmic_bytes"] / roof_steps, "kernel_ms_per_step": k1_ms / roof_steps,
+                        "launches_per_step": k1_launches / roof_steps, "share_of_step": k1_ms / roof_steps / (ms / args.steps),
                         "issued_bytes_per_step": issued,
-                        "issued_frac_of_peak": issued / (k1_ms / args.steps / 1e3) / 1e9 / peak if k1_ms > 0 else None,
+                        "issued_frac_of_peak": issued / (k1_ms / roof_steps / 1e3) / 1e9 / peak if k1_ms > 0 else None,
+                        "timed_on": "one extra pass of the step on a single context (kernels serial); value/e2e use all contexts, "
+                                    "whose kernels overlap, so share_of_step is kernel time of the serial pass / step time of the concurrent one",
                         "note": "algorithmic bytes = sum over scored sets of n*(|S|+1) (SURVEY 8d); the kernels replace most row passes by "
                                 "marginalising tables, so frac > 1 is expected; issued_* = bytes the K1 kernels actually load/store "
                                 "(rank 0, counted by the host plan)",
@@ -355,8 +360,8 @@ def run_gpu(args):
             roofline = {"bound": "fp64", "kernel": "K3 cbic sweep DFS", "achieved": achieved, "peak": 37.0, "unit": "TFLOP/s",
                         "frac": achieved / 37.0 if achieved else None, **traffic_fields("cbic"),
                         "peak_source": "nominal B200 FP64 (no measured FP64 entry in MEASURED_PEAKS.json)",
-                        "algorithmic_flops_per_step": st["algorithmic_flops"] / args.steps, "kernel_ms_per_step": k3_ms / args.steps,
-                        "share_of_step": k3_ms / ms, "family_ms": fam}
+                        "algorithmic_flops_per_step": st["algorithmic_flops"] / roof_steps, "kernel_ms_per_step": k3_ms / roof_steps,
+                        "share_of_step": k3_ms / roof_steps / (ms / args.steps), "family_ms": fam}
         cpu = cpu_baseline(wl, args) if world == 1 and not args.no_cpu_baseline else None
         scaling = "weak" if weak else "strong"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -364,15 +369,16 @@ def run_gpu(args):
                 "dtype": "int32 counts / int64 fixed-point log-likelihood -> f32" if is_bic else "f64 -> f32",
                 "data": "synthetic (seeded numpy generator, urlearning-cpp_b200/datagen.py)",
                 "config": {"workload": wl["name"], "sets_per_step": total_sets,
-                           "parallelism": ("variables dealt to ranks by predicted cost (LPT)" if is_bic else "variables striped v % N") + f", N={world}",
+                           "parallelism": ("variables dealt to ranks by predicted cost (LPT)" if is_bic else "variables striped v % N") + f", N={world}; "
+                                          f"{T} context(s)/stream(s) per GPU, one host thread each (the reference's -t workers)",
                            "l2": "flushed between steps (256 MB write)", "dominant_family": dom},
-                "e2e": e2e, "gpu_launches": int(st["launches_total"]), "clocks": sampler.summary(), "roofline": roofline,
+                "e2e": e2e, "gpu_launches": int(launches_total), "clocks": sampler.summary(), "roofline": roofline,
                 "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
+    pool.close()
 
 
 
@@ -577,6 +583,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="urlgpu", choices=["urlgpu", "reference"])
     ap.add_argument("--workload", default="bic", choices=["bic", "cbic", "cbic5"])
+    ap.add_argument("--threads-per-gpu", type=int, default=4, help="BIC: contexts (streams) per GPU, one host thread each")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="BIC with N > 1 GPUs: weak = N replicas of the configs[3] network in one 60N-variable data set (per-GPU work "
                          "fixed); strong = configs[3] itself split over the ranks")

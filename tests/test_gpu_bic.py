@@ -198,6 +198,29 @@ def test_pipelined_prefetch_matches_plain_fetch(pkg, engine):
             assert pc == sorted(pc)  # canonical order: layer by layer
 
 
+def test_engine_pool_matches_single_engine(pkg, engine):
+    """three contexts on one device driven by three host threads (the reference's -t workers on one GPU): same caches"""
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=18, n=50021, seed=17, window=4, max_indegree=3)
+    nbs = [pkg.two_hop_neighbors(edges, 18, v) for v in range(18)]
+    engine.set_discrete(codes, card)
+    want = {}
+    for v in range(18):
+        r = engine.score_variable(v, nbs[v], 7, pkg.BIC, flags=pkg.PRUNE_DOMINATED)
+        want[v] = r.fetch()
+        r.free()
+    pool = pkg.EnginePool(0, 3)
+    pool.set_discrete(codes, card)
+    items = [(v, nbs[v]) for v in range(18)]
+    for costs in (None, [float(bin(nb).count("1")) for _, nb in items]):
+        got = pool.run(items, 7, pkg.BIC, flags=pkg.PRUNE_DOMINATED, fetch=True, costs=costs)
+        assert sorted(got) == list(range(18))
+        for v in range(18):
+            assert np.array_equal(got[v][0], want[v][0]) and np.array_equal(got[v][1].view(np.uint32), want[v][1].view(np.uint32))
+    scored = pool.run(items, 7, pkg.BIC, fetch=False)
+    assert all(scored[v] > 0 for v in range(18))
+    pool.close()
+
+
 def test_errors_are_loud(pkg, engine):
     with pytest.raises(pkg.UrlGpuError):
         engine.score_variable(99, 1, 1, pkg.BIC)

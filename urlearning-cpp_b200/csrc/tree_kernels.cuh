@@ -423,7 +423,8 @@ struct CubeRoot {
     unsigned long long table_off;            // plain: the root's table in `tables` (int32 elements)
     unsigned long long child_off[kRootMaxChild];   // fused: child b's table in `child_tables`
     uint32_t child_acc[kRootMaxChild];       // and its accumulator
-    uint32_t nchild, pad;
+    uint32_t nchild;                         // fused: children drop bit b, bfirst <= b < nchild (== run length)
+    uint16_t bfirst, score;                  // layers above K only hold sets with their lowest bits forced: the first droppable bit; score the children?
 };
 
 __global__ void root_map_kernel(const CubeRoot *__restrict__ roots, int nroots, uint32_t total, uint32_t *__restrict__ cta_root) {
@@ -544,7 +545,8 @@ __global__ void __launch_bounds__(kRootThreads) bic_root_kernel(TreeVar tv, cons
     }
     // fused root: children b = 0 .. z-1
     const uint32_t cfg_src = S0 / (uint32_t)rv;
-    for (int b = 0; b < z; b++) {
+    const bool score = cr.score != 0;
+    for (int b = cr.bfirst; b < z; b++) {
         const uint32_t r = tv.card[b], pre = tv.pre[b], magic = tv.magic[b];
         const uint32_t cfg_dst = cfg_src / r;
         int *dst = child_tables + cr.child_off[b] + (unsigned long long)si * (S0 / r);
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(kRootThreads) bic_root_kernel(TreeVar tv, cons
                 int nij = 0;
 #pragma unroll
                 for (int k = 0; k < RV; k++) nij += cnt[k];
-                if (nij > 1) {
+                if (score && nij > 1) {
 #pragma unroll
                     for (int k = 0; k < RV; k++)
                         if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
@@ -579,14 +581,16 @@ __global__ void __launch_bounds__(kRootThreads) bic_root_kernel(TreeVar tv, cons
                     for (uint32_t a = 0; a < r; a++) cnt += s_dyn[(size_t)(p0 + a * pre) * rv + k];
                     if (store) dst[(size_t)j * rv + k] = cnt;
                     nij += cnt;
-                    if (cnt > 1) acc += __ldg(&qlog[cnt]);
+                    if (score && cnt > 1) acc += __ldg(&qlog[cnt]);
                 }
-                if (nij > 1) acc -= __ldg(&qlog[nij]);
+                if (score && nij > 1) acc -= __ldg(&qlog[nij]);
             }
         }
-        acc = block_sum_ll(acc, s_red);
-        if (tid == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[cr.child_acc[b]]), (unsigned long long)acc);
-        __syncthreads(); // s_red is reused by the next child
+        if (score) {
+            acc = block_sum_ll(acc, s_red);
+            if (tid == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[cr.child_acc[b]]), (unsigned long long)acc);
+            __syncthreads(); // s_red is reused by the next child
+        }
     }
 }
 

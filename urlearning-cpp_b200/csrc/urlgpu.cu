@@ -902,11 +902,90 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         if (cost < best) { best = cost; Lstar = Ls; }
     }
     if (Lstar < 0) return URLGPU_OK; // does not fit: caller falls back to the direct path
+    // ---- which roots go through bic_root_kernel, and which of those are fused (decided before the offsets: a fused root's
+    // table is never materialised, so it takes no room in the layer buffer) ----
+    const bool score_roots = Lstar <= Kc;
+    TreeVar tv{};
+    const uint32_t RB = ctx->root_budget, seg_cap = 2048;
+    bool packed_ok = ctx->n >= 65536 && ctx->use_slice_count;
+    uint64_t Pd = 1;
+    int dmax = 0;
+    if (packed_ok) {
+        uint64_t maxr = (uint64_t)rv;
+        for (int i = 0; i < c; i++) maxr = std::max(maxr, ccard[i]);
+        tv.c = c; tv.rv = rv; tv.max_parents = K; tv.t = 0;
+        tv.w = maxr <= 4 ? 2 : maxr <= 16 ? 4 : 8;
+        if ((c + 1) * tv.w > 64) packed_ok = false;
+        for (int i = 0; i < c; i++) tv.card[i] = (uint16_t)ccard[i];
+        tv.pre[0] = 1;
+        for (int b = 0; b < kPreMax; b++) tv.pre[b + 1] = (uint32_t)std::min<uint64_t>((uint64_t)tv.pre[b] * (b < c ? ccard[b] : 1), (uint64_t)1 << 31);
+        for (int b = 0; b <= kPreMax; b++) tv.magic[b] = tv.pre[b] > 1 ? 0xFFFFFFFFu / tv.pre[b] : 0;
+        while (dmax < c && dmax < kTreeMaxZone && Pd * ccard[c - 1 - dmax] <= kTreeMaxBuckets) { Pd *= ccard[c - 1 - dmax]; dmax++; }
+        tv.dmax = dmax; tv.P_dmax = (uint32_t)Pd;
+    }
+    // slicing of root P along its top digits until the slice fits the budget; the `zf` lowest digits stay inside the slice
+    auto slice_root = [&](uint32_t P, int zf, TreeRoot &r) {
+        uint64_t H = 1;
+        for (int b = zf; b < c; b++) if ((P >> b) & 1) { H *= ccard[b]; if (H > ((uint64_t)1 << 40)) H = (uint64_t)1 << 40; }
+        const uint64_t U0 = (uint64_t)rv * tv.pre[zf];
+        if (U0 > RB) return false;
+        int depth = 0;
+        uint64_t nslices = 1, nseg = 1;
+        while (U0 * H > RB) {
+            const int b = c - 1 - depth;
+            if (depth == dmax || b < zf) return false;
+            depth++;
+            if ((P >> b) & 1) { H /= ccard[b]; nslices *= ccard[b]; } else nseg *= ccard[b];
+            if (nseg > ((uint64_t)1 << 22)) return false;
+        }
+        if (nslices > 0x3fffffffull) return false;
+        r = TreeRoot{};
+        r.mask = P; r.nslices = (uint32_t)nslices; r.H = (uint32_t)H; r.nseg = (uint32_t)nseg; r.z = (uint8_t)zf;
+        r.size = (uint8_t)__builtin_popcount(P);
+        r.fstride[0] = 1;
+        for (int b = 0; b < zf; b++) r.fstride[b + 1] = (uint16_t)((uint32_t)rv * tv.pre[b]);
+        uint32_t hs = (uint32_t)U0;
+        for (int b = zf; b < c - depth; b++)
+            if ((P >> b) & 1) { r.fstride[b + 1] = (uint16_t)hs; hs *= (uint32_t)ccard[b]; }
+        for (int f = 0; f <= c; f++)
+            if (r.fstride[f]) r.gmask |= (uint8_t)(1u << (f * tv.w / 8));
+        for (int g = 0; g < 8; g++) if ((r.gmask >> g) & 1) r.glist[r.ng++] = (uint8_t)g;
+        uint64_t w = 1;
+        for (int b = c - depth; b < c; b++) {
+            if ((P >> b) & 1) { r.pres_card[r.npres] = (uint16_t)ccard[b]; r.pres_weight[r.npres] = (uint32_t)w; r.npres++; }
+            else { r.abs_card[r.nabs] = (uint16_t)ccard[b]; r.abs_weight[r.nabs] = (uint32_t)w; r.nabs++; }
+            w *= ccard[b];
+        }
+        r.q_stride = (uint32_t)(Pd / w);
+        return true;
+    };
+    std::vector<char> root_kind(layers[Lstar].size(), 0); // 0: small table or RED path, 1: plain root of bic_root_kernel, 2: fused
+    if (packed_ok) {
+        uint64_t total_slices = 0;
+        auto &R = layers[Lstar];
+        for (size_t i = 0; i < R.size(); i++) {
+            if (R[i].cells <= tier1_cells) continue;
+            const uint32_t P = R[i].cube_mask;
+            const int run = std::min(c, (int)__builtin_ctz(~P));
+            TreeRoot r{};
+            // layers above Kc hold only sets with their lowest bits forced: the droppable bits of P start at bfirst
+            const int bfirst = std::max(0, Lstar - 1 - Kc);
+            if (!score_roots && ctx->fuse_roots && Lstar >= 1 && run > bfirst && run <= kRootMaxChild && run <= kPreMax && slice_root(P, run, r)) root_kind[i] = 2;
+            else if (slice_root(P, 0, r)) root_kind[i] = 1;
+            if (root_kind[i]) total_slices += r.nslices;
+        }
+        if (total_slices < 128 || total_slices > 0x7fffffffull) std::fill(root_kind.begin(), root_kind.end(), 0); // too few CTAs to fill the machine
+    }
     // ---- offsets and parent links ----
     size_t max_layer = 0;
     for (int l = 0; l <= Lstar; l++) {
         uint64_t off = 0;
-        for (auto &cs : layers[l]) { cs.off = off; off += (cs.cells + 3) / 4 * 4; }
+        for (size_t i = 0; i < layers[l].size(); i++) {
+            auto &cs = layers[l][i];
+            cs.off = off;
+            if (l == Lstar && root_kind[i] == 2) continue; // never materialised
+            off += (cs.cells + 3) / 4 * 4;
+        }
         max_layer = std::max<size_t>(max_layer, off);
         if (l < Lstar) {
             auto &P = layers[l + 1];
@@ -949,7 +1028,6 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     bool fused_any = false;
     {
         auto &R = layers[Lstar];
-        const bool score_roots = Lstar <= Kc;
         CK(cudaMemsetAsync(dacc.p, 0, R.size() * sizeof(long long), s));
         std::vector<uint32_t> small_m; std::vector<uint64_t> small_off; std::vector<size_t> small_idx;
         std::vector<GlobalSet> big; std::vector<size_t> big_idx;
@@ -991,96 +1069,34 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             std::vector<char> sliced(big.size(), 0);
             std::vector<CubeRoot> croots;
             DevBuf dkeys(ctx), dhist(ctx), doffp(ctx), dcursor(ctx), drows(ctx), dcroots(ctx), dmap(ctx), dtmp(ctx);
-            TreeVar tv{};
             uint64_t rchunk = 0;
-            const uint32_t RB = ctx->root_budget, seg_cap = 2048;
-            bool packed_ok = ctx->n >= 65536 && ctx->use_slice_count;
-            if (packed_ok) {
-                uint64_t maxr = (uint64_t)rv;
-                for (int i = 0; i < c; i++) maxr = std::max(maxr, ccard[i]);
-                tv.c = c; tv.rv = rv; tv.max_parents = K; tv.t = 0;
-                tv.w = maxr <= 4 ? 2 : maxr <= 16 ? 4 : 8;
-                if ((c + 1) * tv.w > 64) packed_ok = false;
-                for (int i = 0; i < c; i++) tv.card[i] = (uint16_t)ccard[i];
-                tv.pre[0] = 1;
-                for (int b = 0; b < kPreMax; b++) tv.pre[b + 1] = (uint32_t)std::min<uint64_t>((uint64_t)tv.pre[b] * (b < c ? ccard[b] : 1), (uint64_t)1 << 31);
-                for (int b = 0; b <= kPreMax; b++) tv.magic[b] = tv.pre[b] > 1 ? 0xFFFFFFFFu / tv.pre[b] : 0;
-            }
-            if (packed_ok) {
-                int dmax = 0;
-                uint64_t Pd = 1;
-                while (dmax < c && dmax < kTreeMaxZone && Pd * ccard[c - 1 - dmax] <= kTreeMaxBuckets) { Pd *= ccard[c - 1 - dmax]; dmax++; }
-                tv.dmax = dmax; tv.P_dmax = (uint32_t)Pd;
+            {
                 auto &Lc = layers[Lstar > 0 ? Lstar - 1 : 0];
                 for (size_t i = 0; i < big.size(); i++) {
+                    const int kind = root_kind[big_idx[i]];
+                    if (!kind) continue; // RED path below
                     const uint32_t P = big[i].mask;
                     const int run = std::min(c, (int)__builtin_ctz(~P));
                     CubeRoot cr{};
-                    TreeRoot &r = cr.t;
-                    // slicing along the top digits until the slice fits; `zf` low digits must stay inside the slice
-                    auto try_slice = [&](int zf) {
-                        uint64_t H = 1;
-                        for (int b = zf; b < c; b++) if ((P >> b) & 1) { H *= ccard[b]; if (H > ((uint64_t)1 << 40)) H = (uint64_t)1 << 40; }
-                        const uint64_t U0 = (uint64_t)rv * tv.pre[zf];
-                        if (U0 > RB) return false;
-                        int depth = 0;
-                        uint64_t nslices = 1, nseg = 1;
-                        while (U0 * H > RB) {
-                            const int b = c - 1 - depth;
-                            if (depth == dmax || b < zf) return false;
-                            depth++;
-                            if ((P >> b) & 1) { H /= ccard[b]; nslices *= ccard[b]; } else nseg *= ccard[b];
-                            if (nseg > ((uint64_t)1 << 22)) return false;
-                        }
-                        if (nslices > 0x3fffffffull) return false;
-                        r = TreeRoot{};
-                        r.mask = P; r.nslices = (uint32_t)nslices; r.H = (uint32_t)H; r.nseg = (uint32_t)nseg; r.z = (uint8_t)zf;
-                        r.size = (uint8_t)__builtin_popcount(P);
-                        r.fstride[0] = 1;
-                        for (int b = 0; b < zf; b++) r.fstride[b + 1] = (uint16_t)((uint32_t)rv * tv.pre[b]);
-                        uint32_t hs = (uint32_t)U0;
-                        for (int b = zf; b < c - depth; b++)
-                            if ((P >> b) & 1) { r.fstride[b + 1] = (uint16_t)hs; hs *= (uint32_t)ccard[b]; }
-                        for (int f = 0; f <= c; f++)
-                            if (r.fstride[f]) r.gmask |= (uint8_t)(1u << (f * tv.w / 8));
-                        for (int g = 0; g < 8; g++) if ((r.gmask >> g) & 1) r.glist[r.ng++] = (uint8_t)g;
-                        uint64_t w = 1;
-                        for (int b = c - depth; b < c; b++) {
-                            if ((P >> b) & 1) { r.pres_card[r.npres] = (uint16_t)ccard[b]; r.pres_weight[r.npres] = (uint32_t)w; r.npres++; }
-                            else { r.abs_card[r.nabs] = (uint16_t)ccard[b]; r.abs_weight[r.nabs] = (uint32_t)w; r.nabs++; }
-                            w *= ccard[b];
-                        }
-                        r.q_stride = (uint32_t)(Pd / w);
-                        return true;
-                    };
-                    bool fused = false;
-                    if (!score_roots && ctx->fuse_roots && Lstar >= 1 && run >= 1 && run <= kRootMaxChild && run <= kPreMax && try_slice(run)) {
-                        fused = true;
+                    if (!slice_root(P, kind == 2 ? run : 0, cr.t)) return ctx->fail(URLGPU_ERR_INTERNAL, "cube: root slicing is not reproducible");
+                    if (kind == 2) {
                         cr.nchild = (uint32_t)run;
-                        for (int b = 0; b < run && fused; b++) {
+                        cr.bfirst = (uint16_t)std::max(0, Lstar - 1 - Kc);
+                        cr.score = Lstar - 1 <= Kc ? 1 : 0;
+                        for (int b = cr.bfirst; b < run; b++) {
                             const uint32_t cm = P & ~(1u << b);
                             auto it = std::lower_bound(Lc.begin(), Lc.end(), cm, [](const CubeSet &a, uint32_t m) { return a.cube_mask < m; });
-                            if (it == Lc.end() || it->cube_mask != cm) { fused = false; break; }
+                            if (it == Lc.end() || it->cube_mask != cm) return ctx->fail(URLGPU_ERR_INTERNAL, "cube: child of a fused root missing");
                             cr.child_off[b] = it->off;
                             cr.child_acc[b] = (uint32_t)(it - Lc.begin());
+                            if (b > 0) ctx->st.k1_bytes_written += 4.0 * (double)it->cells; // only children that have children of their own are stored
                         }
-                    }
-                    if (!fused) {
-                        cr = CubeRoot{};
-                        if (!try_slice(0)) continue; // cannot be cut to the budget: RED path below
-                        cr.table_off = big[i].table_off;
-                    }
-                    r.chunk0 = (uint32_t)rchunk;
-                    rchunk += r.nslices;
+                        fused_root[big_idx[i]] = 1;
+                    } else cr.table_off = big[i].table_off;
+                    cr.t.chunk0 = (uint32_t)rchunk;
+                    rchunk += cr.t.nslices;
                     croots.push_back(cr);
                     sliced[i] = 1;
-                    if (fused) fused_root[big_idx[i]] = 1;
-                    if (fused) { // only the children that have children of their own are stored
-                        for (int b = 1; b < run; b++) ctx->st.k1_bytes_written += 4.0 * (double)big[i].cells / (double)ccard[b];
-                    }
-                }
-                if (rchunk < 128 || rchunk > 0x7fffffffull) { // too few CTAs to fill the machine
-                    croots.clear(); std::fill(sliced.begin(), sliced.end(), 0); std::fill(fused_root.begin(), fused_root.end(), 0); rchunk = 0;
                 }
             }
             if (!croots.empty()) {
@@ -1090,7 +1106,6 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                     fused_any = true;
                     CK(cudaMemsetAsync(dacc.p, 0, layers[Lstar - 1].size() * sizeof(long long), s)); // the children's accumulators
                 }
-                const uint64_t Pd = tv.P_dmax;
                 CK(dkeys.alloc(n * sizeof(uint32_t)));
                 CK(dhist.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
                 CK(doffp.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
