@@ -313,7 +313,7 @@ def run_gpu(args):
 
         def e2e_step():
             if is_bic:
-                pool.set_discrete(host, wl["card"])  # every context uploads its own copy: T x the data set per step
+                pool.set_discrete(host, wl["card"])  # one upload per GPU; the pool's other contexts borrow the device copy
             else:
                 pool.set_continuous(host)
             return step(fetch=True)
@@ -321,7 +321,7 @@ def run_gpu(args):
         e2e_step()
         nst = max(1, min(args.steps, 3))
         ems, stored = timed(nst, e2e_step)
-        h2d = (wl["n"] * wl["p"]) * (1 if is_bic else 8) * world * T
+        h2d = (wl["n"] * wl["p"]) * (1 if is_bic else 8) * world
         if world > 1:
             t = torch.tensor([stored], device="cuda", dtype=torch.int64)
             dist.all_reduce(t)

@@ -68,6 +68,9 @@ int urlgpu_synchronize(urlgpu_ctx *ctx);
 int urlgpu_set_discrete(urlgpu_ctx *ctx, const uint8_t *codes_colmajor, int64_t n, int p, const int32_t *cardinality);
 /* same, but codes_colmajor is a DEVICE pointer on ctx's device (multi-GPU: data arrives by NCCL broadcast) */
 int urlgpu_set_discrete_device(urlgpu_ctx *ctx, const uint8_t *d_codes_colmajor, int64_t n, int p, const int32_t *cardinality);
+/* Several contexts on ONE device (one per host thread, the reference's -t workers) can score from a single device copy:
+ * ctx borrows owner's data set (no copy).  The owner must keep it installed while borrowers score. */
+int urlgpu_share_discrete(urlgpu_ctx *ctx, urlgpu_ctx *owner);
 /* raw continuous data; the engine centres, scales by the sample std (N-1) and forms G = Z^T Z in FP64 */
 int urlgpu_set_continuous(urlgpu_ctx *ctx, const double *x_colmajor, int64_t n, int p);
 int urlgpu_set_continuous_device(urlgpu_ctx *ctx, const double *d_x_colmajor, int64_t n, int p);

@@ -28,7 +28,7 @@ KEEP_ALL, PRUNE_DOMINATED, CBIC_NO_ACCEPT = 0, 2, 4
 # every symbol include/urlgpu.h declares (tests check the built library exports all of them)
 ABI_SYMBOLS = [
     "urlgpu_create", "urlgpu_destroy", "urlgpu_last_error", "urlgpu_device_count", "urlgpu_set_stream",
-    "urlgpu_synchronize", "urlgpu_set_discrete", "urlgpu_set_discrete_device", "urlgpu_set_continuous",
+    "urlgpu_synchronize", "urlgpu_set_discrete", "urlgpu_set_discrete_device", "urlgpu_share_discrete", "urlgpu_set_continuous",
     "urlgpu_set_continuous_device", "urlgpu_shard_begin", "urlgpu_shard_moments", "urlgpu_shard_finish", "urlgpu_get_gram", "urlgpu_set_gram", "urlgpu_score_variable",
     "urlgpu_result_prefetch", "urlgpu_result_count", "urlgpu_result_scored", "urlgpu_result_fetch", "urlgpu_result_free",
     "urlgpu_score_one", "urlgpu_contingency", "urlgpu_prune", "urlgpu_stats_reset", "urlgpu_stats_get",
@@ -78,6 +78,7 @@ def load_library():
     lib.urlgpu_synchronize.argtypes = [vp]
     lib.urlgpu_set_discrete.argtypes = [vp, vp, i64, i32, vp]
     lib.urlgpu_set_discrete_device.argtypes = [vp, vp, i64, i32, vp]
+    lib.urlgpu_share_discrete.argtypes = [vp, vp]
     lib.urlgpu_set_continuous.argtypes = [vp, vp, i64, i32]
     lib.urlgpu_set_continuous_device.argtypes = [vp, vp, i64, i32]
     lib.urlgpu_shard_begin.argtypes = [vp, vp, i64, i32, i32]
@@ -228,6 +229,11 @@ class Engine:
         self._check(self.lib.urlgpu_set_discrete_device(self._h, C.c_void_p(dev_ptr), n, p, card.ctypes.data))
         self.p = p
 
+    def share_discrete(self, owner: "Engine"):
+        """score from `owner`'s device copy of the data set (same device, no copy)"""
+        self._check(self.lib.urlgpu_share_discrete(self._h, owner._h))
+        self.p = owner.p
+
     def set_continuous(self, x: np.ndarray):
         """x: float64 [p, n]."""
         x = np.ascontiguousarray(x, dtype=np.float64)
@@ -341,7 +347,7 @@ class EnginePool:
     the reference's `score` (score_main.cpp:132-139, 372-380) pointed at a single GPU.  Planning, enqueueing and
     reading back one variable overlap with the kernels of another, which closes the gaps a single in-order stream
     leaves between the many small kernels of small families (config 4: 451 -> 380 ms per pass with T = 3).
-    Every context holds its own copy of the data set; results are bit-identical to a single Engine's."""
+    The contexts share one device copy of the data set; results are bit-identical to a single Engine's."""
 
     def __init__(self, device: int = 0, threads: int = 2):
         self.engines = [Engine(device) for _ in range(max(1, threads))]
@@ -367,12 +373,15 @@ class EnginePool:
             raise errs[0]
 
     def set_discrete(self, codes, card):
-        card = list(card)
-        self._each(lambda e: e.set_discrete(codes, card))
+        """one upload; the other contexts borrow the first one's device copy"""
+        self.engines[0].set_discrete(codes, list(card))
+        for e in self.engines[1:]:
+            e.share_discrete(self.engines[0])
 
     def set_discrete_device(self, dev_ptr, n, p, card):
-        card = list(card)
-        self._each(lambda e: e.set_discrete_device(dev_ptr, n, p, card))
+        self.engines[0].set_discrete_device(dev_ptr, n, p, list(card))
+        for e in self.engines[1:]:
+            e.share_discrete(self.engines[0])
 
     def set_continuous(self, x):
         self.engines[0].set_continuous(x)
@@ -452,5 +461,5 @@ class EnginePool:
             e.enable_timing(on)
 
     def close(self):
-        for e in self.engines:
+        for e in reversed(self.engines):  # borrowers first
             e.close()

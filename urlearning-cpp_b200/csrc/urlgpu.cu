@@ -53,6 +53,7 @@ struct urlgpu_ctx {
     long long *d_qlog = nullptr;
     float base = 0.f;
     bool have_discrete = false;
+    bool borrowed_discrete = false; // d_codes/d_qlog belong to another context on the same device (urlgpu_share_discrete)
 
     // continuous data
     int64_t cn = 0;
@@ -317,9 +318,11 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
 }
 
 static void free_discrete(urlgpu_ctx *ctx) {
-    if (ctx->d_codes) cudaFree(ctx->d_codes);
-    if (ctx->d_qlog) cudaFree(ctx->d_qlog);
-    ctx->d_codes = nullptr; ctx->d_qlog = nullptr; ctx->have_discrete = false;
+    if (!ctx->borrowed_discrete) {
+        if (ctx->d_codes) cudaFree(ctx->d_codes);
+        if (ctx->d_qlog) cudaFree(ctx->d_qlog);
+    }
+    ctx->d_codes = nullptr; ctx->d_qlog = nullptr; ctx->have_discrete = false; ctx->borrowed_discrete = false;
 }
 static void free_continuous(urlgpu_ctx *ctx) {
     if (ctx->d_z) cudaFree(ctx->d_z);
@@ -399,29 +402,50 @@ static int set_discrete_common(urlgpu_ctx *ctx, const uint8_t *src, bool src_on_
     if (!ctx || !src || !cardinality || n < 1 || p < 1) return ctx ? ctx->fail(URLGPU_ERR_ARG, "set_discrete: bad arguments") : URLGPU_ERR_ARG;
     if (n > (int64_t)2000000000) return ctx->fail(URLGPU_ERR_LIMIT, "set_discrete: more than 2e9 records");
     CK(cudaSetDevice(ctx->device));
-    free_discrete(ctx);
     for (int i = 0; i < p; i++)
         if (cardinality[i] < 1 || cardinality[i] > 256) return ctx->fail(URLGPU_ERR_ARG, "set_discrete: cardinality must be in 1..256");
+    // a data set of the same shape re-uses the device buffers, and the log table depends on n only
+    const bool same_shape = ctx->have_discrete && !ctx->borrowed_discrete && ctx->n == n && ctx->p == p;
+    if (!same_shape) free_discrete(ctx);
+    ctx->have_discrete = false;
     ctx->n = n; ctx->p = p;
     ctx->n_stride = (n + 15) / 16 * 16;
     ctx->card.assign(cardinality, cardinality + p);
-    CK(cudaMalloc(&ctx->d_codes, (size_t)ctx->n_stride * p));
-    CK(cudaMemsetAsync(ctx->d_codes, 0, (size_t)ctx->n_stride * p, ctx->stream));
+    if (!same_shape) {
+        CK(cudaMalloc(&ctx->d_codes, (size_t)ctx->n_stride * p));
+        CK(cudaMemsetAsync(ctx->d_codes, 0, (size_t)ctx->n_stride * p, ctx->stream));
+    }
     CK(cudaMemcpy2DAsync(ctx->d_codes, (size_t)ctx->n_stride, src, (size_t)n, (size_t)n, (size_t)p,
                          src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-    // the reference's float table ilogi[i] = (float)(i*log(i)) (log_likelihood_calculator.h:30-38), as exact
-    // int64 multiples of 2^-23.  Built on the host with libm's log so it is the same table the reference builds.
-    std::vector<long long> q((size_t)n + 2);
-    q[0] = 0;
-    for (int64_t i = 1; i < n + 2; i++) {
-        const float l = (float)((int)i * std::log((double)(int)i));
-        q[i] = (long long)std::ldexp((double)l, 23);
-    }
-    CK(cudaMalloc(&ctx->d_qlog, q.size() * sizeof(long long)));
-    CK(cudaMemcpyAsync(ctx->d_qlog, q.data(), q.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream)); // q goes out of scope
+    if (!same_shape) {
+        // the reference's float table ilogi[i] = (float)(i*log(i)) (log_likelihood_calculator.h:30-38), as exact
+        // int64 multiples of 2^-23.  Built on the host with libm's log so it is the same table the reference builds.
+        std::vector<long long> q((size_t)n + 2);
+        q[0] = 0;
+        for (int64_t i = 1; i < n + 2; i++) {
+            const float l = (float)((int)i * std::log((double)(int)i));
+            q[i] = (long long)std::ldexp((double)l, 23);
+        }
+        CK(cudaMalloc(&ctx->d_qlog, q.size() * sizeof(long long)));
+        CK(cudaMemcpyAsync(ctx->d_qlog, q.data(), q.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream)); // q goes out of scope
+    } else CK(cudaStreamSynchronize(ctx->stream)); // the caller may reuse its buffer
     ctx->base = (float)(std::log((double)(int)n) / 2); // bic_scoring_function.cpp:13
     ctx->have_discrete = true;
+    ctx->mem_free_sample = 0;
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_share_discrete(urlgpu_ctx *ctx, urlgpu_ctx *owner) {
+    if (!ctx || !owner || ctx == owner) return ctx ? ctx->fail(URLGPU_ERR_ARG, "share_discrete: bad arguments") : URLGPU_ERR_ARG;
+    if (ctx->device != owner->device) return ctx->fail(URLGPU_ERR_ARG, "share_discrete: the contexts are on different devices");
+    if (!owner->have_discrete || owner->borrowed_discrete) return ctx->fail(URLGPU_ERR_ARG, "share_discrete: the owner holds no data set of its own");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(owner->stream)); // the owner's upload has landed
+    free_discrete(ctx);
+    ctx->n = owner->n; ctx->p = owner->p; ctx->n_stride = owner->n_stride; ctx->card = owner->card;
+    ctx->d_codes = owner->d_codes; ctx->d_qlog = owner->d_qlog; ctx->base = owner->base;
+    ctx->have_discrete = true; ctx->borrowed_discrete = true;
     ctx->mem_free_sample = 0;
     return URLGPU_OK;
 }
