@@ -107,12 +107,13 @@ def test_tree_path_slicing_variants(pkg, orc, budget, run, unit):
     eng.close()
 
 
-@pytest.mark.parametrize("fuse,budget", [("1", 22528), ("1", 2048), ("0", 22528), ("1", 40000)])
-def test_cube_roots_counted_in_slices_and_fused(pkg, orc, fuse, budget):
+@pytest.mark.parametrize("fuse,budget,leaves", [("1", 22528, "1"), ("1", 2048, "1"), ("0", 22528, "1"), ("1", 40000, "0"), ("0", 22528, "0")])
+def test_cube_roots_counted_in_slices_and_fused(pkg, orc, fuse, budget, leaves):
     """the cube path's big roots: counted in shared-memory slices of the packed rows; ancestor-only roots (layer K+1) hand
     their children straight to the next layer (fused) or, with URLGPU_FUSE_ROOTS=0 / a run that does not fit the slice
-    budget, are written out and marginalised through HBM.  All variants bit-exact against the oracle."""
-    keys = {"URLGPU_BIC_MODE": "cube", "URLGPU_FUSE_ROOTS": fuse, "URLGPU_ROOT_BUDGET": str(budget)}
+    budget, are written out and marginalised through HBM; sets without the lowest candidate are scored by the pass that
+    produces their parent table (URLGPU_FUSE_LEAVES).  All variants bit-exact against the oracle."""
+    keys = {"URLGPU_BIC_MODE": "cube", "URLGPU_FUSE_ROOTS": fuse, "URLGPU_ROOT_BUDGET": str(budget), "URLGPU_FUSE_LEAVES": leaves}
     old = {k: os.environ.get(k) for k in keys}
     os.environ.update(keys)
     try:

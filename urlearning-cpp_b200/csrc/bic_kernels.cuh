@@ -268,12 +268,16 @@ struct CubePair {
     uint32_t Bc;                      // stride of the dropped digit, in configurations
     uint32_t r;                       // arity of the dropped digit
     uint32_t chunk0;                  // first block of this pair
-    uint32_t acc_index;               // accumulator of the child (its position in the layer)
+    uint32_t acc_index;               // accumulator of the child
     uint32_t leaf;                    // the child has no children of its own (cube bit 0 clear): its table is not written
+    uint32_t leaf_acc;                // accumulator of child \ {cube bit 0}, scored in the same pass (kNoLeafAcc: not fused)
+    uint32_t pad;
 };
+constexpr uint32_t kNoLeafAcc = 0xffffffffu;
 
 constexpr int kCubeThreads = 256;
 constexpr int kCubeConfigsPerBlock = 2048;
+__host__ __device__ inline uint32_t cube_configs_per_block(uint32_t group) { return (uint32_t)kCubeConfigsPerBlock / group * group; }
 
 template <int RV>
 __device__ __forceinline__ void load_cfg(const int *__restrict__ p, int (&v)[RV]) {
@@ -295,30 +299,84 @@ __device__ __forceinline__ void store_cfg(int *__restrict__ p, const int (&v)[RV
 }
 
 // RV > 0: compile-time child arity (2,3,4); RV == 0: generic arity rv_dyn
-template <int RV>
-__global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePair *__restrict__ pairs, int npairs, const int *__restrict__ parent_tab,
-                                                                   int *__restrict__ child_tab, int rv_dyn, const long long *__restrict__ qlog,
-                                                                   long long *__restrict__ acc_out /*null: no scoring*/) {
-    __shared__ long long red[32];
-    __shared__ int s_pair;
-    if (threadIdx.x == 0) { // binary search: last pair with chunk0 <= blockIdx.x
-        int lo = 0, hi = npairs - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (pairs[mid].chunk0 <= blockIdx.x) lo = mid; else hi = mid - 1;
-        }
-        s_pair = lo;
+// block -> pair map (one load per block instead of a dependent binary search by thread 0 while 255 threads wait)
+__global__ void cube_map_kernel(const CubePair *__restrict__ pairs, int npairs, uint32_t total, uint32_t *__restrict__ block_pair) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int lo = 0, hi = npairs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (pairs[mid].chunk0 <= i) lo = mid; else hi = mid - 1;
     }
-    __syncthreads();
-    const int pi = s_pair;
-    const CubePair pr = pairs[pi];
+    block_pair[i] = (uint32_t)lo;
+}
+
+template <int RV>
+__global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePair *__restrict__ pairs, const uint32_t *__restrict__ block_pair, const int *__restrict__ parent_tab,
+                                                                   int *__restrict__ child_tab, int rv_dyn, const long long *__restrict__ qlog,
+                                                                   long long *__restrict__ acc_all, int score_child /*0: the children of this launch are ancestors only*/,
+                                                                   int r0 /*arity of cube bit 0*/) {
+    __shared__ long long red[32];
+    const CubePair pr = pairs[__ldg(&block_pair[blockIdx.x])];
     const int rv = RV > 0 ? RV : rv_dyn;
-    const uint32_t j0 = (blockIdx.x - pr.chunk0) * kCubeConfigsPerBlock;
-    const uint32_t j1 = min(j0 + (uint32_t)kCubeConfigsPerBlock, pr.child_configs);
+    long long *__restrict__ acc_out = score_child ? acc_all : nullptr;
+    // a pair that also scores child \ {bit 0} works on groups of r0 adjacent configurations: blocks hold whole groups
+    const bool fused_leaf = pr.leaf_acc != kNoLeafAcc;
+    const uint32_t cpb = cube_configs_per_block(fused_leaf ? (uint32_t)r0 : 1u);
+    const uint32_t j0 = (blockIdx.x - pr.chunk0) * cpb;
+    const uint32_t j1 = min(j0 + cpb, pr.child_configs);
     const int *__restrict__ P = parent_tab + pr.parent_off;
     int *__restrict__ Cc = child_tab + pr.child_off;
     long long acc = 0;
     if constexpr (RV > 0) {
+        if (fused_leaf) { // uniform per block
+            long long accL = 0;
+            auto score_cfg = [&](const int (&cnt)[RV], long long &a) {
+                int nij = 0;
+#pragma unroll
+                for (int k = 0; k < RV; k++) nij += cnt[k];
+                if (nij > 1) {
+#pragma unroll
+                    for (int k = 0; k < RV; k++)
+                        if (cnt[k] > 1) a += __ldg(&qlog[cnt[k]]);
+                    a -= __ldg(&qlog[nij]);
+                }
+            };
+            // thread = one group of r0 adjacent child configurations (the values of cube bit 0, the least significant
+            // digit): the group's sum is the configuration of child \ {bit 0}
+            for (uint32_t jb = j0 + threadIdx.x * (uint32_t)r0; jb < j1; jb += kCubeThreads * (uint32_t)r0) {
+                const uint32_t hi = jb / pr.Bc, lo = jb - hi * pr.Bc;
+                const uint64_t pc0 = (uint64_t)lo + (uint64_t)hi * pr.r * pr.Bc;
+                int cnt[4][RV], sum[RV];
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (t < r0) load_cfg<RV>(P + (pc0 + t) * RV, cnt[t]);
+                for (uint32_t a = 1; a < pr.r; a++) {
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t < r0) {
+                            int tt[RV];
+                            load_cfg<RV>(P + (pc0 + (uint64_t)a * pr.Bc + t) * RV, tt);
+#pragma unroll
+                            for (int k = 0; k < RV; k++) cnt[t][k] += tt[k];
+                        }
+                }
+#pragma unroll
+                for (int k = 0; k < RV; k++) sum[k] = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (t < r0) {
+                        store_cfg<RV>(Cc + (uint64_t)(jb + t) * RV, cnt[t]);
+                        if (acc_out) score_cfg(cnt[t], acc);
+#pragma unroll
+                        for (int k = 0; k < RV; k++) sum[k] += cnt[t][k];
+                    }
+                score_cfg(sum, accL);
+            }
+            accL = block_sum_ll(accL, red);
+            if (threadIdx.x == 0 && accL != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_all[pr.leaf_acc]), (unsigned long long)accL);
+            __syncthreads(); // red is reused below
+        } else {
         // two configurations per thread and iteration: 2*r independent 128-bit loads in flight before the first add
         auto score_cfg = [&](const int (&cnt)[RV]) {
             int nij = 0;
@@ -357,6 +415,7 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
                 score_cfg(cntA);
                 if (two) score_cfg(cntB);
             }
+        }
         }
     } else {
         for (uint32_t j = j0 + threadIdx.x; j < j1; j += kCubeThreads) {

@@ -73,6 +73,10 @@ struct urlgpu_ctx {
     uint16_t *d_low_sorted = nullptr; int low_bits = -1; std::vector<int> low_off;
     bool use_slice_count = true; // cube path: count big roots in shared-memory slices (URLGPU_SLICE_COUNT=0 disables)
     bool fuse_roots = true;      // cube path: ancestor-only roots hand their children straight to HBM (URLGPU_FUSE_ROOTS=0 disables)
+    // cube path: sets without cube bit 0 scored by the pass that produces their parent (URLGPU_FUSE_LEAVES=1 enables).  Bit-exact and
+    // 16 % fewer issued bytes, but measured neutral to slightly slower at config 4 (the saved reads were L2 hits; the grouped
+    // access pattern halves the sector efficiency of each load), so off by default
+    bool fuse_leaves = false;
     uint32_t root_budget = 22 * 1024; // cells of a root slice (URLGPU_ROOT_BUDGET): 88 KB + segment tables, two 512-thread CTAs per SM
     // K1 strategy (URLGPU_BIC_MODE=cube|tree|direct): 2 = cube (default: roots counted in shared-memory slices, the rest
     // marginalised through HBM), 0 = tree (every table counted or marginalised in shared memory; measured 0.6-0.9x the cube
@@ -295,6 +299,7 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
     ctx->stream = ctx->own_stream;
     if (const char *m = getenv("URLGPU_SLICE_COUNT")) ctx->use_slice_count = atoi(m) != 0;
     if (const char *m = getenv("URLGPU_FUSE_ROOTS")) ctx->fuse_roots = atoi(m) != 0;
+    if (const char *m = getenv("URLGPU_FUSE_LEAVES")) ctx->fuse_leaves = atoi(m) != 0;
     if (const char *m = getenv("URLGPU_ROOT_BUDGET")) ctx->root_budget = (uint32_t)std::max(1024, std::min(atoi(m), 48 * 1024)) / 4 * 4;
     {
         const int smem = (int)((ctx->root_budget + 2 * 2048 + 1) * sizeof(int));
@@ -1033,7 +1038,11 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     size_t max_sets = 0;
     for (int l = 0; l <= Lstar; l++) max_sets = std::max(max_sets, layers[l].size());
     DevBuf dacc(ctx), dres(ctx), dpairs(ctx), dwork(ctx), doffs(ctx), dgsets(ctx);
-    CK(dacc.alloc(max_sets * sizeof(long long)));
+    // one exact accumulator per set of every layer (a pass over layer l+1 may already score sets of layer l)
+    std::vector<size_t> acc_off(Lstar + 2, 0);
+    for (int l = 0; l <= Lstar; l++) acc_off[l + 1] = acc_off[l] + layers[l].size();
+    CK(dacc.alloc(acc_off[Lstar + 1] * sizeof(long long)));
+    CK(cudaMemsetAsync(dacc.p, 0, acc_off[Lstar + 1] * sizeof(long long), s));
     CK(dres.alloc(max_sets * sizeof(uint32_t)));
     CK(dpairs.alloc(max_sets * sizeof(CubePair)));
     std::vector<uint32_t> hres;
@@ -1043,7 +1052,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         for (size_t i = 0; i < L.size(); i++) hres[i] = L[i].res_mask;
         { int rc_ = h2d_async(ctx, dres.p, hres.data(), L.size() * sizeof(uint32_t)); if (rc_) return rc_; }
         Region rg(ctx, F_OTHER, 1);
-        cube_finalize_kernel<<<blocks_for(L.size(), 256), 256, 0, s>>>(bd, ci_res, dres.as<uint32_t>(), dacc.as<long long>(), (int)L.size(), d_table, d_llfixed);
+        cube_finalize_kernel<<<blocks_for(L.size(), 256), 256, 0, s>>>(bd, ci_res, dres.as<uint32_t>(), dacc.as<long long>() + acc_off[l], (int)L.size(), d_table, d_llfixed);
         return URLGPU_OK;
     };
 
@@ -1052,7 +1061,6 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     bool fused_any = false;
     {
         auto &R = layers[Lstar];
-        CK(cudaMemsetAsync(dacc.p, 0, R.size() * sizeof(long long), s));
         std::vector<uint32_t> small_m; std::vector<uint64_t> small_off; std::vector<size_t> small_idx;
         std::vector<GlobalSet> big; std::vector<size_t> big_idx;
         for (size_t i = 0; i < R.size(); i++) {
@@ -1126,10 +1134,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             if (!croots.empty()) {
                 bool any_fused = false;
                 for (auto &cr : croots) any_fused |= cr.nchild > 0;
-                if (any_fused) {
-                    fused_any = true;
-                    CK(cudaMemsetAsync(dacc.p, 0, layers[Lstar - 1].size() * sizeof(long long), s)); // the children's accumulators
-                }
+                if (any_fused) fused_any = true;
                 CK(dkeys.alloc(n * sizeof(uint32_t)));
                 CK(dhist.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
                 CK(doffp.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
@@ -1154,7 +1159,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 const size_t smem = ((size_t)RB + 2 * seg_cap + 1) * sizeof(int);
                 const unsigned grid = (unsigned)rchunk;
                 switch (rv) {
-#define URLGPU_ROOT(RVV) bic_root_kernel<RVV><<<grid, kRootThreads, smem, s>>>(tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, bufP, bufC, dacc.as<long long>(), RB, seg_cap)
+#define URLGPU_ROOT(RVV) bic_root_kernel<RVV><<<grid, kRootThreads, smem, s>>>(tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, bufP, bufC, dacc.as<long long>() + acc_off[Lstar > 0 ? Lstar - 1 : 0], RB, seg_cap)
                 case 2: URLGPU_ROOT(2); break;
                 case 3: URLGPU_ROOT(3); break;
                 case 4: URLGPU_ROOT(4); break;
@@ -1199,7 +1204,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             CK(cudaStreamSynchronize(s));
             for (size_t i = 0; i < hs.size(); i++) ha[small_idx[i]] = hs[i];
             for (size_t i = 0; i < hb.size(); i++) ha[big_idx[i]] = hb[i];
-            { int rc_ = h2d_async(ctx, dacc.p, ha.data(), ha.size() * sizeof(long long)); if (rc_) return rc_; }
+            { int rc_ = h2d_async(ctx, dacc.as<long long>() + acc_off[Lstar], ha.data(), ha.size() * sizeof(long long)); if (rc_) return rc_; }
             CK(cudaStreamSynchronize(s));
             int rc = finalize_layer(Lstar);
             if (rc) return rc;
@@ -1209,7 +1214,14 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     // ---- derived layers ----
     // Pairs are emitted grouped by PARENT: blocks are dispatched in launch order, so the children of one parent run
     // back to back and all but the first read the parent table from L2 (126 MB) instead of HBM.
+    // LEAF FUSION: a set S without cube bit 0 has no children; its table is the marginal of P = S + {0} over the least
+    // significant digit, i.e. the sum of r0 ADJACENT configurations of P.  The pair that produces P therefore scores S
+    // in the same pass (CubePair::leaf_acc) and S gets no pair of its own: half of all sets never cost a table pass.
     std::vector<CubePair> hp;
+    DevBuf dcmap(ctx);
+    const int r0 = (int)ccard[0];
+    const bool fuse_leaves = ctx->fuse_leaves && !only_roots && r0 >= 2 && r0 <= 4 && rv >= 2 && rv <= 4;
+    std::vector<char> by_pair_prev; // layer l+1: table produced by a derive pair of the previous iteration (its leaf child was scored there)
     for (int l = Lstar - 1; l >= 0; l--) {
         auto &L = layers[l];
         auto &P = layers[l + 1];
@@ -1217,8 +1229,18 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         if (l == Lstar - 1)
             for (size_t i = 0; i < P.size(); i++) if (!fused_root[i]) ctx->st.k1_bytes_written += 4.0 * (double)P[i].cells; // root tables that were written
         const bool top = l == Lstar - 1 && fused_any; // children of fused roots were produced by the root kernel
+        // the leaf child of every set of THIS layer (in layer l-1), scored by the pair that produces the set
+        std::vector<uint32_t> leaf_child(L.size(), kNoLeafAcc);
+        if (fuse_leaves && l >= 1 && l - 1 <= Kc) {
+            auto &C = layers[l - 1];
+            for (size_t i = 0; i < C.size(); i++)
+                if ((C[i].cube_mask & 1u) == 0) leaf_child[C[i].parent] = (uint32_t)i; // parent = C[i] + {0}: parent links exist (l-1 < Lstar)
+        }
         std::vector<uint32_t> first(P.size() + 1, 0), order;
-        auto skip = [&](const CubeSet &cs) { return top && fused_root[cs.parent]; };
+        auto skip = [&](const CubeSet &cs) {
+            if (top && fused_root[cs.parent]) return true;
+            return (cs.cube_mask & 1u) == 0 && !by_pair_prev.empty() && by_pair_prev[cs.parent] != 0; // scored while its parent was produced
+        };
         for (auto &cs : L) if (!skip(cs)) first[cs.parent + 1]++;
         for (size_t i = 0; i < P.size(); i++) first[i + 1] += first[i];
         order.resize(first[P.size()]);
@@ -1226,6 +1248,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             std::vector<uint32_t> pos(first.begin(), first.end() - 1);
             for (size_t i = 0; i < L.size(); i++) if (!skip(L[i])) order[pos[L[i].parent]++] = (uint32_t)i;
         }
+        std::vector<char> by_pair(L.size(), 0);
         hp.resize(order.size());
         uint64_t chunk = 0;
         for (size_t k = 0; k < order.size(); k++) {
@@ -1234,26 +1257,33 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             pr.parent_off = P[cs.parent].off; pr.child_off = cs.off;
             pr.child_configs = (uint32_t)(cs.cells / rv);
             pr.Bc = cs.Bc; pr.r = cs.r; pr.chunk0 = (uint32_t)chunk;
-            pr.acc_index = order[k];
+            pr.acc_index = (uint32_t)(acc_off[l] + order[k]);
             pr.leaf = (cs.cube_mask & 1u) == 0; // lowest missing bit is 0: nothing is derived from this set
+            pr.leaf_acc = kNoLeafAcc;
+            if (!pr.leaf && leaf_child[order[k]] != kNoLeafAcc) {
+                pr.leaf_acc = (uint32_t)(acc_off[l - 1] + leaf_child[order[k]]);
+                by_pair[order[k]] = 1;
+            }
             ctx->st.k1_bytes_read += 4.0 * (double)cs.cells * (double)cs.r;
             if (!pr.leaf) ctx->st.k1_bytes_written += 4.0 * (double)cs.cells;
-            chunk += (pr.child_configs + kCubeConfigsPerBlock - 1) / kCubeConfigsPerBlock;
+            const uint32_t cpb = cube_configs_per_block(pr.leaf_acc != kNoLeafAcc ? (uint32_t)r0 : 1u);
+            chunk += (pr.child_configs + cpb - 1) / cpb;
             hp[k] = pr;
         }
+        by_pair_prev.swap(by_pair);
         if (chunk > 0x7fffffffull) return ctx->fail(URLGPU_ERR_LIMIT, "cube: too many blocks in one layer");
         const bool score = l <= Kc;
         { int rc_ = h2d_async(ctx, dpairs.p, hp.data(), hp.size() * sizeof(CubePair)); if (rc_) return rc_; }
-        if (score && !top) CK(cudaMemsetAsync(dacc.p, 0, L.size() * sizeof(long long), s));
         if (chunk > 0) {
-            Region rg(ctx, F_CUBE, 1);
-            long long *accp = score ? dacc.as<long long>() : nullptr;
+            CK(dcmap.alloc(chunk * sizeof(uint32_t)));
+            Region rg(ctx, F_CUBE, 2);
             const unsigned grid = (unsigned)chunk;
+            cube_map_kernel<<<blocks_for(chunk, 256), 256, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), grid, dcmap.as<uint32_t>());
             switch (rv) {
-            case 2: cube_derive_kernel<2><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), bufP, bufC, rv, ctx->d_qlog, accp); break;
-            case 3: cube_derive_kernel<3><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), bufP, bufC, rv, ctx->d_qlog, accp); break;
-            case 4: cube_derive_kernel<4><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), bufP, bufC, rv, ctx->d_qlog, accp); break;
-            default: cube_derive_kernel<0><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), bufP, bufC, rv, ctx->d_qlog, accp); break;
+            case 2: cube_derive_kernel<2><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0); break;
+            case 3: cube_derive_kernel<3><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0); break;
+            case 4: cube_derive_kernel<4><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0); break;
+            default: cube_derive_kernel<0><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0); break;
             }
         }
         if (score) { int rc = finalize_layer(l); if (rc) return rc; }
