@@ -276,7 +276,7 @@ struct CubePair {
 constexpr uint32_t kNoLeafAcc = 0xffffffffu;
 
 constexpr int kCubeThreads = 256;
-constexpr int kCubeConfigsPerBlock = 2048;
+constexpr int kCubeConfigsPerBlock = 4096;
 __host__ __device__ inline uint32_t cube_configs_per_block(uint32_t group) { return (uint32_t)kCubeConfigsPerBlock / group * group; }
 
 template <int RV>

@@ -414,8 +414,6 @@ __global__ void tree_finalize_kernel(BicData d, CandInfo ci_res, const TreeRoot 
 //     child b = root \ {b} on the fly and writes the child's slice to ITS global table unless b == 0 (nothing is
 //     derived from a set that lacks bit 0).  This removes the write and the z reads of the largest layer of tables.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kRootWarps = 16;
-constexpr int kRootThreads = kRootWarps * 32;
 constexpr int kRootMaxChild = 16;
 
 struct CubeRoot {
@@ -438,14 +436,15 @@ __global__ void root_map_kernel(const CubeRoot *__restrict__ roots, int nroots, 
     cta_root[i] = (uint32_t)lo;
 }
 
-template <int RV>
-__global__ void __launch_bounds__(kRootThreads) bic_root_kernel(TreeVar tv, const CubeRoot *__restrict__ roots, const uint32_t *__restrict__ cta_root,
+template <int RV, int NW>
+__global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const CubeRoot *__restrict__ roots, const uint32_t *__restrict__ cta_root,
                                                                 const long long *__restrict__ qlog, int *__restrict__ tables, int *__restrict__ child_tables,
                                                                 long long *__restrict__ acc_out, uint32_t table_budget /*cells*/, uint32_t seg_cap) {
     extern __shared__ __align__(16) int s_dyn[];              // [table_budget] slice table, then segbeg[seg_cap], segoff[seg_cap + 1]
     __shared__ CubeRoot cr;
     __shared__ uint16_t s_lut[8 * 256];
     __shared__ long long s_red[32];
+    constexpr int kRootThreads = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rv = RV > 0 ? RV : tv.rv;
     {
@@ -513,7 +512,7 @@ __global__ void __launch_bounds__(kRootThreads) bic_root_kernel(TreeVar tv, cons
             __syncthreads();
             const uint32_t total = s_segoff[nseg];
             switch (rt.ng) {
-#define URLGPU_ROOT_COUNT(NG) case NG: tree_count<NG, kRootWarps>(tv.rows, s_segbeg, s_segoff, nseg, total, s_dyn, s_lut, rt.glist, warp, lane); break;
+#define URLGPU_ROOT_COUNT(NG) case NG: tree_count<NG, NW>(tv.rows, s_segbeg, s_segoff, nseg, total, s_dyn, s_lut, rt.glist, warp, lane); break;
                 URLGPU_ROOT_COUNT(1) URLGPU_ROOT_COUNT(2) URLGPU_ROOT_COUNT(3) URLGPU_ROOT_COUNT(4)
                 URLGPU_ROOT_COUNT(5) URLGPU_ROOT_COUNT(6) URLGPU_ROOT_COUNT(7) URLGPU_ROOT_COUNT(8)
 #undef URLGPU_ROOT_COUNT
@@ -522,7 +521,7 @@ __global__ void __launch_bounds__(kRootThreads) bic_root_kernel(TreeVar tv, cons
         } else {
             __syncthreads(); // the look-up tables
             switch (rt.ng) {
-#define URLGPU_ROOT_COUNT(NG) case NG: tree_count_fragmented<NG, decltype(seg_bounds), kRootWarps>(tv.rows, seg_bounds, nseg, s_dyn, s_lut, rt.glist, warp, lane); break;
+#define URLGPU_ROOT_COUNT(NG) case NG: tree_count_fragmented<NG, decltype(seg_bounds), NW>(tv.rows, seg_bounds, nseg, s_dyn, s_lut, rt.glist, warp, lane); break;
                 URLGPU_ROOT_COUNT(1) URLGPU_ROOT_COUNT(2) URLGPU_ROOT_COUNT(3) URLGPU_ROOT_COUNT(4)
                 URLGPU_ROOT_COUNT(5) URLGPU_ROOT_COUNT(6) URLGPU_ROOT_COUNT(7) URLGPU_ROOT_COUNT(8)
 #undef URLGPU_ROOT_COUNT

@@ -78,6 +78,8 @@ struct urlgpu_ctx {
     // access pattern halves the sector efficiency of each load), so off by default
     bool fuse_leaves = false;
     uint32_t root_budget = 22 * 1024; // cells of a root slice (URLGPU_ROOT_BUDGET): 88 KB + segment tables, two 512-thread CTAs per SM
+    uint32_t root_seg_cap = 2048;     // row segments of a slice kept in shared memory (URLGPU_ROOT_SEGS)
+    int root_warps = 16;              // warps per CTA of bic_root_kernel (URLGPU_ROOT_WARPS = 8, 12 or 16)
     // K1 strategy (URLGPU_BIC_MODE=cube|tree|direct): 2 = cube (default: roots counted in shared-memory slices, the rest
     // marginalised through HBM), 0 = tree (every table counted or marginalised in shared memory; measured 0.6-0.9x the cube
     // path on config 4, instruction bound — kept as an opt-in strategy), 1 = direct counting of every set
@@ -301,12 +303,15 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
     if (const char *m = getenv("URLGPU_FUSE_ROOTS")) ctx->fuse_roots = atoi(m) != 0;
     if (const char *m = getenv("URLGPU_FUSE_LEAVES")) ctx->fuse_leaves = atoi(m) != 0;
     if (const char *m = getenv("URLGPU_ROOT_BUDGET")) ctx->root_budget = (uint32_t)std::max(1024, std::min(atoi(m), 48 * 1024)) / 4 * 4;
+    if (const char *m = getenv("URLGPU_ROOT_SEGS")) ctx->root_seg_cap = (uint32_t)std::max(32, std::min(atoi(m), 8192));
+    if (const char *m = getenv("URLGPU_ROOT_WARPS")) ctx->root_warps = atoi(m) == 8 ? 8 : atoi(m) == 12 ? 12 : 16;
     {
-        const int smem = (int)((ctx->root_budget + 2 * 2048 + 1) * sizeof(int));
-        cudaFuncSetAttribute(bic_root_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(bic_root_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(bic_root_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(bic_root_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const int smem = (int)((ctx->root_budget + 2 * ctx->root_seg_cap + 1) * sizeof(int));
+#define URLGPU_ROOT_ATTR(RVV, NWW) cudaFuncSetAttribute(bic_root_kernel<RVV, NWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+        URLGPU_ROOT_ATTR(0, 8); URLGPU_ROOT_ATTR(2, 8); URLGPU_ROOT_ATTR(3, 8); URLGPU_ROOT_ATTR(4, 8);
+        URLGPU_ROOT_ATTR(0, 12); URLGPU_ROOT_ATTR(2, 12); URLGPU_ROOT_ATTR(3, 12); URLGPU_ROOT_ATTR(4, 12);
+        URLGPU_ROOT_ATTR(0, 16); URLGPU_ROOT_ATTR(2, 16); URLGPU_ROOT_ATTR(3, 16); URLGPU_ROOT_ATTR(4, 16);
+#undef URLGPU_ROOT_ATTR
     }
     if (const char *m = getenv("URLGPU_BIC_MODE"))
         ctx->bic_mode = strcmp(m, "direct") == 0 ? 1 : strcmp(m, "tree") == 0 ? 0 : 2;
@@ -935,7 +940,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     // table is never materialised, so it takes no room in the layer buffer) ----
     const bool score_roots = Lstar <= Kc;
     TreeVar tv{};
-    const uint32_t RB = ctx->root_budget, seg_cap = 2048;
+    const uint32_t RB = ctx->root_budget, seg_cap = ctx->root_seg_cap;
     bool packed_ok = ctx->n >= 65536 && ctx->use_slice_count;
     uint64_t Pd = 1;
     int dmax = 0;
@@ -1159,12 +1164,19 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 const size_t smem = ((size_t)RB + 2 * seg_cap + 1) * sizeof(int);
                 const unsigned grid = (unsigned)rchunk;
                 switch (rv) {
-#define URLGPU_ROOT(RVV) bic_root_kernel<RVV><<<grid, kRootThreads, smem, s>>>(tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, bufP, bufC, dacc.as<long long>() + acc_off[Lstar > 0 ? Lstar - 1 : 0], RB, seg_cap)
+#define URLGPU_ROOT_ARGS tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, bufP, bufC, dacc.as<long long>() + acc_off[Lstar > 0 ? Lstar - 1 : 0], RB, seg_cap
+#define URLGPU_ROOT(RVV)                                                                             \
+    do {                                                                                             \
+        if (ctx->root_warps == 8) bic_root_kernel<RVV, 8><<<grid, 256, smem, s>>>(URLGPU_ROOT_ARGS); \
+        else if (ctx->root_warps == 12) bic_root_kernel<RVV, 12><<<grid, 384, smem, s>>>(URLGPU_ROOT_ARGS); \
+        else bic_root_kernel<RVV, 16><<<grid, 512, smem, s>>>(URLGPU_ROOT_ARGS);                     \
+    } while (0)
                 case 2: URLGPU_ROOT(2); break;
                 case 3: URLGPU_ROOT(3); break;
                 case 4: URLGPU_ROOT(4); break;
                 default: URLGPU_ROOT(0); break;
 #undef URLGPU_ROOT
+#undef URLGPU_ROOT_ARGS
                 }
             }
             size_t i0 = 0;
