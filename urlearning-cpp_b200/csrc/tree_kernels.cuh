@@ -69,6 +69,8 @@ struct TreeRoot {                       // built on the host, one per root
     uint32_t pres_weight[kTreeMaxZone]; //   weight of the digit inside the zone prefix index
     uint16_t abs_card[kTreeMaxZone];    // absent zone digits, lowest first (segment index is mixed radix over them)
     uint32_t abs_weight[kTreeMaxZone];
+    uint32_t pres_magic[kTreeMaxZone];  // floor((2^32-1)/card) of the zone digits: fast_div instead of a hardware division
+    uint32_t abs_magic[kTreeMaxZone];
 };
 
 // ---- bucketing ---------------------------------------------------------------------------------------------
@@ -279,11 +281,19 @@ __global__ void __launch_bounds__(kTreeThreads) bic_tree_kernel(TreeVar tv, cons
         uint32_t qb = 0;
         {
             uint32_t rem = si;
-            for (int a = 0; a < rt.npres; a++) { const uint32_t cb = rt.pres_card[a]; qb += (rem % cb) * rt.pres_weight[a]; rem /= cb; }
+            for (int a = 0; a < rt.npres; a++) {
+                const uint32_t cb = rt.pres_card[a], qq = fast_div(rem, cb, rt.pres_magic[a]);
+                qb += (rem - qq * cb) * rt.pres_weight[a];
+                rem = qq;
+            }
         }
         auto seg_bounds = [&](uint32_t seg, uint32_t &r0, uint32_t &r1) {
             uint32_t q = qb, rs = seg;
-            for (int a = 0; a < rt.nabs; a++) { const uint32_t cb = rt.abs_card[a]; q += (rs % cb) * rt.abs_weight[a]; rs /= cb; }
+            for (int a = 0; a < rt.nabs; a++) {
+                const uint32_t cb = rt.abs_card[a], qq = fast_div(rs, cb, rt.abs_magic[a]);
+                q += (rs - qq * cb) * rt.abs_weight[a];
+                rs = qq;
+            }
             r0 = __ldg(&tv.prefix_off[(size_t)q * rt.q_stride]);
             r1 = __ldg(&tv.prefix_off[(size_t)(q + 1) * rt.q_stride]);
         };
@@ -443,7 +453,7 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
     extern __shared__ __align__(16) int s_dyn[];              // [table_budget] slice table, then segbeg[seg_cap], segoff[seg_cap + 1]
     __shared__ CubeRoot cr;
     __shared__ uint16_t s_lut[8 * 256];
-    __shared__ long long s_red[32];
+    __shared__ unsigned long long s_cacc[kRootMaxChild]; // per-child exact sums of this CTA
     constexpr int kRootThreads = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rv = RV > 0 ? RV : tv.rv;
@@ -456,6 +466,7 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
     __syncthreads();
     const TreeRoot &rt = cr.t;
     const int z = rt.z;
+    if (tid < kRootMaxChild) s_cacc[tid] = 0;
     const uint32_t S0 = rt.H * (uint32_t)rv * tv.pre[z];
     const uint32_t si = blockIdx.x - rt.chunk0;
     {
@@ -480,11 +491,19 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
         uint32_t qb = 0;
         {
             uint32_t rem = si;
-            for (int a = 0; a < rt.npres; a++) { const uint32_t cb = rt.pres_card[a]; qb += (rem % cb) * rt.pres_weight[a]; rem /= cb; }
+            for (int a = 0; a < rt.npres; a++) {
+                const uint32_t cb = rt.pres_card[a], qq = fast_div(rem, cb, rt.pres_magic[a]);
+                qb += (rem - qq * cb) * rt.pres_weight[a];
+                rem = qq;
+            }
         }
         auto seg_bounds = [&](uint32_t seg, uint32_t &r0, uint32_t &r1) {
             uint32_t q = qb, rs = seg;
-            for (int a = 0; a < rt.nabs; a++) { const uint32_t cb = rt.abs_card[a]; q += (rs % cb) * rt.abs_weight[a]; rs /= cb; }
+            for (int a = 0; a < rt.nabs; a++) {
+                const uint32_t cb = rt.abs_card[a], qq = fast_div(rs, cb, rt.abs_magic[a]);
+                q += (rs - qq * cb) * rt.abs_weight[a];
+                rs = qq;
+            }
             r0 = __ldg(&tv.prefix_off[(size_t)q * rt.q_stride]);
             r1 = __ldg(&tv.prefix_off[(size_t)(q + 1) * rt.q_stride]);
         };
@@ -585,10 +604,16 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
                 if (score && nij > 1) acc -= __ldg(&qlog[nij]);
             }
         }
-        if (score) {
-            acc = block_sum_ll(acc, s_red);
-            if (tid == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[cr.child_acc[b]]), (unsigned long long)acc);
-            __syncthreads(); // s_red is reused by the next child
+        if (score) { // no barrier between children: every warp adds its exact partial sum to the child's shared accumulator
+            acc = warp_sum_ll_redux(acc);
+            if (lane == 0 && acc != 0) atomicAdd(&s_cacc[b], (unsigned long long)acc);
+        }
+    }
+    if (score) {
+        __syncthreads();
+        if (tid >= (int)cr.bfirst && tid < z) {
+            const unsigned long long a = s_cacc[tid];
+            if (a != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[cr.child_acc[tid]]), a);
         }
     }
 }

@@ -77,8 +77,8 @@ struct urlgpu_ctx {
     // 16 % fewer issued bytes, but measured neutral to slightly slower at config 4 (the saved reads were L2 hits; the grouped
     // access pattern halves the sector efficiency of each load), so off by default
     bool fuse_leaves = false;
-    uint32_t root_budget = 22 * 1024; // cells of a root slice (URLGPU_ROOT_BUDGET): 88 KB + segment tables, two 512-thread CTAs per SM
-    uint32_t root_seg_cap = 2048;     // row segments of a slice kept in shared memory (URLGPU_ROOT_SEGS)
+    uint32_t root_budget = 24 * 1024; // cells of a root slice (URLGPU_ROOT_BUDGET): 96 KB + segment tables, two 512-thread CTAs per SM
+    uint32_t root_seg_cap = 1024;     // row segments of a slice kept in shared memory (URLGPU_ROOT_SEGS)
     int root_warps = 16;              // warps per CTA of bic_root_kernel (URLGPU_ROOT_WARPS = 8, 12 or 16)
     // K1 strategy (URLGPU_BIC_MODE=cube|tree|direct): 2 = cube (default: roots counted in shared-memory slices, the rest
     // marginalised through HBM), 0 = tree (every table counted or marginalised in shared memory; measured 0.6-0.9x the cube
@@ -986,8 +986,9 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         for (int g = 0; g < 8; g++) if ((r.gmask >> g) & 1) r.glist[r.ng++] = (uint8_t)g;
         uint64_t w = 1;
         for (int b = c - depth; b < c; b++) {
-            if ((P >> b) & 1) { r.pres_card[r.npres] = (uint16_t)ccard[b]; r.pres_weight[r.npres] = (uint32_t)w; r.npres++; }
-            else { r.abs_card[r.nabs] = (uint16_t)ccard[b]; r.abs_weight[r.nabs] = (uint32_t)w; r.nabs++; }
+            const uint32_t mg = ccard[b] > 1 ? (uint32_t)(0xFFFFFFFFull / ccard[b]) : 0;
+            if ((P >> b) & 1) { r.pres_card[r.npres] = (uint16_t)ccard[b]; r.pres_weight[r.npres] = (uint32_t)w; r.pres_magic[r.npres] = mg; r.npres++; }
+            else { r.abs_card[r.nabs] = (uint16_t)ccard[b]; r.abs_weight[r.nabs] = (uint32_t)w; r.abs_magic[r.nabs] = mg; r.nabs++; }
             w *= ccard[b];
         }
         r.q_stride = (uint32_t)(Pd / w);
@@ -1449,8 +1450,9 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
         for (int g = 0; g < 8; g++) if ((r.gmask >> g) & 1) r.glist[r.ng++] = (uint8_t)g;
         uint64_t w = 1;
         for (int b = c - depth; b < c; b++) {
-            if ((A >> b) & 1) { r.pres_card[r.npres] = (uint16_t)ccard[b]; r.pres_weight[r.npres] = (uint32_t)w; r.npres++; }
-            else { r.abs_card[r.nabs] = (uint16_t)ccard[b]; r.abs_weight[r.nabs] = (uint32_t)w; r.nabs++; }
+            const uint32_t mg = ccard[b] > 1 ? (uint32_t)(0xFFFFFFFFull / ccard[b]) : 0;
+            if ((A >> b) & 1) { r.pres_card[r.npres] = (uint16_t)ccard[b]; r.pres_weight[r.npres] = (uint32_t)w; r.pres_magic[r.npres] = mg; r.npres++; }
+            else { r.abs_card[r.nabs] = (uint16_t)ccard[b]; r.abs_weight[r.nabs] = (uint32_t)w; r.abs_magic[r.nabs] = mg; r.nabs++; }
             w *= ccard[b];
         }
         r.q_stride = (uint32_t)(Pd / w);
