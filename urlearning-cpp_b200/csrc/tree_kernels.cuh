@@ -32,6 +32,7 @@
 #pragma once
 #include "bic_kernels.cuh"
 #include "slice_kernels.cuh"
+#include <type_traits>
 
 namespace urlgpu {
 
@@ -49,6 +50,7 @@ struct TreeVar {                        // per-variable constants (kernel argume
     uint16_t card[kMaxDenseCand];       // cube order
     uint32_t pre[kPreMax + 1];          // pre[b] = prod_{i<b} card[i] (saturating at 2^31)
     uint32_t magic[kPreMax + 1];        // floor((2^32-1) / pre[b]) for fast_div
+    uint32_t cmagic[kPreMax];           // floor((2^32-1) / card[b]) of the lowest digits
     const unsigned long long *rows;     // [n] packed rows, bucketed
     const uint32_t *prefix_off;         // [P_dmax + 1] first row of every bucket
     const uint16_t *cfg_tab;            // [(t+1) << t]: cfg_tab[(z << t) + D] = pre[z] / prod_{i in D} card[i], D subset of {0..z-1}
@@ -561,38 +563,62 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
         }
         return;
     }
-    // fused root: children b = 0 .. z-1
+    // fused root: children b = bfirst .. z-1
     const uint32_t cfg_src = S0 / (uint32_t)rv;
     const bool score = cr.score != 0;
     for (int b = cr.bfirst; b < z; b++) {
         const uint32_t r = tv.card[b], pre = tv.pre[b], magic = tv.magic[b];
-        const uint32_t cfg_dst = cfg_src / r;
-        int *dst = child_tables + cr.child_off[b] + (unsigned long long)si * (S0 / r);
+        const uint32_t cfg_dst = fast_div(cfg_src, r, tv.cmagic[b]); // r divides the run product: exact
+        int *dst = child_tables + cr.child_off[b] + (unsigned long long)si * ((unsigned long long)cfg_dst * rv);
         const bool store = b > 0;
         long long acc = 0;
-        for (uint32_t j = tid; j < cfg_dst; j += kRootThreads) {
-            const uint32_t hi = fast_div(j, pre, magic), lo = j - hi * pre;
-            const uint32_t p0 = lo + hi * r * pre;
-            if constexpr (RV > 0) {
-                int cnt[RV];
-                load_cfg<RV>(s_dyn + (size_t)p0 * RV, cnt);
-                for (uint32_t a = 1; a < r; a++) {
-                    int t[RV];
-                    load_cfg<RV>(s_dyn + (size_t)(p0 + a * pre) * RV, t);
+        if constexpr (RV > 0) {
+            // R = compile-time arity of the digit summed out (2, 3, 4), 0 = run-time loop
+            auto pass = [&](auto RC) {
+                constexpr int R = decltype(RC)::value;
+                for (uint32_t j = tid; j < cfg_dst; j += kRootThreads) {
+                    const uint32_t hi = fast_div(j, pre, magic), lo = j - hi * pre;
+                    const uint32_t p0 = lo + hi * r * pre;
+                    int cnt[RV];
+                    load_cfg<RV>(s_dyn + (size_t)p0 * RV, cnt);
+                    if constexpr (R > 0) {
 #pragma unroll
-                    for (int k = 0; k < RV; k++) cnt[k] += t[k];
+                        for (int a = 1; a < R; a++) {
+                            int t[RV];
+                            load_cfg<RV>(s_dyn + (size_t)(p0 + a * pre) * RV, t);
+#pragma unroll
+                            for (int k = 0; k < RV; k++) cnt[k] += t[k];
+                        }
+                    } else {
+                        for (uint32_t a = 1; a < r; a++) {
+                            int t[RV];
+                            load_cfg<RV>(s_dyn + (size_t)(p0 + a * pre) * RV, t);
+#pragma unroll
+                            for (int k = 0; k < RV; k++) cnt[k] += t[k];
+                        }
+                    }
+                    if (store) store_cfg<RV>(dst + (size_t)j * RV, cnt);
+                    int nij = 0;
+#pragma unroll
+                    for (int k = 0; k < RV; k++) nij += cnt[k];
+                    if (score && nij > 1) {
+#pragma unroll
+                        for (int k = 0; k < RV; k++)
+                            if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
+                        acc -= __ldg(&qlog[nij]);
+                    }
                 }
-                if (store) store_cfg<RV>(dst + (size_t)j * RV, cnt);
-                int nij = 0;
-#pragma unroll
-                for (int k = 0; k < RV; k++) nij += cnt[k];
-                if (score && nij > 1) {
-#pragma unroll
-                    for (int k = 0; k < RV; k++)
-                        if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
-                    acc -= __ldg(&qlog[nij]);
-                }
-            } else {
+            };
+            switch (r) {
+            case 2: pass(std::integral_constant<int, 2>{}); break;
+            case 3: pass(std::integral_constant<int, 3>{}); break;
+            case 4: pass(std::integral_constant<int, 4>{}); break;
+            default: pass(std::integral_constant<int, 0>{}); break;
+            }
+        } else {
+            for (uint32_t j = tid; j < cfg_dst; j += kRootThreads) {
+                const uint32_t hi = fast_div(j, pre, magic), lo = j - hi * pre;
+                const uint32_t p0 = lo + hi * r * pre;
                 int nij = 0;
                 for (int k = 0; k < rv; k++) {
                     int cnt = 0;

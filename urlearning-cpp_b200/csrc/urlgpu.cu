@@ -954,6 +954,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         tv.pre[0] = 1;
         for (int b = 0; b < kPreMax; b++) tv.pre[b + 1] = (uint32_t)std::min<uint64_t>((uint64_t)tv.pre[b] * (b < c ? ccard[b] : 1), (uint64_t)1 << 31);
         for (int b = 0; b <= kPreMax; b++) tv.magic[b] = tv.pre[b] > 1 ? 0xFFFFFFFFu / tv.pre[b] : 0;
+        for (int b = 0; b < kPreMax; b++) tv.cmagic[b] = b < c && ccard[b] > 1 ? (uint32_t)(0xFFFFFFFFull / ccard[b]) : 0;
         while (dmax < c && dmax < kTreeMaxZone && Pd * ccard[c - 1 - dmax] <= kTreeMaxBuckets) { Pd *= ccard[c - 1 - dmax]; dmax++; }
         tv.dmax = dmax; tv.P_dmax = (uint32_t)Pd;
     }
