@@ -171,6 +171,43 @@ def test_score_binary_matches_oracle_pss(pkg, orc, data_dir, tmp_path):
     assert open(out, "rb").read() == open(ref, "rb").read()
 
 
+@pytest.mark.parametrize("arities", [(2, 5, 9), (3, 16), (6, 18)])
+def test_wide_arities_packed_rows(pkg, orc, bic_engine, arities):
+    """arities above 4 switch the packed rows to 4- and 8-bit fields; big root tables (9^6 cells and more) go through the
+    shared-memory root kernel (fused and plain), smaller ones through the other tiers"""
+    engine = bic_engine
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=9, n=70001, seed=41, arities=arities, window=8, max_indegree=2)
+    engine.set_discrete(codes, card)
+    for v, K in ((0, 5), (4, 6), (8, 4)):
+        _check_variable(pkg, orc, engine, codes, card, None, v, K)
+
+
+def test_bic_wide_masks_p_above_64(pkg, orc, engine):
+    """p = 130 variables (three 64-bit words per varset), the shape of bench.py's weak-scaling data set (60 N variables):
+    checked bit for bit against the oracle on the relabelled sub-problem of the variable's 2-hop candidates"""
+    p = 130
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=p, n=20011, seed=23, window=3, max_indegree=2)
+    engine.set_discrete(codes, card)
+    for v in (1, 64, 129):
+        nb = pkg.two_hop_neighbors(edges, p, v)
+        res = engine.score_variable(v, nb, 6, pkg.BIC, flags=pkg.PRUNE_DOMINATED)
+        masks, scores = res.fetch()
+        res.free()
+        assert masks.shape[1] == 3
+        sub = sorted({i for i in range(p) if (nb >> i) & 1} | {v})
+        vs = sub.index(v)
+        om = orc.enumerate_sets(vs, (1 << len(sub)) - 1, len(sub), 6)
+        osc = orc.bic_score_many(codes[sub], card[sub], vs, om)
+        stored = np.array([(s < 1) if m == 0 else (s < 0) for m, s in zip(om, osc)])
+        om, osc = om[stored], osc[stored]
+        keep = orc.prune(om, osc, 6)
+        om, osc = om[keep], osc[keep]
+        order = orc.canonical_order(om)
+        want = [sum(1 << sub[i] for i in range(len(sub)) if (int(om[j]) >> i) & 1) for j in order]
+        assert [pkg.words_to_mask(row) for row in masks] == want
+        assert np.array_equal(scores.view(np.uint32), osc[order].view(np.uint32))
+
+
 def test_pipelined_prefetch_matches_plain_fetch(pkg, engine):
     """prefetch(v) / score(v+1) / fetch(v): the compaction is enqueued behind the scoring kernels and the payload is copied
     on a second stream while the next variable runs; results must equal the unpipelined ones, in canonical order"""
