@@ -171,6 +171,7 @@ struct CbicParams {
     double n;         // row count (num_err, BIC_OLS.cpp:348)
     double lam_logn;  // lambda*log(n)  (:366, evaluated left to right)
     double log_n;     // log(n)
+    int store_mode;   // score stores of the DFS kernel: 0 default, 1 st.global.cs (streaming), 2 st.global.wt, 3 st.global.cg
 };
 
 // packed lower-triangular index, element order (v, cand0, cand1, ...)
@@ -257,8 +258,11 @@ __device__ __forceinline__ void cbic_dfs_inl(const double *A, uint32_t low, int 
         float buf[8];
         cbic_dfs_buf<3, 0u>(A, low, k, prm, buf, out64);
         float4 *o4 = reinterpret_cast<float4 *>(out + low); // low is a multiple of 8 here
-        o4[0] = make_float4(buf[0], buf[1], buf[2], buf[3]);
-        o4[1] = make_float4(buf[4], buf[5], buf[6], buf[7]);
+        const float4 a = make_float4(buf[0], buf[1], buf[2], buf[3]), b = make_float4(buf[4], buf[5], buf[6], buf[7]);
+        if (prm.store_mode == 1) { __stcs(o4, a); __stcs(o4 + 1, b); }
+        else if (prm.store_mode == 2) { __stwt(o4, a); __stwt(o4 + 1, b); }
+        else if (prm.store_mode == 3) { __stcg(o4, a); __stcg(o4 + 1, b); }
+        else { o4[0] = a; o4[1] = b; }
     } else if constexpr (j == 0) {
         const double ts = cbic_the_score64(A[0], k, prm);
         out[low] = (float)ts;
