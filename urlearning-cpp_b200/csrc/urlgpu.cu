@@ -823,10 +823,8 @@ static int h2d_async(urlgpu_ctx *ctx, void *dst, const void *src, size_t bytes) 
     return URLGPU_OK;
 }
 
-// `only_roots` (optional): restrict the work to the sub-forest below these root sets of layer `roots_layer`
-// (cube masks); the slice path hands over the roots it cannot slice.
 static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                                 uint64_t *n_scored, bool *used, const std::vector<uint32_t> *only_roots = nullptr, int roots_layer = -1) {
+                                 uint64_t *n_scored, bool *used) {
     *used = false;
     cudaStream_t s = ctx->stream;
     { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
@@ -855,7 +853,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
 
     // ---- enumerate layers 0..Lmax (layers above Kc: only sets containing the lowest l-Kc cube bits) ----
-    const int Lmax = only_roots ? roots_layer : std::min(Kc + 2, c);
+    const int Lmax = std::min(Kc + 2, c);
     std::vector<std::vector<CubeSet>> layers(Lmax + 1);
     // per-byte lookup tables: cells factor and result-order mask of every 8-bit group of cube bits
     std::vector<uint64_t> cellsT(4 * 256, 1);
@@ -881,14 +879,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         cs.parent = -1;
         return cs;
     };
-    if (only_roots) { // the sub-forest of the given roots: root P, run = trailing ones of P, descendants P ^ D
-        for (uint32_t P : *only_roots) {
-            const int z = std::min(c, (int)__builtin_ctz(~P));
-            for (uint32_t D = 0; D < (1u << z); D++) layers[Lmax - __builtin_popcount(D)].push_back(make_set(P ^ D));
-        }
-        for (auto &L : layers) std::sort(L.begin(), L.end(), [](const CubeSet &a, const CubeSet &b) { return a.cube_mask < b.cube_mask; });
-    }
-    for (int l = 0; l <= Lmax && !only_roots; l++) {
+    for (int l = 0; l <= Lmax; l++) {
         const int j = std::max(0, l - Kc);      // forced low bits
         const int free_bits = c - j, pick = l - j;
         const uint32_t lowmask = (j ? ((1u << j) - 1) : 0);
@@ -922,7 +913,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         for (auto &cs : layers[l]) layer_cells[l] += (double)((cs.cells + 3) / 4 * 4);
     int Lstar = -1;
     double best = 1e300;
-    for (int Ls = only_roots ? Lmax : Kc; Ls <= Lmax; Ls++) {
+    for (int Ls = Kc; Ls <= Lmax; Ls++) {
         double cost = 0, maxl = 0;
         for (auto &cs : layers[Ls]) cost += root_cost(cs, Ls);
         if (cost >= 1e29) continue; // a root table above the 2^30-cell limit
@@ -1234,12 +1225,12 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     std::vector<CubePair> hp;
     DevBuf dcmap(ctx);
     const int r0 = (int)ccard[0];
-    const bool fuse_leaves = ctx->fuse_leaves && !only_roots && r0 >= 2 && r0 <= 4 && rv >= 2 && rv <= 4;
+    const bool fuse_leaves = ctx->fuse_leaves && r0 >= 2 && r0 <= 4 && rv >= 2 && rv <= 4;
     std::vector<char> by_pair_prev; // layer l+1: table produced by a derive pair of the previous iteration (its leaf child was scored there)
     for (int l = Lstar - 1; l >= 0; l--) {
         auto &L = layers[l];
         auto &P = layers[l + 1];
-        if (L.empty()) break; // sub-forest mode: runs shorter than the layer count leave the lower layers empty
+        if (L.empty()) break;
         if (l == Lstar - 1)
             for (size_t i = 0; i < P.size(); i++) if (!fused_root[i]) ctx->st.k1_bytes_written += 4.0 * (double)P[i].cells; // root tables that were written
         const bool top = l == Lstar - 1 && fused_any; // children of fused roots were produced by the root kernel
@@ -1308,7 +1299,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     if (dbg) fprintf(stderr, "[urlgpu cube] v=%d c=%d K=%d L*=%d roots=%zu plan+alloc %.2f ms (cpu %.2f), roots %.2f ms, derive %.2f ms, cpu total %.2f\n", variable, c, K, Lstar,
                      layers[Lstar].size(), tms(T0, T1), C1 - C0, tms(T1, T2), tms(T2, tnow()), cpu_ms() - C0);
     *n_scored = family_size(c, K);
-    if (!only_roots) {
+    {
         double bytes = 0, b = 1;
         for (int l = 0; l <= K && l <= c; l++) { bytes += b * (double)ctx->n * (l + 1); b = b * (c - l) / (l + 1); }
         ctx->st.algorithmic_bytes += bytes;
