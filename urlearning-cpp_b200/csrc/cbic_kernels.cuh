@@ -218,7 +218,10 @@ __device__ __forceinline__ double cbic_the_score64(double rss, int k, const Cbic
 // kInlineLevel are real calls with their matrices on the thread's stack (touched once per 2^j sets); the bottom
 // levels are fully inlined so their matrices live in registers, and the scores of the 8 sets below a level-3 node are
 // collected in registers and written as one full 32-byte sector (two 128-bit stores).
-constexpr int kInlineLevel = 4;
+#ifndef URLGPU_DFS_INLINE
+#define URLGPU_DFS_INLINE 4
+#endif
+constexpr int kInlineLevel = URLGPU_DFS_INLINE;
 #ifndef URLGPU_DFS_MINBLOCKS
 #define URLGPU_DFS_MINBLOCKS 5
 #endif
