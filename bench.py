@@ -248,12 +248,13 @@ def run_gpu(args):
 
     def step(fetch=False):
         """one pass of the hot path over this rank's variables (dealt to the pool's contexts by predicted cost).  fetch: read
-        every surviving cache back to the host, software-pipelined one variable deep (v+1 is enqueued before v is read).
+        every surviving cache back to the host (into the context's page-locked result buffer, as a driver that formats each
+        variable's block as it arrives would), software-pipelined one variable deep (v+1 is enqueued before v is read).
         Returns after every context has drained, so consecutive steps do not overlap."""
         flush.fill_(1)  # L2 flush between steps (inside the timed region: ~40 us of a step of hundreds of ms)
         stream.synchronize()
-        out = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch=fetch, costs=costs)
-        return sum(len(x[1]) for x in out.values()) if fetch else 0
+        out = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch="pinned" if fetch else False, costs=costs)
+        return sum(out.values()) if fetch else 0
 
     def barrier():
         if world > 1:

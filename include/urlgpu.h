@@ -105,6 +105,10 @@ int urlgpu_result_scored(urlgpu_result *res, uint64_t *n_scored);  /* candidate 
 /* canonical order: (|S| ascending, mask ascending as an integer).  masks: n*mask_words words. */
 int urlgpu_result_fetch(urlgpu_result *res, uint64_t offset, uint64_t n, uint64_t *masks, float *scores);
 int urlgpu_result_free(urlgpu_result *res);
+/* page-locked host memory for large result payloads (urlgpu_result_fetch copies into it at PCIe speed; pageable
+ * destinations work too but go through the driver's staging copy).  NULL on failure. */
+void *urlgpu_host_alloc(uint64_t bytes);
+void urlgpu_host_free(void *p);
 
 /* Single parent set, same value ScoringFunction::calculateScore returns (BIC: the score; cBIC: -the_score).
  * value64 (optional): BIC: exact log-likelihood before the float rounding; cBIC: the_score in FP64. */

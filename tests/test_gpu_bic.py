@@ -237,6 +237,24 @@ def test_pipelined_prefetch_matches_plain_fetch(pkg, engine):
             assert pc == sorted(pc)  # canonical order: layer by layer
 
 
+def test_pinned_fetch_equals_plain_fetch(pkg, engine):
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=16, n=30011, seed=19, window=4, max_indegree=3)
+    engine.set_discrete(codes, card)
+    for v in (0, 7, 15):
+        r = engine.score_variable(v, pkg.two_hop_neighbors(edges, 16, v), 6, pkg.BIC)
+        m0, s0 = r.fetch()
+        m1, s1 = r.fetch(pinned=True)
+        assert np.array_equal(m0, m1) and np.array_equal(s0.view(np.uint32), s1.view(np.uint32))
+        r.free()
+    pool = pkg.EnginePool(0, 2)
+    pool.set_discrete(codes, card)
+    items = [(v, pkg.two_hop_neighbors(edges, 16, v)) for v in range(16)]
+    full = pool.run(items, 6, pkg.BIC, fetch=True)
+    counts = pool.run(items, 6, pkg.BIC, fetch="pinned")
+    assert {v: len(x[1]) for v, x in full.items()} == counts
+    pool.close()
+
+
 def test_engine_pool_matches_single_engine(pkg, engine):
     """three contexts on one device driven by three host threads (the reference's -t workers on one GPU): same caches"""
     codes, card, edges, _ = pkg.datagen.discrete_bn(p=18, n=50021, seed=17, window=4, max_indegree=3)

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "urlgpu_synchronize", "urlgpu_set_discrete", "urlgpu_set_discrete_device", "urlgpu_share_discrete", "urlgpu_set_continuous",
     "urlgpu_set_continuous_device", "urlgpu_shard_begin", "urlgpu_shard_moments", "urlgpu_shard_finish", "urlgpu_get_gram", "urlgpu_set_gram", "urlgpu_score_variable",
     "urlgpu_result_prefetch", "urlgpu_result_count", "urlgpu_result_scored", "urlgpu_result_fetch", "urlgpu_result_free",
+    "urlgpu_host_alloc", "urlgpu_host_free",
     "urlgpu_score_one", "urlgpu_contingency", "urlgpu_prune", "urlgpu_stats_reset", "urlgpu_stats_get",
     "urlgpu_stats_enable_timing",
 ]
@@ -92,6 +93,8 @@ def load_library():
     lib.urlgpu_result_scored.argtypes = [vp, P(u64)]
     lib.urlgpu_result_fetch.argtypes = [vp, u64, u64, vp, vp]
     lib.urlgpu_result_free.argtypes = [vp]
+    lib.urlgpu_host_alloc.argtypes = [u64]
+    lib.urlgpu_host_free.argtypes = [vp]
     lib.urlgpu_score_one.argtypes = [vp, i32, vp, i32, i32, C.c_double, P(C.c_float), P(C.c_double)]
     lib.urlgpu_contingency.argtypes = [vp, i32, vp, i32, vp, i64]
     lib.urlgpu_prune.argtypes = [vp, vp, vp, u64, i32, vp]
@@ -99,8 +102,10 @@ def load_library():
     lib.urlgpu_stats_get.argtypes = [vp, P(Stats)]
     lib.urlgpu_stats_enable_timing.argtypes = [vp, i32]
     for name in ABI_SYMBOLS:
-        if name != "urlgpu_last_error":
+        if name not in ("urlgpu_last_error", "urlgpu_host_alloc", "urlgpu_host_free"):
             getattr(lib, name).restype = C.c_int
+    lib.urlgpu_host_alloc.restype = vp
+    lib.urlgpu_host_free.restype = None
     _lib = lib
     return lib
 
@@ -167,12 +172,18 @@ class Result:
         self._eng._check(self._eng.lib.urlgpu_result_scored(self._h, C.byref(n)))
         return n.value
 
-    def fetch(self):
-        """-> (masks uint64[n, words], scores float32[n]) in canonical (|S|, mask) order."""
+    def fetch(self, pinned: bool = False):
+        """-> (masks uint64[n, words], scores float32[n]) in canonical (|S|, mask) order.
+        pinned=True: the arrays are views of the engine's page-locked result buffer (PCIe-speed copy, no page faults on
+        fresh memory); they stay valid until the next pinned fetch on the same engine."""
         n = self.count()
-        masks = np.zeros((n, self.words), dtype=np.uint64)
-        scores = np.zeros(n, dtype=np.float32)
-        self._eng._check(self._eng.lib.urlgpu_result_fetch(self._h, 0, n, masks.ctypes.data, scores.ctypes.data))
+        if pinned:
+            masks, scores = self._eng._pinned_views(n, self.words)
+        else:
+            masks = np.zeros((n, self.words), dtype=np.uint64)
+            scores = np.zeros(n, dtype=np.float32)
+        if n:
+            self._eng._check(self._eng.lib.urlgpu_result_fetch(self._h, 0, n, masks.ctypes.data, scores.ctypes.data))
         return masks, scores
 
     def free(self):
@@ -199,8 +210,30 @@ class Engine:
         self._h = h
         self.p = 0
         self._keep = []
+        self._pin_ptr, self._pin_cap = None, 0
+
+    def _pinned_views(self, n: int, words: int):
+        """views of a page-locked buffer for n result entries, grown geometrically"""
+        need = n * (8 * words + 4) + 64
+        if need > self._pin_cap:
+            if self._pin_ptr:
+                self.lib.urlgpu_host_free(self._pin_ptr)
+            cap = max(need + need // 2, 1 << 20)
+            ptr = self.lib.urlgpu_host_alloc(cap)
+            if not ptr:
+                self._pin_ptr, self._pin_cap = None, 0
+                raise UrlGpuError(f"cannot page-lock {cap} bytes of host memory")
+            self._pin_ptr, self._pin_cap = ptr, cap
+        mbytes = n * 8 * words
+        buf = (C.c_char * self._pin_cap).from_address(self._pin_ptr)
+        masks = np.frombuffer(buf, dtype=np.uint64, count=n * words, offset=0).reshape(n, words)
+        scores = np.frombuffer(buf, dtype=np.float32, count=n, offset=(mbytes + 63) // 64 * 64)
+        return masks, scores
 
     def close(self):
+        if getattr(self, "_pin_ptr", None):
+            self.lib.urlgpu_host_free(self._pin_ptr)
+            self._pin_ptr, self._pin_cap = None, 0
         if getattr(self, "_h", None):
             self.lib.urlgpu_destroy(self._h)
             self._h = None
@@ -399,7 +432,9 @@ class EnginePool:
     def run(self, items, max_parents, score_type=BIC, lam=0.0, flags=KEEP_ALL, fetch=False, costs=None, contexts=None):
         """items: [(variable, neighbors mask)].  Scores every item on one of the pool's contexts (dealt out by `costs`,
         longest first, else round robin).  fetch=True -> {variable: (masks, scores)}, read back one variable behind the
-        one being scored (urlgpu_result_prefetch); fetch=False -> {variable: sets scored}, results dropped on the device.
+        one being scored (urlgpu_result_prefetch); fetch="pinned" -> {variable: stored entries}, every cache is read back
+        into the context's page-locked result buffer (overwritten by the next one: for drivers that consume each cache as
+        it arrives); fetch=False -> {variable: sets scored}, results dropped on the device.
         contexts: use only the first `contexts` contexts (1 = strictly serial kernels, for per-kernel timing)."""
         T = len(self.engines) if contexts is None else max(1, min(contexts, len(self.engines)))
         order = sorted(range(len(items)), key=lambda i: (-(costs[i] if costs is not None else 0.0), i))
@@ -413,6 +448,11 @@ class EnginePool:
         import threading
         errs = []
 
+        def take(res):
+            if fetch == "pinned":
+                return len(res.fetch(pinned=True)[1])
+            return res.fetch()
+
         def work(t):
             eng = self.engines[t]
             try:
@@ -423,14 +463,14 @@ class EnginePool:
                     if fetch:
                         res.prefetch()
                         if prev is not None:
-                            out[prev[0]] = prev[1].fetch()
+                            out[prev[0]] = take(prev[1])
                             prev[1].free()
                         prev = (v, res)
                     else:
                         out[v] = res.scored()
                         res.free()
                 if prev is not None:
-                    out[prev[0]] = prev[1].fetch()
+                    out[prev[0]] = take(prev[1])
                     prev[1].free()
                 eng.synchronize()
             except Exception as ex:

@@ -1926,6 +1926,16 @@ extern "C" int urlgpu_result_fetch(urlgpu_result *res, uint64_t offset, uint64_t
     return URLGPU_OK;
 }
 
+// page-locked host memory for result payloads: device->host copies into it run at PCIe speed and need no staging copy
+extern "C" void *urlgpu_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void urlgpu_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" int urlgpu_result_free(urlgpu_result *res) {
     if (!res) return URLGPU_OK;
     urlgpu_ctx *ctx = res->ctx;
