@@ -177,23 +177,28 @@ struct CbicParams {
 // packed lower-triangular index, element order (v, cand0, cand1, ...)
 __host__ __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }
 
-// Level A: one warp per prefix P (the high c-J candidate bits).  Starting from the (c+1)x(c+1) sub-Gram, walk the
-// high candidates from the top: an included one is swept out (Schur complement), either way it is then dropped.
-// Output: roots[e * n_prefix + P] for the (J+1)(J+2)/2 packed entries e of the remaining matrix.
-__global__ void cbic_roots_kernel(const double *__restrict__ subgram /*packed (c+1)(c+2)/2*/, CbicParams prm, uint32_t n_prefix,
-                                  double *__restrict__ roots) {
+// Level A: one warp per prefix (the high candidate bits).  Starting from a matrix over (v, cand_0 .. cand_{c_in-1}), walk
+// the `bits` highest candidates from the top: an included one is swept out (Schur complement), either way it is then
+// dropped.  The prefix index p = (q << bits) | local: q selects the input matrix (in_stride = 0: one shared matrix),
+// bit (bits-1) of `local` is candidate c_in-1.  Run in two stages (host: 9 + 9 bits at c = 29) so the sweeps of the top
+// bits are shared by the 2^bits prefixes below them; every element still sees the same sequence of FMAs.
+// Output: the remaining matrix over (v, cand_0 .. cand_{c_in-bits-1}), either contiguous per prefix (transposed == 0:
+// out[p * outsz + e], the next stage's input) or entry-major (transposed == 1: out[e * n_out + p], what the DFS reads).
+__global__ void cbic_roots_kernel(const double *__restrict__ in, size_t in_stride, int c_in, int bits, int max_parents, uint32_t n_out,
+                                  double *__restrict__ out, int transposed) {
     extern __shared__ double smat[]; // [warps][tri size]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t P = blockIdx.x * (blockDim.x >> 5) + warp;
-    const int tsz = (prm.c + 1) * (prm.c + 2) / 2;
+    const int tsz = (c_in + 1) * (c_in + 2) / 2;
     double *A = smat + warp * tsz;
-    if (P >= n_prefix) return;
-    if (__popc(P) > prm.max_parents) return; // whole subtree unscored
-    for (int e = lane; e < tsz; e += 32) A[e] = subgram[e];
+    if (P >= n_out) return;
+    if (__popc(P) > max_parents) return; // whole subtree unscored
+    const double *src = in + (size_t)(P >> bits) * in_stride;
+    for (int e = lane; e < tsz; e += 32) A[e] = src[e];
     __syncwarp();
-    for (int cand = prm.c - 1; cand >= prm.J; cand--) {
-        if ((P >> (cand - prm.J)) & 1) {
-            const int piv = cand + 1; // position in (v, c0, c1, ...)
+    for (int t = bits - 1; t >= 0; t--) {
+        if ((P >> t) & 1) {
+            const int piv = c_in - bits + t + 1; // position of the candidate in (v, c0, c1, ...)
             const double inv = 1.0 / A[tri(piv, piv)];
             for (int a = 0; a < piv; a++) {
                 const double f = -A[tri(piv, a)] * inv;
@@ -202,8 +207,10 @@ __global__ void cbic_roots_kernel(const double *__restrict__ subgram /*packed (c
             __syncwarp();
         }
     }
-    const int outsz = (prm.J + 1) * (prm.J + 2) / 2;
-    for (int e = lane; e < outsz; e += 32) roots[(size_t)e * n_prefix + P] = A[e];
+    const int c_out = c_in - bits;
+    const int outsz = (c_out + 1) * (c_out + 2) / 2;
+    if (transposed) { for (int e = lane; e < outsz; e += 32) out[(size_t)e * n_out + P] = A[e]; }
+    else { for (int e = lane; e < outsz; e += 32) out[(size_t)P * outsz + e] = A[e]; }
 }
 
 // the_score of one set from its RSS (BIC_OLS.cpp:302-305,366): k == 0 -> 0.0.

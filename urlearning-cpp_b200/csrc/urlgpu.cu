@@ -1579,15 +1579,27 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
     { static const int sm = getenv("URLGPU_CBIC_STORE") ? atoi(getenv("URLGPU_CBIC_STORE")) : 1; prm.store_mode = sm; }
     const uint32_t n_prefix = 1u << (c - prm.J);
     const int outsz = (prm.J + 1) * (prm.J + 2) / 2;
-    DevBuf dsub(ctx), droots(ctx);
+    DevBuf dsub(ctx), droots(ctx), dmid(ctx);
     CK(dsub.alloc(sub.size() * sizeof(double)));
     CK(droots.alloc((size_t)outsz * n_prefix * sizeof(double)));
     CK(cudaMemcpyAsync(dsub.p, sub.data(), sub.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     {
-        Region rg(ctx, F_CBIC, 2);
+        Region rg(ctx, F_CBIC, 3);
         const int warps = 8;
-        const size_t smem = (size_t)warps * sub.size() * sizeof(double);
-        cbic_roots_kernel<<<blocks_for(n_prefix, warps), warps * 32, smem, s>>>(dsub.as<double>(), prm, n_prefix, droots.as<double>());
+        const int hbits = c - prm.J;               // high candidate bits handled by level A
+        const int b1 = hbits >= 8 ? hbits / 2 : 0; // two stages: the sweeps of the top b1 bits are shared by the prefixes below them
+        if (b1 > 0) {
+            const int c_mid = c - b1;
+            const size_t midsz = (size_t)(c_mid + 1) * (c_mid + 2) / 2;
+            CK(dmid.alloc(midsz * ((size_t)1 << b1) * sizeof(double)));
+            cbic_roots_kernel<<<blocks_for((uint64_t)1 << b1, warps), warps * 32, (size_t)warps * sub.size() * sizeof(double), s>>>(
+                dsub.as<double>(), 0, c, b1, K, 1u << b1, dmid.as<double>(), 0);
+            cbic_roots_kernel<<<blocks_for(n_prefix, warps), warps * 32, (size_t)warps * midsz * sizeof(double), s>>>(
+                dmid.as<double>(), midsz, c_mid, hbits - b1, K, n_prefix, droots.as<double>(), 1);
+        } else {
+            cbic_roots_kernel<<<blocks_for(n_prefix, warps), warps * 32, (size_t)warps * sub.size() * sizeof(double), s>>>(
+                dsub.as<double>(), 0, c, hbits, K, n_prefix, droots.as<double>(), 1);
+        }
         switch (prm.J) {
 #define URLGPU_CASE(JJ) case JJ: launch_cbic_dfs<JJ>(droots.as<double>(), prm, n_prefix, d_table, d_ts64, s); break;
             URLGPU_CASE(0) URLGPU_CASE(1) URLGPU_CASE(2) URLGPU_CASE(3) URLGPU_CASE(4) URLGPU_CASE(5) URLGPU_CASE(6) URLGPU_CASE(7)
