@@ -1570,7 +1570,10 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
         for (int b = 0; b <= a; b++) sub[tri(a, b)] = ctx->h_gram[(size_t)order[a] * p + order[b]];
     CbicParams prm{};
     prm.c = c;
-    prm.J = std::max(std::min(c, 3), std::min(11, c - 10));
+    { // low bits walked by one DFS thread: 11 by default (URLGPU_CBIC_J overrides, 3..11)
+        static const int jmax = getenv("URLGPU_CBIC_J") ? std::max(3, std::min(atoi(getenv("URLGPU_CBIC_J")), 11)) : 11;
+        prm.J = std::max(std::min(c, 3), std::min(jmax, c - 10));
+    }
     prm.max_parents = K;
     prm.n = (double)(int)ctx->cn;
     prm.lam_logn = lambda * std::log((double)(int)ctx->cn);
@@ -1579,26 +1582,33 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
     { static const int sm = getenv("URLGPU_CBIC_STORE") ? atoi(getenv("URLGPU_CBIC_STORE")) : 1; prm.store_mode = sm; }
     const uint32_t n_prefix = 1u << (c - prm.J);
     const int outsz = (prm.J + 1) * (prm.J + 2) / 2;
-    DevBuf dsub(ctx), droots(ctx), dmid(ctx);
+    DevBuf dsub(ctx), droots(ctx), dmid(ctx), dmid2(ctx);
     CK(dsub.alloc(sub.size() * sizeof(double)));
     CK(droots.alloc((size_t)outsz * n_prefix * sizeof(double)));
     CK(cudaMemcpyAsync(dsub.p, sub.data(), sub.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     {
-        Region rg(ctx, F_CBIC, 3);
+        Region rg(ctx, F_CBIC, 4);
         const int warps = 8;
-        const int hbits = c - prm.J;               // high candidate bits handled by level A
-        const int b1 = hbits >= 8 ? hbits / 2 : 0; // two stages: the sweeps of the top b1 bits are shared by the prefixes below them
-        if (b1 > 0) {
-            const int c_mid = c - b1;
-            const size_t midsz = (size_t)(c_mid + 1) * (c_mid + 2) / 2;
-            CK(dmid.alloc(midsz * ((size_t)1 << b1) * sizeof(double)));
-            cbic_roots_kernel<<<blocks_for((uint64_t)1 << b1, warps), warps * 32, (size_t)warps * sub.size() * sizeof(double), s>>>(
-                dsub.as<double>(), 0, c, b1, K, 1u << b1, dmid.as<double>(), 0);
-            cbic_roots_kernel<<<blocks_for(n_prefix, warps), warps * 32, (size_t)warps * midsz * sizeof(double), s>>>(
-                dmid.as<double>(), midsz, c_mid, hbits - b1, K, n_prefix, droots.as<double>(), 1);
-        } else {
-            cbic_roots_kernel<<<blocks_for(n_prefix, warps), warps * 32, (size_t)warps * sub.size() * sizeof(double), s>>>(
-                dsub.as<double>(), 0, c, hbits, K, n_prefix, droots.as<double>(), 1);
+        // level A in stages of <= 7 bits: the sweeps of the higher bits are shared by all the prefixes below them
+        const int hbits = c - prm.J;
+        const int nstages = std::max(1, (hbits + 6) / 7);
+        const double *src = dsub.as<double>();
+        size_t src_stride = 0;
+        int c_in = c, done = 0;
+        DevBuf *mids[2] = {&dmid, &dmid2};
+        for (int st = 0; st < nstages; st++) {
+            const int bits = (hbits - done) / (nstages - st); // even split of what is left
+            const bool last = st == nstages - 1;
+            const int c_out = c_in - bits;
+            const size_t insz = (size_t)(c_in + 1) * (c_in + 2) / 2, osz = (size_t)(c_out + 1) * (c_out + 2) / 2;
+            const uint32_t n_out = 1u << (done + bits);
+            double *dst = droots.as<double>();
+            if (!last) {
+                CK(mids[st & 1]->alloc(osz * n_out * sizeof(double)));
+                dst = mids[st & 1]->as<double>();
+            }
+            cbic_roots_kernel<<<blocks_for(n_out, warps), warps * 32, (size_t)warps * insz * sizeof(double), s>>>(src, src_stride, c_in, bits, K, n_out, dst, last ? 1 : 0);
+            src = dst; src_stride = osz; c_in = c_out; done += bits;
         }
         switch (prm.J) {
 #define URLGPU_CASE(JJ) case JJ: launch_cbic_dfs<JJ>(droots.as<double>(), prm, n_prefix, d_table, d_ts64, s); break;
