@@ -176,7 +176,8 @@ void pool_destroy(urlgpu_ctx *ctx) {
     ctx->pool.clear();
 }
 
-struct DevBuf { // RAII device allocation from the context's pool (stream-ordered use: callers sync before release)
+struct DevBuf { // RAII device allocation from the context's pool.  Released blocks are only ever handed to later work on the SAME stream
+                // (the context's scoring stream), so kernels still in flight keep their buffers without a synchronisation
     urlgpu_ctx *ctx;
     void *p = nullptr;
     explicit DevBuf(urlgpu_ctx *c) : ctx(c) {}
