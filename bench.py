@@ -331,6 +331,7 @@ def run_gpu(args):
         e2e = {"value": total_sets * nst / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int((8 * words + 4) * stored // nst), "steps": nst, "ms_per_step": ems / nst}
 
+    mem_free, mem_total = torch.cuda.mem_get_info()
     if rank == 0:
         peak, peak_src = load_peaks()
         fam = {"count": st["ms_count"], "cube": st["ms_cube"], "tree": st["ms_tree"], "cbic": st["ms_cbic"], "accept": st["ms_accept"],
@@ -372,7 +373,8 @@ def run_gpu(args):
                 "config": {"workload": wl["name"], "sets_per_step": total_sets,
                            "parallelism": ("variables dealt to ranks by predicted cost (LPT)" if is_bic else "variables striped v % N") + f", N={world}; "
                                           f"{T} context(s)/stream(s) per GPU, one host thread each (the reference's -t workers)",
-                           "l2": "flushed between steps (256 MB write)", "dominant_family": dom},
+                           "l2": "flushed between steps (256 MB write)", "dominant_family": dom,
+                           "hbm_in_use_gb": round((mem_total - mem_free) / 1e9, 1)},
                 "e2e": e2e, "gpu_launches": int(launches_total), "clocks": sampler.summary(), "roofline": roofline,
                 "cpu_baseline": cpu}
         print(json.dumps(line))

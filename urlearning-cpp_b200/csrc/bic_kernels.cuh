@@ -276,6 +276,10 @@ struct CubePair {
 constexpr uint32_t kNoLeafAcc = 0xffffffffu;
 
 constexpr int kCubeThreads = 256;
+#ifndef URLGPU_CUBE_UNROLL
+#define URLGPU_CUBE_UNROLL 2
+#endif
+constexpr int kCubeUnroll = URLGPU_CUBE_UNROLL;
 constexpr int kCubeConfigsPerBlock = 4096;
 __host__ __device__ inline uint32_t cube_configs_per_block(uint32_t group) { return (uint32_t)kCubeConfigsPerBlock / group * group; }
 
@@ -377,7 +381,6 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
             if (threadIdx.x == 0 && accL != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_all[pr.leaf_acc]), (unsigned long long)accL);
             __syncthreads(); // red is reused below
         } else {
-        // two configurations per thread and iteration: 2*r independent 128-bit loads in flight before the first add
         auto score_cfg = [&](const int (&cnt)[RV]) {
             int nij = 0;
 #pragma unroll
@@ -389,31 +392,36 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
                 acc -= __ldg(&qlog[nij]);
             }
         };
-        for (uint32_t j = j0 + threadIdx.x; j < j1; j += 2 * kCubeThreads) {
-            const uint32_t jb = j + kCubeThreads;
-            const bool two = jb < j1;
-            const uint32_t hiA = j / pr.Bc, loA = j - hiA * pr.Bc;
-            const uint64_t pcA = (uint64_t)loA + (uint64_t)hiA * pr.r * pr.Bc;
-            const uint32_t jB = two ? jb : j;
-            const uint32_t hiB = jB / pr.Bc, loB = jB - hiB * pr.Bc;
-            const uint64_t pcB = (uint64_t)loB + (uint64_t)hiB * pr.r * pr.Bc;
-            int cntA[RV], cntB[RV];
-            load_cfg<RV>(P + pcA * RV, cntA);
-            load_cfg<RV>(P + pcB * RV, cntB);
-            for (uint32_t a = 1; a < pr.r; a++) {
-                int tA[RV], tB[RV];
-                load_cfg<RV>(P + (pcA + (uint64_t)a * pr.Bc) * RV, tA);
-                load_cfg<RV>(P + (pcB + (uint64_t)a * pr.Bc) * RV, tB);
+        // kCubeUnroll configurations per thread and iteration: r * kCubeUnroll independent 128-bit loads in flight
+        for (uint32_t j = j0 + threadIdx.x; j < j1; j += kCubeUnroll * kCubeThreads) {
+            uint32_t jj[kCubeUnroll];
+            uint64_t pc[kCubeUnroll];
+            bool on[kCubeUnroll];
+            int cnt[kCubeUnroll][RV];
 #pragma unroll
-                for (int k = 0; k < RV; k++) { cntA[k] += tA[k]; cntB[k] += tB[k]; }
+            for (int u = 0; u < kCubeUnroll; u++) {
+                jj[u] = j + u * kCubeThreads;
+                on[u] = jj[u] < j1;
+                const uint32_t ju = on[u] ? jj[u] : j;
+                const uint32_t hi = ju / pr.Bc, lo = ju - hi * pr.Bc;
+                pc[u] = (uint64_t)lo + (uint64_t)hi * pr.r * pr.Bc;
             }
-            if (!pr.leaf) {
-                store_cfg<RV>(Cc + (uint64_t)j * RV, cntA);
-                if (two) store_cfg<RV>(Cc + (uint64_t)jb * RV, cntB);
+#pragma unroll
+            for (int u = 0; u < kCubeUnroll; u++) load_cfg<RV>(P + pc[u] * RV, cnt[u]);
+            for (uint32_t a = 1; a < pr.r; a++) {
+                int t[kCubeUnroll][RV];
+#pragma unroll
+                for (int u = 0; u < kCubeUnroll; u++) load_cfg<RV>(P + (pc[u] + (uint64_t)a * pr.Bc) * RV, t[u]);
+#pragma unroll
+                for (int u = 0; u < kCubeUnroll; u++)
+#pragma unroll
+                    for (int k = 0; k < RV; k++) cnt[u][k] += t[u][k];
             }
-            if (acc_out) {
-                score_cfg(cntA);
-                if (two) score_cfg(cntB);
+#pragma unroll
+            for (int u = 0; u < kCubeUnroll; u++) {
+                if (!on[u]) continue;
+                if (!pr.leaf) store_cfg<RV>(Cc + (uint64_t)jj[u] * RV, cnt[u]);
+                if (acc_out) score_cfg(cnt[u]);
             }
         }
         }

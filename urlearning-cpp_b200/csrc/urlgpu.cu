@@ -1005,16 +1005,20 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         if (total_slices < 128 || total_slices > 0x7fffffffull) std::fill(root_kind.begin(), root_kind.end(), 0); // too few CTAs to fill the machine
     }
     // ---- offsets and parent links ----
-    size_t max_layer = 0;
+    // Layer Lstar lives in buffer A, Lstar-1 in B, Lstar-2 in A again, ...: each buffer is sized for its own layers only.
+    // Tables that are never materialised take no room: fused roots, and below the root layer every set without cube
+    // bit 0 (nothing is derived from it, its table is only scored on the fly).
+    size_t needA = 0, needB = 0;
     for (int l = 0; l <= Lstar; l++) {
         uint64_t off = 0;
         for (size_t i = 0; i < layers[l].size(); i++) {
             auto &cs = layers[l][i];
             cs.off = off;
-            if (l == Lstar && root_kind[i] == 2) continue; // never materialised
+            if (l == Lstar && root_kind[i] == 2) continue;          // fused root
+            if (l < Lstar && (cs.cube_mask & 1u) == 0) continue;    // leaf
             off += (cs.cells + 3) / 4 * 4;
         }
-        max_layer = std::max<size_t>(max_layer, off);
+        if (((Lstar - l) & 1) == 0) needA = std::max<size_t>(needA, off); else needB = std::max<size_t>(needB, off);
         if (l < Lstar) {
             auto &P = layers[l + 1];
             for (auto &cs : layers[l]) {
@@ -1028,8 +1032,9 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             }
         }
     }
-    if (ctx->cubeA_cap < max_layer) { if (ctx->d_cubeA) cudaFree(ctx->d_cubeA); ctx->d_cubeA = nullptr; ctx->cubeA_cap = 0; CK(cudaMalloc(&ctx->d_cubeA, max_layer * sizeof(int))); ctx->cubeA_cap = max_layer; }
-    if (ctx->cubeB_cap < max_layer) { if (ctx->d_cubeB) cudaFree(ctx->d_cubeB); ctx->d_cubeB = nullptr; ctx->cubeB_cap = 0; CK(cudaMalloc(&ctx->d_cubeB, max_layer * sizeof(int))); ctx->cubeB_cap = max_layer; }
+    needA = std::max<size_t>(needA, 4); needB = std::max<size_t>(needB, 4);
+    if (ctx->cubeA_cap < needA) { if (ctx->d_cubeA) cudaFree(ctx->d_cubeA); ctx->d_cubeA = nullptr; ctx->cubeA_cap = 0; CK(cudaMalloc(&ctx->d_cubeA, needA * sizeof(int))); ctx->cubeA_cap = needA; }
+    if (ctx->cubeB_cap < needB) { if (ctx->d_cubeB) cudaFree(ctx->d_cubeB); ctx->d_cubeB = nullptr; ctx->cubeB_cap = 0; CK(cudaMalloc(&ctx->d_cubeB, needB * sizeof(int))); ctx->cubeB_cap = needB; }
     int *bufP = ctx->d_cubeA, *bufC = ctx->d_cubeB;
     const auto T1 = tnow();
     const double C1 = dbg ? cpu_ms() : 0.0;
