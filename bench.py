@@ -556,7 +556,8 @@ def run_reference(args):
     pkg = importlib.import_module("urlearning-cpp_b200")
     wl = make_bic_workload(pkg, 1) if args.workload == "bic" else make_cbic_workload(pkg)
     threads = os.cpu_count() or 1
-    per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    # each step = a bounded sample: the whole run ends within ~1.5 minutes unless --cpu-seconds asks for something else
+    per_step = args.cpu_seconds if args.cpu_seconds_given else max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup):
         cpu_sample(wl, per_step, threads, seed=100 + i)
     done, used = 0, 0.0
@@ -594,6 +595,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.cpu_seconds_given = any(a == "--cpu-seconds" or a.startswith("--cpu-seconds=") for a in sys.argv[1:])
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "cbic5":
