@@ -52,7 +52,7 @@ def test_figures_full_family(pkg, orc, engine, data_dir, fig, fn):
         assert np.all(ulp_diff(scores, val[order]) <= 1)
 
 
-@pytest.mark.parametrize("p,n,K", [(9, 2000, 8), (13, 3000, 12), (14, 1500, 4), (17, 4000, 3)])
+@pytest.mark.parametrize("p,n,K", [(9, 2000, 8), (13, 3000, 12), (14, 1500, 4), (17, 4000, 3), (27, 3000, 3)])
 def test_synthetic_exhaustive_and_limited(pkg, orc, engine, p, n, K):
     x, _ = pkg.datagen.linear_gaussian_sem(p=p, n=n, seed=p)
     engine.set_continuous(x)
