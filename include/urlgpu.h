@@ -147,6 +147,10 @@ int urlgpu_stats_get(urlgpu_ctx *ctx, urlgpu_stats *out);
 /* enable (1) / disable (0) per-kernel CUDA-event timing (adds a stream sync per measured region) */
 int urlgpu_stats_enable_timing(urlgpu_ctx *ctx, int on);
 
+/* Measured FP64 throughput of the context's device in TFLOP/s (register-resident probes, best of three): plain DFMA and
+ * the DMMA tensor path (mma.sync.m8n8k4.f64) the Gram kernel uses.  These are the denominators bench.py divides by. */
+int urlgpu_probe_fp64(urlgpu_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -221,18 +221,22 @@ def test_wide_masks_p_above_64(pkg, orc, engine):
         vs = sub.index(v)
         z = orc.standardise(xs)
         om = orc.enumerate_sets(vs, (1 << len(sub)) - 1, len(sub), 9)
-        ts = np.array([np.float32(orc.cbic_residual(z, vs, int(m), 2.0)) for m in om], dtype=np.float32)
+        full_of = lambda m: sum(1 << sub[i] for i in range(len(sub)) if (int(m) >> i) & 1)
+        # every set's float32 the_score from the engine (within 1 ulp of the oracle's residual form) ...
+        r0 = engine.score_variable(v, nb, 9, pkg.CBIC, lam=2.0, flags=pkg.CBIC_NO_ACCEPT)
+        m0, neg0 = r0.fetch()
+        r0.free()
+        gpu_ts = {pkg.words_to_mask(row): -s for row, s in zip(m0, neg0)}
+        assert len(gpu_ts) == len(om)
+        ts = np.array([gpu_ts[full_of(m)] for m in om], dtype=np.float32)
+        ref_ts = np.array([np.float32(orc.cbic_residual(z, vs, int(m), 2.0)) for m in om], dtype=np.float32)
+        assert np.all(ulp_diff(ts, ref_ts) <= 1)
+        # ... and, given those scores, the acceptance decisions and stored values agree EXACTLY with the oracle's recursion
         stored, val = orc.cbic_accept(vs, len(sub), om, ts)
-        want = {}
-        for m, s, st in zip(om, val, stored):
-            if st:
-                full = sum(1 << sub[i] for i in range(len(sub)) if (int(m) >> i) & 1)
-                want[full] = s
+        want = {full_of(m): s for m, s, st in zip(om, val, stored) if st}
         got = {pkg.words_to_mask(row): s for row, s in zip(masks, scores)}
-        # decisions follow the engine's float32 scores; borderline ulp differences could flip one, so compare loosely
-        assert len(set(got) ^ set(want)) <= 2
-        for k in set(got) & set(want):
-            assert ulp_diff(got[k], want[k]) <= 1
+        assert set(got) == set(want)
+        assert all(np.float32(got[k]).view(np.uint32) == np.float32(want[k]).view(np.uint32) for k in got)
         s1, ts64 = engine.score_one(v, sum(1 << i for i in cand[:3]), pkg.CBIC, 2.0)
         r = orc.cbic_residual(z, vs, sum(1 << sub.index(i) for i in cand[:3]), 2.0)
         assert abs(ts64 - r) <= TOL * max(1.0, abs(r))

@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "urlgpu_result_prefetch", "urlgpu_result_count", "urlgpu_result_scored", "urlgpu_result_fetch", "urlgpu_result_free",
     "urlgpu_host_alloc", "urlgpu_host_free",
     "urlgpu_score_one", "urlgpu_contingency", "urlgpu_prune", "urlgpu_stats_reset", "urlgpu_stats_get",
-    "urlgpu_stats_enable_timing",
+    "urlgpu_stats_enable_timing", "urlgpu_probe_fp64",
 ]
 
 
@@ -101,6 +101,7 @@ def load_library():
     lib.urlgpu_stats_reset.argtypes = [vp]
     lib.urlgpu_stats_get.argtypes = [vp, P(Stats)]
     lib.urlgpu_stats_enable_timing.argtypes = [vp, i32]
+    lib.urlgpu_probe_fp64.argtypes = [vp, P(C.c_double), P(C.c_double)]
     for name in ABI_SYMBOLS:
         if name not in ("urlgpu_last_error", "urlgpu_host_alloc", "urlgpu_host_free"):
             getattr(lib, name).restype = C.c_int
@@ -366,6 +367,12 @@ class Engine:
 
     def enable_timing(self, on: bool = True):
         self._check(self.lib.urlgpu_stats_enable_timing(self._h, int(on)))
+
+    def probe_fp64(self) -> dict:
+        """measured FP64 issue rates of this device in TFLOP/s: {'dfma': ..., 'dmma': ...}"""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.urlgpu_probe_fp64(self._h, C.byref(a), C.byref(b)))
+        return {"dfma": a.value, "dmma": b.value}
 
 
 from . import datagen, pss  # noqa: E402

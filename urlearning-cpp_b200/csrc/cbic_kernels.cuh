@@ -162,6 +162,36 @@ __global__ void gram_combine_kernel(const double *__restrict__ partial, int p, i
     g[b * p + a] = acc;
 }
 
+// FP64 peak probes (urlgpu_probe_fp64): the denominators of the K2/K3 roofline fractions are MEASURED on the device the
+// bench runs on, not taken from a data sheet.  dfma: 8 independent FMA chains per thread; dmma: 8 independent
+// m8n8k4 accumulator tiles per warp.  Operands stay in registers, so the result is the issue rate of the FP64 pipes.
+__global__ void __launch_bounds__(256) probe_dfma_kernel(double *out, int iters, double a, double b) {
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = (double)(threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = fma(x[i], a, b);
+    }
+    double sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) sum += x[i];
+    if (sum == 123.456) out[0] = sum; // never true for the arguments used: keeps the chains alive
+}
+__global__ void __launch_bounds__(256) probe_dmma_kernel(double *out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i][0] = (double)threadIdx.x; c[i][1] = (double)i; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) dmma_8x8x4(c[i][0], c[i][1], a, b);
+    }
+    double sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) sum += c[i][0] + c[i][1];
+    if (sum == 123.456) out[0] = sum;
+}
+
 // ------------------------------------------------------------------------------------------------ K3
 
 struct CbicParams {
@@ -218,6 +248,26 @@ __global__ void cbic_roots_kernel(const double *__restrict__ in, size_t in_strid
 __device__ __forceinline__ double cbic_the_score64(double rss, int k, const CbicParams &prm) {
     if (k == 0) return 0.0;
     return prm.n * (log(rss) - prm.log_n) + prm.lam_logn * (double)k;
+}
+
+// One parent set (urlgpu_score_one, the per-set ScoringFunction::calculateScore plug-in): one warp sweeps every candidate
+// out of the (k+1)x(k+1) sub-Gram over (v, S), highest first — the same sequence of FMAs the family kernels apply to this
+// set — and writes RSS -> the_score.  O(k^3) work, no 2^k tables.
+__global__ void cbic_one_kernel(const double *__restrict__ sub, int k, CbicParams prm, double *__restrict__ out /*[2]: the_score, rss*/) {
+    extern __shared__ double smat[];
+    const int lane = threadIdx.x;
+    const int tsz = (k + 1) * (k + 2) / 2;
+    for (int e = lane; e < tsz; e += 32) smat[e] = sub[e];
+    __syncwarp();
+    for (int piv = k; piv >= 1; piv--) {
+        const double inv = 1.0 / smat[tri(piv, piv)];
+        for (int a = 0; a < piv; a++) {
+            const double f = -smat[tri(piv, a)] * inv;
+            for (int b = lane; b <= a; b += 32) smat[tri(a, b)] = fma(f, smat[tri(piv, b)], smat[tri(a, b)]);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { out[0] = cbic_the_score64(smat[0], k, prm); out[1] = smat[0]; }
 }
 
 // Level B: template-recursive DFS over the J low candidate bits.  A has (j+1)(j+2)/2 packed entries over

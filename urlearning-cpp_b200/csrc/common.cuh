@@ -40,6 +40,14 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
     return r;
 }
 
+// floor(j / d) by multiplication: m = floor((2^32-1) / d) (d >= 2), at most one correction step
+__device__ __forceinline__ uint32_t fast_div(uint32_t j, uint32_t d, uint32_t m) {
+    if (d == 1) return j;
+    uint32_t q = __umulhi(j, m);
+    if (j - q * d >= d) q++;
+    return q;
+}
+
 __global__ void fill_u32_kernel(uint32_t *__restrict__ t, uint64_t n, uint32_t v) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) t[i] = v;

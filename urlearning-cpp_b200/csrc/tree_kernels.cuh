@@ -31,7 +31,6 @@
 //      rounds them to the float32 BIC scores.
 #pragma once
 #include "bic_kernels.cuh"
-#include "slice_kernels.cuh"
 #include <type_traits>
 
 namespace urlgpu {

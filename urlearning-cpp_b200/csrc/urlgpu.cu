@@ -17,7 +17,6 @@
 #include <cub/device/device_scan.cuh>
 
 #include "bic_kernels.cuh"
-#include "slice_kernels.cuh"
 #include "tree_kernels.cuh"
 #include "cbic_kernels.cuh"
 
@@ -377,6 +376,9 @@ extern "C" const char *urlgpu_last_error(urlgpu_ctx *ctx) { return ctx ? ctx->er
 extern "C" int urlgpu_set_stream(urlgpu_ctx *ctx, void *s) {
     if (!ctx) return URLGPU_ERR_ARG;
     fold_events(ctx);
+    // pooled device blocks are recycled in stream order: drain the old stream before work is enqueued on another one
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return URLGPU_OK;
 }
@@ -600,6 +602,40 @@ extern "C" int urlgpu_set_gram(urlgpu_ctx *ctx, const double *g, int64_t n_total
     ctx->cn = n_total; ctx->cp = p;
     ctx->h_gram.assign(g, g + (size_t)p * p);
     ctx->have_gram = true;
+    return URLGPU_OK;
+}
+
+// Measured FP64 issue rates of this device (TFLOP/s): plain DFMA and the DMMA (mma.sync.m8n8k4.f64) tensor path.
+// Best of three timed launches after one warm-up, CUDA events on the context's stream.
+extern "C" int urlgpu_probe_fp64(urlgpu_ctx *ctx, double *dfma_tflops, double *dmma_tflops) {
+    if (!ctx) return URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DevBuf out(ctx);
+    CK(out.alloc(64));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int iters = 1 << 14, threads = 256;
+    const unsigned grid = (unsigned)ctx->sm_count * 8;
+    double best[2] = {0, 0};
+    for (int kind = 0; kind < 2; kind++)
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaEventRecord(e0, s));
+            if (kind == 0) probe_dfma_kernel<<<grid, threads, 0, s>>>(out.as<double>(), iters, 0.999999, 1e-9);
+            else probe_dmma_kernel<<<grid, threads, 0, s>>>(out.as<double>(), iters, 0.999999, 1e-9);
+            CK(cudaEventRecord(e1, s));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            // dfma: 2 flop x 8 chains per thread and iteration; dmma: 8 tiles x (8*8*4*2 = 512 flop) per warp and iteration
+            const double flop = kind == 0 ? 2.0 * 8 * iters * (double)threads * grid : 512.0 * 8 * iters * (double)(threads / 32) * grid;
+            if (rep > 0) best[kind] = std::max(best[kind], flop / (ms * 1e-3) / 1e12);
+        }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    ctx->st.launches_total += 8; ctx->st.launches_other += 8;
+    if (dfma_tflops) *dfma_tflops = best[0];
+    if (dmma_tflops) *dmma_tflops = best[1];
     return URLGPU_OK;
 }
 
@@ -1988,7 +2024,6 @@ extern "C" int urlgpu_result_free(urlgpu_result *res) {
 static int compact_of(urlgpu_ctx *ctx, int p, int variable, const uint64_t *parents, int mask_words, std::vector<int> &cand) {
     int rc = candidates_from_mask(ctx, p, variable, parents, mask_words, cand);
     if (rc) return rc;
-    if ((int)cand.size() > kMaxDenseCand) return ctx->fail(URLGPU_ERR_LIMIT, "more than 30 parents in one set");
     return URLGPU_OK;
 }
 
@@ -2004,39 +2039,59 @@ extern "C" int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *p
     std::vector<int> cand;
     int rc = compact_of(ctx, p, variable, parents, mask_words, cand);
     if (rc) return rc;
-    // the set itself is the whole candidate list: its compact mask is all ones
+    // the set itself is the whole candidate list (compact mask all ones).  It is scored directly: one contingency table for
+    // BIC, one (k+1)x(k+1) Schur sweep for cBIC — no 2^k tables
     const int c = (int)cand.size();
-    const uint64_t n_masks = (uint64_t)1 << c;
-    const uint32_t full = (uint32_t)(n_masks - 1);
     cudaStream_t s = ctx->stream;
-    DevBuf tab(ctx), aux(ctx);
-    CK(tab.alloc(n_masks * sizeof(float)));
     if (bic) {
-        CK(aux.alloc(n_masks * sizeof(long long)));
+        if (c > kMaxDenseCand) return ctx->fail(URLGPU_ERR_LIMIT, "score_one: more than 30 parents in one set");
+        const uint32_t full = (uint32_t)(((uint64_t)1 << c) - 1);
+        DevBuf out(ctx);
+        CK(out.alloc(sizeof(float) + sizeof(long long) + 8));
         BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
         CandInfo ci = make_candinfo(ctx, variable, cand, c);
         uint64_t cells = ci.rv;
         for (int b = 0; b < c; b++) { cells *= (uint64_t)ci.card[b]; if (cells > kCellLimit) return ctx->fail(URLGPU_ERR_LIMIT, "contingency table exceeds 2^30 cells"); }
         std::vector<uint32_t> one(1, full);
-        rc = bic_run_global_tier(ctx, bd, ci, one, tab.as<float>(), aux.as<long long>(), nullptr, 0);
+        // the kernels index their outputs by compact mask: shift the bases so that entry `full` is element 0
+        long long *d_ll = out.as<long long>();
+        float *d_sc = reinterpret_cast<float *>(d_ll + 1);
+        rc = bic_run_global_tier(ctx, bd, ci, one, d_sc - full, d_ll - full, nullptr, 0);
         if (rc) return rc;
         long long fx = 0;
-        CK(cudaMemcpyAsync(score, tab.as<float>() + full, sizeof(float), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(&fx, aux.as<long long>() + full, sizeof fx, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(score, d_sc, sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&fx, d_ll, sizeof fx, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         if (value64) *value64 = std::ldexp((double)fx, -23);
     } else {
-        CK(aux.alloc(n_masks * sizeof(double)));
-        uint64_t ns;
-        rc = cbic_score_family(ctx, variable, cand, c, lambda, tab.as<float>(), aux.as<double>(), &ns);
-        if (rc) return rc;
-        float ts = 0;
-        double ts64 = 0;
-        CK(cudaMemcpyAsync(&ts, tab.as<float>() + full, sizeof(float), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(&ts64, aux.as<double>() + full, sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (c > 200) return ctx->fail(URLGPU_ERR_LIMIT, "score_one: more than 200 parents in one set");
+        const int p_ = ctx->cp;
+        std::vector<int> order(1, variable);
+        order.insert(order.end(), cand.begin(), cand.end());
+        std::vector<double> sub((size_t)(c + 1) * (c + 2) / 2);
+        for (int a = 0; a <= c; a++)
+            for (int b = 0; b <= a; b++) sub[tri(a, b)] = ctx->h_gram[(size_t)order[a] * p_ + order[b]];
+        CbicParams prm{};
+        prm.c = c; prm.J = 0; prm.max_parents = c;
+        prm.n = (double)(int)ctx->cn;
+        prm.lam_logn = lambda * std::log((double)(int)ctx->cn);
+        prm.log_n = std::log((double)(int)ctx->cn);
+        DevBuf dsub(ctx), dout(ctx);
+        CK(dsub.alloc(sub.size() * sizeof(double)));
+        CK(dout.alloc(2 * sizeof(double)));
+        CK(cudaMemcpyAsync(dsub.p, sub.data(), sub.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        const size_t smem = sub.size() * sizeof(double);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(cbic_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            Region rg(ctx, F_CBIC, 1);
+            cbic_one_kernel<<<1, 32, smem, s>>>(dsub.as<double>(), c, prm, dout.as<double>());
+        }
+        double h[2] = {0, 0};
+        CK(cudaMemcpyAsync(h, dout.p, sizeof h, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        *score = -ts; // BIC_OLS.cpp:223,245,275
-        if (value64) *value64 = ts64;
+        CK(cudaGetLastError());
+        *score = -(float)h[0]; // BIC_OLS.cpp:223,245,275
+        if (value64) *value64 = h[0];
     }
     return URLGPU_OK;
 }
@@ -2050,6 +2105,7 @@ extern "C" int urlgpu_contingency(urlgpu_ctx *ctx, int variable, const uint64_t 
     int rc = compact_of(ctx, ctx->p, variable, parents, mask_words, cand);
     if (rc) return rc;
     const int c = (int)cand.size();
+    if (c > kMaxDenseCand) return ctx->fail(URLGPU_ERR_LIMIT, "contingency: more than 30 parents in one set");
     BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
     CandInfo ci = make_candinfo(ctx, variable, cand, c);
     uint64_t cells = ci.rv;
@@ -2062,6 +2118,7 @@ extern "C" int urlgpu_contingency(urlgpu_ctx *ctx, int variable, const uint64_t 
 extern "C" int urlgpu_prune(urlgpu_ctx *ctx, const uint64_t *masks, const float *scores, uint64_t n, int mask_words, uint8_t *keep) {
     if (!ctx || !masks || !scores || !keep || mask_words < 1) return ctx ? ctx->fail(URLGPU_ERR_ARG, "prune: bad argument") : URLGPU_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    if (n == 0) return URLGPU_OK;
     // compact the union of all masks to <= 30 bits
     std::vector<uint64_t> uni(mask_words, 0);
     for (uint64_t i = 0; i < n; i++)
