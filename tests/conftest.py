@@ -33,20 +33,37 @@ def engine(pkg):
     eng.close()
 
 
-@pytest.fixture(scope="session", params=["cube", "tree", "direct"])
+def engine_with_env(pkg, env):
+    """an Engine created under the given environment overrides (the library reads its strategy switches at urlgpu_create)"""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return pkg.Engine(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.fixture(scope="session", params=["cube", "tree", "direct", "cube-rank", "tree-rank", "direct-rank"])
 def bic_engine(pkg, request):
     """BIC engines for the K1 strategies: 'cube' (the default: roots counted into global tables, the rest marginalised through
     HBM), 'tree' (tables counted in shared-memory slices of bucketed packed rows, subtrees marginalised on chip; falls back
-    to cube when a family cannot be laid out that way) and 'direct' (every set counted from the rows)."""
-    old = os.environ.get("URLGPU_BIC_MODE")
-    os.environ["URLGPU_BIC_MODE"] = request.param
-    try:
-        eng = pkg.Engine(0)
-    finally:
-        if old is None:
-            os.environ.pop("URLGPU_BIC_MODE", None)
-        else:
-            os.environ["URLGPU_BIC_MODE"] = old
+    to cube when a family cannot be laid out that way) and 'direct' (every set counted from the rows); '-rank': the same
+    strategies writing into the rank-space (colex) layout of the score cache instead of the dense 2^c table."""
+    mode, _, layout = request.param.partition("-")
+    eng = engine_with_env(pkg, {"URLGPU_BIC_MODE": mode, "URLGPU_LAYOUT": layout or "dense"})
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session", params=["dense", "rank"])
+def cbic_engine(pkg, request):
+    """cBIC engines for the two cache layouts: 'dense' (2^c table by compact mask: level-A sweeps + DFS, segment DPs) and
+    'rank' (colex-rank table: per-set sweeps, per-layer DPs; used whenever the parent limit allows, else dense)."""
+    eng = engine_with_env(pkg, {"URLGPU_LAYOUT": request.param})
     yield eng
     eng.close()
 

@@ -290,5 +290,5 @@ def test_errors_are_loud(pkg, engine):
         engine.score_variable(99, 1, 1, pkg.BIC)
     codes = np.zeros((40, 100), dtype=np.uint8)
     engine.set_discrete(codes, [1] * 40)
-    with pytest.raises(pkg.UrlGpuError, match="candidate"):
-        engine.score_variable(0, (1 << 40) - 1, 2, pkg.BIC)
+    with pytest.raises(pkg.UrlGpuError, match="2\\^32 parent sets"):
+        engine.score_variable(0, (1 << 40) - 1, 20, pkg.BIC)  # 39 candidates, sets of up to 20: beyond 32-bit ranks

@@ -30,7 +30,8 @@ def test_gram_matches_extended_precision(pkg, orc, engine):
 
 
 @pytest.mark.parametrize("fig,fn", [("Figure_1", "raw_data_8000.csv"), ("Figure_2", "raw_data_5000.csv")])
-def test_figures_full_family(pkg, orc, engine, data_dir, fig, fn):
+def test_figures_full_family(pkg, orc, cbic_engine, data_dir, fig, fn):
+    engine = cbic_engine
     t = orc.Table(os.path.join(data_dir, fig, fn))
     x = t.values()
     assert x.shape == (4, 5000)
@@ -53,7 +54,8 @@ def test_figures_full_family(pkg, orc, engine, data_dir, fig, fn):
 
 
 @pytest.mark.parametrize("p,n,K", [(9, 2000, 8), (13, 3000, 12), (14, 1500, 4), (17, 4000, 3), (27, 3000, 3)])
-def test_synthetic_exhaustive_and_limited(pkg, orc, engine, p, n, K):
+def test_synthetic_exhaustive_and_limited(pkg, orc, cbic_engine, p, n, K):
+    engine = cbic_engine
     x, _ = pkg.datagen.linear_gaussian_sem(p=p, n=n, seed=p)
     engine.set_continuous(x)
     g = engine.gram()
@@ -203,9 +205,10 @@ def test_row_sharded_gram_protocol(pkg, orc):
         e.close()
 
 
-def test_wide_masks_p_above_64(pkg, orc, engine):
+def test_wide_masks_p_above_64(pkg, orc, cbic_engine):
     """p = 90 > 63 (unrepresentable in the reference): two-word masks; checked against the oracle on the
     relabelled sub-problem of the variable's candidates"""
+    engine = cbic_engine
     p, n = 90, 4000
     x, _ = pkg.datagen.linear_gaussian_sem(p=p, n=n, seed=12, mean_indegree=1.5)
     engine.set_continuous(x)

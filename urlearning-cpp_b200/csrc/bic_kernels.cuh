@@ -37,6 +37,26 @@ struct CandInfo {
     int card[kMaxDenseCand];
 };
 
+// Where a set's score goes.  DENSE layout: a table of 2^c floats indexed by the compact mask.  RANK layout
+// (rank_kernels.cuh): a table of sum_{l<=K} C(c,l) floats indexed by layer base + colex rank of the set, which is the
+// reference's enumeration order (score_calculator.cpp:76-120); binom == nullptr selects the dense layout.
+constexpr int kMaxRankCand = 255;
+constexpr int kMaxRankLayers = 32;
+struct RankSpace {                       // kernel argument, by value
+    int c, K;                            // candidates, largest set size
+    int bstride;                         // columns of the binomial table (K + 2)
+    const uint32_t *binom;               // device: [256][bstride], binom[b * bstride + i] = C(b, i) saturating at 2^32 - 1
+    uint32_t layer_base[kMaxRankLayers + 2];   // first index of layer l; [K + 1] = T
+};
+// compact mask (c <= 64) -> table index
+__device__ __forceinline__ uint64_t out_index(const RankSpace &rs, uint64_t mask) {
+    if (rs.binom == nullptr) return mask;
+    uint32_t r = 0;
+    int i = 0;
+    for (uint64_t m = mask; m; m &= m - 1) { i++; r += __ldg(rs.binom + (__ffsll((long long)m) - 1) * rs.bstride + i); }
+    return (uint64_t)rs.layer_base[i] + r;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K6a: classify every compact mask with popcount <= max_parents by table size and append it to a tier list.
 // tier 0: cells <= t0 (small shared-memory tables), tier 1: cells <= t1 (one CTA per SM), tier 2: global.
@@ -167,7 +187,7 @@ __device__ __forceinline__ float bic_finalize(long long acc, float tval, float b
 __global__ void bic_count_smem_kernel(BicData d, CandInfo ci, const uint32_t *__restrict__ work, float *__restrict__ scores,
                                       long long *__restrict__ ll_fixed /*optional, dense by mask*/,
                                       const uint64_t *__restrict__ table_offs /*optional, per work item*/, int *__restrict__ tables_out,
-                                      long long *__restrict__ acc_out /*optional, per work item*/) {
+                                      long long *__restrict__ acc_out /*optional, per work item*/, RankSpace om) {
     extern __shared__ __align__(16) int hist[];
     __shared__ SetCols sc;
     __shared__ long long red[32];
@@ -186,8 +206,8 @@ __global__ void bic_count_smem_kernel(BicData d, CandInfo ci, const uint32_t *__
     long long acc = score_configs(hist, ci.rv, 0, sc.cells / ci.rv, d.qlog, threadIdx.x, blockDim.x);
     acc = block_sum_ll(acc, red);
     if (threadIdx.x == 0) {
-        if (scores) scores[mask] = bic_finalize(acc, sc.tval, d.base);
-        if (ll_fixed) ll_fixed[mask] = acc;
+        if (scores) scores[out_index(om, mask)] = bic_finalize(acc, sc.tval, d.base);
+        if (ll_fixed) ll_fixed[out_index(om, mask)] = acc;
         if (acc_out) acc_out[blockIdx.x] = acc;
     }
 }
@@ -229,15 +249,16 @@ __global__ void bic_score_tables_kernel(BicData d, CandInfo ci, const GlobalSet 
 }
 
 __global__ void bic_finalize_kernel(BicData d, CandInfo ci, const GlobalSet *__restrict__ sets, const long long *__restrict__ acc, int nsets,
-                                    float *__restrict__ scores, long long *__restrict__ ll_fixed) {
+                                    float *__restrict__ scores, long long *__restrict__ ll_fixed, RankSpace om) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsets) return;
     const uint32_t mask = sets[i].mask;
     float pen = (float)(ci.rv - 1);
     for (int b = 0; b < ci.c; b++)
         if ((mask >> b) & 1) pen = __fmul_rn(pen, (float)ci.card[b]);
-    scores[mask] = bic_finalize(acc[i], pen, d.base);
-    if (ll_fixed) ll_fixed[mask] = acc[i];
+    const uint64_t o = out_index(om, mask);
+    scores[o] = bic_finalize(acc[i], pen, d.base);
+    if (ll_fixed) ll_fixed[o] = acc[i];
 }
 
 // store rule of the caller: empty set stored iff score < 1, others iff score < 0 (score_calculator.cpp:59,111)
@@ -448,15 +469,16 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
 
 // scores[res_mask] from the exact accumulators; tVal multiplied in ascending variable order (result-order CandInfo)
 __global__ void cube_finalize_kernel(BicData d, CandInfo ci_res, const uint32_t *__restrict__ res_masks, const long long *__restrict__ acc, int nsets,
-                                     float *__restrict__ scores, long long *__restrict__ ll_fixed) {
+                                     float *__restrict__ scores, long long *__restrict__ ll_fixed, RankSpace om) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsets) return;
     const uint32_t mask = res_masks[i];
     float pen = (float)(ci_res.rv - 1);
     for (int b = 0; b < ci_res.c; b++)
         if ((mask >> b) & 1) pen = __fmul_rn(pen, (float)ci_res.card[b]);
-    scores[mask] = bic_finalize(acc[i], pen, d.base);
-    if (ll_fixed) ll_fixed[mask] = acc[i];
+    const uint64_t o = out_index(om, mask);
+    scores[o] = bic_finalize(acc[i], pen, d.base);
+    if (ll_fixed) ll_fixed[o] = acc[i];
 }
 
 } // namespace urlgpu

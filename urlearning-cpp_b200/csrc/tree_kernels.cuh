@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(kTreeThreads) bic_tree_kernel(TreeVar tv, cons
 
 // scores[res_mask(A ^ D)] for every (root, D) whose set is in the scored family
 __global__ void tree_finalize_kernel(BicData d, CandInfo ci_res, const TreeRoot *__restrict__ roots, int nroots, const uint8_t *__restrict__ perm /*cube bit -> result bit*/,
-                                     const long long *__restrict__ acc, uint32_t total, float *__restrict__ scores, long long *__restrict__ ll_fixed) {
+                                     const long long *__restrict__ acc, uint32_t total, float *__restrict__ scores, long long *__restrict__ ll_fixed, RankSpace om) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int lo = 0, hi = nroots - 1;
@@ -412,8 +412,9 @@ __global__ void tree_finalize_kernel(BicData d, CandInfo ci_res, const TreeRoot 
     float pen = (float)(ci_res.rv - 1);
     for (int b = 0; b < ci_res.c; b++)
         if ((rm >> b) & 1) pen = __fmul_rn(pen, (float)ci_res.card[b]);
-    scores[rm] = bic_finalize(acc[i], pen, d.base);
-    if (ll_fixed) ll_fixed[rm] = acc[i];
+    const uint64_t o = out_index(om, rm);
+    scores[o] = bic_finalize(acc[i], pen, d.base);
+    if (ll_fixed) ll_fixed[o] = acc[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------

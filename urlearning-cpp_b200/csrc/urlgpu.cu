@@ -19,6 +19,7 @@
 #include "bic_kernels.cuh"
 #include "tree_kernels.cuh"
 #include "cbic_kernels.cuh"
+#include "rank_kernels.cuh"
 
 using namespace urlgpu;
 
@@ -86,6 +87,11 @@ struct urlgpu_ctx {
     uint32_t tree_budget = 8 * 1024;    // cells of a slice table (URLGPU_TREE_BUDGET); the warps' stacks get the same
     int tree_run = 6;                   // run limit t (URLGPU_TREE_RUN)
     uint32_t tree_unit_cap = 1024;      // largest unit table r_v * prod_{i<t} r_i (URLGPU_TREE_UNIT)
+
+    // rank-space layout: binomial tables [256][K + 2] per parent limit K (tiny; kept for the life of the context so kernels in
+    // flight never lose theirs), and the layout policy (URLGPU_LAYOUT=dense|rank|auto)
+    uint32_t *d_binom[kMaxRankLayers + 1] = {nullptr};
+    int layout_policy = 0;       // 0 auto, 1 dense whenever possible, 2 rank whenever possible
 
     // pinned staging arena for host->device descriptor uploads (pageable cudaMemcpyAsync would sync the stream)
     // two arenas used alternately per call, each guarded by an event recorded when its call has been enqueued, so the
@@ -242,17 +248,30 @@ uint64_t family_size(int c, int K) {
     return total;
 }
 
+// C(b, i) saturating at 2^32 - 1
+uint32_t binom_sat(int b, int i) {
+    if (i < 0 || i > b) return 0;
+    unsigned __int128 r = 1;
+    for (int k = 1; k <= i; k++) {
+        r = r * (unsigned)(b - i + k) / (unsigned)k;
+        if (r > 0xFFFFFFFFull) return 0xFFFFFFFFu;
+    }
+    return (uint32_t)r;
+}
+
 } // namespace
 
 struct urlgpu_result {
     urlgpu_ctx *ctx = nullptr;
     int variable = 0, c = 0, max_parents = 0, mask_words = 1;
     std::vector<int> cand;          // compact bit -> variable index
-    float *d_table = nullptr;       // 2^c floats
-    uint64_t n_masks = 0, n_scored = 0;
+    float *d_table = nullptr;       // dense layout: 2^c floats by compact mask; rank layout: rs.layer_base[K+1] floats by colex index
+    bool rank_layout = false;
+    RankSpace rs{};
+    uint64_t n_masks = 0, n_scored = 0;   // n_masks = entries of d_table
     // compaction into canonical order (|S|, mask): enqueued on the context's stream by urlgpu_result_prefetch, no host sync
     bool prefetched = false, counted = false;
-    uint32_t *d_masks = nullptr;    // compact masks, canonical order (capacity n_scored)
+    uint32_t *d_masks = nullptr;    // dense: compact masks, rank: indices; canonical order (capacity n_scored)
     float *d_vals = nullptr;
     uint32_t *d_segcnt = nullptr;   // [32 layers][segments] stored entries, then their exclusive prefix
     unsigned long long *d_counts = nullptr;  // [33]: stored entries per layer, total
@@ -313,6 +332,7 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
         URLGPU_ROOT_ATTR(0, 16); URLGPU_ROOT_ATTR(2, 16); URLGPU_ROOT_ATTR(3, 16); URLGPU_ROOT_ATTR(4, 16);
 #undef URLGPU_ROOT_ATTR
     }
+    if (const char *m = getenv("URLGPU_LAYOUT")) ctx->layout_policy = strcmp(m, "dense") == 0 ? 1 : strcmp(m, "rank") == 0 ? 2 : 0;
     if (const char *m = getenv("URLGPU_BIC_MODE"))
         ctx->bic_mode = strcmp(m, "direct") == 0 ? 1 : strcmp(m, "tree") == 0 ? 0 : 2;
     if (const char *m = getenv("URLGPU_TREE_BUDGET")) ctx->tree_budget = (uint32_t)std::max(1024, std::min(atoi(m), 26 * 1024)) / 4 * 4;
@@ -365,6 +385,7 @@ extern "C" int urlgpu_destroy(urlgpu_ctx *ctx) {
     for (auto *hp : ctx->free_pinned) cudaFreeHost(hp);
     if (ctx->d_fetch_wide) cudaFree(ctx->d_fetch_wide);
     if (ctx->d_fetch_cand) cudaFree(ctx->d_fetch_cand);
+    for (auto *b : ctx->d_binom) if (b) cudaFree(b);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -676,7 +697,8 @@ static CandInfo make_candinfo(urlgpu_ctx *ctx, int variable, const std::vector<i
 
 // Score the listed compact masks (device list for the shared-memory tiers, host list for the global tier)
 static int bic_run_global_tier(urlgpu_ctx *ctx, const BicData &bd, const CandInfo &ci, const std::vector<uint32_t> &masks,
-                               float *d_table, long long *d_llfixed, int *keep_tables_of_first /*optional host out*/, int64_t keep_cells) {
+                               float *d_table, long long *d_llfixed, int *keep_tables_of_first /*optional host out*/, int64_t keep_cells,
+                               const RankSpace &om = RankSpace{}) {
     if (masks.empty()) return URLGPU_OK;
     cudaStream_t s = ctx->stream;
     std::vector<GlobalSet> sets(masks.size());
@@ -734,7 +756,7 @@ static int bic_run_global_tier(urlgpu_ctx *ctx, const BicData &bd, const CandInf
     if (d_table) {
         Region rg(ctx, F_OTHER, 1);
         bic_finalize_kernel<<<blocks_for(sets.size(), 256), 256, 0, s>>>(bd, ci, dsets.as<GlobalSet>(), dacc.as<long long>(), (int)sets.size(), d_table,
-                                                                         d_llfixed);
+                                                                         d_llfixed, om);
     }
     CK(cudaStreamSynchronize(s)); // dsets/dacc are freed on return
     CK(cudaGetLastError());
@@ -742,7 +764,7 @@ static int bic_run_global_tier(urlgpu_ctx *ctx, const BicData &bd, const CandInf
 }
 
 static int bic_score_family_direct(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                                   uint64_t *n_scored) {
+                                   uint64_t *n_scored, const RankSpace &om) {
     cudaStream_t s = ctx->stream;
     const int c = (int)cand.size();
     const uint64_t n_masks = (uint64_t)1 << c;
@@ -769,18 +791,18 @@ static int bic_score_family_direct(urlgpu_ctx *ctx, int variable, const std::vec
     if (hc[0]) {
         Region rg(ctx, F_COUNT, 1);
         const int threads = ctx->n >= 65536 ? 256 : 128;
-        bic_count_smem_kernel<<<(unsigned)hc[0], threads, kTier0Cells * sizeof(int), s>>>(bd, ci, l0, d_table, d_llfixed, nullptr, nullptr, nullptr);
+        bic_count_smem_kernel<<<(unsigned)hc[0], threads, kTier0Cells * sizeof(int), s>>>(bd, ci, l0, d_table, d_llfixed, nullptr, nullptr, nullptr, om);
     }
     if (hc[1]) {
         Region rg(ctx, F_COUNT, 1);
-        bic_count_smem_kernel<<<(unsigned)hc[1], 1024, (size_t)tier1_cells * sizeof(int), s>>>(bd, ci, l1, d_table, d_llfixed, nullptr, nullptr, nullptr);
+        bic_count_smem_kernel<<<(unsigned)hc[1], 1024, (size_t)tier1_cells * sizeof(int), s>>>(bd, ci, l1, d_table, d_llfixed, nullptr, nullptr, nullptr, om);
     }
     if (hc[2]) {
         std::vector<uint32_t> m2(hc[2]);
         CK(cudaMemcpyAsync(m2.data(), l2, hc[2] * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         std::sort(m2.begin(), m2.end());
-        int rc = bic_run_global_tier(ctx, bd, ci, m2, d_table, d_llfixed, nullptr, 0);
+        int rc = bic_run_global_tier(ctx, bd, ci, m2, d_table, d_llfixed, nullptr, 0, om);
         if (rc) return rc;
     }
     // algorithmic bytes: n*(k+1) per set
@@ -861,7 +883,7 @@ static int h2d_async(urlgpu_ctx *ctx, void *dst, const void *src, size_t bytes) 
 }
 
 static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                                 uint64_t *n_scored, bool *used) {
+                                 uint64_t *n_scored, bool *used, const RankSpace &om) {
     *used = false;
     cudaStream_t s = ctx->stream;
     { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
@@ -1092,7 +1114,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         for (size_t i = 0; i < L.size(); i++) hres[i] = L[i].res_mask;
         { int rc_ = h2d_async(ctx, dres.p, hres.data(), L.size() * sizeof(uint32_t)); if (rc_) return rc_; }
         Region rg(ctx, F_OTHER, 1);
-        cube_finalize_kernel<<<blocks_for(L.size(), 256), 256, 0, s>>>(bd, ci_res, dres.as<uint32_t>(), dacc.as<long long>() + acc_off[l], (int)L.size(), d_table, d_llfixed);
+        cube_finalize_kernel<<<blocks_for(L.size(), 256), 256, 0, s>>>(bd, ci_res, dres.as<uint32_t>(), dacc.as<long long>() + acc_off[l], (int)L.size(), d_table, d_llfixed, om);
         return URLGPU_OK;
     };
 
@@ -1126,7 +1148,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             const int threads = tiny ? (ctx->n >= 65536 ? 256 : 128) : 1024;
             const size_t smem = (tiny ? (size_t)kTier0Cells : (size_t)tier1_cells) * sizeof(int);
             bic_count_smem_kernel<<<(unsigned)small_m.size(), threads, smem, s>>>(bd, ci_cube, dwork.as<uint32_t>(), nullptr, nullptr, doffs.as<uint64_t>(), bufP,
-                                                                               score_roots ? dacc_small.as<long long>() : nullptr);
+                                                                               score_roots ? dacc_small.as<long long>() : nullptr, RankSpace{});
         }
         if (!big.empty()) {
             CK(dgsets.alloc(big.size() * sizeof(GlobalSet)));
@@ -1352,21 +1374,22 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
 }
 
 static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                                 uint64_t *n_scored, bool *used);
+                                 uint64_t *n_scored, bool *used, const RankSpace &om);
 
+// c <= 30 candidates: the mask-based K1 strategies; `om` says where a set's score goes (dense by mask, or rank space)
 static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                            uint64_t *n_scored) {
+                            uint64_t *n_scored, const RankSpace &om) {
     if (ctx->bic_mode == 0) {
         bool used = false;
-        int rc = bic_score_family_tree(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used);
+        int rc = bic_score_family_tree(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used, om);
         if (rc || used) return rc;
     }
     if (ctx->bic_mode != 1) {
         bool used = false;
-        int rc = bic_score_family_cube(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used);
+        int rc = bic_score_family_cube(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used, om);
         if (rc || used) return rc;
     }
-    return bic_score_family_direct(ctx, variable, cand, K, d_table, d_llfixed, n_scored);
+    return bic_score_family_direct(ctx, variable, cand, K, d_table, d_llfixed, n_scored, om);
 }
 
 
@@ -1384,7 +1407,7 @@ static void launch_tree(const TreeVar &tv, const TreeRoot *roots, const uint32_t
 }
 
 static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                                 uint64_t *n_scored, bool *used) {
+                                 uint64_t *n_scored, bool *used, const RankSpace &om) {
     *used = false;
     cudaStream_t s = ctx->stream;
     const int c = (int)cand.size();
@@ -1574,7 +1597,7 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
     {
         Region rg(ctx, F_OTHER, 1);
         tree_finalize_kernel<<<blocks_for(acc_total, 256), 256, 0, s>>>(bd, ci_res, droots.as<TreeRoot>(), (int)roots.size(), dperm.as<uint8_t>(), dacc.as<long long>(),
-                                                                     (uint32_t)acc_total, d_table, d_llfixed);
+                                                                     (uint32_t)acc_total, d_table, d_llfixed, om);
     }
     CK(cudaGetLastError());
     { int rc_ = stage_end(ctx); if (rc_) return rc_; }
@@ -1730,6 +1753,270 @@ static int run_segment_dp(urlgpu_ctx *ctx, float *d_table, int c, int K) {
 static int run_accept(urlgpu_ctx *ctx, float *d_table, int c, int K) { return run_segment_dp<0>(ctx, d_table, c, K); }
 static int run_prune(urlgpu_ctx *ctx, float *d_table, int c, int K) { return run_segment_dp<1>(ctx, d_table, c, K); }
 
+// ============================================================================================ rank-space layout
+// (rank_kernels.cuh)  index(S) = layer_base[|S|] + colex rank of S among the |S|-subsets of the c candidates.
+
+static int ensure_binom(urlgpu_ctx *ctx, int K, const uint32_t **out) {
+    if (K < 0 || K > kMaxRankLayers) return ctx->fail(URLGPU_ERR_LIMIT, "rank layout: parent limit above " + std::to_string(kMaxRankLayers));
+    if (!ctx->d_binom[K]) {
+        const int bs = K + 2;
+        std::vector<uint32_t> h((size_t)(kMaxRankCand + 1) * bs);
+        for (int b = 0; b <= kMaxRankCand; b++)
+            for (int i = 0; i < bs; i++) h[(size_t)b * bs + i] = binom_sat(b, i);
+        CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_binom[K]), h.size() * sizeof(uint32_t)));
+        CK(cudaMemcpy(ctx->d_binom[K], h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    *out = ctx->d_binom[K];
+    return URLGPU_OK;
+}
+
+// fills rs for (c, K); URLGPU_ERR_LIMIT when the family does not fit 32-bit indices
+static int make_rank_space(urlgpu_ctx *ctx, int c, int K, RankSpace &rs) {
+    if (c > kMaxRankCand) return ctx->fail(URLGPU_ERR_LIMIT, std::to_string(c) + " candidate parents; at most " + std::to_string(kMaxRankCand) + " are supported");
+    K = std::min(K, c);
+    rs = RankSpace{};
+    rs.c = c; rs.K = K; rs.bstride = K + 2;
+    uint64_t base = 0;
+    for (int l = 0; l <= K; l++) {
+        rs.layer_base[l] = (uint32_t)base;
+        const uint32_t b = binom_sat(c, l);
+        base += b;
+        if (b == 0xFFFFFFFFu || base > 0xFFFFFFF0ull)
+            return ctx->fail(URLGPU_ERR_LIMIT, "the candidate family (" + std::to_string(c) + " candidates, sets of up to " + std::to_string(K) +
+                                                   " parents) has more than 2^32 parent sets");
+    }
+    for (int l = K + 1; l < kMaxRankLayers + 2; l++) rs.layer_base[l] = (uint32_t)base;
+    return ensure_binom(ctx, K, &rs.binom);
+}
+
+// host-side unrank (planning of the global BIC tier)
+static void host_unrank(int c, int l, uint32_t r, int *e) {
+    int hi = c - 1;
+    for (int i = l; i >= 1; i--) {
+        int b = hi;
+        while (b >= i && binom_sat(b, i) > r) b--;
+        if (b < i) b = i - 1;
+        e[i - 1] = b;
+        r -= binom_sat(b, i);
+        hi = b - 1;
+    }
+}
+
+// ---- K3 in rank space: per-set Schur sweeps, one launch per layer, entries [first, first + count) of the index space
+static int cbic_score_rank(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, const RankSpace &rs, double lambda, uint32_t first, uint32_t count,
+                           float *d_scores /*indexed by global index*/, double *d_ts64) {
+    cudaStream_t s = ctx->stream;
+    const int c = rs.c, p = ctx->cp;
+    if (rs.K > kRankGenericMaxL) return ctx->fail(URLGPU_ERR_LIMIT, "cBIC over more than 30 candidates handles sets of at most " + std::to_string(kRankGenericMaxL) + " parents");
+    // candidate Gram over (v, cand_0, ..): full square, row-major
+    std::vector<int> order(1, variable);
+    order.insert(order.end(), cand.begin(), cand.end());
+    const int ld = c + 1;
+    std::vector<double> g((size_t)ld * ld);
+    double dmax = 0;
+    for (int a = 0; a <= c; a++) {
+        for (int b = 0; b <= c; b++) g[(size_t)a * ld + b] = ctx->h_gram[(size_t)order[a] * p + order[b]];
+        dmax = std::max(dmax, g[(size_t)a * ld + a]);
+    }
+    DevBuf dg(ctx);
+    CK(dg.alloc(g.size() * sizeof(double)));
+    { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
+    { int rc_ = h2d_async(ctx, dg.p, g.data(), g.size() * sizeof(double)); if (rc_) return rc_; }
+    CbicParams prm{};
+    prm.c = c; prm.J = 0; prm.max_parents = rs.K;
+    prm.n = (double)(int)ctx->cn;
+    prm.lam_logn = lambda * std::log((double)(int)ctx->cn);
+    prm.log_n = std::log((double)(int)ctx->cn);
+    const double piv_tol = 1e-10 * dmax;
+    const size_t smem = rs_binom_bytes(rs);
+    const uint64_t last = (uint64_t)first + count;
+    int launches = 0;
+    for (int l = 0; l <= rs.K; l++) {
+        const uint64_t b0 = std::max<uint64_t>(rs.layer_base[l], first), b1 = std::min<uint64_t>(rs.layer_base[l + 1], last);
+        if (b0 >= b1) continue;
+        launches++;
+    }
+    {
+        Region rg(ctx, F_CBIC, launches);
+        for (int l = 0; l <= rs.K; l++) {
+            const uint64_t b0 = std::max<uint64_t>(rs.layer_base[l], first), b1 = std::min<uint64_t>(rs.layer_base[l + 1], last);
+            if (b0 >= b1) continue;
+            const uint32_t cnt = (uint32_t)(b1 - b0);
+            const unsigned grid = blocks_for(((uint64_t)cnt + kRankRun - 1) / kRankRun, 128);
+#define URLGPU_RANK_CBIC(LL) rank_cbic_kernel<LL><<<grid, 128, smem, s>>>(rs, dg.as<double>(), prm, piv_tol, l, (uint32_t)b0, cnt, d_scores, d_ts64)
+            switch (l) {
+            case 1: URLGPU_RANK_CBIC(1); break;
+            case 2: URLGPU_RANK_CBIC(2); break;
+            case 3: URLGPU_RANK_CBIC(3); break;
+            case 4: URLGPU_RANK_CBIC(4); break;
+            case 5: URLGPU_RANK_CBIC(5); break;
+            case 6: URLGPU_RANK_CBIC(6); break;
+            case 7: URLGPU_RANK_CBIC(7); break;
+            case 8: URLGPU_RANK_CBIC(8); break;
+            default: URLGPU_RANK_CBIC(0); break;   // layer 0 (the empty set: the_score 0) and layers above 8
+            }
+#undef URLGPU_RANK_CBIC
+        }
+    }
+    { int rc_ = stage_end(ctx); if (rc_) return rc_; }
+    {
+        double flops = 0;
+        for (int l = 0; l <= rs.K; l++) {
+            const uint64_t b0 = std::max<uint64_t>(rs.layer_base[l], first), b1 = std::min<uint64_t>(rs.layer_base[l + 1], last);
+            if (b0 < b1) flops += (double)(b1 - b0) * ((double)l * l * l / 3.0 + 2.0 * l * l + 2.0 * l);
+        }
+        ctx->st.algorithmic_flops += flops;
+        ctx->st.sets_scored += count;
+    }
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+// ---- K1 in rank space for families the mask-based strategies cannot hold (more than 30 candidates): every set of
+// [first, first + count) is counted from the rows, in three tiers by table size like bic_score_family_direct
+static int bic_score_rank_direct(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, const RankSpace &rs, uint32_t first, uint32_t count, float *d_scores) {
+    cudaStream_t s = ctx->stream;
+    const int c = rs.c;
+    if (rs.K + 1 > kMaxCols) return ctx->fail(URLGPU_ERR_LIMIT, "BIC: more than 31 parents in one set");
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+    const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
+    std::vector<int> hv(2 * (size_t)std::max(c, 1));
+    for (int i = 0; i < c; i++) { hv[i] = cand[i]; hv[c + i] = ctx->card[cand[i]]; }
+    DevBuf dcand(ctx), lists(ctx), counters(ctx);
+    CK(dcand.alloc(hv.size() * sizeof(int)));
+    CK(lists.alloc(3 * (size_t)count * sizeof(uint32_t)));
+    CK(counters.alloc(4 * sizeof(unsigned long long)));
+    CK(cudaMemcpyAsync(dcand.p, hv.data(), hv.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), s));
+    RankCand rc{variable, ctx->card[variable], dcand.as<int>(), dcand.as<int>() + c};
+    uint32_t *l0 = lists.as<uint32_t>(), *l1 = l0 + count, *l2 = l1 + count;
+    const size_t bsm = rs_binom_bytes(rs);
+    {
+        Region rg(ctx, F_OTHER, 1);
+        rank_bic_classify_kernel<<<blocks_for(count, 256), 256, bsm, s>>>(rs, rc, first, count, kTier0Cells, tier1_cells, kCellLimit, l0, l1, l2,
+                                                                          counters.as<unsigned long long>());
+    }
+    unsigned long long hc[4];
+    CK(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (hc[3]) return ctx->fail(URLGPU_ERR_LIMIT, "a contingency table of this family has more than 2^30 cells");
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(rank_bic_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 2048); attr_set = true; }
+    if (hc[0]) {
+        Region rg(ctx, F_COUNT, 1);
+        const int threads = ctx->n >= 65536 ? 256 : 128;
+        rank_bic_count_smem_kernel<<<(unsigned)hc[0], threads, kTier0Cells * sizeof(int), s>>>(bd, rs, rc, l0, d_scores);
+    }
+    if (hc[1]) {
+        Region rg(ctx, F_COUNT, 1);
+        rank_bic_count_smem_kernel<<<(unsigned)hc[1], 1024, (size_t)tier1_cells * sizeof(int), s>>>(bd, rs, rc, l1, d_scores);
+    }
+    if (hc[2]) { // tables in an L2-resident scratch batch, RED atomics
+        std::vector<uint32_t> m2(hc[2]);
+        CK(cudaMemcpyAsync(m2.data(), l2, hc[2] * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        std::sort(m2.begin(), m2.end());
+        std::vector<RankGlobalSet> sets(m2.size());
+        size_t max_cells = 0;
+        for (size_t i = 0; i < m2.size(); i++) {
+            int l = 0;
+            while (l < rs.K && m2[i] >= rs.layer_base[l + 1]) l++;
+            int e[kMaxRankLayers];
+            host_unrank(c, l, m2[i] - rs.layer_base[l], e);
+            uint64_t cells = (uint64_t)rc.rv;
+            for (int j = 0; j < l; j++) cells *= (uint64_t)ctx->card[cand[e[j]]];
+            sets[i].idx = m2[i]; sets[i].cells = (uint32_t)cells; sets[i].table_off = 0;
+            max_cells = std::max<size_t>(max_cells, cells);
+        }
+        int rcode = ensure_tables(ctx, std::max(kBatchTableElems, max_cells));
+        if (rcode) return rcode;
+        DevBuf dsets(ctx), dacc(ctx);
+        CK(dsets.alloc(sets.size() * sizeof(RankGlobalSet)));
+        CK(dacc.alloc(sets.size() * sizeof(long long)));
+        CK(cudaMemsetAsync(dacc.p, 0, sets.size() * sizeof(long long), s));
+        std::vector<std::pair<size_t, size_t>> batches;
+        for (size_t i0 = 0; i0 < sets.size();) {
+            size_t used = 0, i1 = i0;
+            while (i1 < sets.size() && (i1 == i0 || used + sets[i1].cells <= ctx->tables_cap) && i1 - i0 < 65535) {
+                sets[i1].table_off = used;
+                used += (sets[i1].cells + 3) / 4 * 4;
+                i1++;
+            }
+            batches.push_back({i0, i1});
+            i0 = i1;
+        }
+        CK(cudaMemcpyAsync(dsets.p, sets.data(), sets.size() * sizeof(RankGlobalSet), cudaMemcpyHostToDevice, s));
+        const int threads = 256;
+        for (auto &bt : batches) {
+            const size_t B = bt.second - bt.first;
+            const size_t used = sets[bt.second - 1].table_off + sets[bt.second - 1].cells;
+            Region rg(ctx, F_COUNT, 3);
+            CK(cudaMemsetAsync(ctx->d_tables, 0, used * sizeof(int), s));
+            int64_t R = std::max<int64_t>(1, (int64_t)(ctx->sm_count * 8 + B - 1) / (int64_t)B);
+            int64_t rps = (bd.n + R - 1) / R;
+            rps = std::max<int64_t>((rps + 15) / 16 * 16, 16 * threads);
+            R = (bd.n + rps - 1) / rps;
+            rank_bic_count_global_kernel<<<dim3((unsigned)B, (unsigned)R), threads, 0, s>>>(bd, rs, rc, dsets.as<RankGlobalSet>() + bt.first, ctx->d_tables, rps);
+            uint32_t maxc = 0;
+            for (size_t i = bt.first; i < bt.second; i++) maxc = std::max(maxc, sets[i].cells);
+            const int64_t nconf = maxc / rc.rv;
+            const int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((nconf + threads * 4 - 1) / (threads * 4), (ctx->sm_count * 8 + (int64_t)B - 1) / (int64_t)B));
+            const int64_t cpc = (nconf + chunks - 1) / chunks;
+            rank_bic_score_tables_kernel<<<dim3((unsigned)B, (unsigned)chunks), threads, 0, s>>>(bd, rc.rv, dsets.as<RankGlobalSet>() + bt.first, ctx->d_tables,
+                                                                                             dacc.as<long long>() + bt.first, cpc);
+        }
+        {
+            Region rg(ctx, F_OTHER, 1);
+            rank_bic_finalize_kernel<<<blocks_for(sets.size(), 256), 256, 0, s>>>(bd, rs, rc, dsets.as<RankGlobalSet>(), dacc.as<long long>(), (int)sets.size(), d_scores);
+        }
+    }
+    {
+        double bytes = 0;
+        const uint64_t last = (uint64_t)first + count;
+        for (int l = 0; l <= rs.K; l++) {
+            const uint64_t b0 = std::max<uint64_t>(rs.layer_base[l], first), b1 = std::min<uint64_t>(rs.layer_base[l + 1], last);
+            if (b0 < b1) bytes += (double)(b1 - b0) * (double)ctx->n * (l + 1);
+        }
+        ctx->st.algorithmic_bytes += bytes;
+        ctx->st.sets_scored += count;
+    }
+    CK(cudaStreamSynchronize(s)); // dcand / lists are freed on return
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+// K4 (MODE 0) / K5 (MODE 1) in rank space: one launch per layer, ascending
+template <int MODE>
+static int run_rank_dp(urlgpu_ctx *ctx, const RankSpace &rs, float *d_scores) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t total = rs.layer_base[rs.K + 1];
+    DevBuf aux(ctx);
+    CK(aux.alloc((size_t)total * sizeof(float)));
+    const size_t smem = rs_binom_bytes(rs);
+    {
+        Region rg(ctx, MODE == 0 ? F_ACCEPT : F_PRUNE, rs.K + 1);
+        for (int l = 0; l <= rs.K; l++) {
+            const uint32_t nl = rs.layer_base[l + 1] - rs.layer_base[l];
+            if (nl == 0) continue;
+            rank_dp_kernel<MODE><<<blocks_for(nl, 256), 256, smem, s>>>(rs, l, d_scores, aux.as<float>());
+        }
+    }
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+// dense (2^c floats by compact mask) or rank layout for this family?
+static bool choose_rank_layout(urlgpu_ctx *ctx, int c, int K, bool bic) {
+    if (c > kMaxDenseCand) return true;
+    const int Kc = std::min(K, c);
+    if (ctx->layout_policy == 1) return false;
+    if (!bic && Kc > kRankGenericMaxL) return false;            // cBIC per-set sweeps hold up to 16 parents; larger limits are the DFS's domain
+    if (Kc > kMaxRankLayers - 1) return false;
+    if (ctx->layout_policy == 2) return true;
+    // auto: rank space when the family is a small part of the 2^c lattice (the dense DPs and the compaction walk all 2^c entries)
+    return c >= 16 && (double)family_size(c, Kc) * 8.0 < std::ldexp(1.0, c);
+}
+
 extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type,
                                      double lambda, unsigned filter_flags, urlgpu_result **out) {
     if (!ctx || !neighbors || !out) return ctx ? ctx->fail(URLGPU_ERR_ARG, "score_variable: null argument") : URLGPU_ERR_ARG;
@@ -1748,39 +2035,73 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     int rc = candidates_from_mask(ctx, p, variable, neighbors, mask_words, cand);
     if (rc) return rc;
     const int c = (int)cand.size();
-    if (c > kMaxDenseCand)
-        return ctx->fail(URLGPU_ERR_LIMIT, "score_variable: " + std::to_string(c) + " candidate parents; this build handles at most " +
-                                               std::to_string(kMaxDenseCand) + " (dense 2^c score table)");
     int K = std::max(0, std::min(max_parents, c));
+    const bool rank = choose_rank_layout(ctx, c, K, bic);
     auto *res = new urlgpu_result();
     res->ctx = ctx; res->variable = variable; res->c = c; res->max_parents = K; res->mask_words = mask_words; res->cand = cand;
-    res->n_masks = (uint64_t)1 << c;
+    res->rank_layout = rank;
+    if (rank) {
+        rc = make_rank_space(ctx, c, K, res->rs);
+        if (rc) { delete res; return rc; }
+        res->n_masks = res->rs.layer_base[K + 1];
+    } else res->n_masks = (uint64_t)1 << c;
     cudaError_t e = pool_alloc(ctx, reinterpret_cast<void **>(&res->d_table), res->n_masks * sizeof(float));
     if (e != cudaSuccess) { delete res; return ctx->cuda_fail(e, "cudaMalloc(score table)", __LINE__); }
     cudaStream_t s = ctx->stream;
     auto cleanup = [&](int code) { pool_free(ctx, res->d_table); delete res; return code; };
-    fill_u32_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), res->n_masks, kSentinelBits);
     const double t_alloc = since(T0);
-    if (bic) {
-        rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored);
-        if (rc) return cleanup(rc);
-        Region rg(ctx, F_OTHER, 1);
-        bic_store_rule_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(res->d_table, res->n_masks, K);
-    } else {
-        rc = cbic_score_family(ctx, variable, cand, K, lambda, res->d_table, nullptr, &res->n_scored);
-        if (rc) return cleanup(rc);
-        if (filter_flags & URLGPU_CBIC_NO_ACCEPT) {
+    double t_score = 0;
+    if (rank) {
+        const RankSpace &rs = res->rs;
+        const uint32_t total = (uint32_t)res->n_masks;
+        res->n_scored = total;
+        if (bic) {
+            if (c <= kMaxDenseCand) { // the mask-based K1 strategies, writing by rank
+                fill_u32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), total, kSentinelBits);
+                rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored, rs);
+            } else rc = bic_score_rank_direct(ctx, variable, cand, rs, 0, total, res->d_table);
+            if (rc) return cleanup(rc);
             Region rg(ctx, F_OTHER, 1);
-            cbic_negate_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(res->d_table, res->n_masks);
+            rank_store_rule_kernel<<<blocks_for(total, 256), 256, 0, s>>>(res->d_table, total);
         } else {
-            rc = run_accept(ctx, res->d_table, c, K);
+            rc = cbic_score_rank(ctx, variable, cand, rs, lambda, 0, total, res->d_table, nullptr);
+            if (rc) return cleanup(rc);
+            if (filter_flags & URLGPU_CBIC_NO_ACCEPT) {
+                Region rg(ctx, F_OTHER, 1);
+                rank_negate_kernel<<<blocks_for(total, 256), 256, 0, s>>>(res->d_table, total);
+            } else {
+                rc = run_rank_dp<0>(ctx, rs, res->d_table);
+                if (rc) return cleanup(rc);
+            }
+        }
+        t_score = since(T0);
+        if (filter_flags & URLGPU_PRUNE_DOMINATED) {
+            rc = run_rank_dp<1>(ctx, rs, res->d_table);
             if (rc) return cleanup(rc);
         }
-    }
-    const double t_score = since(T0);
-    if (filter_flags & URLGPU_PRUNE_DOMINATED) {
-        rc = run_prune(ctx, res->d_table, c, K);
-        if (rc) return cleanup(rc);
+    } else {
+        fill_u32_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), res->n_masks, kSentinelBits);
+        if (bic) {
+            rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored, RankSpace{});
+            if (rc) return cleanup(rc);
+            Region rg(ctx, F_OTHER, 1);
+            bic_store_rule_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(res->d_table, res->n_masks, K);
+        } else {
+            rc = cbic_score_family(ctx, variable, cand, K, lambda, res->d_table, nullptr, &res->n_scored);
+            if (rc) return cleanup(rc);
+            if (filter_flags & URLGPU_CBIC_NO_ACCEPT) {
+                Region rg(ctx, F_OTHER, 1);
+                cbic_negate_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(res->d_table, res->n_masks);
+            } else {
+                rc = run_accept(ctx, res->d_table, c, K);
+                if (rc) return cleanup(rc);
+            }
+        }
+        t_score = since(T0);
+        if (filter_flags & URLGPU_PRUNE_DOMINATED) {
+            rc = run_prune(ctx, res->d_table, c, K);
+            if (rc) return cleanup(rc);
+        }
     }
     if (dbg) fprintf(stderr, "[urlgpu score_variable] v=%d alloc %.2f ms, score %.2f ms, prune %.2f ms\n", variable, t_alloc, t_score - t_alloc, since(T0) - t_score);
     e = cudaGetLastError();
@@ -1907,16 +2228,23 @@ static int result_prefetch_impl(urlgpu_result *res) {
     if (res->prefetched) return URLGPU_OK;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const uint32_t nseg = (uint32_t)((res->n_masks + kCompactSeg - 1) / kCompactSeg);
+    const uint32_t nseg = res->rank_layout ? (uint32_t)((res->n_masks + kRankCompactSeg - 1) / kRankCompactSeg) : (uint32_t)((res->n_masks + kCompactSeg - 1) / kCompactSeg);
     const uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>(res->n_scored, res->n_masks));
     CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_masks), cap * sizeof(uint32_t)));
     CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_vals), cap * sizeof(float)));
-    CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_segcnt), (size_t)32 * nseg * sizeof(uint32_t)));
+    CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_segcnt), (size_t)(res->rank_layout ? 1 : 32) * nseg * sizeof(uint32_t)));
     CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_counts), (33 + 32) * sizeof(unsigned long long)));
     if (!ctx->free_pinned.empty()) { res->h_counts = ctx->free_pinned.back(); ctx->free_pinned.pop_back(); }
     else CK(cudaHostAlloc(reinterpret_cast<void **>(&res->h_counts), 33 * sizeof(unsigned long long), cudaHostAllocDefault));
     res->ready = get_event(ctx);
-    {
+    if (res->rank_layout) { // index order is the canonical order: one order-preserving compaction of the whole table
+        Region rg(ctx, F_OTHER, 3);
+        const uint32_t total = (uint32_t)res->n_masks;
+        CK(cudaMemsetAsync(res->d_counts, 0, 33 * sizeof(unsigned long long), s));
+        rank_compact_count_kernel<<<nseg, kRankCompactThreads, 0, s>>>(res->d_table, total, res->d_segcnt);
+        rank_compact_scan_kernel<<<1, 1024, 0, s>>>(res->d_segcnt, nseg, res->d_counts);
+        rank_compact_write_kernel<<<nseg, kRankCompactThreads, 0, s>>>(res->d_table, total, res->d_segcnt, res->d_masks, res->d_vals);
+    } else {
         Region rg(ctx, F_OTHER, 4);
         compact_count_kernel<<<nseg, kCompactThreads, 0, s>>>(res->d_table, res->n_masks, nseg, res->d_segcnt);
         compact_scan_kernel<<<32, 1024, 0, s>>>(res->d_segcnt, nseg, res->d_counts);
@@ -1979,9 +2307,12 @@ extern "C" int urlgpu_result_fetch(urlgpu_result *res, uint64_t offset, uint64_t
             CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_fetch_wide), cap));
             ctx->fetch_wide_cap = cap;
         }
-        if (!ctx->d_fetch_cand) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_fetch_cand), (kMaxDenseCand + 2) * sizeof(int)));
+        if (!ctx->d_fetch_cand) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_fetch_cand), (kMaxRankCand + 2) * sizeof(int)));
         if (!res->cand.empty()) CK(cudaMemcpyAsync(ctx->d_fetch_cand, res->cand.data(), res->cand.size() * sizeof(int), cudaMemcpyHostToDevice, cs));
-        expand_masks_kernel<<<blocks_for(n, 256), 256, 0, cs>>>(res->d_masks + offset, n, ctx->d_fetch_cand, res->c, res->mask_words, ctx->d_fetch_wide);
+        if (res->rank_layout)
+            rank_expand_kernel<<<blocks_for(n, 256), 256, rs_binom_bytes(res->rs), cs>>>(res->rs, res->d_masks + offset, n, ctx->d_fetch_cand, res->mask_words, ctx->d_fetch_wide);
+        else
+            expand_masks_kernel<<<blocks_for(n, 256), 256, 0, cs>>>(res->d_masks + offset, n, ctx->d_fetch_cand, res->c, res->mask_words, ctx->d_fetch_wide);
         CK(cudaMemcpyAsync(masks, ctx->d_fetch_wide, need, cudaMemcpyDeviceToHost, cs));
     }
     if (scores) CK(cudaMemcpyAsync(scores, res->d_vals + offset, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
