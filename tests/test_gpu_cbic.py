@@ -243,3 +243,48 @@ def test_wide_masks_p_above_64(pkg, orc, cbic_engine):
         s1, ts64 = engine.score_one(v, sum(1 << i for i in cand[:3]), pkg.CBIC, 2.0)
         r = orc.cbic_residual(z, vs, sum(1 << sub.index(i) for i in cand[:3]), 2.0)
         assert abs(ts64 - r) <= TOL * max(1.0, abs(r))
+
+
+def test_collinear_columns_pivot_guard(pkg, orc, cbic_engine):
+    """duplicate and linearly dependent columns (SURVEY Q13): the reference's arma::solve falls back to a least-squares
+    solution for the rank-deficient normal equations (BIC_OLS.cpp:313-315), i.e. RSS(S + redundant column) = RSS(S) and
+    only the penalty grows.  The engine's Schur sweeps skip a pivot that has lost all its digits instead of dividing by
+    it: no Inf/NaN reaches the cache, and the scores obey exactly that identity."""
+    engine = cbic_engine
+    p, n, lam = 12, 3000, 2.0
+    x, _ = pkg.datagen.linear_gaussian_sem(p=p, n=n, seed=44)
+    x[5] = x[2]                       # exact duplicate
+    x[7] = 2.0 * x[1] - 3.0 * x[4]    # exact linear combination
+    engine.set_continuous(x)
+    z = orc.standardise(x)
+    v = 10
+    nb = (1 << p) - 1
+    res = engine.score_variable(v, nb, 6, pkg.CBIC, lam=lam, flags=pkg.CBIC_NO_ACCEPT)
+    masks, neg = res.fetch()
+    res.free()
+    ts = {int(m): -float(s) for m, s in zip(masks[:, 0], neg)}
+    assert all(np.isfinite(t) for t in ts.values())
+    pen = lam * np.log(n)
+    checked = 0
+    for m, t in ts.items():
+        k = bin(m).count("1")
+        if k >= 6:
+            continue
+        # a set containing 2 (or 5): adding the twin changes nothing but the penalty
+        if (m >> 2) & 1 and not (m >> 5) & 1:
+            assert abs(ts[m | (1 << 5)] - (t + pen)) <= 1e-6 * max(1.0, abs(t)), (m, t, ts[m | (1 << 5)])
+            checked += 1
+        # a set containing 1 and 4: adding 7 = 2 x1 - 3 x4 changes nothing but the penalty
+        if (m >> 1) & 1 and (m >> 4) & 1 and not (m >> 7) & 1 and not ((m >> 2) & 1 and (m >> 5) & 1):
+            assert abs(ts[m | (1 << 7)] - (t + pen)) <= 1e-6 * max(1.0, abs(t)), (m, t, ts[m | (1 << 7)])
+            checked += 1
+        # sets free of redundancy still match the oracle's residual form
+        if not ((m >> 2) & 1 and (m >> 5) & 1) and not ((m >> 1) & 1 and (m >> 4) & 1 and (m >> 7) & 1) and checked % 7 == 0:
+            r = orc.cbic_residual(z, v, m, lam)
+            assert abs(t - r) <= 1e-5 * max(1.0, abs(r))
+    assert checked > 200
+    # filters run on such data without NaNs poisoning the DP
+    r2 = engine.score_variable(v, nb, 6, pkg.CBIC, lam=lam, flags=pkg.PRUNE_DOMINATED)
+    m2, s2 = r2.fetch()
+    r2.free()
+    assert len(s2) > 0 and np.all(np.isfinite(s2))

@@ -37,7 +37,7 @@ def _oracle_bic_cache(orc, codes, card, v, nb, p, K, prune):
     return om[order], osc[order]
 
 
-@pytest.mark.parametrize("p,n,K,arities", [(50, 500, 3, (2, 3)), (63, 300, 2, (2, 3, 4)), (36, 4001, 4, (2, 3, 18))])
+@pytest.mark.parametrize("p,n,K,arities", [(50, 500, 3, (2, 3)), (62, 300, 2, (2, 3, 4)), (36, 4001, 4, (2, 3, 18))])
 def test_bic_more_than_30_candidates(pkg, orc, engine, p, n, K, arities):
     """no skeleton: every other variable is a candidate (c = p - 1 > 30).  The (36, K=4, arity 18) case has tables of
     18^5 = 1.9M cells: shared-memory tiers and the global (L2 scratch) tier all run."""

@@ -202,7 +202,13 @@ struct CbicParams {
     double lam_logn;  // lambda*log(n)  (:366, evaluated left to right)
     double log_n;     // log(n)
     int store_mode;   // score stores of the DFS kernel: 0 default, 1 st.global.cs (streaming), 2 st.global.wt, 3 st.global.cg
+    // Pivot guard: a candidate whose Schur pivot has dropped to <= piv_tol (1e-10 * the largest diagonal entry of
+    // the candidate Gram) is a linear combination of the candidates already swept.  Its sweep is skipped (inv = 0 turns every
+    // FMA of the sweep into the identity), so RSS equals the least-squares RSS without that column — what arma::solve's
+    // rank-deficient fallback gives the reference (BIC_OLS.cpp:313-315) — instead of Inf/NaN; the penalty still counts it.
+    double piv_tol;
 };
+__device__ __forceinline__ double guarded_inv(double d, double tol) { return d > tol ? 1.0 / d : 0.0; }
 
 // packed lower-triangular index, element order (v, cand0, cand1, ...)
 __host__ __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }
@@ -215,7 +221,7 @@ __host__ __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) /
 // Output: the remaining matrix over (v, cand_0 .. cand_{c_in-bits-1}), either contiguous per prefix (transposed == 0:
 // out[p * outsz + e], the next stage's input) or entry-major (transposed == 1: out[e * n_out + p], what the DFS reads).
 __global__ void cbic_roots_kernel(const double *__restrict__ in, size_t in_stride, int c_in, int bits, int max_parents, uint32_t n_out,
-                                  double *__restrict__ out, int transposed) {
+                                  double *__restrict__ out, int transposed, double piv_tol) {
     extern __shared__ double smat[]; // [warps][tri size]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t P = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -229,7 +235,7 @@ __global__ void cbic_roots_kernel(const double *__restrict__ in, size_t in_strid
     for (int t = bits - 1; t >= 0; t--) {
         if ((P >> t) & 1) {
             const int piv = c_in - bits + t + 1; // position of the candidate in (v, c0, c1, ...)
-            const double inv = 1.0 / A[tri(piv, piv)];
+            const double inv = guarded_inv(A[tri(piv, piv)], piv_tol);
             for (int a = 0; a < piv; a++) {
                 const double f = -A[tri(piv, a)] * inv;
                 for (int b = lane; b <= a; b += 32) A[tri(a, b)] = fma(f, A[tri(piv, b)], A[tri(a, b)]);
@@ -260,7 +266,7 @@ __global__ void cbic_one_kernel(const double *__restrict__ sub, int k, CbicParam
     for (int e = lane; e < tsz; e += 32) smat[e] = sub[e];
     __syncwarp();
     for (int piv = k; piv >= 1; piv--) {
-        const double inv = 1.0 / smat[tri(piv, piv)];
+        const double inv = guarded_inv(smat[tri(piv, piv)], prm.piv_tol);
         for (int a = 0; a < piv; a++) {
             const double f = -smat[tri(piv, a)] * inv;
             for (int b = lane; b <= a; b += 32) smat[tri(a, b)] = fma(f, smat[tri(piv, b)], smat[tri(a, b)]);
@@ -284,8 +290,8 @@ constexpr int kInlineLevel = URLGPU_DFS_INLINE;
 #endif
 
 template <int j>
-__device__ __forceinline__ void cbic_sweep(const double *A, double *B) {
-    const double inv = 1.0 / A[tri(j, j)];
+__device__ __forceinline__ void cbic_sweep(const double *A, double *B, double piv_tol) {
+    const double inv = guarded_inv(A[tri(j, j)], piv_tol);
 #pragma unroll
     for (int a = 0; a < j; a++) {
         const double f = -A[tri(j, a)] * inv;
@@ -308,7 +314,7 @@ __device__ __forceinline__ void cbic_dfs_buf(const double *A, uint32_t low, int 
         cbic_dfs_buf<j - 1, LOCAL>(A, low, k, prm, buf, out64);
         if (k < prm.max_parents) {
             double B[j * (j + 1) / 2];
-            cbic_sweep<j>(A, B);
+            cbic_sweep<j>(A, B, prm.piv_tol);
             cbic_dfs_buf<j - 1, (LOCAL | (1u << (j - 1)))>(B, low, k + 1, prm, buf, out64);
         } else {
 #pragma unroll
@@ -340,7 +346,7 @@ __device__ __forceinline__ void cbic_dfs_inl(const double *A, uint32_t low, int 
         cbic_dfs_inl<j - 1>(A, low, k, prm, out, out64); // candidate j-1 excluded: leading principal submatrix
         if (k < prm.max_parents) {
             double B[j * (j + 1) / 2];
-            cbic_sweep<j>(A, B);
+            cbic_sweep<j>(A, B, prm.piv_tol);
             cbic_dfs_inl<j - 1>(B, low | (1u << (j - 1)), k + 1, prm, out, out64);
         } else {
             for (uint32_t m = 0; m < (1u << (j - 1)); m++) out[low | (1u << (j - 1)) | m] = sentinel();
@@ -357,7 +363,7 @@ __device__ __noinline__ void cbic_dfs_call(const double *A, uint32_t low, int k,
         cbic_dfs_call<j - 1>(A, low, k, prm, out, out64);
         if (k < prm.max_parents) {
             double B[j * (j + 1) / 2];
-            cbic_sweep<j>(A, B);
+            cbic_sweep<j>(A, B, prm.piv_tol);
             cbic_dfs_call<j - 1>(B, low | (1u << (j - 1)), k + 1, prm, out, out64);
         } else {
             for (uint32_t m = 0; m < (1u << (j - 1)); m++) out[low | (1u << (j - 1)) | m] = sentinel();

@@ -82,9 +82,7 @@ __global__ void rank_negate_kernel(float *__restrict__ scores, uint32_t total) {
 // One thread scores kRankRun consecutive sets of layer L: unrank the first, colex successor for the rest.  The set's
 // (L+1)x(L+1) sub-Gram over (v, e_1..e_L) is gathered from the candidate Gram (row-major, (c+1)^2, position 0 = v) and the
 // candidates are swept out highest first — the FMA sequence of cbic_roots_kernel / cbic_sweep / cbic_one_kernel.
-// A pivot that has lost all its digits (relative to piv_tol = 1e-10 * max diag G: the candidate is a linear combination
-// of the ones already swept) is skipped: RSS then equals the least-squares RSS without that column, which is what
-// arma::solve's rank-deficient fallback gives the reference (BIC_OLS.cpp:313-315); the penalty still counts it.
+// Pivot guard: see CbicParams::piv_tol (cbic_kernels.cuh).
 constexpr int kRankRun = 4;
 
 template <int L>
@@ -100,15 +98,12 @@ __device__ __forceinline__ double rank_cbic_rss(const double *__restrict__ G, in
         for (int b = 0; b <= a; b++) A[tri(a, b)] = __ldg(G + pos[a] * ld + pos[b]);
 #pragma unroll
     for (int piv = L; piv >= 1; piv--) {
-        const double d = A[tri(piv, piv)];
-        if (d > piv_tol) {
-            const double inv = 1.0 / d;
+        const double inv = guarded_inv(A[tri(piv, piv)], piv_tol);
 #pragma unroll
-            for (int a = 0; a < piv; a++) {
-                const double f = -A[tri(piv, a)] * inv;
+        for (int a = 0; a < piv; a++) {
+            const double f = -A[tri(piv, a)] * inv;
 #pragma unroll
-                for (int b = 0; b <= a; b++) A[tri(a, b)] = fma(f, A[tri(piv, b)], A[tri(a, b)]);
-            }
+            for (int b = 0; b <= a; b++) A[tri(a, b)] = fma(f, A[tri(piv, b)], A[tri(a, b)]);
         }
     }
     return A[0];
@@ -120,13 +115,10 @@ __device__ __noinline__ double rank_cbic_rss_generic(const double *__restrict__ 
         for (int b = 0; b <= a; b++) A[tri(a, b)] = __ldg(G + pa * ld + (b ? (int)e[b - 1] + 1 : 0));
     }
     for (int piv = L; piv >= 1; piv--) {
-        const double d = A[tri(piv, piv)];
-        if (d > piv_tol) {
-            const double inv = 1.0 / d;
-            for (int a = 0; a < piv; a++) {
-                const double f = -A[tri(piv, a)] * inv;
-                for (int b = 0; b <= a; b++) A[tri(a, b)] = fma(f, A[tri(piv, b)], A[tri(a, b)]);
-            }
+        const double inv = guarded_inv(A[tri(piv, piv)], piv_tol);
+        for (int a = 0; a < piv; a++) {
+            const double f = -A[tri(piv, a)] * inv;
+            for (int b = 0; b <= a; b++) A[tri(a, b)] = fma(f, A[tri(piv, b)], A[tri(a, b)]);
         }
     }
     return A[0];

@@ -62,6 +62,7 @@ struct urlgpu_ctx {
     double *d_zcache = nullptr; size_t zcache_cap = 0;
     double *d_x = nullptr; const double *d_x_view = nullptr; int64_t shard_n = 0; bool borrow_device_x = false; // attached raw rows (sharded protocol)
     std::vector<double> h_gram;
+    double gram_dmax = 0;   // largest diagonal entry of the Gram: scale of the pivot guard (CbicParams::piv_tol)
     bool have_gram = false;
 
     // scratch
@@ -581,6 +582,8 @@ static int shard_finish_impl(urlgpu_ctx *ctx, const double *mean_host, const dou
     if (!borrowed) { if (keep_z) ctx->d_z = zbuf; else cudaFree(zbuf); }
     ctx->d_x = nullptr; ctx->d_x_view = nullptr;
     ctx->cn = n_total;
+    ctx->gram_dmax = 0;
+    for (int i = 0; i < p; i++) ctx->gram_dmax = std::max(ctx->gram_dmax, ctx->h_gram[(size_t)i * p + i]);
     ctx->have_gram = true;
     return URLGPU_OK;
 }
@@ -622,6 +625,8 @@ extern "C" int urlgpu_set_gram(urlgpu_ctx *ctx, const double *g, int64_t n_total
     free_continuous(ctx);
     ctx->cn = n_total; ctx->cp = p;
     ctx->h_gram.assign(g, g + (size_t)p * p);
+    ctx->gram_dmax = 0;
+    for (int i = 0; i < p; i++) ctx->gram_dmax = std::max(ctx->gram_dmax, g[(size_t)i * p + i]);
     ctx->have_gram = true;
     return URLGPU_OK;
 }
@@ -1635,6 +1640,7 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
         for (int b = 0; b <= a; b++) sub[tri(a, b)] = ctx->h_gram[(size_t)order[a] * p + order[b]];
     CbicParams prm{};
     prm.c = c;
+    prm.piv_tol = 1e-10 * ctx->gram_dmax;
     { // low bits walked by one DFS thread: 11 by default (URLGPU_CBIC_J overrides, 3..11)
         static const int jmax = getenv("URLGPU_CBIC_J") ? std::max(3, std::min(atoi(getenv("URLGPU_CBIC_J")), 11)) : 11;
         prm.J = std::max(std::min(c, 3), std::min(jmax, c - 10));
@@ -1672,7 +1678,7 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
                 CK(mids[st & 1]->alloc(osz * n_out * sizeof(double)));
                 dst = mids[st & 1]->as<double>();
             }
-            cbic_roots_kernel<<<blocks_for(n_out, warps), warps * 32, (size_t)warps * insz * sizeof(double), s>>>(src, src_stride, c_in, bits, K, n_out, dst, last ? 1 : 0);
+            cbic_roots_kernel<<<blocks_for(n_out, warps), warps * 32, (size_t)warps * insz * sizeof(double), s>>>(src, src_stride, c_in, bits, K, n_out, dst, last ? 1 : 0, prm.piv_tol);
             src = dst; src_stride = osz; c_in = c_out; done += bits;
         }
         switch (prm.J) {
@@ -1813,11 +1819,8 @@ static int cbic_score_rank(urlgpu_ctx *ctx, int variable, const std::vector<int>
     order.insert(order.end(), cand.begin(), cand.end());
     const int ld = c + 1;
     std::vector<double> g((size_t)ld * ld);
-    double dmax = 0;
-    for (int a = 0; a <= c; a++) {
+    for (int a = 0; a <= c; a++)
         for (int b = 0; b <= c; b++) g[(size_t)a * ld + b] = ctx->h_gram[(size_t)order[a] * p + order[b]];
-        dmax = std::max(dmax, g[(size_t)a * ld + a]);
-    }
     DevBuf dg(ctx);
     CK(dg.alloc(g.size() * sizeof(double)));
     { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
@@ -1827,7 +1830,8 @@ static int cbic_score_rank(urlgpu_ctx *ctx, int variable, const std::vector<int>
     prm.n = (double)(int)ctx->cn;
     prm.lam_logn = lambda * std::log((double)(int)ctx->cn);
     prm.log_n = std::log((double)(int)ctx->cn);
-    const double piv_tol = 1e-10 * dmax;
+    const double piv_tol = 1e-10 * ctx->gram_dmax;
+    prm.piv_tol = piv_tol;
     const size_t smem = rs_binom_bytes(rs);
     const uint64_t last = (uint64_t)first + count;
     int launches = 0;
@@ -2407,6 +2411,7 @@ extern "C" int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *p
         prm.n = (double)(int)ctx->cn;
         prm.lam_logn = lambda * std::log((double)(int)ctx->cn);
         prm.log_n = std::log((double)(int)ctx->cn);
+        prm.piv_tol = 1e-10 * ctx->gram_dmax;
         DevBuf dsub(ctx), dout(ctx);
         CK(dsub.alloc(sub.size() * sizeof(double)));
         CK(dout.alloc(2 * sizeof(double)));
