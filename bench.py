@@ -427,13 +427,43 @@ def run_gpu(args):
 
 # ---------------------------------------------------------------------------------------------- config 5 (optional workload)
 
+def degree_bounded_dag(p, seed, max_degree=16, max_indegree=8):
+    """random DAG over a random topological order whose undirected skeleton has degree <= max_degree everywhere (BASELINE
+    configs[4]: "skeleton degree <= 16"): node i draws up to max_indegree parents among its predecessors that still have
+    room.  Non-local, so 2-hop neighbourhoods cover a large part of the network.  -> (order, parents, weights, edges)"""
+    rng = np.random.default_rng(seed)
+    order = rng.permutation(p)
+    deg = np.zeros(p, dtype=np.int64)
+    parents, weights = [[] for _ in range(p)], [[] for _ in range(p)]
+    for pos, v in enumerate(order):
+        want = int(rng.integers(1, max_indegree + 1))
+        pool = [int(u) for u in order[:pos] if deg[u] < max_degree]
+        k = min(want, len(pool), max_degree - int(deg[v]))
+        if k > 0:
+            pa = sorted(int(u) for u in rng.choice(pool, size=k, replace=False))
+            parents[v] = pa
+            weights[v] = [float(rng.uniform(0.3, 0.9) * rng.choice([-1.0, 1.0])) for _ in pa]
+            for u in pa:
+                deg[u] += 1
+                deg[v] += 1
+    edges = [0] * p
+    for v in range(p):
+        for u in parents[v]:
+            edges[v] |= 1 << u
+            edges[u] |= 1 << v
+    return [int(v) for v in order], parents, weights, edges
+
+
 def run_gpu_cbic5(args):
-    """BASELINE configs[4]: linear-Gaussian p=200, n=1e7, skeleton degree <= 16, cBIC lambda=2, rows sharded across the
-    ranks.  Step = sharded standardise + FP64 Gram (DMMA) + two all-gathers + Gram all-gather, then every owned
-    variable's family (2-hop neighbourhood, explicit -p 4: the reference's default p-1 over the 2-hop set is
-    astronomically large and p=200 does not fit its 64-bit varset) with accept + prune."""
+    """BASELINE configs[4]: linear-Gaussian p=200, n=1e7, skeleton degree <= 16, cBIC lambda=2, sharded by
+    (variable, parent-set range) across the ranks.  A step = (1) row-sharded standardise + FP64 Gram (DMMA), moments and
+    Gram partials all-gathered and summed in rank order; (2) every rank scores its contiguous piece of the concatenated
+    family index space (urlgpu_score_range: 2-hop candidates, explicit -p 4 — the reference's default p-1 over the 2-hop set
+    is astronomically large and p=200 does not fit its 64-bit varset) into an NCCL buffer; (3) one all-to-all
+    moves the raw scores to the variables' owners; (4) owners apply acceptance + prune (urlgpu_result_from_scores)."""
     import torch
     pkg = importlib.import_module("urlearning-cpp_b200")
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -442,37 +472,27 @@ def run_gpu_cbic5(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    p, n_total, K, lam = 200, args.n5, 4, 2.0
+    p, n_total, K, lam = 200, args.n5, args.k5, 2.0
     n_local = n_total // world
     n_total = n_local * world
-    # same DAG and weights on every rank (seeded), rank-specific noise; generated on the device
-    rng = np.random.default_rng(5)
-    window, indeg = 7, 3
-    parents, weights = [], []
-    for i in range(p):
-        cands = np.arange(max(0, i - window), i)
-        k = min(indeg, len(cands))
-        pa = sorted(rng.choice(cands, size=k, replace=False).tolist()) if k else []
-        parents.append(pa)
-        weights.append([float(rng.uniform(0.5, 1.5) * rng.choice([-1.0, 1.0])) for _ in pa])
-    edges = [0] * p
-    for i in range(p):
-        for j in parents[i]:
-            edges[i] |= 1 << j
-            edges[j] |= 1 << i
+    order, parents, weights, edges = degree_bounded_dag(p, 5)
+    maxdeg = max(bin(e).count("1") for e in edges)
     gen = torch.Generator(device="cuda")
-    gen.manual_seed(1000 + rank)
+    gen.manual_seed(1000 + rank)     # same DAG and weights on every rank, rank-specific rows; generated on the device
     x = torch.randn((p, n_local), dtype=torch.float64, device="cuda", generator=gen)
-    for i in range(p):
-        for j, w in zip(parents[i], weights[i]):
-            x[i] += w * x[j]
+    for v in order:
+        for u, w in zip(parents[v], weights[v]):
+            x[v] += w * x[u]
     nbs = [pkg.two_hop_neighbors(edges, p, v) for v in range(p)]
-    cmax = max(bin(nb & ~(1 << v)).count("1") for v, nb in enumerate(nbs))
+    cs = [bin(nb & ~(1 << v)).count("1") for v, nb in enumerate(nbs)]
     eng = pkg.Engine(local)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
-    mine = [v for v in range(p) if v % world == rank]
-    sets_total = sum(family_size(bin(nbs[v] & ~(1 << v)).count("1"), K) for v in range(p))
+    sizes = [family_size(c, K) for c in cs]
+    sets_total = sum(sizes)
+    pieces, owner = D.plan_ranges(sizes, world)
+    my_total = sum(c for _, _, c in pieces[rank])
+    score_buf = torch.empty(max(1, my_total), dtype=torch.float32, device="cuda")
 
     def allsum(a):
         if world == 1:
@@ -485,6 +505,8 @@ def run_gpu_cbic5(args):
             out += q
         return out.cpu().numpy()
 
+    stored_box = [0]
+
     def step():
         eng.shard_begin(x.data_ptr(), n_local, p)
         s1, _ = eng.shard_moments(None)
@@ -495,9 +517,25 @@ def run_gpu_cbic5(args):
         eng.shard_finish(mean, dev, n_total)
         g = allsum(eng.gram())
         eng.set_gram(g, n_total)
-        for v in mine:
-            res = eng.score_variable(v, nbs[v], K, pkg.CBIC, lam=lam, flags=pkg.PRUNE_DOMINATED)
-            res.free()
+        mine, off = {}, 0
+        for (v, first, count) in pieces[rank]:
+            t = score_buf[off:off + count]
+            eng.score_range(v, nbs[v], K, pkg.CBIC, first, count, lam=lam, out_device_ptr=t.data_ptr())
+            mine[(v, first, count)] = t
+            off += count
+        full = D.exchange_ranges(pieces, owner, sizes, mine, "cuda")
+        stored = 0
+        prev = None
+        for v, t in full.items():
+            res = eng.result_from_scores(v, nbs[v], K, pkg.CBIC, t.data_ptr(), n=sizes[v], flags=pkg.PRUNE_DOMINATED).prefetch()
+            if prev is not None:
+                stored += prev.count()
+                prev.free()
+            prev = res
+        if prev is not None:
+            stored += prev.count()
+            prev.free()
+        stored_box[0] = stored
 
     def barrier():
         if world > 1:
@@ -518,27 +556,35 @@ def run_gpu_cbic5(args):
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    stored = stored_box[0]
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        t = torch.tensor([stored], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        stored = int(t.item())
     st = eng.stats()
     sampler.stop_flag = True
     sampler.join(timeout=2)
     if rank == 0:
         gram_tf = st["gram_flops"] / (st["ms_gram"] / 1e3) / 1e12 if st["ms_gram"] > 0 else None
         fp64 = eng.probe_fp64()
+        k3_rate = my_total * args.steps / (st["ms_cbic"] / 1e3) if st["ms_cbic"] > 0 else None
         line = {"metric": METRIC, "value": sets_total * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64 -> f32", "data": "synthetic (seeded, generated on the device with torch)",
-                "config": {"workload": f"configs[4]: linear-Gaussian p=200 n={n_total} (rows sharded over {world} GPU(s)), skeleton degree<=16 "
-                                       f"(window {window}, in-degree {indeg}), 2-hop candidates (max {cmax}), explicit -p {K}, cBIC lambda=2, accept + prune",
-                           "sets_per_step": sets_total, "parallelism": f"rows sharded n/{world} for the Gram, variables striped v % {world}"},
+                "config": {"workload": f"configs[4]: linear-Gaussian p=200 n={n_total} (rows sharded over {world} GPU(s)), random DAG with skeleton degree<="
+                                       f"{maxdeg}, 2-hop candidates ({min(cs)}..{max(cs)} per variable), explicit -p {K}, cBIC lambda=2, accept + prune",
+                           "sets_per_step": sets_total, "stored_after_prune": stored,
+                           "parallelism": f"rows sharded n/{world} for the Gram; scoring sharded by (variable, parent-set range): {world} contiguous pieces of the "
+                                          f"concatenated family index space, one all-to-all of raw scores to the variables' owners, N={world}"},
                 "e2e": None, "gpu_launches": int(st["launches_total"]), "clocks": sampler.summary(),
                 "roofline": {"bound": "fp64", "kernel": "K2 gram_partial_kernel (DMMA m8n8k4.f64) incl. standardise + moments", "achieved": gram_tf,
                              "peak": fp64["dmma"], "unit": "TFLOP/s", "frac": gram_tf / fp64["dmma"] if gram_tf else None, "traffic": None,
                              "peak_source": "measured in this run (urlgpu_probe_fp64: register-resident DMMA m8n8k4.f64 chains); DFMA: %.1f TFLOP/s" % fp64["dfma"],
                              "gram_ms_per_step_rank0": st["ms_gram"] / args.steps, "gram_flops_per_step_rank0": st["gram_flops"] / args.steps,
+                             "k3_rank_sets_per_s_rank0": k3_rate,
                              "family_ms": {"gram": st["ms_gram"], "cbic": st["ms_cbic"], "accept": st["ms_accept"], "prune": st["ms_prune"]}},
                 "cpu_baseline": None}
         print(json.dumps(line))
@@ -633,6 +679,7 @@ def main():
                     help="BIC with N > 1 GPUs: weak = N replicas of the configs[3] network in one 60N-variable data set (per-GPU work "
                          "fixed); strong = configs[3] itself split over the ranks")
     ap.add_argument("--n5", type=int, default=10_000_000, help="total rows of the cbic5 workload")
+    ap.add_argument("--k5", type=int, default=4, help="explicit parent limit (-p) of the cbic5 workload")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--one-pass", action="store_true", help="profiling aid: one warm pass, then one pass on one context inside cudaProfilerStart/Stop; no bench line")

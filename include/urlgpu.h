@@ -110,6 +110,20 @@ int urlgpu_result_free(urlgpu_result *res);
 void *urlgpu_host_alloc(uint64_t bytes);
 void urlgpu_host_free(void *p);
 
+/* (variable, parent-set range) shards — the multi-GPU unit of work SURVEY.md 8(e) / BASELINE.json north_star name.
+ * The canonical order of a family (layer by layer, each layer in the reference's Gosper order, score_calculator.cpp:76-120)
+ * numbers its sets 0 .. family_size-1; a contiguous range of that numbering is scored independently of the rest:
+ *   urlgpu_family_size        number of sets: sum_{l<=max_parents} C(candidates, l)  (fails above 2^32)
+ *   urlgpu_score_range        RAW scores of sets [first, first+count) (BIC: the score, cBIC: the_score before negation),
+ *                             into a host buffer or, on_device=1, a device buffer on ctx's device (e.g. an NCCL send buffer)
+ *   urlgpu_result_from_scores the variable's owner, holding all family_size raw scores (gathered from the ranks), applies
+ *                             the store rule / acceptance and the optional prune; the result then behaves like any other */
+int urlgpu_family_size(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type, uint64_t *n);
+int urlgpu_score_range(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type,
+                       double lambda, uint64_t first, uint64_t count, float *scores, int on_device);
+int urlgpu_result_from_scores(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type,
+                              const float *scores, uint64_t n, int on_device, unsigned filter_flags, urlgpu_result **out);
+
 /* Single parent set, same value ScoringFunction::calculateScore returns (BIC: the score; cBIC: -the_score).
  * value64 (optional): BIC: exact log-likelihood before the float rounding; cBIC: the_score in FP64. */
 int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *parents, int mask_words, int score_type,

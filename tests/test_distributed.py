@@ -105,3 +105,49 @@ def test_family_cost_matches_brute_force():
     cand = [2, 3, 4]
     want = sum(card[v] * np.prod([card[i] for i in s]) for l in range(K + 1) for s in itertools.combinations(cand, l))
     assert D.family_cost(card, v, nb, K) == want
+
+
+def test_plan_ranges_covers_every_set_once():
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 3, 8):
+        for sizes in ([10], [5, 1000000, 7, 300000], list(rng.integers(1, 500000, size=37)), [1 << 20] * 3):
+            pieces, owner = D.plan_ranges(sizes, world, min_chunk=1000)
+            seen = [np.zeros(int(s), dtype=np.int32) for s in sizes]
+            for r in range(world):
+                for (v, first, count) in pieces[r]:
+                    assert count > 0 and first + count <= sizes[v]
+                    seen[v][first:first + count] += 1
+            assert all((x == 1).all() for x in seen)
+            assert len(owner) == len(sizes) and set(owner) <= set(range(world))
+            loads = [sum(c for _, _, c in pieces[r]) for r in range(world)]
+            assert max(loads) - min(loads) <= 2 * 1000 * world + max(1, sum(sizes) // world // 50 + 2000)
+            assert (pieces, owner) == D.plan_ranges(list(sizes), world, min_chunk=1000)
+
+
+def _range_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
+    sizes = [1000, 50000, 3, 20000, 12345]
+    pieces, owner = D.plan_ranges(sizes, world, min_chunk=100)
+    # "score" of set i of variable v = v + i / 2^20 (exact in float32 for these sizes)
+    mine = {(v, f, c): (torch.arange(f, f + c, dtype=torch.float32) / 1048576.0 + v) for (v, f, c) in pieces[rank]}
+    got = D.exchange_ranges(pieces, owner, sizes, mine, "cpu")
+    ok = all(torch.equal(t, torch.arange(0, sizes[v], dtype=torch.float32) / 1048576.0 + v) for v, t in got.items())
+    owned = sorted(got)
+    res = [None] * world
+    dist.all_gather_object(res, (ok, owned))
+    if rank == 0:
+        json.dump({"ok": all(r[0] for r in res), "owned": sorted(sum((r[1] for r in res), []))}, open(out_path, "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_range_exchange(tmp_path):
+    out = str(tmp_path / "ranges.json")
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_range_worker, args=(2, port, out), nprocs=2, join=True)
+    r = json.load(open(out))
+    assert r["ok"] and r["owned"] == [0, 1, 2, 3, 4]

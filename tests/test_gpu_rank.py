@@ -177,3 +177,36 @@ def test_layouts_agree_bit_for_bit(pkg):
             assert np.array_equal(ma, mb) and np.array_equal(sa.view(np.uint32), sb.view(np.uint32))
     d.close()
     r.close()
+
+
+def test_parent_set_range_shards_reassemble_to_the_same_cache(pkg):
+    """(variable, parent-set range) shards: ranges of a family's canonical numbering scored by two contexts
+    (two ranks' stand-ins), raw scores concatenated, filters applied by the owner: identical to urlgpu_score_variable."""
+    a, b = pkg.Engine(0), pkg.Engine(0)
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=40, n=30011, seed=6, window=5, max_indegree=3)
+    x, _ = pkg.datagen.linear_gaussian_sem(p=40, n=4000, seed=8)
+    for e in (a, b):
+        e.set_discrete(codes, card)
+        e.set_continuous(x)
+    allbits = (1 << 40) - 1
+    cases = [(pkg.BIC, 3, allbits, 3), (pkg.BIC, 17, pkg.two_hop_neighbors(edges, 40, 17), 6), (pkg.CBIC, 9, allbits, 4),
+             (pkg.CBIC, 30, sum(1 << i for i in range(0, 40, 2)), 7)]
+    for st, v, nb, K in cases:
+        total = a.family_size(v, nb, K, st)
+        cut1, cut2 = total // 3, total // 3 + 1
+        parts = [a.score_range(v, nb, K, st, 0, cut1, lam=2.0), b.score_range(v, nb, K, st, cut1, cut2 - cut1, lam=2.0),
+                 a.score_range(v, nb, K, st, cut2, total - cut2, lam=2.0)]
+        raw = np.concatenate(parts)
+        assert len(raw) == total
+        for flags in (0, pkg.PRUNE_DOMINATED):
+            want = a.score_variable(v, nb, K, st, lam=2.0, flags=flags)
+            got = b.result_from_scores(v, nb, K, st, raw, flags=flags)
+            (mw, sw), (mg, sg) = want.fetch(), got.fetch()
+            assert want.scored() == got.scored() == total
+            want.free()
+            got.free()
+            assert np.array_equal(mw, mg) and np.array_equal(sw.view(np.uint32), sg.view(np.uint32))
+    with pytest.raises(pkg.UrlGpuError, match="exceeds the family"):
+        a.score_range(3, allbits, 3, pkg.BIC, 10, a.family_size(3, allbits, 3, pkg.BIC))
+    a.close()
+    b.close()

@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "urlgpu_result_prefetch", "urlgpu_result_count", "urlgpu_result_scored", "urlgpu_result_fetch", "urlgpu_result_free",
     "urlgpu_host_alloc", "urlgpu_host_free",
     "urlgpu_score_one", "urlgpu_contingency", "urlgpu_prune", "urlgpu_stats_reset", "urlgpu_stats_get",
-    "urlgpu_stats_enable_timing", "urlgpu_probe_fp64",
+    "urlgpu_stats_enable_timing", "urlgpu_probe_fp64", "urlgpu_family_size", "urlgpu_score_range", "urlgpu_result_from_scores",
 ]
 
 
@@ -102,6 +102,9 @@ def load_library():
     lib.urlgpu_stats_get.argtypes = [vp, P(Stats)]
     lib.urlgpu_stats_enable_timing.argtypes = [vp, i32]
     lib.urlgpu_probe_fp64.argtypes = [vp, P(C.c_double), P(C.c_double)]
+    lib.urlgpu_family_size.argtypes = [vp, i32, vp, i32, i32, i32, P(u64)]
+    lib.urlgpu_score_range.argtypes = [vp, i32, vp, i32, i32, i32, C.c_double, u64, u64, vp, i32]
+    lib.urlgpu_result_from_scores.argtypes = [vp, i32, vp, i32, i32, i32, vp, u64, i32, C.c_uint, P(vp)]
     for name in ABI_SYMBOLS:
         if name not in ("urlgpu_last_error", "urlgpu_host_alloc", "urlgpu_host_free"):
             getattr(lib, name).restype = C.c_int
@@ -328,6 +331,44 @@ class Engine:
         h = C.c_void_p()
         self._check(self.lib.urlgpu_score_variable(self._h, variable, nb.ctypes.data, words, max_parents, score_type,
                                                    float(lam), flags, C.byref(h)))
+        return Result(self, h, words)
+
+    # (variable, parent-set range) shards ------------------------------------------------
+    def family_size(self, variable: int, neighbors: int, max_parents: int, score_type: int = BIC) -> int:
+        words = mask_words_for(self.p)
+        nb = mask_to_words(neighbors, words)
+        n = C.c_uint64()
+        self._check(self.lib.urlgpu_family_size(self._h, variable, nb.ctypes.data, words, max_parents, score_type, C.byref(n)))
+        return n.value
+
+    def score_range(self, variable: int, neighbors: int, max_parents: int, score_type: int, first: int, count: int,
+                    lam: float = 0.0, out_device_ptr: int | None = None):
+        """raw scores of the family's sets [first, first+count) in canonical order -> float32 array, or written to a
+        device buffer (out_device_ptr, e.g. a torch CUDA tensor's data_ptr()) when given"""
+        words = mask_words_for(self.p)
+        nb = mask_to_words(neighbors, words)
+        if out_device_ptr is not None:
+            self._check(self.lib.urlgpu_score_range(self._h, variable, nb.ctypes.data, words, max_parents, score_type, float(lam),
+                                                    first, count, C.c_void_p(out_device_ptr), 1))
+            return None
+        out = np.zeros(count, dtype=np.float32)
+        self._check(self.lib.urlgpu_score_range(self._h, variable, nb.ctypes.data, words, max_parents, score_type, float(lam),
+                                                first, count, out.ctypes.data, 0))
+        return out
+
+    def result_from_scores(self, variable: int, neighbors: int, max_parents: int, score_type: int, scores, n: int | None = None,
+                           flags: int = KEEP_ALL) -> "Result":
+        """scores: float32 numpy array of the whole family's raw scores, or a device pointer (int) with n entries"""
+        words = mask_words_for(self.p)
+        nb = mask_to_words(neighbors, words)
+        h = C.c_void_p()
+        if isinstance(scores, int):
+            self._check(self.lib.urlgpu_result_from_scores(self._h, variable, nb.ctypes.data, words, max_parents, score_type,
+                                                           C.c_void_p(scores), n, 1, flags, C.byref(h)))
+        else:
+            scores = np.ascontiguousarray(scores, dtype=np.float32)
+            self._check(self.lib.urlgpu_result_from_scores(self._h, variable, nb.ctypes.data, words, max_parents, score_type,
+                                                           scores.ctypes.data, len(scores), 0, flags, C.byref(h)))
         return Result(self, h, words)
 
     def score_one(self, variable: int, parents: int, score_type: int = BIC, lam: float = 0.0):

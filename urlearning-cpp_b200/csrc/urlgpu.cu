@@ -2021,6 +2021,45 @@ static bool choose_rank_layout(urlgpu_ctx *ctx, int c, int K, bool bic) {
     return c >= 16 && (double)family_size(c, Kc) * 8.0 < std::ldexp(1.0, c);
 }
 
+// store rule / acceptance and the optional prune on a table of RAW scores (BIC: the score, cBIC: the_score)
+static int apply_filters(urlgpu_ctx *ctx, urlgpu_result *res, bool bic, unsigned filter_flags) {
+    cudaStream_t s = ctx->stream;
+    const int c = res->c, K = res->max_parents;
+    int rc = URLGPU_OK;
+    if (res->rank_layout) {
+        const RankSpace &rs = res->rs;
+        const uint32_t total = (uint32_t)res->n_masks;
+        if (bic) {
+            Region rg(ctx, F_OTHER, 1);
+            rank_store_rule_kernel<<<blocks_for(total, 256), 256, 0, s>>>(res->d_table, total);
+        } else if (filter_flags & URLGPU_CBIC_NO_ACCEPT) {
+            Region rg(ctx, F_OTHER, 1);
+            rank_negate_kernel<<<blocks_for(total, 256), 256, 0, s>>>(res->d_table, total);
+        } else if ((rc = run_rank_dp<0>(ctx, rs, res->d_table))) return rc;
+        if (filter_flags & URLGPU_PRUNE_DOMINATED) rc = run_rank_dp<1>(ctx, rs, res->d_table);
+    } else {
+        if (bic) {
+            Region rg(ctx, F_OTHER, 1);
+            bic_store_rule_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(res->d_table, res->n_masks, K);
+        } else if (filter_flags & URLGPU_CBIC_NO_ACCEPT) {
+            Region rg(ctx, F_OTHER, 1);
+            cbic_negate_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(res->d_table, res->n_masks);
+        } else if ((rc = run_accept(ctx, res->d_table, c, K))) return rc;
+        if (filter_flags & URLGPU_PRUNE_DOMINATED) rc = run_prune(ctx, res->d_table, c, K);
+    }
+    return rc;
+}
+
+static int check_score_args(urlgpu_ctx *ctx, const char *who, int variable, const uint64_t *neighbors, int mask_words, int score_type, std::vector<int> &cand) {
+    const bool bic = score_type == URLGPU_BIC;
+    if (!bic && score_type != URLGPU_CBIC) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": unknown score type");
+    if (bic && !ctx->have_discrete) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": BIC needs urlgpu_set_discrete first");
+    if (!bic && !ctx->have_gram) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": cBIC needs urlgpu_set_continuous first");
+    const int p = bic ? ctx->p : ctx->cp;
+    if (variable < 0 || variable >= p) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": variable out of range");
+    return candidates_from_mask(ctx, p, variable, neighbors, mask_words, cand);
+}
+
 extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type,
                                      double lambda, unsigned filter_flags, urlgpu_result **out) {
     if (!ctx || !neighbors || !out) return ctx ? ctx->fail(URLGPU_ERR_ARG, "score_variable: null argument") : URLGPU_ERR_ARG;
@@ -2030,13 +2069,8 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     CK(cudaSetDevice(ctx->device));
     const bool bic = score_type == URLGPU_BIC;
-    if (!bic && score_type != URLGPU_CBIC) return ctx->fail(URLGPU_ERR_ARG, "score_variable: unknown score type");
-    if (bic && !ctx->have_discrete) return ctx->fail(URLGPU_ERR_ARG, "score_variable: BIC needs urlgpu_set_discrete first");
-    if (!bic && !ctx->have_gram) return ctx->fail(URLGPU_ERR_ARG, "score_variable: cBIC needs urlgpu_set_continuous first");
-    const int p = bic ? ctx->p : ctx->cp;
-    if (variable < 0 || variable >= p) return ctx->fail(URLGPU_ERR_ARG, "score_variable: variable out of range");
     std::vector<int> cand;
-    int rc = candidates_from_mask(ctx, p, variable, neighbors, mask_words, cand);
+    int rc = check_score_args(ctx, "score_variable", variable, neighbors, mask_words, score_type, cand);
     if (rc) return rc;
     const int c = (int)cand.size();
     int K = std::max(0, std::min(max_parents, c));
@@ -2054,62 +2088,107 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     cudaStream_t s = ctx->stream;
     auto cleanup = [&](int code) { pool_free(ctx, res->d_table); delete res; return code; };
     const double t_alloc = since(T0);
-    double t_score = 0;
     if (rank) {
-        const RankSpace &rs = res->rs;
         const uint32_t total = (uint32_t)res->n_masks;
         res->n_scored = total;
         if (bic) {
             if (c <= kMaxDenseCand) { // the mask-based K1 strategies, writing by rank
                 fill_u32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), total, kSentinelBits);
-                rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored, rs);
-            } else rc = bic_score_rank_direct(ctx, variable, cand, rs, 0, total, res->d_table);
-            if (rc) return cleanup(rc);
-            Region rg(ctx, F_OTHER, 1);
-            rank_store_rule_kernel<<<blocks_for(total, 256), 256, 0, s>>>(res->d_table, total);
-        } else {
-            rc = cbic_score_rank(ctx, variable, cand, rs, lambda, 0, total, res->d_table, nullptr);
-            if (rc) return cleanup(rc);
-            if (filter_flags & URLGPU_CBIC_NO_ACCEPT) {
-                Region rg(ctx, F_OTHER, 1);
-                rank_negate_kernel<<<blocks_for(total, 256), 256, 0, s>>>(res->d_table, total);
-            } else {
-                rc = run_rank_dp<0>(ctx, rs, res->d_table);
-                if (rc) return cleanup(rc);
-            }
-        }
-        t_score = since(T0);
-        if (filter_flags & URLGPU_PRUNE_DOMINATED) {
-            rc = run_rank_dp<1>(ctx, rs, res->d_table);
-            if (rc) return cleanup(rc);
-        }
+                rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored, res->rs);
+            } else rc = bic_score_rank_direct(ctx, variable, cand, res->rs, 0, total, res->d_table);
+        } else rc = cbic_score_rank(ctx, variable, cand, res->rs, lambda, 0, total, res->d_table, nullptr);
     } else {
         fill_u32_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), res->n_masks, kSentinelBits);
-        if (bic) {
-            rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored, RankSpace{});
-            if (rc) return cleanup(rc);
-            Region rg(ctx, F_OTHER, 1);
-            bic_store_rule_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(res->d_table, res->n_masks, K);
-        } else {
-            rc = cbic_score_family(ctx, variable, cand, K, lambda, res->d_table, nullptr, &res->n_scored);
-            if (rc) return cleanup(rc);
-            if (filter_flags & URLGPU_CBIC_NO_ACCEPT) {
-                Region rg(ctx, F_OTHER, 1);
-                cbic_negate_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(res->d_table, res->n_masks);
-            } else {
-                rc = run_accept(ctx, res->d_table, c, K);
-                if (rc) return cleanup(rc);
-            }
-        }
-        t_score = since(T0);
-        if (filter_flags & URLGPU_PRUNE_DOMINATED) {
-            rc = run_prune(ctx, res->d_table, c, K);
-            if (rc) return cleanup(rc);
-        }
+        if (bic) rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored, RankSpace{});
+        else rc = cbic_score_family(ctx, variable, cand, K, lambda, res->d_table, nullptr, &res->n_scored);
     }
-    if (dbg) fprintf(stderr, "[urlgpu score_variable] v=%d alloc %.2f ms, score %.2f ms, prune %.2f ms\n", variable, t_alloc, t_score - t_alloc, since(T0) - t_score);
+    if (rc) return cleanup(rc);
+    const double t_score = since(T0);
+    rc = apply_filters(ctx, res, bic, filter_flags);
+    if (rc) return cleanup(rc);
+    if (dbg) fprintf(stderr, "[urlgpu score_variable] v=%d alloc %.2f ms, score %.2f ms, filters %.2f ms\n", variable, t_alloc, t_score - t_alloc, since(T0) - t_score);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cleanup(ctx->cuda_fail(e, "score_variable", __LINE__));
+    *out = res;
+    return URLGPU_OK;
+}
+
+// ---- (variable, parent-set range) shards: SURVEY.md 8(e), BASELINE.json north_star -------------------------------------
+// A family's canonical order IS the rank-space index order, so a contiguous index range is a self-contained unit of
+// scoring work: N ranks score N ranges of one variable (or a deal of ranges over many variables), the raw scores are
+// exchanged (NCCL all-gather / all-to-all of float arrays, urlearning-cpp_b200/distributed.py) and the variable's owner
+// applies the filters, which need the whole subset-closed family, with urlgpu_result_from_scores.
+
+extern "C" int urlgpu_family_size(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type, uint64_t *n) {
+    if (!ctx || !neighbors || !n) return ctx ? ctx->fail(URLGPU_ERR_ARG, "family_size: null argument") : URLGPU_ERR_ARG;
+    std::vector<int> cand;
+    int rc = check_score_args(ctx, "family_size", variable, neighbors, mask_words, score_type, cand);
+    if (rc) return rc;
+    RankSpace rs{};
+    rc = make_rank_space(ctx, (int)cand.size(), std::max(0, max_parents), rs);
+    if (rc) return rc;
+    *n = rs.layer_base[rs.K + 1];
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_score_range(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type, double lambda,
+                                  uint64_t first, uint64_t count, float *scores, int on_device) {
+    if (!ctx || !neighbors || !scores) return ctx ? ctx->fail(URLGPU_ERR_ARG, "score_range: null argument") : URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const bool bic = score_type == URLGPU_BIC;
+    std::vector<int> cand;
+    int rc = check_score_args(ctx, "score_range", variable, neighbors, mask_words, score_type, cand);
+    if (rc) return rc;
+    RankSpace rs{};
+    rc = make_rank_space(ctx, (int)cand.size(), std::max(0, max_parents), rs);
+    if (rc) return rc;
+    const uint64_t total = rs.layer_base[rs.K + 1];
+    if (first + count > total) return ctx->fail(URLGPU_ERR_ARG, "score_range: the range exceeds the family (" + std::to_string(total) + " sets)");
+    if (count == 0) return URLGPU_OK;
+    cudaStream_t s = ctx->stream;
+    DevBuf tmp(ctx);
+    float *d_out = scores;
+    if (!on_device) { CK(tmp.alloc(count * sizeof(float))); d_out = tmp.as<float>(); }
+    // the kernels index by global family index: shift the base so that entry `first` lands on d_out[0]
+    float *d_base = d_out - first;
+    if (bic) rc = bic_score_rank_direct(ctx, variable, cand, rs, (uint32_t)first, (uint32_t)count, d_base);
+    else rc = cbic_score_rank(ctx, variable, cand, rs, lambda, (uint32_t)first, (uint32_t)count, d_base, nullptr);
+    if (rc) return rc;
+    if (!on_device) {
+        CK(cudaMemcpyAsync(scores, d_out, count * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_result_from_scores(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type,
+                                         const float *scores, uint64_t n, int on_device, unsigned filter_flags, urlgpu_result **out) {
+    if (!ctx || !neighbors || !scores || !out) return ctx ? ctx->fail(URLGPU_ERR_ARG, "result_from_scores: null argument") : URLGPU_ERR_ARG;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    const bool bic = score_type == URLGPU_BIC;
+    std::vector<int> cand;
+    int rc = check_score_args(ctx, "result_from_scores", variable, neighbors, mask_words, score_type, cand);
+    if (rc) return rc;
+    const int c = (int)cand.size();
+    const int K = std::max(0, std::min(max_parents, c));
+    auto *res = new urlgpu_result();
+    res->ctx = ctx; res->variable = variable; res->c = c; res->max_parents = K; res->mask_words = mask_words; res->cand = cand;
+    res->rank_layout = true;
+    rc = make_rank_space(ctx, c, K, res->rs);
+    if (rc) { delete res; return rc; }
+    res->n_masks = res->rs.layer_base[K + 1];
+    res->n_scored = res->n_masks;
+    if (n != res->n_masks) { delete res; return ctx->fail(URLGPU_ERR_ARG, "result_from_scores: expected " + std::to_string(res->n_masks) + " scores"); }
+    cudaError_t e = pool_alloc(ctx, reinterpret_cast<void **>(&res->d_table), res->n_masks * sizeof(float));
+    if (e != cudaSuccess) { delete res; return ctx->cuda_fail(e, "cudaMalloc(score table)", __LINE__); }
+    auto cleanup = [&](int code) { pool_free(ctx, res->d_table); delete res; return code; };
+    e = cudaMemcpyAsync(res->d_table, scores, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return cleanup(ctx->cuda_fail(e, "copy of the scores", __LINE__));
+    if (!on_device) { e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) return cleanup(ctx->cuda_fail(e, "copy of the scores", __LINE__)); }
+    rc = apply_filters(ctx, res, bic, filter_flags);
+    if (rc) return cleanup(rc);
     *out = res;
     return URLGPU_OK;
 }

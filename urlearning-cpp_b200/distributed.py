@@ -2,9 +2,12 @@
 
 The path shards by variable — the reference stripes ``variable % threadCount`` (score_main.cpp:136-139); here the
 variables can also be dealt out by predicted cost (:func:`assign_lpt`), because candidate families differ in size by
-orders of magnitude — and needs exactly two exchange steps: the input (packed codes, or the p*p
-Gram) is broadcast from rank 0 (or all-gathered when every rank produced a block of columns), and the per-variable
-caches are gathered to rank 0, which writes the .pss.  Scoring itself uses no collective.
+orders of magnitude — or by (variable, parent-set range) (:func:`plan_ranges`, :func:`exchange_ranges`): a family's
+canonical order numbers its sets, any contiguous range of that numbering is scored independently
+(``urlgpu_score_range``), and the raw scores travel to the variable's owner, which applies the filters that need the
+whole family (``urlgpu_result_from_scores``).  Exchange steps: the input (packed codes, or the p*p
+Gram) is broadcast from rank 0 (or all-gathered when every rank produced a block of columns); range shards add one
+all-to-all of float32 score arrays; the per-variable caches are gathered to rank 0, which writes the .pss.
 """
 from __future__ import annotations
 
@@ -97,4 +100,73 @@ def gather_caches(local: dict, p: int, words: int, device, dst: int = 0, owner=N
             scores = buf[off:off + k, words].astype(np.int32).view(np.float32)
             out[v] = (masks.copy(), scores.copy())
             off += k
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (variable, parent-set range) shards
+
+def plan_ranges(sizes, world: int, owner=None, min_chunk: int = 1 << 16):
+    """Deal the concatenated index space of all families (sizes[v] = sets of variable v, in variable order) into `world`
+    contiguous pieces of (almost) equal size.  -> (pieces, owner): pieces[r] = [(variable, first, count), ...] scored by
+    rank r; owner[v] = the rank that assembles variable v's family and filters it (default: the rank scoring the largest
+    part of it, ties to the lower rank).  Deterministic: every rank computes the same plan without communication.
+    Pieces shorter than `min_chunk` sets are not split off a family's end (a launch per few sets costs more than it saves)."""
+    total = int(sum(sizes))
+    pieces = [[] for _ in range(world)]
+    share = [dict() for _ in range(len(sizes))]
+    bounds = [(total * r) // world for r in range(world + 1)]
+    # snap the cut points to family ends when the remainder would be tiny
+    starts = np.concatenate([[0], np.cumsum(np.asarray(sizes, dtype=np.int64))])
+    for r in range(1, world):
+        v = int(np.searchsorted(starts, bounds[r], side="right") - 1)
+        if v < len(sizes):
+            if bounds[r] - starts[v] < min_chunk:
+                bounds[r] = int(starts[v])
+            elif starts[v + 1] - bounds[r] < min_chunk:
+                bounds[r] = int(starts[v + 1])
+    for r in range(world):
+        lo, hi = max(bounds[r], bounds[r - 1] if r else 0), bounds[r + 1]
+        bounds[r] = lo
+        v = int(np.searchsorted(starts, lo, side="right") - 1)
+        while lo < hi and v < len(sizes):
+            end = min(hi, int(starts[v + 1]))
+            if end > lo:
+                pieces[r].append((v, lo - int(starts[v]), end - lo))
+                share[v][r] = share[v].get(r, 0) + end - lo
+            lo = end
+            v += 1
+    if owner is None:
+        owner = [min(sh, key=lambda r: (-sh[r], r)) if sh else v % world for v, sh in enumerate(share)]
+    return pieces, owner
+
+
+def exchange_ranges(pieces, owner, sizes, my_scores, device):
+    """my_scores: {(variable, first, count): float32 tensor on `device`} for this rank's pieces.  One all_to_all_single moves
+    every piece to its variable's owner.  -> {variable: float32 tensor [sizes[variable]]} for the variables this rank owns."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    send_counts = [0] * world
+    for (v, first, count) in pieces[rank]:
+        send_counts[owner[v]] += count
+    recv_counts = [sum(c for (v, f, c) in pieces[r] if owner[v] == rank) for r in range(world)]
+    # send buffer: grouped by destination, pieces in plan order
+    send = torch.empty(max(1, sum(send_counts)), dtype=torch.float32, device=device)
+    off = [0] * world
+    base = np.concatenate([[0], np.cumsum(send_counts)]).astype(np.int64)
+    for (v, first, count) in pieces[rank]:
+        d = owner[v]
+        send[int(base[d]) + off[d]: int(base[d]) + off[d] + count] = my_scores[(v, first, count)]
+        off[d] += count
+    recv = torch.empty(max(1, sum(recv_counts)), dtype=torch.float32, device=device)
+    if world > 1:
+        dist.all_to_all_single(recv[:sum(recv_counts)], send[:sum(send_counts)], output_split_sizes=recv_counts, input_split_sizes=send_counts)
+    else:
+        recv[:sum(recv_counts)] = send[:sum(send_counts)]
+    out = {v: torch.empty(int(sizes[v]), dtype=torch.float32, device=device) for v in range(len(sizes)) if owner[v] == rank}
+    pos = 0
+    for r in range(world):
+        for (v, first, count) in pieces[r]:
+            if owner[v] == rank:
+                out[v][first:first + count] = recv[pos:pos + count]
+                pos += count
     return out
