@@ -32,6 +32,21 @@ public:
     dynamic_bitset &flip(size_type i) { w[i >> 6] ^= 1ULL << (i & 63); return *this; }
     bool test(size_type i) const { return (w[i >> 6] >> (i & 63)) & 1; }
     bool operator[](size_type i) const { return test(i); }
+    class reference { // proxy of a single bit, as in boost (b[i] = x, b[i] |= x, ~b[i], bool(b[i]))
+    public:
+        reference(dynamic_bitset &b, size_type i) : b(b), i(i) {}
+        reference &operator=(bool v) { b.set(i, v); return *this; }
+        reference &operator=(const reference &o) { b.set(i, (bool)o); return *this; }
+        reference &operator|=(bool v) { if (v) b.set(i); return *this; }
+        reference &operator&=(bool v) { if (!v) b.reset(i); return *this; }
+        reference &flip() { b.flip(i); return *this; }
+        operator bool() const { return b.test(i); }
+        bool operator~() const { return !b.test(i); }
+    private:
+        dynamic_bitset &b;
+        size_type i;
+    };
+    reference operator[](size_type i) { return reference(*this, i); }
     bool any() const { for (auto x : w) if (x) return true; return false; }
     bool none() const { return !any(); }
     size_type count() const { size_type c = 0; for (auto x : w) c += (size_type)__builtin_popcountll(x); return c; }

@@ -144,7 +144,7 @@ def plan_ranges(sizes, world: int, owner=None, min_chunk: int = 1 << 16):
 def exchange_ranges(pieces, owner, sizes, my_scores, device):
     """my_scores: {(variable, first, count): float32 tensor on `device`} for this rank's pieces.  One all_to_all_single moves
     every piece to its variable's owner.  -> {variable: float32 tensor [sizes[variable]]} for the variables this rank owns."""
-    world, rank = dist.get_world_size(), dist.get_rank()
+    world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
     send_counts = [0] * world
     for (v, first, count) in pieces[rank]:
         send_counts[owner[v]] += count
