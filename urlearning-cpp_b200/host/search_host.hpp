@@ -11,7 +11,7 @@
 //
 // These stay on the host (BASELINE.json north_star): they consume the GPU-written `.pss` unchanged.  The restatement
 // exists so that "the downstream A* DAG is identical" can be checked inside this repository; tests/test_search.py pins
-// it against the reference's own classes compiled into oracle/_ref/libref_search.so.  Variable sets are 64-bit, as in
+// it against the reference's own classes compiled from their sources (test infrastructure, outside this package).  Variable sets are 64-bit, as in
 // the reference (typedefs.h:469).  Equal scores: the reference's entry order among ties is boost::unordered_map
 // iteration order followed by an unstable std::sort; here ties are ordered by (|S|, mask), deterministic.
 #pragma once
