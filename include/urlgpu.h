@@ -21,6 +21,7 @@
  *                                                                     scoring_function/score_calculator.cpp:150-197
  *   urlgpu_score_one         ScoringFunction::calculateScore          scoring_function/scoring_function.h:19
  *   urlgpu_contingency       ADTree::makeContab                       ad_tree/ad_tree.cpp:95-137
+ *   urlgpu_spg_build/query   SparseParentBitwise::initialize/getScore  score_cache/sparse_parent_bitwise.cpp:24-110
  *   urlgpu_prune             ScoreCalculator::prune                   scoring_function/score_calculator.cpp:150-197
  *   urlgpu_result_*          FloatMap iteration in scoringThread      score/score_main.cpp:187-200, base/typedefs.h:816
  *
@@ -135,6 +136,17 @@ int urlgpu_contingency(urlgpu_ctx *ctx, int variable, const uint64_t *parents, i
 /* Standalone prune of a caller-supplied cache (masks over <=30 distinct variables): keep[i]=0 iff some other
  * entry j with masks[j] subset of masks[i] has scores[j] >= scores[i] (ties: the subset wins). */
 int urlgpu_prune(urlgpu_ctx *ctx, const uint64_t *masks, const float *scores, uint64_t n, int mask_words, uint8_t *keep);
+
+/* The sparse parent graph of one variable as a device query structure: replaces
+ * bestscorecalculators::SparseParentBitwise (score_cache/sparse_parent_bitwise.cpp:24-110).  Built from a variable's cache
+ * with the SEARCH side's sign (scores negated on read, score_cache.cpp:151: lower is better); a query names the variables
+ * allowed as parents and returns the best (lowest) score among the cached subsets of that set, FLT_MAX when there is none
+ * (:104-106), optionally the winning parent set / its index in score order.  Batches of queries run one warp each. */
+typedef struct urlgpu_spg urlgpu_spg;
+int urlgpu_spg_build(urlgpu_ctx *ctx, const uint64_t *masks, const float *scores, uint64_t n, int mask_words, int variable_count, urlgpu_spg **out);
+int urlgpu_spg_query(urlgpu_spg *spg, const uint64_t *allowed /* nq*mask_words */, uint64_t nq, float *best_scores, uint64_t *best_parents /* optional */,
+                     int64_t *best_index /* optional */);
+int urlgpu_spg_free(urlgpu_spg *spg);
 
 /* Measurement hooks: device time (CUDA events on the context's stream) and launch counts per kernel family,
  * accumulated since the last reset. */

@@ -91,3 +91,53 @@ def test_reference_reader_round_trips_the_gpu_pss(pkg, tmp_path):
         got = dict(zip(map(int, rm), rs))
         assert got == want
     eng.close()
+
+
+def test_device_sparse_parent_graph_equals_host_and_reference(pkg, S, orc, engine, tmp_path):
+    """urlgpu_spg_*: SparseParentBitwise::getScore as a batched device look-up (SURVEY 8f-3): same best score as the host
+    restatement (and through it the reference's own list / bitwise / tree structures, tests/test_search.py) for random
+    allowed sets, the empty set, the full set and sets with no cached subset; multi-word variable sets as well"""
+    inp = os.path.join(DATA, "hepatitis.clean.csv")
+    pss = str(tmp_path / "hep.pss")
+    subprocess.check_call([EXE, inp, pss, "-s", "-f", "BIC", "--quiet"], stdout=subprocess.DEVNULL)
+    cache = S.ScoreCache(pss)
+    rng = np.random.default_rng(11)
+    for v in (0, 7, 19):
+        masks, scores = cache.entries(v)
+        perm = rng.permutation(len(masks))       # the build sorts
+        spg = engine.sparse_parent_graph(masks[perm], scores[perm], cache.p)
+        q = rng.integers(0, 1 << 20, size=3000, dtype=np.uint64) & ~np.uint64(1 << v)
+        q[:2] = [0, (1 << 20) - 1 - (1 << v)]
+        best, parents, index = spg.query(q)
+        hb, hp = cache.best_scores(v, q, "bitwise")
+        assert np.array_equal(best.view(np.uint32), hb.view(np.uint32))
+        assert np.array_equal(parents[:, 0], hp)            # same deterministic order among equal scores
+        assert np.array_equal(masks[index], parents[:, 0])
+        spg.free()
+    # entries that all need variable 3: queries without it find nothing (FLT_MAX, sparse_parent_bitwise.cpp:104-106)
+    m = np.array([0b1000, 0b1010, 0b1001], dtype=np.uint64)
+    spg = engine.sparse_parent_graph(m, np.array([5.0, 3.0, 4.0], dtype=np.float32), 6)
+    best, parents, index = spg.query(np.array([0b0111, 0b1000, 0b1011], dtype=np.uint64))
+    assert best[0] == np.finfo(np.float32).max and index[0] == -1 and parents[0, 0] == 0
+    assert list(best[1:]) == [5.0, 3.0] and list(parents[1:, 0]) == [0b1000, 0b1010]
+    spg.free()
+    # 150 variables (three words), 50000 entries: against a brute-force scan
+    p, n = 150, 50000
+    ent = np.zeros((n, 3), dtype=np.uint64)
+    for i in range(n):
+        for b in rng.choice(p, size=int(rng.integers(0, 4)), replace=False):
+            ent[i, b >> 6] |= np.uint64(1 << int(b & 63))
+    sc = rng.normal(100, 30, size=n).astype(np.float32)
+    spg = engine.sparse_parent_graph(ent, sc, p)
+    qs = np.zeros((200, 3), dtype=np.uint64)
+    for i in range(200):
+        for b in rng.choice(p, size=int(rng.integers(0, 120)), replace=False):
+            qs[i, b >> 6] |= np.uint64(1 << int(b & 63))
+    best, parents, index = spg.query(qs)
+    for i in range(200):
+        ok = np.all((ent & ~qs[i]) == 0, axis=1)
+        want = sc[ok].min() if ok.any() else np.finfo(np.float32).max
+        assert best[i] == want
+        if ok.any():
+            assert np.all((parents[i] & ~qs[i]) == 0)
+    spg.free()

@@ -34,6 +34,7 @@ ABI_SYMBOLS = [
     "urlgpu_host_alloc", "urlgpu_host_free",
     "urlgpu_score_one", "urlgpu_contingency", "urlgpu_prune", "urlgpu_stats_reset", "urlgpu_stats_get",
     "urlgpu_stats_enable_timing", "urlgpu_probe_fp64", "urlgpu_family_size", "urlgpu_score_range", "urlgpu_result_from_scores",
+    "urlgpu_spg_build", "urlgpu_spg_query", "urlgpu_spg_free",
 ]
 
 
@@ -102,6 +103,9 @@ def load_library():
     lib.urlgpu_stats_get.argtypes = [vp, P(Stats)]
     lib.urlgpu_stats_enable_timing.argtypes = [vp, i32]
     lib.urlgpu_probe_fp64.argtypes = [vp, P(C.c_double), P(C.c_double)]
+    lib.urlgpu_spg_build.argtypes = [vp, vp, vp, u64, i32, i32, P(vp)]
+    lib.urlgpu_spg_query.argtypes = [vp, vp, u64, vp, vp, vp]
+    lib.urlgpu_spg_free.argtypes = [vp]
     lib.urlgpu_family_size.argtypes = [vp, i32, vp, i32, i32, i32, P(u64)]
     lib.urlgpu_score_range.argtypes = [vp, i32, vp, i32, i32, i32, C.c_double, u64, u64, vp, i32]
     lib.urlgpu_result_from_scores.argtypes = [vp, i32, vp, i32, i32, i32, vp, u64, i32, C.c_uint, P(vp)]
@@ -371,6 +375,10 @@ class Engine:
                                                            scores.ctypes.data, len(scores), 0, flags, C.byref(h)))
         return Result(self, h, words)
 
+    def sparse_parent_graph(self, masks: np.ndarray, scores: np.ndarray, variable_count: int) -> "SparseParentGraph":
+        """device query structure over one variable's cache; scores with the search side's sign (lower is better)"""
+        return SparseParentGraph(self, masks, scores, variable_count)
+
     def score_one(self, variable: int, parents: int, score_type: int = BIC, lam: float = 0.0):
         """ScoringFunction::calculateScore -> (float32 score, float64 pre-rounding value)."""
         words = mask_words_for(self.p)
@@ -414,6 +422,43 @@ class Engine:
         a, b = C.c_double(), C.c_double()
         self._check(self.lib.urlgpu_probe_fp64(self._h, C.byref(a), C.byref(b)))
         return {"dfma": a.value, "dmma": b.value}
+
+
+class SparseParentGraph:
+    """urlgpu_spg_*: SparseParentBitwise (score_cache/sparse_parent_bitwise.cpp) on the device, batched getScore."""
+
+    def __init__(self, eng: Engine, masks, scores, variable_count: int):
+        masks = np.ascontiguousarray(masks, dtype=np.uint64)
+        if masks.ndim == 1:
+            masks = masks.reshape(-1, 1)
+        scores = np.ascontiguousarray(scores, dtype=np.float32)
+        self._eng, self.words = eng, masks.shape[1]
+        h = C.c_void_p()
+        eng._check(eng.lib.urlgpu_spg_build(eng._h, masks.ctypes.data, scores.ctypes.data, len(scores), self.words, variable_count, C.byref(h)))
+        self._h = h
+
+    def query(self, allowed):
+        """allowed: uint64 [nq] or [nq, words] sets of variables allowed as parents -> (best float32 [nq], parents uint64 [nq, words], index int64 [nq])"""
+        q = np.ascontiguousarray(allowed, dtype=np.uint64)
+        if q.ndim == 1:
+            q = q.reshape(-1, 1)
+        nq = q.shape[0]
+        best = np.zeros(nq, dtype=np.float32)
+        parents = np.zeros((nq, self.words), dtype=np.uint64)
+        index = np.zeros(nq, dtype=np.int64)
+        self._eng._check(self._eng.lib.urlgpu_spg_query(self._h, q.ctypes.data, nq, best.ctypes.data, parents.ctypes.data, index.ctypes.data))
+        return best, parents, index
+
+    def free(self):
+        if self._h is not None:
+            self._eng.lib.urlgpu_spg_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 from . import datagen, pss  # noqa: E402

@@ -20,6 +20,7 @@
 #include "tree_kernels.cuh"
 #include "cbic_kernels.cuh"
 #include "rank_kernels.cuh"
+#include "spg_kernels.cuh"
 
 using namespace urlgpu;
 
@@ -2430,6 +2431,101 @@ extern "C" int urlgpu_result_free(urlgpu_result *res) {
     }
     if (res->ready) ctx->free_events.push_back(res->ready);
     delete res;
+    return URLGPU_OK;
+}
+
+// ============================================================================================ sparse parent graph (device query structure)
+
+struct urlgpu_spg {
+    urlgpu_ctx *ctx = nullptr;
+    uint64_t n = 0, bw = 0;
+    int words = 1, variable_count = 0;
+    uint64_t *d_masks = nullptr;
+    float *d_scores = nullptr;
+    uint64_t *d_not_used = nullptr;
+    std::vector<uint64_t> h_masks;   // sorted order, for best_parents
+};
+
+extern "C" int urlgpu_spg_build(urlgpu_ctx *ctx, const uint64_t *masks, const float *scores, uint64_t n, int mask_words, int variable_count, urlgpu_spg **out) {
+    if (!ctx || !out || (n && (!masks || !scores)) || mask_words < 1 || mask_words > kSpgMaxWords || variable_count < 1 || variable_count > mask_words * 64)
+        return ctx ? ctx->fail(URLGPU_ERR_ARG, "spg_build: bad argument") : URLGPU_ERR_ARG;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    // sorted by (score ascending, |S|, mask): sparse_parent_bitwise.cpp:33-46 sorts by score; ties get a deterministic order
+    std::vector<uint64_t> order(n);
+    for (uint64_t i = 0; i < n; i++) order[i] = i;
+    auto card = [&](uint64_t i) { int c = 0; for (int w = 0; w < mask_words; w++) c += __builtin_popcountll(masks[i * mask_words + w]); return c; };
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+        if (scores[a] != scores[b]) return scores[a] < scores[b];
+        const int ca = card(a), cb = card(b);
+        if (ca != cb) return ca < cb;
+        for (int w = mask_words - 1; w >= 0; w--)
+            if (masks[a * mask_words + w] != masks[b * mask_words + w]) return masks[a * mask_words + w] < masks[b * mask_words + w];
+        return a < b;
+    });
+    auto *sp = new urlgpu_spg();
+    sp->ctx = ctx; sp->n = n; sp->words = mask_words; sp->variable_count = variable_count; sp->bw = (n + 63) / 64;
+    sp->h_masks.resize(n * mask_words);
+    std::vector<float> hs(n);
+    for (uint64_t i = 0; i < n; i++) {
+        memcpy(&sp->h_masks[i * mask_words], &masks[order[i] * mask_words], mask_words * sizeof(uint64_t));
+        hs[i] = scores[order[i]];
+    }
+    cudaStream_t s = ctx->stream;
+    auto fail = [&](cudaError_t e, int line) { if (sp->d_masks) cudaFree(sp->d_masks); if (sp->d_scores) cudaFree(sp->d_scores); if (sp->d_not_used) cudaFree(sp->d_not_used); delete sp; return ctx->cuda_fail(e, "spg_build", line); };
+    cudaError_t e;
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&sp->d_masks), std::max<size_t>(8, n * mask_words * sizeof(uint64_t)))) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&sp->d_scores), std::max<size_t>(4, n * sizeof(float)))) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&sp->d_not_used), std::max<size_t>(8, sp->bw * variable_count * sizeof(uint64_t)))) != cudaSuccess) return fail(e, __LINE__);
+    if (n) {
+        if ((e = cudaMemcpyAsync(sp->d_masks, sp->h_masks.data(), n * mask_words * sizeof(uint64_t), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, __LINE__);
+        if ((e = cudaMemcpyAsync(sp->d_scores, hs.data(), n * sizeof(float), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, __LINE__);
+        {
+            Region rg(ctx, F_OTHER, 1);
+            spg_build_kernel<<<blocks_for(sp->bw * variable_count, 256), 256, 0, s>>>(sp->d_masks, n, mask_words, variable_count, sp->bw, sp->d_not_used);
+        }
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, __LINE__); // hs goes out of scope
+    }
+    *out = sp;
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_spg_query(urlgpu_spg *sp, const uint64_t *allowed, uint64_t nq, float *best_scores, uint64_t *best_parents, int64_t *best_index) {
+    if (!sp) return URLGPU_ERR_ARG;
+    urlgpu_ctx *ctx = sp->ctx;
+    if (!allowed || !best_scores) return ctx->fail(URLGPU_ERR_ARG, "spg_query: null argument");
+    if (nq == 0) return URLGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DevBuf dq(ctx), db(ctx), di(ctx);
+    CK(dq.alloc(nq * sp->words * sizeof(uint64_t)));
+    CK(db.alloc(nq * sizeof(float)));
+    CK(di.alloc(nq * sizeof(long long)));
+    CK(cudaMemcpyAsync(dq.p, allowed, nq * sp->words * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    {
+        Region rg(ctx, F_OTHER, 1);
+        spg_query_kernel<<<blocks_for(nq * 32, 256), 256, 0, s>>>(sp->d_not_used, sp->d_scores, sp->n, sp->bw, sp->variable_count, sp->words, dq.as<uint64_t>(), nq,
+                                                                 db.as<float>(), di.as<long long>());
+    }
+    std::vector<long long> hi(nq);
+    CK(cudaMemcpyAsync(best_scores, db.p, nq * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hi.data(), di.p, nq * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    for (uint64_t i = 0; i < nq; i++) {
+        if (best_index) best_index[i] = hi[i];
+        if (best_parents)
+            for (int w = 0; w < sp->words; w++) best_parents[i * sp->words + w] = hi[i] >= 0 ? sp->h_masks[(uint64_t)hi[i] * sp->words + w] : 0;
+    }
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_spg_free(urlgpu_spg *sp) {
+    if (!sp) return URLGPU_OK;
+    cudaSetDevice(sp->ctx->device);
+    cudaStreamSynchronize(sp->ctx->stream);
+    cudaFree(sp->d_masks); cudaFree(sp->d_scores); cudaFree(sp->d_not_used);
+    delete sp;
     return URLGPU_OK;
 }
 
