@@ -63,91 +63,145 @@ __global__ void dev_kernel(const double *__restrict__ acc2, const double *__rest
     if (col < p) dev[col] = sqrt((acc2[col] - acc3[col] * acc3[col] / n) / (n - 1.0));
 }
 // z = (x - mean) / dev   (BIC_OLS.cpp:76-77)
-__global__ void standardise_kernel(const double *__restrict__ x, int64_t n, int64_t stride, const double *__restrict__ mean,
-                                   const double *__restrict__ dev, double *__restrict__ z) {
+// x has row pitch x_stride; z has row pitch z_stride >= n and is zero beyond n (the Gram kernel streams whole chunks)
+__global__ void standardise_kernel(const double *__restrict__ x, int64_t n, int64_t x_stride, const double *__restrict__ mean,
+                                   const double *__restrict__ dev, double *__restrict__ z, int64_t z_stride) {
     const int col = blockIdx.y;
     const double m = mean[col], d = dev[col];
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
-        z[(int64_t)col * stride + r] = __ddiv_rn(x[(int64_t)col * stride + r] - m, d);
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < z_stride; r += (int64_t)gridDim.x * blockDim.x)
+        z[(int64_t)col * z_stride + r] = r < n ? __ddiv_rn(x[(int64_t)col * x_stride + r] - m, d) : 0.0;
 }
 
 // Gram partials on the FP64 tensor pipe (DMMA): G = Z^T Z is the only dense contraction of the path.
-// tcgen05/wgmma have no f64 kind, so this is mma.sync.m8n8k4.f64 (SASS DMMA).  Z is variable-major ([p][n], records
-// contiguous), which is exactly the fragment layout of both operands: lane l holds Z[a0 + l/4][r0 + l%4] for A (row
-// major, 8 variables x 4 records) and Z[b0 + l/4][r0 + l%4] for B (column major, 4 records x 8 variables), so
-// fragments are loaded straight from global/L2 as 32-byte runs, no shared-memory staging.  One warp owns a 32x32
-// block of G (4x4 MMA tiles, 32 FP64 accumulators per lane); the 4 warps of a CTA split the CTA's row slice and are
-// combined in fixed order.  Grid = (upper-triangular tile pair, row slice) with the tile pair fastest, so the CTAs
-// running together work on the same rows and Z is fetched from HBM once (L2 serves the p/32-fold reuse).
-constexpr int kGramTile = 32;
-constexpr int kGramWarps = 4;
+// tcgen05/wgmma have no f64 kind, so the math is mma.sync.m8n8k4.f64 (SASS DMMA); the operand stream is TMA:
+//   * Z is variable-major ([p][n_stride], records contiguous, n_stride a multiple of kGramKC with zeros beyond n).
+//   * A CTA owns one 64x64 tile pair (ta <= tb) of G for one row slice.  A producer warp streams the slice in chunks of
+//     kGramKC records: per chunk one bulk copy (cp.async.bulk, 256 B) per variable row of the A and B tiles into a
+//     kGramStages-deep ring of padded shared-memory tiles, completion on an mbarrier (expect_tx); four consumer warps
+//     (one 32x32 sub-tile each: 4x4 MMA tiles, 32 FP64 accumulators per lane) wait on the stage's full barrier, read
+//     their fragments from shared memory (row pitch 36 doubles: the 8 rows x 4 records of a fragment fall into 32 distinct
+//     8-byte bank pairs) and hand the stage back through an empty barrier.
+//   * lane l holds Z[a0 + l/4][r + l%4] for A (row major, 8 variables x 4 records) and Z[b0 + l/4][r + l%4] for B (column
+//     major): both operands are the same layout, which is why no transposition is ever needed.
+// Every (tile pair, slice) partial is produced by one warp in ascending record order and the slices are combined in fixed
+// order: the Gram is bit-identical for any scheduling.  Grid = (tile pair, row slice) with the tile pair fastest, so the
+// CTAs running together stream the same rows and Z comes from HBM once (L2 serves the p/64-fold reuse).
+constexpr int kGramTile = 64;
+constexpr int kGramKC = 32;                       // records per chunk: 256-byte bulk copies
+constexpr int kGramPitch = kGramKC + 4;           // doubles per shared-memory row
+constexpr int kGramStages = 3;
+constexpr int kGramConsumers = 4;                 // warps
+constexpr int kGramThreads = (kGramConsumers + 1) * 32;
+constexpr size_t kGramStageDoubles = (size_t)2 * kGramTile * kGramPitch;
+constexpr size_t kGramSmemBytes = kGramStages * kGramStageDoubles * sizeof(double) + 2 * kGramStages * sizeof(unsigned long long);
 
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS UBLKCP); 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
-__global__ void __launch_bounds__(kGramWarps * 32) gram_partial_kernel(const double *__restrict__ z, int64_t n, int64_t stride, int p, int64_t rows_per_slice, int tiles,
-                                                                      double *__restrict__ partial /*[slices][p][p]*/) {
-    __shared__ double red[kGramWarps][32][33];
+__global__ void __launch_bounds__(kGramThreads) gram_partial_kernel(const double *__restrict__ z, int64_t n_stride, int p, int64_t rows_per_slice, int tiles,
+                                                                   double *__restrict__ partial /*[slices][p][p]*/) {
+    extern __shared__ __align__(128) unsigned char gram_smem[];
+    double *tilebuf = reinterpret_cast<double *>(gram_smem);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(gram_smem + kGramStages * kGramStageDoubles * sizeof(double));
+    unsigned long long *empty = full + kGramStages;
     // blockIdx.x enumerates the upper-triangular tile pairs (ta <= tb)
     int ta = 0, rem = blockIdx.x;
     while (rem >= tiles - ta) { rem -= tiles - ta; ta++; }
     const int tb = ta + rem;
+    const bool diag = ta == tb;
     const int slice = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t s0 = (int64_t)slice * rows_per_slice;
-    const int64_t s1 = min(s0 + rows_per_slice, n);
-    // each warp takes a contiguous quarter of the slice (multiple of 4 rows)
-    const int64_t per = ((s1 - s0 + kGramWarps - 1) / kGramWarps + 3) / 4 * 4;
-    const int64_t r0 = min(s0 + warp * per, s1), r1 = min(r0 + per, s1);
-    const int vrow = lane >> 2, kk = lane & 3;
-    const double *pa[4], *pb[4];
-    bool va[4], vb[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        const int a = ta * kGramTile + t * 8 + vrow, b = tb * kGramTile + t * 8 + vrow;
-        va[t] = a < p; vb[t] = b < p;
-        pa[t] = z + (int64_t)(va[t] ? a : 0) * stride + kk;
-        pb[t] = z + (int64_t)(vb[t] ? b : 0) * stride + kk;
+    const int64_t s0 = (int64_t)slice * rows_per_slice;           // multiples of kGramKC
+    const int64_t s1 = min(s0 + rows_per_slice, n_stride);
+    const int nchunks = (int)((s1 - s0) / kGramKC);
+    const int rows_a = min(kGramTile, p - ta * kGramTile), rows_b = diag ? 0 : min(kGramTile, p - tb * kGramTile);
+    // rows of the tiles beyond p are never copied: zero them once in every stage
+    for (int st = 0; st < kGramStages; st++) {
+        double *A = tilebuf + st * kGramStageDoubles, *B = A + kGramTile * kGramPitch;
+        for (int i = threadIdx.x; i < (kGramTile - rows_a) * kGramPitch; i += kGramThreads) A[rows_a * kGramPitch + i] = 0.0;
+        if (!diag) for (int i = threadIdx.x; i < (kGramTile - rows_b) * kGramPitch; i += kGramThreads) B[rows_b * kGramPitch + i] = 0.0;
     }
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < kGramStages; st++) { mbar_init(&full[st], 1); mbar_init(&empty[st], kGramConsumers); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == kGramConsumers) { // ---- producer warp: lane l copies rows l, l + 32 of A and of B
+        const uint32_t chunk_bytes = (uint32_t)((rows_a + rows_b) * kGramKC * sizeof(double));
+        for (int c = 0; c < nchunks; c++) {
+            const int st = c % kGramStages;
+            if (c >= kGramStages) mbar_wait(&empty[st], ((c / kGramStages) - 1) & 1);
+            double *A = tilebuf + st * kGramStageDoubles, *B = A + kGramTile * kGramPitch;
+            if (lane == 0) mbar_arrive_expect_tx(&full[st], chunk_bytes);
+            __syncwarp();
+            const int64_t r = s0 + (int64_t)c * kGramKC;
+            for (int row = lane; row < rows_a; row += 32)
+                bulk_g2s(A + row * kGramPitch, z + (int64_t)(ta * kGramTile + row) * n_stride + r, kGramKC * sizeof(double), &full[st]);
+            for (int row = lane; row < rows_b; row += 32)
+                bulk_g2s(B + row * kGramPitch, z + (int64_t)(tb * kGramTile + row) * n_stride + r, kGramKC * sizeof(double), &full[st]);
+        }
+        return;
+    }
+    // ---- consumer warps: warp w owns rows [32 (w/2), +32) of the A tile and columns [32 (w%2), +32) of the B tile
+    const int wa = (warp >> 1) * 32, wb = (warp & 1) * 32;
+    const int vrow = lane >> 2, kk = lane & 3;
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int64_t r = r0; r < r1; r += 4) {
-        const bool in = r + kk < r1;
-        double fa[4], fb[4];
+    for (int c = 0; c < nchunks; c++) {
+        const int st = c % kGramStages;
+        mbar_wait(&full[st], (c / kGramStages) & 1);
+        const double *A = tilebuf + st * kGramStageDoubles;
+        const double *B = diag ? A : A + kGramTile * kGramPitch;
+        const double *pa = A + (wa + vrow) * kGramPitch + kk, *pb = B + (wb + vrow) * kGramPitch + kk;
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            fa[t] = (in && va[t]) ? __ldg(pa[t] + r) : 0.0;
-            fb[t] = (in && vb[t]) ? __ldg(pb[t] + r) : 0.0;
+        for (int k = 0; k < kGramKC; k += 4) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) { fa[t] = pa[t * 8 * kGramPitch + k]; fb[t] = pb[t * 8 * kGramPitch + k]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
         }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
     }
     // C fragment: lane holds C[row = lane/4][col = (lane%4)*2 + {0,1}] of each 8x8 tile
+    double *out = partial + (int64_t)slice * p * p;
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            red[warp][i * 8 + vrow][j * 8 + kk * 2 + 0] = acc[i][j][0];
-            red[warp][i * 8 + vrow][j * 8 + kk * 2 + 1] = acc[i][j][1];
+            const int a = ta * kGramTile + wa + i * 8 + vrow, b = tb * kGramTile + wb + j * 8 + kk * 2;
+            if (a < p && b < p) out[(int64_t)a * p + b] = acc[i][j][0];
+            if (a < p && b + 1 < p) out[(int64_t)a * p + b + 1] = acc[i][j][1];
         }
-    __syncthreads();
-    double *out = partial + (int64_t)slice * p * p;
-    for (int e = threadIdx.x; e < kGramTile * kGramTile; e += blockDim.x) {
-        const int i = e / kGramTile, j = e % kGramTile;
-        const int a = ta * kGramTile + i, b = tb * kGramTile + j;
-        if (a < p && b < p) {
-            double sum = red[0][i][j];
-#pragma unroll
-            for (int w = 1; w < kGramWarps; w++) sum += red[w][i][j]; // fixed order
-            out[a * p + b] = sum;
-        }
-    }
 }
 // G[a][b] = sum over slices in slice order (fixed order); mirror to the lower triangle
 __global__ void gram_combine_kernel(const double *__restrict__ partial, int p, int slices, double *__restrict__ g) {
@@ -387,6 +441,98 @@ __global__ void __launch_bounds__(128, URLGPU_DFS_MINBLOCKS) cbic_dfs_kernel(con
 #pragma unroll
     for (int e = 0; e < (J + 1) * (J + 2) / 2; e++) A[e] = roots[(size_t)e * n_prefix + P];
     cbic_dfs_call<J>(A, 0u, k0, prm, out, out64);
+}
+
+// Level B, CTA form (J >= 7): the DFS above keeps the matrices of its upper levels on the thread's stack — 2.9 KB per
+// thread at J = 11, 270 MB over the resident threads, which spills out of L2 and tripled the DRAM traffic of K3 (ncu,
+// round 1).  Here one CTA of 2^(J-4) threads owns one prefix: the levels J .. 5 are expanded BREADTH FIRST in shared
+// memory, all threads sharing each level's element-wise sweeps, and every thread then walks its own 4-bit subtree
+// (16 sets) with all matrices in registers.  An "exclude" child is the leading principal submatrix of its parent, i.e. a
+// PREFIX of the parent's packed array: it is never copied, only "include" children get storage (2802 doubles = 22 KB at
+// J = 11).  Every element sees exactly the FMA sequence of the DFS, so scores are bit-identical.  No local memory.
+constexpr int kTreeJB = 4;
+__host__ __device__ constexpr int tri_size(int j) { return (j + 1) * (j + 2) / 2; }   // packed entries of a matrix over (v, cand_0 .. cand_{j-1})
+template <int J> __host__ __device__ constexpr int cbic_tree_base(int level) {          // first double of the include-children of `level` (level < J)
+    int off = tri_size(J);
+    for (int l = J - 1; l > level; l--) off += (1 << (J - 1 - l)) * tri_size(l);
+    return off;
+}
+template <int J> __host__ __device__ constexpr int cbic_tree_doubles() { return cbic_tree_base<J>(kTreeJB - 1); }
+
+template <int J>
+__device__ __forceinline__ int cbic_tree_offset(int level, uint32_t m) { // storage of matrix m of `level`
+    if (m == 0) return 0;
+    const int t = __ffs(m) - 1;                 // trailing exclude decisions: a view of an ancestor's storage
+    const int l = level + t;
+    int off = tri_size(J);
+    for (int q = J - 1; q > l; q--) off += (1 << (J - 1 - q)) * tri_size(q);
+    return off + (int)((m >> t) >> 1) * tri_size(l);
+}
+
+template <int J, int LEVEL>
+__device__ __forceinline__ void cbic_tree_expand(double *S, double *inv /*[2][2^(J-kTreeJB)]*/, const unsigned char *tri_row, int k0, const CbicParams &prm, int tid) {
+    if constexpr (LEVEL > kTreeJB) {
+        constexpr int j = LEVEL;                        // parents: matrices over (v, cand_0 .. cand_{j-1}); pivot = row j
+        constexpr int P = 1 << (J - j), E = tri_size(j - 1), NT = 1 << (J - kTreeJB);
+        const double *inv_in = inv + (j & 1) * NT;
+        double *inv_out = inv + ((j - 1) & 1) * NT;
+        for (int w = tid; w < P * E; w += NT) {
+            const int m = w / E, e = w - m * E;
+            const int a = tri_row[e], b = e - a * (a + 1) / 2;
+            const double *A = S + cbic_tree_offset<J>(j, (uint32_t)m);
+            const bool last = e == E - 1;               // element (j-1, j-1): the next pivot of both children
+            if (last) inv_out[2 * m] = guarded_inv(A[e], prm.piv_tol);
+            if (k0 + __popc(m) < prm.max_parents) {
+                const double f = -A[tri(j, a)] * inv_in[m];
+                const double x = fma(f, A[tri(j, b)], A[e]);
+                S[cbic_tree_base<J>(j - 1) + m * E + e] = x;
+                if (last) inv_out[2 * m + 1] = guarded_inv(x, prm.piv_tol);
+            }
+        }
+        __syncthreads();
+        cbic_tree_expand<J, LEVEL - 1>(S, inv, tri_row, k0, prm, tid);
+    }
+}
+
+template <int J>
+__global__ void __launch_bounds__(1 << (J - kTreeJB)) cbic_tree_kernel(const double *__restrict__ roots /*[n_prefix][tri_size(J)]*/, CbicParams prm, uint32_t n_prefix,
+                                                                        float *__restrict__ ts_out, double *__restrict__ ts64_out) {
+    constexpr int NT = 1 << (J - kTreeJB);
+    __shared__ double S[cbic_tree_doubles<J>()];
+    __shared__ double inv[2 * NT];
+    __shared__ unsigned char tri_row[tri_size(J - 1)];
+    const uint32_t P = blockIdx.x;
+    const int tid = threadIdx.x;
+    float *out = ts_out + ((size_t)P << J);
+    double *out64 = ts64_out ? ts64_out + ((size_t)P << J) : nullptr;
+    const int k0 = __popc(P);
+    if (k0 > prm.max_parents) { // whole subtree unscored
+        for (uint32_t m = tid; m < (1u << J); m += NT) out[m] = sentinel();
+        return;
+    }
+    for (int e = tid; e < tri_size(J); e += NT) S[e] = roots[(size_t)P * tri_size(J) + e];
+    for (int e = tid; e < tri_size(J - 1); e += NT) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= e) a++;
+        tri_row[e] = (unsigned char)a;
+    }
+    __syncthreads();
+    if (tid == 0) inv[(J & 1) * NT] = guarded_inv(S[tri(J, J)], prm.piv_tol);
+    __syncthreads();
+    cbic_tree_expand<J, J>(S, inv, tri_row, k0, prm, tid);
+    // every thread: its level-4 matrix into registers, 16 sets, 64 contiguous bytes of scores
+    const int k = k0 + __popc(tid);
+    const uint32_t low = (uint32_t)tid << kTreeJB;
+    if (k > prm.max_parents) {
+#pragma unroll
+        for (int q = 0; q < (1 << kTreeJB); q++) out[low + q] = sentinel();
+        return;
+    }
+    double A[tri_size(kTreeJB)];
+    const double *src = S + cbic_tree_offset<J>(kTreeJB, (uint32_t)tid);
+#pragma unroll
+    for (int e = 0; e < tri_size(kTreeJB); e++) A[e] = src[e];
+    cbic_dfs_inl<kTreeJB>(A, low, k, prm, out, out64);
 }
 
 // ------------------------------------------------------------------------------------------------ K4 / K5 rules

@@ -62,6 +62,7 @@ struct urlgpu_ctx {
     double *d_z = nullptr;
     double *d_zcache = nullptr; size_t zcache_cap = 0;
     double *d_x = nullptr; const double *d_x_view = nullptr; int64_t shard_n = 0; bool borrow_device_x = false; // attached raw rows (sharded protocol)
+    int64_t shard_stride = 0;   // row pitch of d_x_view: shard_n for a borrowed buffer, shard_n rounded up to kGramKC for the engine's own copy
     std::vector<double> h_gram;
     double gram_dmax = 0;   // largest diagonal entry of the Gram: scale of the pivot guard (CbicParams::piv_tol)
     bool have_gram = false;
@@ -502,12 +503,14 @@ static int shard_begin_impl(urlgpu_ctx *ctx, const double *src, bool src_on_devi
     free_continuous(ctx);
     if (ctx->d_x) { cudaFree(ctx->d_x); ctx->d_x = nullptr; }
     ctx->shard_n = n_local; ctx->cp = p;
-    const size_t bytes = (size_t)n_local * p * sizeof(double);
-    if (src_on_device && ctx->borrow_device_x) ctx->d_x_view = src; // no copy: the caller keeps the buffer alive until shard_finish
-    else {
-        CK(cudaMalloc(&ctx->d_x, bytes));
-        CK(cudaMemcpyAsync(ctx->d_x, src, bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (src_on_device && ctx->borrow_device_x) { ctx->d_x_view = src; ctx->shard_stride = n_local; } // no copy: the caller keeps the buffer alive until shard_finish
+    else { // the engine's own copy has the padded row pitch of the Gram kernel, so it can be standardised in place
+        const int64_t pitch = (n_local + kGramKC - 1) / kGramKC * kGramKC;
+        CK(cudaMalloc(&ctx->d_x, (size_t)pitch * p * sizeof(double)));
+        CK(cudaMemcpy2DAsync(ctx->d_x, (size_t)pitch * sizeof(double), src, (size_t)n_local * sizeof(double), (size_t)n_local * sizeof(double), (size_t)p,
+                             src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
         ctx->d_x_view = ctx->d_x;
+        ctx->shard_stride = pitch;
     }
     return URLGPU_OK;
 }
@@ -532,7 +535,7 @@ static int shard_moments_impl(urlgpu_ctx *ctx, const double *shift_host, double 
         const unsigned pb = blocks_for(p, 128);
         for (int mode = 0; mode < 2; mode++) {
             if ((mode == 0 && !sum1) || (mode == 1 && !sum2)) continue;
-            col_partial_kernel<<<rgrid, kRedThreads, 0, s>>>(ctx->d_x_view, n, n, shift_host ? shift.as<double>() : nullptr, mode, part.as<double>());
+            col_partial_kernel<<<rgrid, kRedThreads, 0, s>>>(ctx->d_x_view, n, ctx->shard_stride, shift_host ? shift.as<double>() : nullptr, mode, part.as<double>());
             col_combine_kernel<<<pb, 128, 0, s>>>(part.as<double>(), p, out.as<double>() + (size_t)mode * p);
         }
     }
@@ -554,25 +557,29 @@ static int shard_finish_impl(urlgpu_ctx *ctx, const double *mean_host, const dou
     CK(md.alloc((size_t)2 * p * sizeof(double)));
     CK(cudaMemcpyAsync(md.p, mean_host, p * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(md.as<double>() + p, dev_host, p * sizeof(double), cudaMemcpyHostToDevice, s));
-    // standardise in place when the engine owns the copy, else into a fresh buffer
+    // standardise in place when the engine owns the (padded) copy, else into a cached padded buffer
+    const int64_t z_stride = (n + kGramKC - 1) / kGramKC * kGramKC;
     double *zbuf = ctx->d_x;
     const bool borrowed = zbuf == nullptr;
-    if (borrowed) { // caller's device buffer is left untouched: standardise into a cached scratch buffer
-        const size_t need = (size_t)n * p * sizeof(double);
+    if (borrowed) { // caller's device buffer is left untouched
+        const size_t need = (size_t)z_stride * p * sizeof(double);
         if (ctx->zcache_cap < need) { if (ctx->d_zcache) cudaFree(ctx->d_zcache); ctx->d_zcache = nullptr; ctx->zcache_cap = 0; CK(cudaMalloc(&ctx->d_zcache, need)); ctx->zcache_cap = need; }
         zbuf = ctx->d_zcache;
     }
     {
         Region rg(ctx, F_GRAM, 3);
-        standardise_kernel<<<dim3(ctx->sm_count * 2, p), 256, 0, s>>>(ctx->d_x_view, n, n, md.as<double>(), md.as<double>() + p, zbuf);
+        standardise_kernel<<<dim3(ctx->sm_count * 2, p), 256, 0, s>>>(ctx->d_x_view, n, ctx->shard_stride, md.as<double>(), md.as<double>() + p, zbuf, z_stride);
         const int tiles = (p + kGramTile - 1) / kGramTile;
-        // row slices: all p columns of one slice stay L2 resident (<= ~48 MB) so every tile pair re-reads them from L2
-        int64_t rps = std::max<int64_t>(4096, std::min<int64_t>(((int64_t)48 << 20) / ((int64_t)p * 8), 65536));
-        rps = rps / 16 * 16;
-        const int slices = (int)((n + rps - 1) / rps);
+        const int pairs = tiles * (tiles + 1) / 2;
+        // row slices (multiples of the chunk): enough CTAs to fill the machine several times over, at least 1024 records each
+        int64_t rps = std::max<int64_t>(1024, std::min<int64_t>(8192, z_stride * pairs / ((int64_t)ctx->sm_count * 8)));
+        rps = (rps + kGramKC - 1) / kGramKC * kGramKC;
+        const int slices = (int)((z_stride + rps - 1) / rps);
         CK(gpart.alloc((size_t)slices * p * p * sizeof(double)));
         CK(g.alloc((size_t)p * p * sizeof(double)));
-        gram_partial_kernel<<<dim3(tiles * (tiles + 1) / 2, slices), kGramWarps * 32, 0, s>>>(zbuf, n, n, p, rps, tiles, gpart.as<double>());
+        static bool attr = false;
+        if (!attr) { CK(cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmemBytes)); attr = true; }
+        gram_partial_kernel<<<dim3(pairs, slices), kGramThreads, kGramSmemBytes, s>>>(zbuf, z_stride, p, rps, tiles, gpart.as<double>());
         gram_combine_kernel<<<blocks_for((uint64_t)p * p, 256), 256, 0, s>>>(gpart.as<double>(), p, slices, g.as<double>());
         ctx->st.gram_flops += 2.0 * (double)n * p * p;
     }
@@ -1626,6 +1633,10 @@ static void launch_cbic_dfs(const double *roots, const CbicParams &prm, uint32_t
     const int threads = 128;
     cbic_dfs_kernel<J><<<blocks_for(n_prefix, threads), threads, 0, s>>>(roots, prm, n_prefix, ts, ts64);
 }
+template <int J>
+static void launch_cbic_tree(const double *roots, const CbicParams &prm, uint32_t n_prefix, float *ts, double *ts64, cudaStream_t s) {
+    cbic_tree_kernel<J><<<n_prefix, 1 << (J - kTreeJB), 0, s>>>(roots, prm, n_prefix, ts, ts64);
+}
 
 static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, double lambda, float *d_table, double *d_ts64,
                              uint64_t *n_scored) {
@@ -1654,6 +1665,9 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
     { static const int sm = getenv("URLGPU_CBIC_STORE") ? atoi(getenv("URLGPU_CBIC_STORE")) : 1; prm.store_mode = sm; }
     const uint32_t n_prefix = 1u << (c - prm.J);
     const int outsz = (prm.J + 1) * (prm.J + 2) / 2;
+    // level B: one CTA per prefix with the upper levels in shared memory (J >= 7), else one thread per prefix
+    static const bool tree_off = getenv("URLGPU_CBIC_TREE") && atoi(getenv("URLGPU_CBIC_TREE")) == 0;
+    const bool use_tree = prm.J >= 7 && !tree_off;
     DevBuf dsub(ctx), droots(ctx), dmid(ctx), dmid2(ctx);
     CK(dsub.alloc(sub.size() * sizeof(double)));
     CK(droots.alloc((size_t)outsz * n_prefix * sizeof(double)));
@@ -1679,9 +1693,18 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
                 CK(mids[st & 1]->alloc(osz * n_out * sizeof(double)));
                 dst = mids[st & 1]->as<double>();
             }
-            cbic_roots_kernel<<<blocks_for(n_out, warps), warps * 32, (size_t)warps * insz * sizeof(double), s>>>(src, src_stride, c_in, bits, K, n_out, dst, last ? 1 : 0, prm.piv_tol);
+            cbic_roots_kernel<<<blocks_for(n_out, warps), warps * 32, (size_t)warps * insz * sizeof(double), s>>>(src, src_stride, c_in, bits, K, n_out, dst, last && !use_tree ? 1 : 0, prm.piv_tol);
             src = dst; src_stride = osz; c_in = c_out; done += bits;
         }
+        if (use_tree) {
+            switch (prm.J) {
+            case 7: launch_cbic_tree<7>(droots.as<double>(), prm, n_prefix, d_table, d_ts64, s); break;
+            case 8: launch_cbic_tree<8>(droots.as<double>(), prm, n_prefix, d_table, d_ts64, s); break;
+            case 9: launch_cbic_tree<9>(droots.as<double>(), prm, n_prefix, d_table, d_ts64, s); break;
+            case 10: launch_cbic_tree<10>(droots.as<double>(), prm, n_prefix, d_table, d_ts64, s); break;
+            default: launch_cbic_tree<11>(droots.as<double>(), prm, n_prefix, d_table, d_ts64, s); break;
+            }
+        } else
         switch (prm.J) {
 #define URLGPU_CASE(JJ) case JJ: launch_cbic_dfs<JJ>(droots.as<double>(), prm, n_prefix, d_table, d_ts64, s); break;
             URLGPU_CASE(0) URLGPU_CASE(1) URLGPU_CASE(2) URLGPU_CASE(3) URLGPU_CASE(4) URLGPU_CASE(5) URLGPU_CASE(6) URLGPU_CASE(7)
