@@ -405,6 +405,21 @@ def run_gpu(args):
                         "algorithmic_flops_per_step": st["algorithmic_flops"] / roof_steps, "kernel_ms_per_step": k3_ms / roof_steps,
                         "share_of_step": k3_ms / roof_steps / (ms / args.steps), "family_ms": fam}
         cpu = cpu_baseline(wl, args) if world == 1 and not args.no_cpu_baseline else None
+        # the rest of BASELINE.json's metric ("BIC & cBIC ...; score-file wall time"), measured by the same default command
+        extra = {}
+        if world == 1 and is_bic and not args.no_subrecords:
+            pool.close()
+            pool = None
+            import tempfile
+            try:
+                extra["cbic"] = measure_cbic_subrecord(pkg, torch, local)
+            except Exception as ex:  # reported, never hidden
+                extra["cbic"] = {"error": repr(ex)}
+            try:
+                with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+                    extra["score_file"] = measure_score_file(pkg, wl, td)
+            except Exception as ex:
+                extra["score_file"] = {"error": repr(ex)}
         scaling = "weak" if weak else "strong"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -416,13 +431,96 @@ def run_gpu(args):
                            "l2": "flushed between steps (256 MB write)", "dominant_family": dom,
                            "hbm_in_use_gb": round((mem_total - mem_free) / 1e9, 1)},
                 "e2e": e2e, "gpu_launches": int(launches_total), "clocks": sampler.summary(), "roofline": roofline,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, **extra}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    pool.close()
+    if pool is not None:
+        pool.close()
 
+
+
+# ---------------------------------------------------------------------------------------------- sub-records of the default line
+
+def fast_write_csv(path, codes):
+    """codes uint8 [p, n] with single-digit values -> CSV, one record per line (numpy only: np.savetxt takes minutes at n = 1e6)"""
+    p, n = codes.shape
+    buf = np.empty((n, 2 * p), dtype=np.uint8)
+    buf[:, 0::2] = codes.T + ord("0")
+    buf[:, 1::2] = ord(",")
+    buf[:, -1] = ord("\n")
+    buf.tofile(path)
+
+
+def measure_cbic_subrecord(pkg, torch, device):
+    """BASELINE configs[2] next to the default line (the metric is "BIC & cBIC"): p=30, n=1e5, 2^29 sets per variable,
+    acceptance + prune, results left on the device.  One warm-up step and two timed ones (CUDA events), then one pass with
+    the library's per-family events."""
+    wl = make_cbic_workload(pkg)
+    eng = pkg.Engine(device)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_continuous(wl["x"])
+    sets = sum(sets_of(wl, v) for v in range(wl["p"]))
+
+    def step():
+        for v in range(wl["p"]):
+            eng.score_variable(v, wl["nbs"][v], wl["K"], pkg.CBIC, lam=wl["lam"], flags=pkg.PRUNE_DOMINATED).free()
+    step()
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nst = 2
+    e0.record(stream)
+    for _ in range(nst):
+        step()
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1)
+    eng.reset_stats()
+    eng.enable_timing(True)
+    step()
+    st = eng.stats()
+    fp64 = eng.probe_fp64()
+    eng.close()
+    return {"workload": wl["name"], "value": sets * nst / (ms / 1e3), "unit": UNIT, "steps": nst, "warmup": 1, "ms_per_step": ms / nst, "sets_per_step": sets,
+            "family_ms": {"cbic": st["ms_cbic"], "accept": st["ms_accept"], "prune": st["ms_prune"], "gram": st["ms_gram"]},
+            "fp64_peak_tflops_measured": fp64}
+
+
+def measure_score_file(pkg, wl, tmpdir):
+    """the other half of BASELINE.json's metric: wall time of `score` from a CSV on disk to a finished .pss.  (a) configs[0]
+    hepatitis as the reference runs it; (b) configs[3] itself written as a 120 MB CSV, with its skeleton, -p 12, --prune, -t 4
+    (four contexts on this GPU sharing one device copy).  Times are the binary's own phase clocks plus the wall time of the
+    whole process (CUDA context creation included)."""
+    import re
+    exe = os.path.join(ROOT, "urlearning-cpp_b200", "score")
+    out = {}
+
+    def run(tag, args, pss):
+        t0 = time.perf_counter()
+        r = subprocess.run([exe] + args + [pss, "--quiet"], capture_output=True, text=True)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            out[tag] = {"error": r.stderr[-300:]}
+            return
+        m = re.search(r"Scored (\d+) parent sets in ([\d.]+) s .*; parse ([\d.]+) s, write ([\d.]+) s, total ([\d.]+) s wall", r.stdout)
+        out[tag] = {"process_wall_s": wall, "sets_scored": int(m.group(1)), "score_s": float(m.group(2)), "parse_s": float(m.group(3)), "write_s": float(m.group(4)),
+                    "total_s": float(m.group(5)), "pss_bytes": os.path.getsize(pss), "args": " ".join(a if not a.startswith(tmpdir) else os.path.basename(a) for a in args)}
+
+    hep = os.path.join(ROOT, "tests", "data", "hepatitis.clean.csv")
+    run("configs[0] hepatitis -s -f BIC", [hep, "-s", "-f", "BIC"], os.path.join(tmpdir, "hep.pss"))
+    csv, skel = os.path.join(tmpdir, "cfg3.csv"), os.path.join(tmpdir, "cfg3_skel.csv")
+    fast_write_csv(csv, wl["codes"])
+    pkg.datagen.write_skeleton_matrix(skel, wl["edges"], wl["p"])
+    run("configs[3] p=60 n=1e6 -k skeleton -p 12 --prune -t 4", [csv, "-k", skel, "-f", "BIC", "-p", "12", "--prune", "-t", "4"], os.path.join(tmpdir, "cfg3.pss"))
+    out["csv_bytes"] = os.path.getsize(csv)
+    for f in ("hep.pss", "cfg3.pss", "cfg3.csv", "cfg3_skel.csv"):
+        try:
+            os.remove(os.path.join(tmpdir, f))
+        except OSError:
+            pass
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- config 5 (optional workload)
@@ -633,7 +731,9 @@ def cpu_baseline(wl, args):
     rate, n_done, t_used = cpu_sample(wl, args.cpu_seconds, threads)
     return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n_done} parent sets drawn uniformly from the workload's candidate families, {t_used:.1f} s, "
-                      "oracle direct counting / per-set OLS refit (the reference's algorithmic structure), no pruning"}
+                      "oracle direct counting / per-set OLS refit (the reference's algorithmic structure), no pruning",
+            "why_port": "the reference's own AD-tree code (oracle/_ref) cannot hold this workload: its leaf lists are n-bit sets per node "
+                        "(SURVEY Q6; measured 640 sets/s at n=2e4, p=12 and ~1/n beyond), so the faster direct-counting port is the conservative CPU arm"}
 
 
 def run_reference(args):
@@ -682,6 +782,7 @@ def main():
     ap.add_argument("--k5", type=int, default=4, help="explicit parent limit (-p) of the cbic5 workload")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-subrecords", action="store_true", help="skip the cBIC configs[2] and score-file wall-time sub-records of the default line")
     ap.add_argument("--one-pass", action="store_true", help="profiling aid: one warm pass, then one pass on one context inside cudaProfilerStart/Stop; no bench line")
     args = ap.parse_args()
     args.cpu_seconds_given = any(a == "--cpu-seconds" or a.startswith("--cpu-seconds=") for a in sys.argv[1:])

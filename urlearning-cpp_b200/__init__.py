@@ -15,6 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import weakref
 from typing import Iterable, Sequence
 
 import numpy as np
@@ -164,6 +165,7 @@ class Result:
 
     def __init__(self, eng: "Engine", handle, words: int):
         self._eng, self._h, self.words = eng, handle, words
+        eng._live[id(self)] = weakref.ref(self)   # Engine.close() frees what is still alive: a result must not outlive its context
 
     def prefetch(self) -> "Result":
         """enqueue the on-device compaction behind the scoring kernels (no host sync); fetch() then only waits for it"""
@@ -196,7 +198,9 @@ class Result:
 
     def free(self):
         if self._h is not None:
-            self._eng.lib.urlgpu_result_free(self._h)
+            self._eng._live.pop(id(self), None)
+            if self._eng._h is not None:          # after Engine.close() the context (and everything it owned) is gone already
+                self._eng.lib.urlgpu_result_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -218,6 +222,7 @@ class Engine:
         self._h = h
         self.p = 0
         self._keep = []
+        self._live = {}
         self._pin_ptr, self._pin_cap = None, 0
 
     def _pinned_views(self, n: int, words: int):
@@ -239,6 +244,10 @@ class Engine:
         return masks, scores
 
     def close(self):
+        for ref in list(getattr(self, "_live", {}).values()):   # results still alive are freed with their context
+            r = ref()
+            if r is not None:
+                r.free()
         if getattr(self, "_pin_ptr", None):
             self.lib.urlgpu_host_free(self._pin_ptr)
             self._pin_ptr, self._pin_cap = None, 0

@@ -6,6 +6,7 @@
 #include "../../include/urlgpu.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <ctime>
 #include <cmath>
@@ -27,6 +28,7 @@ using namespace urlgpu;
 namespace {
 
 thread_local std::string g_create_error;
+std::atomic<int> g_ctx_on_device[64];   // live contexts per device: each budgets its share of the free memory
 
 enum Family { F_COUNT = 0, F_CUBE, F_CBIC, F_ACCEPT, F_PRUNE, F_GRAM, F_TREE, F_OTHER, F_N };
 
@@ -346,6 +348,7 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
     cudaFuncSetAttribute(bic_tree_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ctx->tree_budget * sizeof(int)));
     cudaFuncSetAttribute(bic_tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ctx->tree_budget * sizeof(int)));
     cudaFuncSetAttribute(bic_tree_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * ctx->tree_budget * sizeof(int)));
+    if (device_id < 64) g_ctx_on_device[device_id]++;
     *out = ctx;
     return URLGPU_OK;
 }
@@ -391,6 +394,7 @@ extern "C" int urlgpu_destroy(urlgpu_ctx *ctx) {
     for (auto *b : ctx->d_binom) if (b) cudaFree(b);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->device < 64) g_ctx_on_device[ctx->device]--;
     delete ctx;
     return URLGPU_OK;
 }
@@ -979,7 +983,9 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         CK(cudaMemGetInfo(&free_b, &total_b));
         ctx->mem_free_sample = free_b + (ctx->cubeA_cap + ctx->cubeB_cap) * sizeof(int);
     }
-    const double mem_budget = (double)ctx->mem_free_sample * 0.7;
+    // several contexts may share the device (EnginePool, `score -t T`): each plans with its share of what was free
+    const int sharers = std::max(1, ctx->device < 64 ? g_ctx_on_device[ctx->device].load() : 1);
+    const double mem_budget = (double)ctx->mem_free_sample * 0.7 / sharers;
     std::vector<double> layer_cells(Lmax + 1, 0.0);
     for (int l = 0; l <= Lmax; l++)
         for (auto &cs : layers[l]) layer_cells[l] += (double)((cs.cells + 3) / 4 * 4);
@@ -1104,8 +1110,27 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         }
     }
     needA = std::max<size_t>(needA, 4); needB = std::max<size_t>(needB, 4);
-    if (ctx->cubeA_cap < needA) { if (ctx->d_cubeA) cudaFree(ctx->d_cubeA); ctx->d_cubeA = nullptr; ctx->cubeA_cap = 0; CK(cudaMalloc(&ctx->d_cubeA, needA * sizeof(int))); ctx->cubeA_cap = needA; }
-    if (ctx->cubeB_cap < needB) { if (ctx->d_cubeB) cudaFree(ctx->d_cubeB); ctx->d_cubeB = nullptr; ctx->cubeB_cap = 0; CK(cudaMalloc(&ctx->d_cubeB, needB * sizeof(int))); ctx->cubeB_cap = needB; }
+    // layer buffers: on an allocation failure give the pool's cached blocks back to the driver and retry once; if the device
+    // still cannot hold them (other contexts took the memory since the sample) the family goes through the direct path
+    auto grow = [&](int *&buf, size_t &cap, size_t need) -> bool {
+        if (cap >= need) return true;
+        if (buf) cudaFree(buf);
+        buf = nullptr; cap = 0;
+        if (cudaMalloc(&buf, need * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            for (size_t i = 0; i < ctx->pool.size();) {
+                if (!ctx->pool[i].used) { cudaFree(ctx->pool[i].p); ctx->pool.erase(ctx->pool.begin() + i); } else i++;
+            }
+            if (cudaMalloc(&buf, need * sizeof(int)) != cudaSuccess) { cudaGetLastError(); buf = nullptr; return false; }
+        }
+        cap = need;
+        return true;
+    };
+    if (!grow(ctx->d_cubeA, ctx->cubeA_cap, needA) || !grow(ctx->d_cubeB, ctx->cubeB_cap, needB)) {
+        ctx->mem_free_sample = 0; // re-sample next time
+        { int rc_ = stage_end(ctx); if (rc_) return rc_; }
+        return URLGPU_OK;          // *used stays false: the caller takes the direct path
+    }
     int *bufP = ctx->d_cubeA, *bufC = ctx->d_cubeB;
     const auto T1 = tnow();
     const double C1 = dbg ? cpu_ms() : 0.0;

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "urlearning_host.hpp"
@@ -22,16 +23,32 @@ namespace scoring {
 using urlhost::Varset;
 typedef Varset varset;
 
-// FloatMap stand-in: the entries of one variable in canonical order (|S|, mask).  The reference's
+// FloatMap stand-in: the entries of one variable in canonical order (|S|, mask) plus a hash index.  The reference's
 // boost::unordered_map iteration order is an artefact of Boost's hash; see SURVEY.md Q4.
+struct VarsetHash {
+    size_t operator()(const varset &k) const {
+        uint64_t h = 0x9e3779b97f4a7c15ull;
+        for (auto w : k.w) { h ^= w + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); }
+        return (size_t)h;
+    }
+};
 struct FloatMap {
     std::vector<varset> keys;
     std::vector<float> values;
+    std::unordered_map<varset, size_t, VarsetHash> index;   // built on demand (find / put)
     size_t size() const { return keys.size(); }
-    void clear() { keys.clear(); values.clear(); }
-    const float *find(const varset &k) const {
-        for (size_t i = 0; i < keys.size(); i++) if (keys[i] == k) return &values[i];
-        return nullptr;
+    void clear() { keys.clear(); values.clear(); index.clear(); }
+    void reindex() { if (index.size() != keys.size()) { index.clear(); for (size_t i = 0; i < keys.size(); i++) index[keys[i]] = i; } }
+    const float *find(const varset &k) {
+        reindex();
+        auto it = index.find(k);
+        return it == index.end() ? nullptr : &values[it->second];
+    }
+    void put(const varset &k, float v) { // cache[k] = v
+        reindex();
+        auto it = index.find(k);
+        if (it != index.end()) values[it->second] = v;
+        else { index[k] = keys.size(); keys.push_back(k); values.push_back(v); }
     }
 };
 
@@ -68,6 +85,12 @@ public:
         }
         g.check(urlgpu_set_discrete(g.ctx, codes.data(), recordCount, p, card.data()));
     }
+    // the same from packed codes (column-major, value indices in first-appearance order)
+    GpuBICScoringFunction(GpuContext &g, const uint8_t *codes, int64_t recordCount, int p, const int32_t *card) : g(g) {
+        g.check(urlgpu_set_discrete(g.ctx, codes, recordCount, p, card));
+    }
+    // a worker thread on the same device borrows the owner's device copy of the data set (no second upload)
+    GpuBICScoringFunction(GpuContext &g, GpuContext &owner) : g(g) { g.check(urlgpu_share_discrete(g.ctx, owner.ctx)); }
     float calculateScore(int variable, varset parents, FloatMap &) override {
         float s;
         g.check(urlgpu_score_one(g.ctx, variable, parents.w, urlhost::kVarsetWords, URLGPU_BIC, 0.0, &s, nullptr));
@@ -89,15 +112,55 @@ public:
             for (int r = 0; r < n; r++) x[(size_t)i * n + r] = strtod(rf.records[r][i].c_str(), nullptr); // mlpack::data::Load, BIC_OLS.cpp:48
         g.check(urlgpu_set_continuous(g.ctx, x.data(), n, p));
     }
-    float calculateScore(int variable, varset parents, FloatMap &) override {
+    GpuBICOLSFunction(GpuContext &g, const double *x_colmajor, int64_t n, int p, double lambda) : g(g), lambda(lambda) {
+        g.check(urlgpu_set_continuous(g.ctx, x_colmajor, n, p));
+    }
+    // a worker thread installs the owner's Gram (the rows are not needed for scoring)
+    GpuBICOLSFunction(GpuContext &g, GpuContext &owner, int64_t n, int p, double lambda) : g(g), lambda(lambda) {
+        std::vector<double> gram((size_t)p * p);
+        owner.check(urlgpu_get_gram(owner.ctx, gram.data()));
+        g.check(urlgpu_set_gram(g.ctx, gram.data(), n, p));
+    }
+    // BIC_OLS.cpp:174-276 per set: the score comes from the device, the acceptance test against the best cached subset
+    // (find_best_subset_score :125-172, "clean" recursion) and the callee-side store (:249) run here on the
+    // caller's cache, so this plug-in behaves like the reference's under the reference's own enumeration loop
+    // (score_calculator.cpp:54-135).  The batched path (ScoreCalculator::calculateScores) does all of this on the device.
+    float calculateScore(int variable, varset parents, FloatMap &cache) override {
         float s;
         g.check(urlgpu_score_one(g.ctx, variable, parents.w, urlhost::kVarsetWords, URLGPU_CBIC, lambda, &s, nullptr));
-        return s;
+        const float the_score = -s;
+        parents.clear(variable);
+        const int num_parents = parents.cardinality();
+        if (num_parents > 0 && the_score >= 0.0f) return -the_score;                      // :213-224 (bic_threshold = 0, :57)
+        std::unordered_map<varset, float, VarsetHash> memo;
+        const float best = bestSubsetScore(parents, cache, memo);
+        if (num_parents > 0 && best + 0.0f >= -the_score) return -the_score;              // :234-246: dominated, stored nowhere
+        cache.put(parents, -the_score);                                                   // :249
+        return -the_score;
     }
     int scoreType() const override { return URLGPU_CBIC; }
     double getLambda() const override { return lambda; }
     urlgpu_ctx *context() override { return g.ctx; }
 private:
+    // F(S) = max(0, max over i in S with S\i non-empty of g(S\i)),  g(T) = cached(T) ? value : F(T)
+    static float bestSubsetScore(const varset &parents, FloatMap &cache, std::unordered_map<varset, float, VarsetHash> &memo) {
+        float best = 0;
+        for (int i = 0; i < urlhost::kVarsetWords * 64; i++) {
+            if (!parents.get(i)) continue;
+            varset thin = parents;
+            thin.clear(i);
+            if (thin.cardinality() == 0) continue;                                        // `checked` is seeded with the empty set (:231)
+            float sc;
+            if (const float *hit = cache.find(thin)) sc = *hit;
+            else {
+                auto it = memo.find(thin);
+                if (it != memo.end()) sc = it->second;
+                else { sc = bestSubsetScore(thin, cache, memo); memo[thin] = sc; }
+            }
+            if (sc > best) best = sc;
+        }
+        return best;
+    }
     GpuContext &g;
     double lambda;
 };

@@ -14,6 +14,7 @@
 #include <memory>
 #include <thread>
 
+#include "fast_io.hpp"
 #include "gpu_scoring.hpp"
 
 using namespace urlhost;
@@ -116,20 +117,26 @@ int main(int argc, char **argv) {
         printf("Enable end-of-scoring pruning: '%s'\n", o.prune ? "true" : "False");
 
         printf("Parsing input file.\n");
-        RecordFile recordFile(o.inputFile, o.delimiter, o.hasHeader);
-        recordFile.read();
+        // RecordFile::read + BayesianNetwork::initialize in one parallel pass (fast_io.hpp): value indices in first-appearance order
+        ParsedCsv csv = parse_csv(o.inputFile, o.delimiter, o.hasHeader);
         printf("Initializing data specifications.\n");
-        BayesianNetwork network;
-        network.initialize(recordFile);
-        const int p = network.size();
+        const int p = csv.p;
+        const int64_t recordCount = csv.n;
         if (p > kVarsetWords * 64) throw std::runtime_error("more than 256 variables");
+        if (recordCount > 2000000000) throw std::runtime_error("more than 2e9 records");
+        std::vector<std::string> names(p);
+        std::vector<int32_t> card(p);
+        for (int i = 0; i < p; i++) {
+            names[i] = (o.hasHeader && i < (int)csv.header.size()) ? csv.header[i] : "Variable_" + std::to_string(i); // bayesian_network.cpp:25-42
+            card[i] = (int32_t)csv.values[i].size();
+        }
 
         std::string sf = o.sf;
         for (auto &ch : sf) ch = (char)std::tolower((unsigned char)ch); // score_main.cpp:294
         int maxParents = o.maxParents;
         if (maxParents > p || maxParents < 1) maxParents = p - 1; // :296-298
         if (sf == "bic") {
-            int maxParentCount = (int)std::log(2 * recordFile.size() / std::log((double)recordFile.size())); // :301
+            int maxParentCount = (int)std::log(2 * (int)recordCount / std::log((double)(int)recordCount)); // :301
             if (maxParentCount < maxParents) maxParents = maxParentCount;
         } else if (sf != "cbic") {
             throw std::runtime_error("Invalid scoring function.  The GPU score path offers 'BIC' and 'cBIC'.");
@@ -145,16 +152,50 @@ int main(int argc, char **argv) {
         int ndev = urlgpu_device_count();
         if (ndev < 1) throw std::runtime_error("urlgpu: no CUDA device available; the score path has no CPU fallback");
 
+        // device input, built once: packed codes (BIC) or the FP64 matrix (cBIC; mlpack::data::Load parses numbers, BIC_OLS.cpp:48)
+        const bool isBic = sf == "bic";
+        std::vector<uint8_t> codes;
+        std::vector<double> x;
+        if (isBic) {
+            codes.resize((size_t)p * recordCount);
+            for (int i = 0; i < p; i++) {
+                if (card[i] > 256) throw std::runtime_error("Variable '" + names[i] + "' has more than 256 values");
+                const int32_t *src = csv.codes[i].data();
+                uint8_t *dst = codes.data() + (size_t)i * recordCount;
+                for (int64_t r = 0; r < recordCount; r++) dst[r] = (uint8_t)src[r];
+            }
+        } else {
+            x.resize((size_t)p * recordCount);
+            for (int i = 0; i < p; i++) {
+                std::vector<double> val(csv.values[i].size());
+                for (size_t k = 0; k < val.size(); k++) val[k] = strtod(csv.values[i][k].c_str(), nullptr);
+                for (int64_t r = 0; r < recordCount; r++) x[(size_t)i * recordCount + r] = val[csv.codes[i][r]];
+            }
+        }
+        // one context per worker thread (-t), thread t on device t % ndev; the first context of a device holds the data, the
+        // others borrow its device copy (BIC) or install its Gram (cBIC): one upload per device, not one per thread
+        std::vector<std::unique_ptr<scoring::GpuContext>> gpus(o.threadCount);
+        std::vector<std::unique_ptr<scoring::ScoringFunction>> functions(o.threadCount);
+        for (int t = 0; t < o.threadCount; t++) {
+            gpus[t].reset(new scoring::GpuContext(t % ndev));
+            const int owner = t % ndev;
+            if (t == owner) {
+                if (isBic) functions[t].reset(new scoring::GpuBICScoringFunction(*gpus[t], codes.data(), recordCount, p, card.data()));
+                else functions[t].reset(new scoring::GpuBICOLSFunction(*gpus[t], x.data(), recordCount, p, o.lambda));
+            } else {
+                if (isBic) functions[t].reset(new scoring::GpuBICScoringFunction(*gpus[t], *gpus[owner]));
+                else functions[t].reset(new scoring::GpuBICOLSFunction(*gpus[t], *gpus[owner], recordCount, p, o.lambda));
+            }
+        }
+
         std::vector<std::string> blocks(p);
         std::vector<uint64_t> scored(p, 0);
         std::vector<std::string> errors(o.threadCount);
+        const int formatThreads = (int)std::max(1u, std::thread::hardware_concurrency() / (unsigned)o.threadCount);
         auto scoringThread = [&](int thread) { // score_main.cpp:132-207
             try {
-                scoring::GpuContext gpu(thread % ndev);
-                std::unique_ptr<scoring::ScoringFunction> scoringFunction;
-                if (sf == "bic") scoringFunction.reset(new scoring::GpuBICScoringFunction(gpu, network, recordFile.size()));
-                else scoringFunction.reset(new scoring::GpuBICOLSFunction(gpu, recordFile, o.lambda));
-                scoring::ScoreCalculator scoreCalculator(scoringFunction.get(), maxParents, p, o.prune);
+                scoring::ScoringFunction *scoringFunction = functions[thread].get();
+                scoring::ScoreCalculator scoreCalculator(scoringFunction, maxParents, p, o.prune);
                 // two-hop candidate mask (:145-153)
                 auto neighbors_of = [&](int variable, Varset &orig) {
                     orig = skeleton.get_neighbors(variable);
@@ -162,6 +203,19 @@ int main(int argc, char **argv) {
                     for (int j = 0; j < p; j++)
                         if (orig.get(j) && j != variable) nb = nb | skeleton.get_neighbors(j);
                     return nb;
+                };
+                // lines [i0, i1) of a variable's block: "%f " + ("<parent> ")* + "\n" (:187-200)
+                auto format_range = [&](const scoring::FloatMap &sc, size_t i0, size_t i1, std::string &out) {
+                    char buf[80];
+                    out.reserve((i1 - i0) * 24);
+                    for (size_t i = i0; i < i1; i++) {
+                        int len = format_score(sc.values[i], buf);                                         // :191
+                        buf[len++] = ' ';
+                        out.append(buf, (size_t)len);
+                        for (int w = 0; w < kVarsetWords; w++)
+                            for (uint64_t m = sc.keys[i].w[w]; m; m &= m - 1) { out += names[w * 64 + __builtin_ctzll(m)]; out += ' '; } // :193-197
+                        out += '\n';
+                    }
                 };
                 auto emit = [&](scoring::ScoreCalculator::Pending &pd) { // the variable's .pss block (:173-203)
                     const int variable = pd.variable;
@@ -173,15 +227,20 @@ int main(int argc, char **argv) {
                         printf("Thread: %d, Variable: %d, Size %s pruning: %d, neighbor cardinality %d/%d\n", thread, variable,
                                o.prune ? "after" : "before", (int)sc.size(), orig.cardinality(), nb.cardinality());
                     std::string &out = blocks[variable];
-                    char buf[64];
-                    out += "VAR " + network.get(variable).name + "\n";                                   // :177
-                    out += "META arity=" + std::to_string(network.getCardinality(variable)) + "\n";      // :178
-                    for (size_t i = 0; i < sc.size(); i++) {
-                        snprintf(buf, sizeof buf, "%f ", sc.values[i]);                                    // :191
-                        out += buf;
-                        for (int q = 0; q < p; q++)
-                            if (sc.keys[i].get(q)) { out += network.get(q).name; out += " "; }             // :193-197
-                        out += "\n";
+                    out += "VAR " + names[variable] + "\n";                                               // :177
+                    out += "META arity=" + std::to_string(card[variable]) + "\n";                         // :178
+                    const size_t n = sc.size();
+                    const int parts = (int)std::min<size_t>((size_t)formatThreads, n / 100000 + 1);        // big blocks are formatted in parallel
+                    if (parts <= 1) format_range(sc, 0, n, out);
+                    else {
+                        std::vector<std::string> piece(parts);
+                        std::vector<std::thread> th;
+                        for (int q = 0; q < parts; q++) th.emplace_back([&, q] { format_range(sc, n * q / parts, n * (q + 1) / parts, piece[q]); });
+                        for (auto &t : th) t.join();
+                        size_t total = out.size();
+                        for (auto &s : piece) total += s.size();
+                        out.reserve(total + 2);
+                        for (auto &s : piece) out += s;
                     }
                     out += "\n";
                 };
@@ -206,10 +265,12 @@ int main(int argc, char **argv) {
 
         std::ofstream out(o.outputFile, std::ios_base::out | std::ios_base::binary);
         if (!out.good()) throw std::runtime_error("Could not open the output file: '" + o.outputFile + "'");
-        out << "META pss_version = 0.1\nMETA input_file=" << o.inputFile << "\nMETA num_records=" << recordFile.size() << "\n"; // :387
+        out << "META pss_version = 0.1\nMETA input_file=" << o.inputFile << "\nMETA num_records=" << recordCount << "\n"; // :387
         out << "META parent_limit=" << maxParents << "\nMETA score_type=" << sf << "\nMETA ess=" << lexicalFloat(o.ess) << "\n\n"; // :388
-        for (int v = 0; v < p; v++) out << blocks[v];
+        for (int v = 0; v < p; v++) out.write(blocks[v].data(), (std::streamsize)blocks[v].size());
         out.close();
+        functions.clear();
+        gpus.clear();
         const auto t3 = std::chrono::steady_clock::now();
         uint64_t total = 0;
         for (auto s : scored) total += s;
