@@ -192,37 +192,44 @@ def run_gpu(args):
         eng.set_stream(stream.cuda_stream)
     weak = is_bic and args.scaling == "weak"
 
-    # ---- inputs.  The exchange step of the path over NCCL/NVLink:
-    #   weak BIC: every rank generates one 60-variable block, the blocks are all-gathered into the 60N-variable data set;
-    #   strong BIC: rank 0 generates configs[3], broadcast;  cBIC: rank 0 forms the Gram, the p*p Gram is broadcast.
-    dev = None
-    if is_bic:
+    # ---- inputs.
+    #   weak BIC (the default with N > 1): rank r owns replica r of the configs[3] network — same arities, DAG and skeleton, its
+    #     own CPTs and rows — generates it, uploads only those 60 columns and scores its 60 variables; the per-variable caches
+    #     are gathered to rank 0 over NCCL (inside the timed region of the e2e arm).  Work per GPU is fixed exactly.
+    #   strong BIC (--scaling strong, and the `scaling_strong` sub-record of every N > 1 line): rank 0 generates configs[3], the
+    #     packed codes are broadcast over NCCL, variables are dealt out by predicted cost (LPT), caches gathered to rank 0.
+    #   cBIC: rank 0 forms the Gram, the p*p Gram is broadcast.
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
+
+    def strong_inputs():
+        wl_ = make_bic_workload(pkg, 1) if rank == 0 else None
         if world == 1:
-            wl = make_bic_workload(pkg, 1)
-        elif weak:
+            return wl_, None
+        box = [None if wl_ is None else {k: v for k, v in wl_.items() if k != "codes"}]
+        dist.broadcast_object_list(box, src=0)
+        dev_ = torch.empty((box[0]["p"], box[0]["n"]), dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            dev_.copy_(torch.from_numpy(wl_["codes"]))
+        dist.broadcast(dev_, src=0)
+        return (wl_ if rank == 0 else dict(box[0])), dev_
+
+    dev = None
+    shift, p_global = 0, None
+    if is_bic:
+        if world > 1 and weak:
             codes_b, card_b, _, _ = bic_block(pkg, rank)
-            mine_dev = torch.from_numpy(codes_b).cuda()
-            dev = torch.empty((60 * world, codes_b.shape[1]), dtype=torch.uint8, device="cuda")
-            dist.all_gather_into_tensor(dev, mine_dev)
-            cards = torch.empty(60 * world, dtype=torch.int32, device="cuda")
-            dist.all_gather_into_tensor(cards, torch.from_numpy(np.asarray(card_b, dtype=np.int32)).cuda())
-            del mine_dev
-            wl = make_bic_workload(pkg, world, codes=False, card=cards.cpu().numpy())
+            wl = make_bic_workload(pkg, 1, codes=codes_b, card=card_b)
+            wl["name"] = BIC_NAME + f"; weak scaling: {world} replicas of that network (own CPTs and rows), replica r on GPU r"
+            shift, p_global = 60 * rank, 60 * world
         else:
-            wl = make_bic_workload(pkg, 1) if rank == 0 else None
-            box = [None if wl is None else {k: v for k, v in wl.items() if k != "codes"}]
-            dist.broadcast_object_list(box, src=0)
-            dev = torch.empty((box[0]["p"], box[0]["n"]), dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                dev.copy_(torch.from_numpy(wl["codes"]))
-            dist.broadcast(dev, src=0)
-            wl = wl if rank == 0 else dict(box[0])
+            wl, dev = strong_inputs()
     else:
         wl = make_cbic_workload(pkg) if rank == 0 else None
         if world > 1:
             box = [None if wl is None else {k: v for k, v in wl.items() if k != "x"}]
             dist.broadcast_object_list(box, src=0)
             wl = wl if rank == 0 else dict(box[0])
+    p_global = p_global or wl["p"]
     flags = pkg.PRUNE_DOMINATED
     stype = pkg.BIC if is_bic else pkg.CBIC
     lam = wl.get("lam", 0.0)
@@ -249,12 +256,30 @@ def run_gpu(args):
             if rank != 0:
                 eng.set_gram(g.cpu().numpy(), wl["n"])
 
-    owner = owners_of(pkg, wl, world)
+    if is_bic and world > 1 and weak:
+        owner = [rank] * wl["p"]                       # local view: every variable of my replica is mine
+        owner_global = [v // 60 for v in range(p_global)]
+    else:
+        owner = owners_of(pkg, wl, world)
+        owner_global = owner
     mine = [v for v in range(wl["p"]) if owner[v] == rank]
     sets_mine = sum(sets_of(wl, v) for v in mine)
     items = [(v, wl["nbs"][v]) for v in mine]
-    D = importlib.import_module("urlearning-cpp_b200.distributed")
     costs = [D.family_cost(wl["card"], v, wl["nbs"][v], wl["K"]) for v in mine] if is_bic else None
+    words_global = pkg.mask_words_for(p_global)
+
+    def to_global(masks):
+        """local one-word masks [n, 1] -> [n, words_global] with every variable index shifted by `shift`"""
+        m = np.ascontiguousarray(masks, dtype=np.uint64).reshape(len(masks), -1)
+        if shift == 0 and m.shape[1] == words_global:
+            return m
+        out = np.zeros((len(m), words_global), dtype=np.uint64)
+        w0, b = shift // 64, shift % 64
+        out[:, w0] = m[:, 0] << np.uint64(b)
+        if b and w0 + 1 < words_global:
+            out[:, w0 + 1] = m[:, 0] >> np.uint64(64 - b)
+        return out
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step(fetch=False):
@@ -264,6 +289,14 @@ def run_gpu(args):
         Returns after every context has drained, so consecutive steps do not overlap."""
         flush.fill_(1)  # L2 flush between steps (inside the timed region: ~40 us of a step of hundreds of ms)
         stream.synchronize()
+        if fetch and world > 1 and is_bic:
+            # N > 1: the caches travel to rank 0 (the .pss writer) over NCCL inside the timed region
+            got = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch=True, costs=costs)
+            local = {v + shift: (to_global(m), sc) for v, (m, sc) in got.items()}
+            allc = D.gather_caches(local, p_global, words_global, "cuda", owner=owner_global)
+            if rank == 0:
+                assert len(allc) == p_global
+            return sum(len(sc) for _, sc in got.values())
         out = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch="pinned" if fetch else False, costs=costs)
         return sum(out.values()) if fetch else 0
 
@@ -331,8 +364,9 @@ def run_gpu(args):
         total_sets = int(t.item())
     value = total_sets * args.steps / (ms / 1e3)
 
-    # ---- e2e: the public API with HOST buffers: the H2D copy of the data from pinned memory (every rank uploads the
-    # columns of the whole data set) and the D2H fetch of every surviving (mask, score) list are inside the timed region
+    # ---- e2e: the public API with HOST buffers: the H2D copy of the data from pinned memory (every rank uploads the columns
+    # its variables need: its own replica in the weak arm), the D2H fetch of every surviving (mask, score) list and, with
+    # N > 1, the NCCL gather of the caches to rank 0 are inside the timed region
     e2e = None
     if is_bic or world == 1:
         host = pinned.numpy()
@@ -347,7 +381,7 @@ def run_gpu(args):
         e2e_step()
         nst = max(1, min(args.steps, 3))
         ems, stored = timed(nst, e2e_step)
-        h2d = (wl["n"] * wl["p"]) * (1 if is_bic else 8) * world
+        h2d = (wl["n"] * wl["p"]) * (1 if is_bic else 8) * world   # per rank: the columns of its own data set
         if world > 1:
             t = torch.tensor([stored], device="cuda", dtype=torch.int64)
             dist.all_reduce(t)
@@ -355,6 +389,8 @@ def run_gpu(args):
         words = pkg.mask_words_for(wl["p"])
         e2e = {"value": total_sets * nst / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int((8 * words + 4) * stored // nst), "steps": nst, "ms_per_step": ems / nst}
+        if world > 1:
+            e2e["gather_to_rank0"] = "NCCL, inside the timed region: %d bytes per step" % int((8 * (words_global + 1)) * stored // nst)
 
     mem_free, mem_total = torch.cuda.mem_get_info()
     if rank == 0:
@@ -678,12 +714,13 @@ def run_gpu_cbic5(args):
                            "parallelism": f"rows sharded n/{world} for the Gram; scoring sharded by (variable, parent-set range): {world} contiguous pieces of the "
                                           f"concatenated family index space, one all-to-all of raw scores to the variables' owners, N={world}"},
                 "e2e": None, "gpu_launches": int(st["launches_total"]), "clocks": sampler.summary(),
-                "roofline": {"bound": "fp64", "kernel": "K2 gram_partial_kernel (DMMA m8n8k4.f64) incl. standardise + moments", "achieved": gram_tf,
+                "roofline": {"bound": "fp64", "kernel": "K2 gram_partial_kernel (TMA bulk copies -> shared memory -> DMMA m8n8k4.f64) + fixed-order combine", "achieved": gram_tf,
                              "peak": fp64["dmma"], "unit": "TFLOP/s", "frac": gram_tf / fp64["dmma"] if gram_tf else None, "traffic": None,
                              "peak_source": "measured in this run (urlgpu_probe_fp64: register-resident DMMA m8n8k4.f64 chains); DFMA: %.1f TFLOP/s" % fp64["dfma"],
                              "gram_ms_per_step_rank0": st["ms_gram"] / args.steps, "gram_flops_per_step_rank0": st["gram_flops"] / args.steps,
                              "k3_rank_sets_per_s_rank0": k3_rate,
-                             "family_ms": {"gram": st["ms_gram"], "cbic": st["ms_cbic"], "accept": st["ms_accept"], "prune": st["ms_prune"]}},
+                             "family_ms": {"moments+standardise": st["ms_standardise"], "gram": st["ms_gram"], "cbic": st["ms_cbic"], "accept": st["ms_accept"],
+                                           "prune": st["ms_prune"]}},
                 "cpu_baseline": None}
         print(json.dumps(line))
     if world > 1:

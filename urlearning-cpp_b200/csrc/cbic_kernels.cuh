@@ -13,6 +13,7 @@
 // member is bit j costs j(j+1)/2 FMAs and on average ~4 FMAs per set, instead of a k^3/3 factorisation.
 #pragma once
 #include "common.cuh"
+#include "log_table.cuh"
 
 namespace urlgpu {
 
@@ -262,7 +263,36 @@ struct CbicParams {
     // rank-deficient fallback gives the reference (BIC_OLS.cpp:313-315) — instead of Inf/NaN; the penalty still counts it.
     double piv_tol;
 };
-__device__ __forceinline__ double guarded_inv(double d, double tol) { return d > tol ? 1.0 / d : 0.0; }
+// 1/d for a positive, normal pivot: hardware seed (MUFU.RCP64H) + two Newton steps = full double precision (<= 1 ulp), without
+// the special-case slow path of the IEEE division.  Every cBIC kernel divides through this function, so all of them
+// (dense DFS / tree, rank space, per-set) see the same bits.
+__device__ __forceinline__ double pivot_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double guarded_inv(double d, double tol) { return d > tol ? pivot_rcp(d) : 0.0; }
+
+// ln(x) in FP64 for the score n*ln(RSS/n): x = 2^e * m, m in [1, 2) falls into one of 128 intervals with centre c_i;
+// ln(m) = -ln(1/c_i) + ln1p(r), r = m * (1/c_i) - 1 (one FMA, |r| <= 2^-8), ln1p by a degree-5 polynomial (truncation
+// 6e-16 absolute).  Accuracy ~2e-16 relative to |ln x| >= 1 (measured against libm over 1e-300..1e300), at a third of the
+// instructions of the library routine, which K3 — instruction-issue bound at one logarithm per parent set — is made of.
+// Zero, negative, subnormal, infinite and NaN arguments go to the library routine (same results as before for those).
+__device__ __forceinline__ double cbic_log(double x) {
+    const long long ix = __double_as_longlong(x);
+    const int hi = (int)(ix >> 32);
+    if (hi < 0x00100000 || hi >= 0x7ff00000) return log(x);
+    const int e = (hi >> 20) - 1023;
+    const double2 t = __ldg(&kLogTable[(hi >> 13) & 0x7f]);
+    const double m = __longlong_as_double((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    const double r = fma(m, t.x, -1.0);
+    double q = fma(r, 0.2, -0.25);
+    q = fma(q, r, 0.33333333333333331);
+    q = fma(q, r, -0.5);
+    return fma((double)e, 0.69314718055994529, t.y + fma(r * r, q, r));
+}
 
 // packed lower-triangular index, element order (v, cand0, cand1, ...)
 __host__ __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }
@@ -307,7 +337,7 @@ __global__ void cbic_roots_kernel(const double *__restrict__ in, size_t in_strid
 // n*log(RSS/n) is evaluated as n*(log(RSS) - log(n)) with log(n) hoisted: one FP64 division less per set.
 __device__ __forceinline__ double cbic_the_score64(double rss, int k, const CbicParams &prm) {
     if (k == 0) return 0.0;
-    return prm.n * (log(rss) - prm.log_n) + prm.lam_logn * (double)k;
+    return prm.n * (cbic_log(rss) - prm.log_n) + prm.lam_logn * (double)k;
 }
 
 // One parent set (urlgpu_score_one, the per-set ScoringFunction::calculateScore plug-in): one warp sweeps every candidate
@@ -459,38 +489,42 @@ template <int J> __host__ __device__ constexpr int cbic_tree_base(int level) {  
 }
 template <int J> __host__ __device__ constexpr int cbic_tree_doubles() { return cbic_tree_base<J>(kTreeJB - 1); }
 
-template <int J>
-__device__ __forceinline__ int cbic_tree_offset(int level, uint32_t m) { // storage of matrix m of `level`
+// storage of matrix m of `level`: trailing exclude decisions make it a view (prefix) of an ancestor's storage
+__device__ __forceinline__ int cbic_tree_offset(const int *s_base, int level, uint32_t m) {
     if (m == 0) return 0;
-    const int t = __ffs(m) - 1;                 // trailing exclude decisions: a view of an ancestor's storage
+    const int t = __ffs(m) - 1;
     const int l = level + t;
-    int off = tri_size(J);
-    for (int q = J - 1; q > l; q--) off += (1 << (J - 1 - q)) * tri_size(q);
-    return off + (int)((m >> t) >> 1) * tri_size(l);
+    return s_base[l] + (int)((m >> t) >> 1) * ((l + 1) * (l + 2) / 2);
 }
 
+// one level of the breadth-first expansion: the 2^(J-j) parents of level j share the CTA's threads evenly (a power of two
+// of threads per parent), so everything that depends on the parent is computed once per thread and level
 template <int J, int LEVEL>
-__device__ __forceinline__ void cbic_tree_expand(double *S, double *inv /*[2][2^(J-kTreeJB)]*/, const unsigned char *tri_row, int k0, const CbicParams &prm, int tid) {
+__device__ __forceinline__ void cbic_tree_expand(double *S, double *inv /*[2][2^(J-kTreeJB)]*/, const unsigned char *tri_row, const int *s_base, int k0,
+                                                 const CbicParams &prm, int tid) {
     if constexpr (LEVEL > kTreeJB) {
         constexpr int j = LEVEL;                        // parents: matrices over (v, cand_0 .. cand_{j-1}); pivot = row j
-        constexpr int P = 1 << (J - j), E = tri_size(j - 1), NT = 1 << (J - kTreeJB);
-        const double *inv_in = inv + (j & 1) * NT;
+        constexpr int P = 1 << (J - j), E = tri_size(j - 1), NT = 1 << (J - kTreeJB), TPP = NT / P;
+        const int m = tid / TPP, part = tid % TPP;
+        const double *A = S + cbic_tree_offset(s_base, j, (uint32_t)m);
+        const double inv_m = inv[(j & 1) * NT + m];
         double *inv_out = inv + ((j - 1) & 1) * NT;
-        for (int w = tid; w < P * E; w += NT) {
-            const int m = w / E, e = w - m * E;
+        double *out = S + cbic_tree_base<J>(j - 1) + m * E;
+        const bool include = k0 + __popc(m) < prm.max_parents;
+        const double *prow = A + tri(j, 0);
+        for (int e = part; e < E; e += TPP) {
             const int a = tri_row[e], b = e - a * (a + 1) / 2;
-            const double *A = S + cbic_tree_offset<J>(j, (uint32_t)m);
             const bool last = e == E - 1;               // element (j-1, j-1): the next pivot of both children
             if (last) inv_out[2 * m] = guarded_inv(A[e], prm.piv_tol);
-            if (k0 + __popc(m) < prm.max_parents) {
-                const double f = -A[tri(j, a)] * inv_in[m];
-                const double x = fma(f, A[tri(j, b)], A[e]);
-                S[cbic_tree_base<J>(j - 1) + m * E + e] = x;
+            if (include) {
+                const double f = -prow[a] * inv_m;
+                const double x = fma(f, prow[b], A[e]);
+                out[e] = x;
                 if (last) inv_out[2 * m + 1] = guarded_inv(x, prm.piv_tol);
             }
         }
         __syncthreads();
-        cbic_tree_expand<J, LEVEL - 1>(S, inv, tri_row, k0, prm, tid);
+        cbic_tree_expand<J, LEVEL - 1>(S, inv, tri_row, s_base, k0, prm, tid);
     }
 }
 
@@ -501,6 +535,7 @@ __global__ void __launch_bounds__(1 << (J - kTreeJB)) cbic_tree_kernel(const dou
     __shared__ double S[cbic_tree_doubles<J>()];
     __shared__ double inv[2 * NT];
     __shared__ unsigned char tri_row[tri_size(J - 1)];
+    __shared__ int s_base[J + 1];
     const uint32_t P = blockIdx.x;
     const int tid = threadIdx.x;
     float *out = ts_out + ((size_t)P << J);
@@ -516,10 +551,15 @@ __global__ void __launch_bounds__(1 << (J - kTreeJB)) cbic_tree_kernel(const dou
         while ((a + 1) * (a + 2) / 2 <= e) a++;
         tri_row[e] = (unsigned char)a;
     }
+    if (tid <= J) { // first double of the include-children of each level
+        int off = tri_size(J);
+        for (int l = J - 1; l > tid; l--) off += (1 << (J - 1 - l)) * tri_size(l);
+        s_base[tid] = tid == J ? 0 : off;
+    }
     __syncthreads();
     if (tid == 0) inv[(J & 1) * NT] = guarded_inv(S[tri(J, J)], prm.piv_tol);
     __syncthreads();
-    cbic_tree_expand<J, J>(S, inv, tri_row, k0, prm, tid);
+    cbic_tree_expand<J, J>(S, inv, tri_row, s_base, k0, prm, tid);
     // every thread: its level-4 matrix into registers, 16 sets, 64 contiguous bytes of scores
     const int k = k0 + __popc(tid);
     const uint32_t low = (uint32_t)tid << kTreeJB;
@@ -529,7 +569,7 @@ __global__ void __launch_bounds__(1 << (J - kTreeJB)) cbic_tree_kernel(const dou
         return;
     }
     double A[tri_size(kTreeJB)];
-    const double *src = S + cbic_tree_offset<J>(kTreeJB, (uint32_t)tid);
+    const double *src = S + cbic_tree_offset(s_base, kTreeJB, (uint32_t)tid);
 #pragma unroll
     for (int e = 0; e < tri_size(kTreeJB); e++) A[e] = src[e];
     cbic_dfs_inl<kTreeJB>(A, low, k, prm, out, out64);

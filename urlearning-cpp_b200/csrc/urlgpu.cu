@@ -30,7 +30,7 @@ namespace {
 thread_local std::string g_create_error;
 std::atomic<int> g_ctx_on_device[64];   // live contexts per device: each budgets its share of the free memory
 
-enum Family { F_COUNT = 0, F_CUBE, F_CBIC, F_ACCEPT, F_PRUNE, F_GRAM, F_TREE, F_OTHER, F_N };
+enum Family { F_COUNT = 0, F_CUBE, F_CBIC, F_ACCEPT, F_PRUNE, F_GRAM, F_TREE, F_OTHER, F_STD, F_N };
 
 struct EvPair { cudaEvent_t a, b; int fam; };
 
@@ -211,7 +211,7 @@ void fold_events(urlgpu_ctx *ctx) {
         if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
             double *dst = ep.fam == F_COUNT ? &ctx->st.ms_count : ep.fam == F_CUBE ? &ctx->st.ms_cube : ep.fam == F_CBIC ? &ctx->st.ms_cbic
                         : ep.fam == F_ACCEPT ? &ctx->st.ms_accept : ep.fam == F_PRUNE ? &ctx->st.ms_prune : ep.fam == F_GRAM ? &ctx->st.ms_gram
-                        : ep.fam == F_TREE ? &ctx->st.ms_tree : nullptr;
+                        : ep.fam == F_TREE ? &ctx->st.ms_tree : ep.fam == F_STD ? &ctx->st.ms_standardise : nullptr;
             if (dst) *dst += ms;
         }
         ctx->free_events.push_back(ep.a);
@@ -534,7 +534,7 @@ static int shard_moments_impl(urlgpu_ctx *ctx, const double *shift_host, double 
         CK(cudaMemcpyAsync(shift.p, shift_host, p * sizeof(double), cudaMemcpyHostToDevice, s));
     }
     {
-        Region rg(ctx, F_GRAM, 4);
+        Region rg(ctx, F_STD, 4);
         const dim3 rgrid(kRedBlocks, p);
         const unsigned pb = blocks_for(p, 128);
         for (int mode = 0; mode < 2; mode++) {
@@ -571,8 +571,11 @@ static int shard_finish_impl(urlgpu_ctx *ctx, const double *mean_host, const dou
         zbuf = ctx->d_zcache;
     }
     {
-        Region rg(ctx, F_GRAM, 3);
+        Region rg(ctx, F_STD, 1);
         standardise_kernel<<<dim3(ctx->sm_count * 2, p), 256, 0, s>>>(ctx->d_x_view, n, ctx->shard_stride, md.as<double>(), md.as<double>() + p, zbuf, z_stride);
+    }
+    {
+        Region rg(ctx, F_GRAM, 2);
         const int tiles = (p + kGramTile - 1) / kGramTile;
         const int pairs = tiles * (tiles + 1) / 2;
         // row slices (multiples of the chunk): enough CTAs to fill the machine several times over, at least 1024 records each
