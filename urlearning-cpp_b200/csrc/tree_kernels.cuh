@@ -84,6 +84,26 @@ __global__ void tree_key_kernel(BicData d, CandInfo ci_cube, int dmax, uint32_t 
     atomicAdd(&hist[key], 1u);
 }
 
+// exclusive prefix sum of the bucket histogram (<= 2^20 + 1 entries): one CTA, every thread a contiguous run
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ off, uint32_t n) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; i++) sum += hist[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele over the 1024 partial sums
+    for (uint32_t o = 1; o < blockDim.x; o <<= 1) {
+        const uint32_t x = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += x;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (uint32_t i = b; i < e; i++) { const uint32_t t = hist[i]; off[i] = run; run += t; }
+}
+
 __global__ void tree_scatter_kernel(BicData d, CandInfo ci_cube, TreeVar tv, const uint32_t *__restrict__ keys, uint32_t *__restrict__ cursor,
                                     unsigned long long *__restrict__ out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -15,8 +15,6 @@
 #include <string>
 #include <vector>
 
-#include <cub/device/device_scan.cuh>
-
 #include "bic_kernels.cuh"
 #include "tree_kernels.cuh"
 #include "cbic_kernels.cuh"
@@ -986,9 +984,13 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         CK(cudaMemGetInfo(&free_b, &total_b));
         ctx->mem_free_sample = free_b + (ctx->cubeA_cap + ctx->cubeB_cap) * sizeof(int);
     }
-    // several contexts may share the device (EnginePool, `score -t T`): each plans with its share of what was free
-    const int sharers = std::max(1, ctx->device < 64 ? g_ctx_on_device[ctx->device].load() : 1);
-    const double mem_budget = (double)ctx->mem_free_sample * 0.7 / sharers;
+    // The test below is deliberately generous: it counts every table of a layer, although fused roots and leaf sets are never
+    // materialised (the buffers that are really allocated, needA / needB further down, are several times smaller), and several
+    // contexts on one device (EnginePool, `score -t T`) each see the whole free memory.  Dividing the budget by the number of
+    // contexts pushed big families to root layer K (3x the row counting; measured 314 -> 716 ms per step at configs[3]).  An
+    // allocation that does fail is handled where it happens: cached pool blocks are released, and if that is not enough
+    // the family takes the direct path.
+    const double mem_budget = (double)ctx->mem_free_sample * 0.7;
     std::vector<double> layer_cells(Lmax + 1, 0.0);
     for (int l = 0; l <= Lmax; l++)
         for (auto &cs : layers[l]) layer_cells[l] += (double)((cs.cells + 3) / 4 * 4);
@@ -1245,9 +1247,6 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 CK(drows.alloc(n * sizeof(unsigned long long)));
                 CK(dcroots.alloc(croots.size() * sizeof(CubeRoot)));
                 CK(dmap.alloc(rchunk * sizeof(uint32_t)));
-                size_t tmp_bytes = 0;
-                CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, dhist.as<uint32_t>(), doffp.as<uint32_t>(), (int)(Pd + 1), s));
-                CK(dtmp.alloc(tmp_bytes));
                 { int rc_ = h2d_async(ctx, dcroots.p, croots.data(), croots.size() * sizeof(CubeRoot)); if (rc_) return rc_; }
                 tv.rows = drows.as<unsigned long long>();
                 tv.prefix_off = doffp.as<uint32_t>();
@@ -1255,7 +1254,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 Region rg(ctx, F_COUNT, 6);
                 CK(cudaMemsetAsync(dhist.p, 0, ((size_t)Pd + 1) * sizeof(uint32_t), s));
                 tree_key_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, tv.dmax, dkeys.as<uint32_t>(), dhist.as<uint32_t>());
-                CK(cub::DeviceScan::ExclusiveSum(dtmp.p, tmp_bytes, dhist.as<uint32_t>(), doffp.as<uint32_t>(), (int)(Pd + 1), s));
+                bucket_scan_kernel<<<1, 1024, 0, s>>>(dhist.as<uint32_t>(), doffp.as<uint32_t>(), (uint32_t)(Pd + 1));
                 CK(cudaMemcpyAsync(dcursor.p, doffp.p, ((size_t)Pd + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
                 tree_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, tv, dkeys.as<uint32_t>(), dcursor.as<uint32_t>(), drows.as<unsigned long long>());
                 root_map_kernel<<<blocks_for(rchunk, 256), 256, 0, s>>>(dcroots.as<CubeRoot>(), (int)croots.size(), (uint32_t)rchunk, dmap.as<uint32_t>());
@@ -1594,9 +1593,6 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
     CK(dmap.alloc(chunk * sizeof(uint32_t)));
     CK(dacc.alloc(acc_total * sizeof(long long)));
     CK(dperm.alloc(kMaxDenseCand));
-    size_t tmp_bytes = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, dhist.as<uint32_t>(), doff.as<uint32_t>(), (int)(Pd + 1), s));
-    CK(dtmp.alloc(tmp_bytes));
     uint8_t hperm[kMaxDenseCand] = {0};
     for (int i = 0; i < c; i++) hperm[i] = (uint8_t)perm[i];
     std::vector<uint16_t> cfgtab((size_t)(t + 1) << t, 0);
@@ -1618,7 +1614,7 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
         Region rg(ctx, F_COUNT, 5);
         CK(cudaMemsetAsync(dhist.p, 0, ((size_t)Pd + 1) * sizeof(uint32_t), s));
         tree_key_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, dmax, dkeys.as<uint32_t>(), dhist.as<uint32_t>());
-        CK(cub::DeviceScan::ExclusiveSum(dtmp.p, tmp_bytes, dhist.as<uint32_t>(), doff.as<uint32_t>(), (int)(Pd + 1), s));
+        bucket_scan_kernel<<<1, 1024, 0, s>>>(dhist.as<uint32_t>(), doff.as<uint32_t>(), (uint32_t)(Pd + 1));
         CK(cudaMemcpyAsync(dcursor.p, doff.p, ((size_t)Pd + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
         tree_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, tv, dkeys.as<uint32_t>(), dcursor.as<uint32_t>(), drows.as<unsigned long long>());
         tree_map_kernel<<<blocks_for(chunk, 256), 256, 0, s>>>(droots.as<TreeRoot>(), (int)roots.size(), (uint32_t)chunk, dmap.as<uint32_t>());
@@ -1699,7 +1695,10 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
     DevBuf dsub(ctx), droots(ctx), dmid(ctx), dmid2(ctx);
     CK(dsub.alloc(sub.size() * sizeof(double)));
     CK(droots.alloc((size_t)outsz * n_prefix * sizeof(double)));
-    CK(cudaMemcpyAsync(dsub.p, sub.data(), sub.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    // the sub-Gram travels through the pinned staging arena: truly asynchronous, `sub` may go out of scope, and the call
+    // returns without a stream synchronisation (variable v + 1 is planned and enqueued while v still runs)
+    { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
+    { int rc_ = h2d_async(ctx, dsub.p, sub.data(), sub.size() * sizeof(double)); if (rc_) return rc_; }
     {
         Region rg(ctx, F_CBIC, 4);
         const int warps = 8;
@@ -1747,7 +1746,7 @@ static int cbic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<in
         ctx->st.algorithmic_flops += flops;
         ctx->st.sets_scored += *n_scored;
     }
-    CK(cudaStreamSynchronize(s));
+    { int rc_ = stage_end(ctx); if (rc_) return rc_; }
     CK(cudaGetLastError());
     return URLGPU_OK;
 }
