@@ -540,9 +540,9 @@ def measure_score_file(pkg, wl, tmpdir):
         if r.returncode != 0:
             out[tag] = {"error": r.stderr[-300:]}
             return
-        m = re.search(r"Scored (\d+) parent sets in ([\d.]+) s .*; parse ([\d.]+) s, write ([\d.]+) s, total ([\d.]+) s wall", r.stdout)
-        out[tag] = {"process_wall_s": wall, "sets_scored": int(m.group(1)), "score_s": float(m.group(2)), "parse_s": float(m.group(3)), "write_s": float(m.group(4)),
-                    "total_s": float(m.group(5)), "pss_bytes": os.path.getsize(pss), "args": " ".join(a if not a.startswith(tmpdir) else os.path.basename(a) for a in args)}
+        m = re.search(r"Scored (\d+) parent sets in ([\d.]+) s .*; parse ([\d.]+) s, init ([\d.]+) s, write ([\d.]+) s, total ([\d.]+) s wall", r.stdout)
+        out[tag] = {"process_wall_s": wall, "sets_scored": int(m.group(1)), "score_s": float(m.group(2)), "parse_csv_s": float(m.group(3)),
+                    "cuda_init_and_upload_s": float(m.group(4)), "write_pss_s": float(m.group(5)), "total_s": float(m.group(6)), "pss_bytes": os.path.getsize(pss), "args": " ".join(a if not a.startswith(tmpdir) else os.path.basename(a) for a in args)}
 
     hep = os.path.join(ROOT, "tests", "data", "hepatitis.clean.csv")
     run("configs[0] hepatitis -s -f BIC", [hep, "-s", "-f", "BIC"], os.path.join(tmpdir, "hep.pss"))
