@@ -392,6 +392,41 @@ def run_gpu(args):
         if world > 1:
             e2e["gather_to_rank0"] = "NCCL, inside the timed region: %d bytes per step" % int((8 * (words_global + 1)) * stored // nst)
 
+    # ---- strong-scaling sub-record of every N > 1 weak line: configs[3] ITSELF split over the ranks (codes broadcast over NCCL,
+    # variables dealt out by predicted cost, device-resident timing like `value`, then one e2e pass with the NCCL gather)
+    strong = None
+    if is_bic and world > 1 and weak:
+        wl_s, dev_s = strong_inputs()
+        torch.cuda.synchronize()
+        pool.set_discrete_device(dev_s.data_ptr(), wl_s["n"], wl_s["p"], wl_s["card"])
+        del dev_s
+        owner_s = owners_of(pkg, wl_s, world)
+        mine_s = [v for v in range(wl_s["p"]) if owner_s[v] == rank]
+        items_s = [(v, wl_s["nbs"][v]) for v in mine_s]
+        costs_s = [D.family_cost(wl_s["card"], v, wl_s["nbs"][v], wl_s["K"]) for v in mine_s]
+        sets_s = sum(sets_of(wl_s, v) for v in range(wl_s["p"]))
+        words_s = pkg.mask_words_for(wl_s["p"])
+
+        def step_s(fetch=False):
+            flush.fill_(1)
+            stream.synchronize()
+            if not fetch:
+                pool.run(items_s, wl_s["K"], stype, flags=flags, fetch=False, costs=costs_s)
+                return 0
+            got = pool.run(items_s, wl_s["K"], stype, flags=flags, fetch=True, costs=costs_s)
+            allc = D.gather_caches(got, wl_s["p"], words_s, "cuda", owner=owner_s)
+            if rank == 0:
+                assert len(allc) == wl_s["p"]
+            return sum(len(sc) for _, sc in got.values())
+        step_s()
+        nss = max(1, min(args.steps, 5))
+        sms, _ = timed(nss, step_s)
+        step_s(True)
+        ems_s, _ = timed(1, lambda: step_s(True))
+        strong = {"workload": wl_s["name"], "scaling": "strong", "value": sets_s * nss / (sms / 1e3), "unit": UNIT, "steps": nss, "ms_per_step": sms / nss,
+                  "e2e_gather_ms_per_step": ems_s, "sets_per_step": sets_s,
+                  "parallelism": f"configs[3] itself: codes broadcast over NCCL, 60 variables dealt to {world} ranks by predicted cost (LPT), caches gathered to rank 0"}
+
     mem_free, mem_total = torch.cuda.mem_get_info()
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -467,7 +502,7 @@ def run_gpu(args):
                            "l2": "flushed between steps (256 MB write)", "dominant_family": dom,
                            "hbm_in_use_gb": round((mem_total - mem_free) / 1e9, 1)},
                 "e2e": e2e, "gpu_launches": int(launches_total), "clocks": sampler.summary(), "roofline": roofline,
-                "cpu_baseline": cpu, **extra}
+                "cpu_baseline": cpu, **extra, **({"scaling_strong": strong} if strong else {})}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

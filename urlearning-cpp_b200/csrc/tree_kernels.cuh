@@ -84,24 +84,50 @@ __global__ void tree_key_kernel(BicData d, CandInfo ci_cube, int dmax, uint32_t 
     atomicAdd(&hist[key], 1u);
 }
 
-// exclusive prefix sum of the bucket histogram (<= 2^20 + 1 entries): one CTA, every thread a contiguous run
-__global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ off, uint32_t n) {
-    __shared__ uint32_t part[1024];
-    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
-    const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
-    uint32_t sum = 0;
-    for (uint32_t i = b; i < e; i++) sum += hist[i];
-    part[threadIdx.x] = sum;
+// exclusive prefix sum of the bucket histogram (<= 2^20 + 1 entries) in three small kernels: per-tile sums (4096 entries per CTA),
+// a one-CTA scan of the tile sums, per-tile rescan.  (cub::DeviceScan did this in round 1; the hot path carries no library kernel.)
+constexpr int kScanTile = 4096, kScanThreads = 256, kScanPer = kScanTile / kScanThreads;
+__global__ void __launch_bounds__(kScanThreads) bucket_scan_sums_kernel(const uint32_t *__restrict__ hist, uint32_t n, uint32_t *__restrict__ tile_sum) {
+    __shared__ uint32_t red[kScanThreads / 32];
+    const uint32_t base = blockIdx.x * kScanTile;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPer; k++) { const uint32_t i = base + k * kScanThreads + threadIdx.x; if (i < n) s += hist[i]; }
+    s = __reduce_add_sync(0xffffffffu, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
-    // Hillis-Steele over the 1024 partial sums
-    for (uint32_t o = 1; o < blockDim.x; o <<= 1) {
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < kScanThreads / 32; w++) t += red[w]; tile_sum[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) bucket_scan_tiles_kernel(uint32_t *__restrict__ tile_sum, uint32_t ntiles) { // in place, exclusive; ntiles <= 1024
+    __shared__ uint32_t part[1024];
+    const uint32_t v = threadIdx.x < ntiles ? tile_sum[threadIdx.x] : 0;
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
         const uint32_t x = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
         __syncthreads();
         part[threadIdx.x] += x;
         __syncthreads();
     }
-    uint32_t run = part[threadIdx.x] - sum;
-    for (uint32_t i = b; i < e; i++) { const uint32_t t = hist[i]; off[i] = run; run += t; }
+    if (threadIdx.x < ntiles) tile_sum[threadIdx.x] = part[threadIdx.x] - v;
+}
+__global__ void __launch_bounds__(kScanThreads) bucket_scan_final_kernel(const uint32_t *__restrict__ hist, uint32_t n, const uint32_t *__restrict__ tile_off,
+                                                                         uint32_t *__restrict__ off) {
+    __shared__ uint32_t wsum[kScanThreads / 32];
+    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanPer;   // every thread a contiguous run of 16 entries (64 bytes)
+    uint32_t v[kScanPer], s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPer; k++) { v[k] = base + k < n ? hist[base + k] : 0; s += v[k]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    uint32_t run = tile_off[blockIdx.x] + x - s;
+    for (int w = 0; w < warp; w++) run += wsum[w];
+#pragma unroll
+    for (int k = 0; k < kScanPer; k++) { if (base + k < n) off[base + k] = run; run += v[k]; }
 }
 
 __global__ void tree_scatter_kernel(BicData d, CandInfo ci_cube, TreeVar tv, const uint32_t *__restrict__ keys, uint32_t *__restrict__ cursor,

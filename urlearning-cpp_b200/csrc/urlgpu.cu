@@ -1251,10 +1251,16 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 tv.rows = drows.as<unsigned long long>();
                 tv.prefix_off = doffp.as<uint32_t>();
                 tv.cfg_tab = nullptr;
-                Region rg(ctx, F_COUNT, 6);
+                Region rg(ctx, F_COUNT, 8);
                 CK(cudaMemsetAsync(dhist.p, 0, ((size_t)Pd + 1) * sizeof(uint32_t), s));
                 tree_key_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, tv.dmax, dkeys.as<uint32_t>(), dhist.as<uint32_t>());
-                bucket_scan_kernel<<<1, 1024, 0, s>>>(dhist.as<uint32_t>(), doffp.as<uint32_t>(), (uint32_t)(Pd + 1));
+                {
+                    const uint32_t nscan = (uint32_t)(Pd + 1), ntiles = (nscan + kScanTile - 1) / kScanTile;   // <= 257 tiles
+                    CK(dtmp.alloc(1024 * sizeof(uint32_t)));
+                    bucket_scan_sums_kernel<<<ntiles, kScanThreads, 0, s>>>(dhist.as<uint32_t>(), nscan, dtmp.as<uint32_t>());
+                    bucket_scan_tiles_kernel<<<1, 1024, 0, s>>>(dtmp.as<uint32_t>(), ntiles);
+                    bucket_scan_final_kernel<<<ntiles, kScanThreads, 0, s>>>(dhist.as<uint32_t>(), nscan, dtmp.as<uint32_t>(), doffp.as<uint32_t>());
+                }
                 CK(cudaMemcpyAsync(dcursor.p, doffp.p, ((size_t)Pd + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
                 tree_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, tv, dkeys.as<uint32_t>(), dcursor.as<uint32_t>(), drows.as<unsigned long long>());
                 root_map_kernel<<<blocks_for(rchunk, 256), 256, 0, s>>>(dcroots.as<CubeRoot>(), (int)croots.size(), (uint32_t)rchunk, dmap.as<uint32_t>());
@@ -1614,7 +1620,13 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
         Region rg(ctx, F_COUNT, 5);
         CK(cudaMemsetAsync(dhist.p, 0, ((size_t)Pd + 1) * sizeof(uint32_t), s));
         tree_key_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, dmax, dkeys.as<uint32_t>(), dhist.as<uint32_t>());
-        bucket_scan_kernel<<<1, 1024, 0, s>>>(dhist.as<uint32_t>(), doff.as<uint32_t>(), (uint32_t)(Pd + 1));
+        {
+            const uint32_t nscan = (uint32_t)(Pd + 1), ntiles = (nscan + kScanTile - 1) / kScanTile;
+            CK(dtmp.alloc(1024 * sizeof(uint32_t)));
+            bucket_scan_sums_kernel<<<ntiles, kScanThreads, 0, s>>>(dhist.as<uint32_t>(), nscan, dtmp.as<uint32_t>());
+            bucket_scan_tiles_kernel<<<1, 1024, 0, s>>>(dtmp.as<uint32_t>(), ntiles);
+            bucket_scan_final_kernel<<<ntiles, kScanThreads, 0, s>>>(dhist.as<uint32_t>(), nscan, dtmp.as<uint32_t>(), doff.as<uint32_t>());
+        }
         CK(cudaMemcpyAsync(dcursor.p, doff.p, ((size_t)Pd + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
         tree_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(bd, ci_cube, tv, dkeys.as<uint32_t>(), dcursor.as<uint32_t>(), drows.as<unsigned long long>());
         tree_map_kernel<<<blocks_for(chunk, 256), 256, 0, s>>>(droots.as<TreeRoot>(), (int)roots.size(), (uint32_t)chunk, dmap.as<uint32_t>());
