@@ -497,7 +497,9 @@ def run_gpu(args):
                 "dtype": "int32 counts / int64 fixed-point log-likelihood -> f32" if is_bic else "f64 -> f32",
                 "data": "synthetic (seeded numpy generator, urlearning-cpp_b200/datagen.py)",
                 "config": {"workload": wl["name"], "sets_per_step": total_sets,
-                           "parallelism": ("variables dealt to ranks by predicted cost (LPT)" if is_bic else "variables striped v % N") + f", N={world}; "
+                           "parallelism": (("replica r of the network on GPU r (its own 60 columns uploaded there), caches gathered to rank 0 over NCCL"
+                                            if (weak and world > 1) else "variables dealt to ranks by predicted cost (LPT)") if is_bic
+                                           else "variables striped v % N") + f", N={world}; "
                                           f"{T} context(s)/stream(s) per GPU, one host thread each (the reference's -t workers)",
                            "l2": "flushed between steps (256 MB write)", "dominant_family": dom,
                            "hbm_in_use_gb": round((mem_total - mem_free) / 1e9, 1)},
