@@ -124,6 +124,14 @@ int urlgpu_score_range(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors,
                        double lambda, uint64_t first, uint64_t count, float *scores, int on_device);
 int urlgpu_result_from_scores(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type,
                               const float *scores, uint64_t n, int on_device, unsigned filter_flags, urlgpu_result **out);
+/* One of `parts` disjoint parts of a variable's family, chosen by the ENGINE so that each part is as cheap as possible: for
+ * discrete BIC a sub-forest of the marginalisation forest (the root tables i with i % parts == part and everything derived
+ * from them: counting and marginalising are both split), else a contiguous range.  `scores` receives all family_size
+ * entries; those outside the part hold the "not scored" bit pattern 0x7fc0beef, which as an int32 is larger than any finite
+ * float's pattern: an element-wise MIN over the int32 views of the parts' arrays (one NCCL all-reduce) is the complete raw
+ * score array for urlgpu_result_from_scores. */
+int urlgpu_score_part(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type,
+                      double lambda, int part, int parts, float *scores, int on_device);
 
 /* Single parent set, same value ScoringFunction::calculateScore returns (BIC: the score; cBIC: -the_score).
  * value64 (optional): BIC: exact log-likelihood before the float rounding; cBIC: the_score in FP64. */

@@ -210,3 +210,33 @@ def test_parent_set_range_shards_reassemble_to_the_same_cache(pkg):
         a.score_range(3, allbits, 3, pkg.BIC, 10, a.family_size(3, allbits, 3, pkg.BIC))
     a.close()
     b.close()
+
+
+def test_family_parts_merge_to_the_whole(pkg):
+    """urlgpu_score_part: a variable's K1 work split into sub-forests of its root tables (BIC cube path) or ranges; the parts
+    are disjoint, cover the family, and their int32-MIN merge gives the cache of the one-call path, bit for bit"""
+    eng = pkg.Engine(0)
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=20, n=70001, seed=12, window=7, max_indegree=3)
+    x, _ = pkg.datagen.linear_gaussian_sem(p=20, n=4000, seed=2)
+    eng.set_discrete(codes, card)
+    eng.set_continuous(x)
+    NOT_SCORED = np.uint32(0x7FC0BEEF)
+    for st, v, nb, K in [(pkg.BIC, 10, pkg.two_hop_neighbors(edges, 20, 10), 9), (pkg.BIC, 3, (1 << 20) - 1, 4), (pkg.BIC, 19, pkg.two_hop_neighbors(edges, 20, 19), 11),
+                         (pkg.CBIC, 7, (1 << 20) - 1, 5)]:
+        total = eng.family_size(v, nb, K, st)
+        for parts in (2, 3, 8):
+            arrs = [eng.score_part(v, nb, K, st, part, parts, lam=2.0) for part in range(parts)]
+            bits = np.stack([a.view(np.uint32) for a in arrs])
+            scored = bits != NOT_SCORED
+            assert np.all(scored.sum(axis=0) == 1), "every set belongs to exactly one part"
+            if st == pkg.BIC and K >= 9:
+                assert all(s.sum() > 0 for s in scored), "no empty part for a big family"
+            merged = np.min(np.stack([a.view(np.int32) for a in arrs]), axis=0).view(np.float32)
+            for flags in (0, pkg.PRUNE_DOMINATED):
+                want = eng.score_variable(v, nb, K, st, lam=2.0, flags=flags)
+                got = eng.result_from_scores(v, nb, K, st, merged, flags=flags)
+                (mw, sw), (mg, sg) = want.fetch(), got.fetch()
+                want.free()
+                got.free()
+                assert len(sw) > 0 and np.array_equal(mw, mg) and np.array_equal(sw.view(np.uint32), sg.view(np.uint32))
+    eng.close()

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "urlgpu_result_prefetch", "urlgpu_result_count", "urlgpu_result_scored", "urlgpu_result_fetch", "urlgpu_result_free",
     "urlgpu_host_alloc", "urlgpu_host_free",
     "urlgpu_score_one", "urlgpu_contingency", "urlgpu_prune", "urlgpu_stats_reset", "urlgpu_stats_get",
-    "urlgpu_stats_enable_timing", "urlgpu_probe_fp64", "urlgpu_family_size", "urlgpu_score_range", "urlgpu_result_from_scores",
+    "urlgpu_stats_enable_timing", "urlgpu_probe_fp64", "urlgpu_family_size", "urlgpu_score_range", "urlgpu_result_from_scores", "urlgpu_score_part",
     "urlgpu_spg_build", "urlgpu_spg_query", "urlgpu_spg_free",
 ]
 
@@ -110,6 +110,7 @@ def load_library():
     lib.urlgpu_spg_free.argtypes = [vp]
     lib.urlgpu_family_size.argtypes = [vp, i32, vp, i32, i32, i32, P(u64)]
     lib.urlgpu_score_range.argtypes = [vp, i32, vp, i32, i32, i32, C.c_double, u64, u64, vp, i32]
+    lib.urlgpu_score_part.argtypes = [vp, i32, vp, i32, i32, i32, C.c_double, i32, i32, vp, i32]
     lib.urlgpu_result_from_scores.argtypes = [vp, i32, vp, i32, i32, i32, vp, u64, i32, C.c_uint, P(vp)]
     for name in ABI_SYMBOLS:
         if name not in ("urlgpu_last_error", "urlgpu_host_alloc", "urlgpu_host_free"):
@@ -368,6 +369,21 @@ class Engine:
         out = np.zeros(count, dtype=np.float32)
         self._check(self.lib.urlgpu_score_range(self._h, variable, nb.ctypes.data, words, max_parents, score_type, float(lam),
                                                 first, count, out.ctypes.data, 0))
+        return out
+
+    def score_part(self, variable: int, neighbors: int, max_parents: int, score_type: int, part: int, parts: int,
+                   lam: float = 0.0, out_device_ptr: int | None = None):
+        """one of `parts` disjoint parts of the family (engine-chosen: a sub-forest of root tables for BIC, a range otherwise):
+        all family_size raw scores, NOT_SCORED (0x7fc0beef) outside the part; merge the parts with an int32 MIN"""
+        words = mask_words_for(self.p)
+        nb = mask_to_words(neighbors, words)
+        if out_device_ptr is not None:
+            self._check(self.lib.urlgpu_score_part(self._h, variable, nb.ctypes.data, words, max_parents, score_type, float(lam),
+                                                   part, parts, C.c_void_p(out_device_ptr), 1))
+            return None
+        out = np.zeros(self.family_size(variable, neighbors, max_parents, score_type), dtype=np.float32)
+        self._check(self.lib.urlgpu_score_part(self._h, variable, nb.ctypes.data, words, max_parents, score_type, float(lam),
+                                               part, parts, out.ctypes.data, 0))
         return out
 
     def result_from_scores(self, variable: int, neighbors: int, max_parents: int, score_type: int, scores, n: int | None = None,

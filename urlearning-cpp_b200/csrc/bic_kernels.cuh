@@ -473,6 +473,7 @@ __global__ void cube_finalize_kernel(BicData d, CandInfo ci_res, const uint32_t 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsets) return;
     const uint32_t mask = res_masks[i];
+    if (mask == 0xffffffffu) return; // a set outside this call's part of the family (urlgpu_score_part)
     float pen = (float)(ci_res.rv - 1);
     for (int b = 0; b < ci_res.c; b++)
         if ((mask >> b) & 1) pen = __fmul_rn(pen, (float)ci_res.card[b]);

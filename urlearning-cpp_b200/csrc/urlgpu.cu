@@ -900,8 +900,10 @@ static int h2d_async(urlgpu_ctx *ctx, void *dst, const void *src, size_t bytes) 
     return URLGPU_OK;
 }
 
+// part / parts: score only the sub-forest of the roots i with i % parts == part (and everything derived from them); the parts
+// are disjoint and cover the family (urlgpu_score_part: one variable's K1 work split over several GPUs)
 static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                                 uint64_t *n_scored, bool *used, const RankSpace &om) {
+                                 uint64_t *n_scored, bool *used, const RankSpace &om, int part = 0, int parts = 1) {
     *used = false;
     cudaStream_t s = ctx->stream;
     { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
@@ -1070,10 +1072,14 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         return true;
     };
     std::vector<char> root_kind(layers[Lstar].size(), 0); // 0: small table or RED path, 1: plain root of bic_root_kernel, 2: fused
+    std::vector<std::vector<char>> mine(Lstar + 1);        // sets of this call's sub-forest (all of them when parts == 1)
+    mine[Lstar].assign(layers[Lstar].size(), 1);
+    if (parts > 1) for (size_t i = 0; i < layers[Lstar].size(); i++) mine[Lstar][i] = (int)(i % (size_t)parts) == part;
     if (packed_ok) {
         uint64_t total_slices = 0;
         auto &R = layers[Lstar];
         for (size_t i = 0; i < R.size(); i++) {
+            if (!mine[Lstar][i]) continue;
             if (R[i].cells <= tier1_cells) continue;
             const uint32_t P = R[i].cube_mask;
             const int run = std::min(c, (int)__builtin_ctz(~P));
@@ -1084,7 +1090,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             else if (slice_root(P, 0, r)) root_kind[i] = 1;
             if (root_kind[i]) total_slices += r.nslices;
         }
-        if (total_slices < 128 || total_slices > 0x7fffffffull) std::fill(root_kind.begin(), root_kind.end(), 0); // too few CTAs to fill the machine
+        if (total_slices < (uint64_t)std::max(1, 128 / parts) || total_slices > 0x7fffffffull) std::fill(root_kind.begin(), root_kind.end(), 0); // too few CTAs to fill the machine
     }
     // ---- offsets and parent links ----
     // Layer Lstar lives in buffer A, Lstar-1 in B, Lstar-2 in A again, ...: each buffer is sized for its own layers only.
@@ -1113,6 +1119,10 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 cs.r = (uint32_t)ccard[z];
             }
         }
+    }
+    for (int l = Lstar - 1; l >= 0; l--) { // a set belongs to the sub-forest of its parent
+        mine[l].resize(layers[l].size());
+        for (size_t i = 0; i < layers[l].size(); i++) mine[l][i] = mine[l + 1][layers[l][i].parent];
     }
     needA = std::max<size_t>(needA, 4); needB = std::max<size_t>(needB, 4);
     // layer buffers: on an allocation failure give the pool's cached blocks back to the driver and retry once; if the device
@@ -1154,7 +1164,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     auto finalize_layer = [&](int l) -> int {
         auto &L = layers[l];
         hres.resize(L.size());
-        for (size_t i = 0; i < L.size(); i++) hres[i] = L[i].res_mask;
+        for (size_t i = 0; i < L.size(); i++) hres[i] = mine[l][i] ? L[i].res_mask : 0xffffffffu; // 0xffffffff: not this call's set
         { int rc_ = h2d_async(ctx, dres.p, hres.data(), L.size() * sizeof(uint32_t)); if (rc_) return rc_; }
         Region rg(ctx, F_OTHER, 1);
         cube_finalize_kernel<<<blocks_for(L.size(), 256), 256, 0, s>>>(bd, ci_res, dres.as<uint32_t>(), dacc.as<long long>() + acc_off[l], (int)L.size(), d_table, d_llfixed, om);
@@ -1169,6 +1179,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         std::vector<uint32_t> small_m; std::vector<uint64_t> small_off; std::vector<size_t> small_idx;
         std::vector<GlobalSet> big; std::vector<size_t> big_idx;
         for (size_t i = 0; i < R.size(); i++) {
+            if (!mine[Lstar][i]) continue;
             ctx->st.k1_bytes_read += 8.0 * (double)n;  // one packed row word per record and root (L2 resident)
             if (R[i].cells <= tier1_cells) { small_m.push_back(R[i].cube_mask); small_off.push_back(R[i].off); small_idx.push_back(i); }
             else { big.push_back(GlobalSet{R[i].cube_mask, (uint32_t)R[i].cells, R[i].off}); big_idx.push_back(i); }
@@ -1342,17 +1353,18 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
         auto &P = layers[l + 1];
         if (L.empty()) break;
         if (l == Lstar - 1)
-            for (size_t i = 0; i < P.size(); i++) if (!fused_root[i]) ctx->st.k1_bytes_written += 4.0 * (double)P[i].cells; // root tables that were written
+            for (size_t i = 0; i < P.size(); i++) if (!fused_root[i] && mine[l + 1][i]) ctx->st.k1_bytes_written += 4.0 * (double)P[i].cells; // root tables that were written
         const bool top = l == Lstar - 1 && fused_any; // children of fused roots were produced by the root kernel
         // the leaf child of every set of THIS layer (in layer l-1), scored by the pair that produces the set
         std::vector<uint32_t> leaf_child(L.size(), kNoLeafAcc);
         if (fuse_leaves && l >= 1 && l - 1 <= Kc) {
             auto &C = layers[l - 1];
             for (size_t i = 0; i < C.size(); i++)
-                if ((C[i].cube_mask & 1u) == 0) leaf_child[C[i].parent] = (uint32_t)i; // parent = C[i] + {0}: parent links exist (l-1 < Lstar)
+                if ((C[i].cube_mask & 1u) == 0 && mine[l - 1][i]) leaf_child[C[i].parent] = (uint32_t)i; // parent = C[i] + {0}: parent links exist (l-1 < Lstar)
         }
         std::vector<uint32_t> first(P.size() + 1, 0), order;
         auto skip = [&](const CubeSet &cs) {
+            if (!mine[l + 1][cs.parent]) return true;   // outside this call's sub-forest
             if (top && fused_root[cs.parent]) return true;
             return (cs.cube_mask & 1u) == 0 && !by_pair_prev.empty() && by_pair_prev[cs.parent] != 0; // scored while its parent was produced
         };
@@ -1410,10 +1422,13 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                      layers[Lstar].size(), tms(T0, T1), C1 - C0, tms(T1, T2), tms(T2, tnow()), cpu_ms() - C0);
     *n_scored = family_size(c, K);
     {
-        double bytes = 0, b = 1;
-        for (int l = 0; l <= K && l <= c; l++) { bytes += b * (double)ctx->n * (l + 1); b = b * (c - l) / (l + 1); }
+        double bytes = 0;
+        uint64_t cnt = 0;
+        for (int l = 0; l <= Kc; l++)
+            for (size_t i = 0; i < layers[l].size(); i++) if (mine[l][i]) { bytes += (double)ctx->n * (l + 1); cnt++; }
         ctx->st.algorithmic_bytes += bytes;
-        ctx->st.sets_scored += *n_scored;
+        ctx->st.sets_scored += cnt;
+        if (parts > 1) *n_scored = cnt;
     }
     *used = true;
     return URLGPU_OK;
@@ -2219,6 +2234,47 @@ extern "C" int urlgpu_score_range(urlgpu_ctx *ctx, int variable, const uint64_t 
     if (rc) return rc;
     if (!on_device) {
         CK(cudaMemcpyAsync(scores, d_out, count * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
+extern "C" int urlgpu_score_part(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type, double lambda,
+                                 int part, int parts, float *scores, int on_device) {
+    if (!ctx || !neighbors || !scores || parts < 1 || part < 0 || part >= parts) return ctx ? ctx->fail(URLGPU_ERR_ARG, "score_part: bad argument") : URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const bool bic = score_type == URLGPU_BIC;
+    std::vector<int> cand;
+    int rc = check_score_args(ctx, "score_part", variable, neighbors, mask_words, score_type, cand);
+    if (rc) return rc;
+    const int c = (int)cand.size();
+    const int K = std::max(0, std::min(max_parents, c));
+    RankSpace rs{};
+    rc = make_rank_space(ctx, c, K, rs);
+    if (rc) return rc;
+    const uint32_t total = rs.layer_base[rs.K + 1];
+    cudaStream_t s = ctx->stream;
+    DevBuf tmp(ctx);
+    float *d_out = scores;
+    if (!on_device) { CK(tmp.alloc((size_t)total * sizeof(float))); d_out = tmp.as<float>(); }
+    fill_u32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(d_out), total, kSentinelBits);
+    bool done = false;
+    if (bic && c <= kMaxDenseCand && ctx->bic_mode == 2) { // the cube path: part = a sub-forest of the root tables
+        uint64_t ns = 0;
+        rc = bic_score_family_cube(ctx, variable, cand, K, d_out, nullptr, &ns, &done, rs, part, parts);
+        if (rc) return rc;
+    }
+    if (!done) { // a contiguous range of the canonical numbering
+        const uint64_t b0 = (uint64_t)total * part / parts, b1 = (uint64_t)total * (part + 1) / parts;
+        if (b1 > b0) {
+            if (bic) rc = bic_score_rank_direct(ctx, variable, cand, rs, (uint32_t)b0, (uint32_t)(b1 - b0), d_out);
+            else rc = cbic_score_rank(ctx, variable, cand, rs, lambda, (uint32_t)b0, (uint32_t)(b1 - b0), d_out, nullptr);
+            if (rc) return rc;
+        }
+    }
+    if (!on_device) {
+        CK(cudaMemcpyAsync(scores, d_out, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     }
     CK(cudaGetLastError());
