@@ -502,6 +502,7 @@ def run_gpu(args):
                                            else "variables striped v % N") + f", N={world}; "
                                           f"{T} context(s)/stream(s) per GPU, one host thread each (the reference's -t workers)",
                            "l2": "flushed between steps (256 MB write)", "dominant_family": dom,
+                           "table16_fallbacks": int(pool.stats().get("table16_fallbacks", 0)) if pool is not None else None,
                            "hbm_in_use_gb": round((mem_total - mem_free) / 1e9, 1)},
                 "e2e": e2e, "gpu_launches": int(launches_total), "clocks": sampler.summary(), "roofline": roofline,
                 "cpu_baseline": cpu, **extra, **({"scaling_strong": strong} if strong else {})}

@@ -176,6 +176,7 @@ typedef struct urlgpu_stats {
     double k1_bytes_read;      /* cube path: bytes the K1 kernels load from global memory (rows + parent tables; L2 may absorb re-reads) */
     double k1_bytes_written;   /* cube path: bytes of contingency tables the K1 kernels store */
     double ms_standardise;     /* K2: column moments + standardisation passes (HBM bound); ms_gram is the DMMA Gram kernel + combine */
+    uint64_t table16_fallbacks; /* K1 cube path: variables recomputed with 32-bit tables because a cell count did not fit 16 bits */
 } urlgpu_stats;
 int urlgpu_stats_reset(urlgpu_ctx *ctx);
 int urlgpu_stats_get(urlgpu_ctx *ctx, urlgpu_stats *out);

@@ -292,3 +292,41 @@ def test_errors_are_loud(pkg, engine):
     engine.set_discrete(codes, [1] * 40)
     with pytest.raises(pkg.UrlGpuError, match="2\\^32 parent sets"):
         engine.score_variable(0, (1 << 40) - 1, 20, pkg.BIC)  # 39 candidates, sets of up to 20: beyond 32-bit ranks
+
+
+def test_speculative_16bit_tables_and_their_fallback(pkg, orc):
+    """cube path: tables of the deep layers are written with uint16 cells; a count that does not fit raises a flag and the
+    variable is recomputed with 32-bit tables.  (a) skewed data whose modal configuration holds > 65535 records: the fallback
+    runs and the cache is still exact; (b) 16-bit cells forced down to layer 1 on ordinary data: exact either way;
+    (c) ordinary data at the default setting: no fallback."""
+    from conftest import engine_with_env
+    rng = np.random.default_rng(8)
+    p, n = 12, 200_003
+    skew = (rng.random((p, n)) < 0.04).astype(np.uint8)            # every column ~96 % zeros: the all-zero configuration is huge
+    skew[:, :3] = np.array([[0, 1, 0]] * p, dtype=np.uint8)        # value 0 appears first in every column
+    card = np.full(p, 2, dtype=np.int32)
+    eng = engine_with_env(pkg, {"URLGPU_BIC_MODE": "cube", "URLGPU_LAYOUT": "dense"})
+    eng.set_discrete(skew, card)
+    eng.reset_stats()
+    for v in (0, 11):
+        _check_variable(pkg, orc, eng, skew, card, None, v, 10)
+        _check_variable(pkg, orc, eng, skew, card, None, v, 10, flags=pkg.PRUNE_DOMINATED)
+    assert eng.stats()["table16_fallbacks"] >= 2
+    eng.close()
+    codes, card2, edges, _ = pkg.datagen.discrete_bn(p=14, n=90001, seed=31, arities=(2, 3, 4), window=6, max_indegree=3)
+    forced = engine_with_env(pkg, {"URLGPU_BIC_MODE": "cube", "URLGPU_TABLE16_MINLAYER": "1"})
+    forced.set_discrete(codes, card2)
+    for v, K in ((2, 9), (11, 8), (5, 10)):
+        _check_variable(pkg, orc, forced, codes, card2, None, v, K)
+    forced.close()
+    plain = engine_with_env(pkg, {"URLGPU_BIC_MODE": "cube"})
+    plain.set_discrete(codes, card2)
+    plain.reset_stats()
+    for v, K in ((2, 9), (7, 11)):
+        _check_variable(pkg, orc, plain, codes, card2, None, v, K, flags=pkg.PRUNE_DOMINATED)
+    assert plain.stats()["table16_fallbacks"] == 0
+    off = engine_with_env(pkg, {"URLGPU_BIC_MODE": "cube", "URLGPU_TABLE16": "0"})
+    off.set_discrete(codes, card2)
+    _check_variable(pkg, orc, off, codes, card2, None, 2, 9)
+    off.close()
+    plain.close()

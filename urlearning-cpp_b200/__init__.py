@@ -52,7 +52,7 @@ class Stats(C.Structure):
         ("ms_prune", C.c_double), ("ms_gram", C.c_double),
         ("sets_scored", C.c_uint64), ("algorithmic_bytes", C.c_double), ("algorithmic_flops", C.c_double), ("gram_flops", C.c_double),
         ("launches_tree", C.c_uint64), ("ms_tree", C.c_double), ("k1_bytes_read", C.c_double), ("k1_bytes_written", C.c_double),
-        ("ms_standardise", C.c_double),
+        ("ms_standardise", C.c_double), ("table16_fallbacks", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -17,6 +17,7 @@
 // (bic_scoring_function.cpp:73).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace urlgpu {
 
@@ -292,7 +293,7 @@ struct CubePair {
     uint32_t acc_index;               // accumulator of the child
     uint32_t leaf;                    // the child has no children of its own (cube bit 0 clear): its table is not written
     uint32_t leaf_acc;                // accumulator of child \ {cube bit 0}, scored in the same pass (kNoLeafAcc: not fused)
-    uint32_t pad;
+    uint32_t fmt;                     // bit 0: the parent table holds uint16 cells, bit 1: the child table does (see "16-bit tables")
 };
 constexpr uint32_t kNoLeafAcc = 0xffffffffu;
 
@@ -323,6 +324,34 @@ __device__ __forceinline__ void store_cfg(int *__restrict__ p, const int (&v)[RV
     }
 }
 
+// 16-bit tables.  At the layers that carry almost all of the cube path's traffic (|S| >= 8 at n = 1e6) a table has far more
+// cells than any cell has records — the largest count in such tables of configs[3] is ~2e4 — so they are written with
+// uint16 cells: half the bytes through HBM for the kernel that is bound by them.  This is SPECULATIVE: a store that
+// would not fit saturates and raises a per-call flag; the caller then discards the variable's scores and recomputes them
+// with 32-bit tables (urlgpu.cu: table16 fallback), so results stay exact for any data.
+template <int RV>
+__device__ __forceinline__ void load_cfg16(const uint16_t *__restrict__ p, int (&v)[RV]) {
+    if constexpr (RV == 4) { const uint2 t = *reinterpret_cast<const uint2 *>(p); v[0] = t.x & 0xffff; v[1] = t.x >> 16; v[2] = t.y & 0xffff; v[3] = t.y >> 16; }
+    else if constexpr (RV == 2) { const uint32_t t = *reinterpret_cast<const uint32_t *>(p); v[0] = t & 0xffff; v[1] = t >> 16; }
+    else {
+#pragma unroll
+        for (int k = 0; k < RV; k++) v[k] = p[k];
+    }
+}
+template <int RV>
+__device__ __forceinline__ bool store_cfg16(uint16_t *__restrict__ p, const int (&v)[RV]) { // true: a count did not fit
+    int mx = v[0];
+#pragma unroll
+    for (int k = 1; k < RV; k++) mx = max(mx, v[k]);
+    if constexpr (RV == 4) *reinterpret_cast<uint2 *>(p) = make_uint2((uint32_t)min(v[0], 65535) | ((uint32_t)min(v[1], 65535) << 16), (uint32_t)min(v[2], 65535) | ((uint32_t)min(v[3], 65535) << 16));
+    else if constexpr (RV == 2) *reinterpret_cast<uint32_t *>(p) = (uint32_t)min(v[0], 65535) | ((uint32_t)min(v[1], 65535) << 16);
+    else {
+#pragma unroll
+        for (int k = 0; k < RV; k++) p[k] = (uint16_t)min(v[k], 65535);
+    }
+    return mx > 65535;
+}
+
 // RV > 0: compile-time child arity (2,3,4); RV == 0: generic arity rv_dyn
 // block -> pair map (one load per block instead of a dependent binary search by thread 0 while 255 threads wait)
 __global__ void cube_map_kernel(const CubePair *__restrict__ pairs, int npairs, uint32_t total, uint32_t *__restrict__ block_pair) {
@@ -340,7 +369,7 @@ template <int RV>
 __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePair *__restrict__ pairs, const uint32_t *__restrict__ block_pair, const int *__restrict__ parent_tab,
                                                                    int *__restrict__ child_tab, int rv_dyn, const long long *__restrict__ qlog,
                                                                    long long *__restrict__ acc_all, int score_child /*0: the children of this launch are ancestors only*/,
-                                                                   int r0 /*arity of cube bit 0*/) {
+                                                                   int r0 /*arity of cube bit 0*/, int *__restrict__ ovf_flag /*16-bit tables: a count did not fit*/) {
     __shared__ long long red[32];
     const CubePair pr = pairs[__ldg(&block_pair[blockIdx.x])];
     const int rv = RV > 0 ? RV : rv_dyn;
@@ -413,37 +442,57 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
                 acc -= __ldg(&qlog[nij]);
             }
         };
-        // kCubeUnroll configurations per thread and iteration: r * kCubeUnroll independent 128-bit loads in flight
-        for (uint32_t j = j0 + threadIdx.x; j < j1; j += kCubeUnroll * kCubeThreads) {
-            uint32_t jj[kCubeUnroll];
-            uint64_t pc[kCubeUnroll];
-            bool on[kCubeUnroll];
-            int cnt[kCubeUnroll][RV];
+        // kCubeUnroll configurations per thread and iteration: r * kCubeUnroll independent 128-bit loads in flight.
+        // P16 / C16 (compile time per instantiation, uniform per block): parent / child table in uint16 cells
+        auto run = [&](auto P16c, auto C16c) {
+            constexpr bool P16 = decltype(P16c)::value, C16 = decltype(C16c)::value;
+            const uint16_t *__restrict__ Ph = reinterpret_cast<const uint16_t *>(P);
+            uint16_t *__restrict__ Ch = reinterpret_cast<uint16_t *>(Cc);
+            bool ovf = false;
+            for (uint32_t j = j0 + threadIdx.x; j < j1; j += kCubeUnroll * kCubeThreads) {
+                uint32_t jj[kCubeUnroll];
+                uint64_t pc[kCubeUnroll];
+                bool on[kCubeUnroll];
+                int cnt[kCubeUnroll][RV];
 #pragma unroll
-            for (int u = 0; u < kCubeUnroll; u++) {
-                jj[u] = j + u * kCubeThreads;
-                on[u] = jj[u] < j1;
-                const uint32_t ju = on[u] ? jj[u] : j;
-                const uint32_t hi = ju / pr.Bc, lo = ju - hi * pr.Bc;
-                pc[u] = (uint64_t)lo + (uint64_t)hi * pr.r * pr.Bc;
+                for (int u = 0; u < kCubeUnroll; u++) {
+                    jj[u] = j + u * kCubeThreads;
+                    on[u] = jj[u] < j1;
+                    const uint32_t ju = on[u] ? jj[u] : j;
+                    const uint32_t hi = ju / pr.Bc, lo = ju - hi * pr.Bc;
+                    pc[u] = (uint64_t)lo + (uint64_t)hi * pr.r * pr.Bc;
+                }
+#pragma unroll
+                for (int u = 0; u < kCubeUnroll; u++) {
+                    if constexpr (P16) load_cfg16<RV>(Ph + pc[u] * RV, cnt[u]); else load_cfg<RV>(P + pc[u] * RV, cnt[u]);
+                }
+                for (uint32_t a = 1; a < pr.r; a++) {
+                    int t[kCubeUnroll][RV];
+#pragma unroll
+                    for (int u = 0; u < kCubeUnroll; u++) {
+                        if constexpr (P16) load_cfg16<RV>(Ph + (pc[u] + (uint64_t)a * pr.Bc) * RV, t[u]); else load_cfg<RV>(P + (pc[u] + (uint64_t)a * pr.Bc) * RV, t[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kCubeUnroll; u++)
+#pragma unroll
+                        for (int k = 0; k < RV; k++) cnt[u][k] += t[u][k];
+                }
+#pragma unroll
+                for (int u = 0; u < kCubeUnroll; u++) {
+                    if (!on[u]) continue;
+                    if (!pr.leaf) {
+                        if constexpr (C16) ovf |= store_cfg16<RV>(Ch + (uint64_t)jj[u] * RV, cnt[u]); else store_cfg<RV>(Cc + (uint64_t)jj[u] * RV, cnt[u]);
+                    }
+                    if (acc_out) score_cfg(cnt[u]);
+                }
             }
-#pragma unroll
-            for (int u = 0; u < kCubeUnroll; u++) load_cfg<RV>(P + pc[u] * RV, cnt[u]);
-            for (uint32_t a = 1; a < pr.r; a++) {
-                int t[kCubeUnroll][RV];
-#pragma unroll
-                for (int u = 0; u < kCubeUnroll; u++) load_cfg<RV>(P + (pc[u] + (uint64_t)a * pr.Bc) * RV, t[u]);
-#pragma unroll
-                for (int u = 0; u < kCubeUnroll; u++)
-#pragma unroll
-                    for (int k = 0; k < RV; k++) cnt[u][k] += t[u][k];
-            }
-#pragma unroll
-            for (int u = 0; u < kCubeUnroll; u++) {
-                if (!on[u]) continue;
-                if (!pr.leaf) store_cfg<RV>(Cc + (uint64_t)jj[u] * RV, cnt[u]);
-                if (acc_out) score_cfg(cnt[u]);
-            }
+            if (ovf) *ovf_flag = 1;
+        };
+        switch (pr.fmt & 3u) {
+        case 0: run(std::false_type{}, std::false_type{}); break;
+        case 1: run(std::true_type{}, std::false_type{}); break;
+        case 2: run(std::false_type{}, std::true_type{}); break;
+        default: run(std::true_type{}, std::true_type{}); break;
         }
         }
     } else {
@@ -451,10 +500,15 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
             const uint32_t hi = j / pr.Bc, lo = j - hi * pr.Bc;
             const uint64_t pc0 = (uint64_t)lo + (uint64_t)hi * pr.r * pr.Bc;
             int nij = 0;
+            const uint16_t *Ph = reinterpret_cast<const uint16_t *>(P);
+            uint16_t *Ch = reinterpret_cast<uint16_t *>(Cc);
             for (int k = 0; k < rv; k++) {
                 int cnt = 0;
-                for (uint32_t a = 0; a < pr.r; a++) cnt += P[(pc0 + (uint64_t)a * pr.Bc) * rv + k];
-                if (!pr.leaf) Cc[(uint64_t)j * rv + k] = cnt;
+                for (uint32_t a = 0; a < pr.r; a++) cnt += (pr.fmt & 1u) ? (int)Ph[(pc0 + (uint64_t)a * pr.Bc) * rv + k] : P[(pc0 + (uint64_t)a * pr.Bc) * rv + k];
+                if (!pr.leaf) {
+                    if (pr.fmt & 2u) { Ch[(uint64_t)j * rv + k] = (uint16_t)min(cnt, 65535); if (cnt > 65535) *ovf_flag = 1; }
+                    else Cc[(uint64_t)j * rv + k] = cnt;
+                }
                 nij += cnt;
                 if (acc_out && cnt > 1) acc += __ldg(&qlog[cnt]);
             }

@@ -481,6 +481,8 @@ struct CubeRoot {
     uint32_t child_acc[kRootMaxChild];       // and its accumulator
     uint32_t nchild;                         // fused: children drop bit b, bfirst <= b < nchild (== run length)
     uint16_t bfirst, score;                  // layers above K only hold sets with their lowest bits forced: the first droppable bit; score the children?
+    uint32_t child16;                        // bit b: child b's table holds uint16 cells (bic_kernels.cuh, "16-bit tables")
+    uint32_t pad16;
 };
 
 __global__ void root_map_kernel(const CubeRoot *__restrict__ roots, int nroots, uint32_t total, uint32_t *__restrict__ cta_root) {
@@ -497,7 +499,8 @@ __global__ void root_map_kernel(const CubeRoot *__restrict__ roots, int nroots, 
 template <int RV, int NW>
 __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const CubeRoot *__restrict__ roots, const uint32_t *__restrict__ cta_root,
                                                                 const long long *__restrict__ qlog, int *__restrict__ tables, int *__restrict__ child_tables,
-                                                                long long *__restrict__ acc_out, uint32_t table_budget /*cells*/, uint32_t seg_cap) {
+                                                                long long *__restrict__ acc_out, uint32_t table_budget /*cells*/, uint32_t seg_cap,
+                                                                int *__restrict__ ovf_flag) {
     extern __shared__ __align__(16) int s_dyn[];              // [table_budget] slice table, then segbeg[seg_cap], segoff[seg_cap + 1]
     __shared__ CubeRoot cr;
     __shared__ uint16_t s_lut[8 * 256];
@@ -615,8 +618,11 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
     for (int b = cr.bfirst; b < z; b++) {
         const uint32_t r = tv.card[b], pre = tv.pre[b], magic = tv.magic[b];
         const uint32_t cfg_dst = fast_div(cfg_src, r, tv.cmagic[b]); // r divides the run product: exact
-        int *dst = child_tables + cr.child_off[b] + (unsigned long long)si * ((unsigned long long)cfg_dst * rv);
+        const bool c16 = (cr.child16 >> b) & 1u;
+        int *dst = child_tables + cr.child_off[b] + (c16 ? 0ull : (unsigned long long)si * ((unsigned long long)cfg_dst * rv));
+        uint16_t *dst16 = reinterpret_cast<uint16_t *>(child_tables + cr.child_off[b]) + (unsigned long long)si * ((unsigned long long)cfg_dst * rv);
         const bool store = b > 0;
+        bool ovf = false;
         long long acc = 0;
         if constexpr (RV > 0) {
             // R = compile-time arity of the digit summed out (2, 3, 4), 0 = run-time loop
@@ -643,7 +649,10 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
                             for (int k = 0; k < RV; k++) cnt[k] += t[k];
                         }
                     }
-                    if (store) store_cfg<RV>(dst + (size_t)j * RV, cnt);
+                    if (store) {
+                        if (c16) ovf |= store_cfg16<RV>(dst16 + (size_t)j * RV, cnt);
+                        else store_cfg<RV>(dst + (size_t)j * RV, cnt);
+                    }
                     int nij = 0;
 #pragma unroll
                     for (int k = 0; k < RV; k++) nij += cnt[k];
@@ -669,13 +678,17 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
                 for (int k = 0; k < rv; k++) {
                     int cnt = 0;
                     for (uint32_t a = 0; a < r; a++) cnt += s_dyn[(size_t)(p0 + a * pre) * rv + k];
-                    if (store) dst[(size_t)j * rv + k] = cnt;
+                    if (store) {
+                        if (c16) { dst16[(size_t)j * rv + k] = (uint16_t)min(cnt, 65535); ovf |= cnt > 65535; }
+                        else dst[(size_t)j * rv + k] = cnt;
+                    }
                     nij += cnt;
                     if (score && cnt > 1) acc += __ldg(&qlog[cnt]);
                 }
                 if (score && nij > 1) acc -= __ldg(&qlog[nij]);
             }
         }
+        if (ovf) *ovf_flag = 1;
         if (score) { // no barrier between children: every warp adds its exact partial sum to the child's shared accumulator
             acc = warp_sum_ll_redux(acc);
             if (lane == 0 && acc != 0) atomicAdd(&s_cacc[b], (unsigned long long)acc);

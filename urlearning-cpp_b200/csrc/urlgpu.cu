@@ -80,6 +80,10 @@ struct urlgpu_ctx {
     // 16 % fewer issued bytes, but measured neutral to slightly slower at config 4 (the saved reads were L2 hits; the grouped
     // access pattern halves the sector efficiency of each load), so off by default
     bool fuse_leaves = false;
+    // cube path: tables of layers >= table16_min_layer are written with uint16 cells, speculatively (URLGPU_TABLE16=0 disables,
+    // URLGPU_TABLE16_MINLAYER sets the layer); a count that does not fit flags the call and the variable is recomputed in 32 bits
+    bool table16 = true;
+    int table16_min_layer = 8;
     uint32_t root_budget = 24 * 1024; // cells of a root slice (URLGPU_ROOT_BUDGET): 96 KB + segment tables, two 512-thread CTAs per SM
     uint32_t root_seg_cap = 1024;     // row segments of a slice kept in shared memory (URLGPU_ROOT_SEGS)
     int root_warps = 16;              // warps per CTA of bic_root_kernel (URLGPU_ROOT_WARPS = 8, 12 or 16)
@@ -271,6 +275,11 @@ struct urlgpu_result {
     float *d_table = nullptr;       // dense layout: 2^c floats by compact mask; rank layout: rs.layer_base[K+1] floats by colex index
     bool rank_layout = false;
     RankSpace rs{};
+    // speculative 16-bit tables (cube path): d_ovf is raised by a count that did not fit; checked when the result is first
+    // read (the flag travels with the compaction counters), and the variable is then recomputed with 32-bit tables
+    int *d_ovf = nullptr;
+    bool is_bic = false;
+    unsigned filter_flags = 0;
     uint64_t n_masks = 0, n_scored = 0;   // n_masks = entries of d_table
     // compaction into canonical order (|S|, mask): enqueued on the context's stream by urlgpu_result_prefetch, no host sync
     bool prefetched = false, counted = false;
@@ -324,6 +333,8 @@ extern "C" int urlgpu_create(urlgpu_ctx **out, int device_id) {
     if (const char *m = getenv("URLGPU_SLICE_COUNT")) ctx->use_slice_count = atoi(m) != 0;
     if (const char *m = getenv("URLGPU_FUSE_ROOTS")) ctx->fuse_roots = atoi(m) != 0;
     if (const char *m = getenv("URLGPU_FUSE_LEAVES")) ctx->fuse_leaves = atoi(m) != 0;
+    if (const char *m = getenv("URLGPU_TABLE16")) ctx->table16 = atoi(m) != 0;
+    if (const char *m = getenv("URLGPU_TABLE16_MINLAYER")) ctx->table16_min_layer = std::max(1, atoi(m));
     if (const char *m = getenv("URLGPU_ROOT_BUDGET")) ctx->root_budget = (uint32_t)std::max(1024, std::min(atoi(m), 48 * 1024)) / 4 * 4;
     if (const char *m = getenv("URLGPU_ROOT_SEGS")) ctx->root_seg_cap = (uint32_t)std::max(32, std::min(atoi(m), 8192));
     if (const char *m = getenv("URLGPU_ROOT_WARPS")) ctx->root_warps = atoi(m) == 8 ? 8 : atoi(m) == 12 ? 12 : 16;
@@ -850,6 +861,7 @@ struct CubeSet {
     uint64_t cells, off;
     int parent;       // index in the layer above
     uint32_t Bc, r;
+    bool t16;         // the table is stored with uint16 cells
 };
 inline uint32_t gosper_next(uint32_t v) {
     const uint32_t t = (v | (v - 1)) + 1;
@@ -903,7 +915,7 @@ static int h2d_async(urlgpu_ctx *ctx, void *dst, const void *src, size_t bytes) 
 // part / parts: score only the sub-forest of the roots i with i % parts == part (and everything derived from them); the parts
 // are disjoint and cover the family (urlgpu_score_part: one variable's K1 work split over several GPUs)
 static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                                 uint64_t *n_scored, bool *used, const RankSpace &om, int part = 0, int parts = 1) {
+                                 uint64_t *n_scored, bool *used, const RankSpace &om, int part = 0, int parts = 1, int *d_ovf = nullptr) {
     *used = false;
     cudaStream_t s = ctx->stream;
     { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
@@ -1096,15 +1108,18 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     // Layer Lstar lives in buffer A, Lstar-1 in B, Lstar-2 in A again, ...: each buffer is sized for its own layers only.
     // Tables that are never materialised take no room: fused roots, and below the root layer every set without cube
     // bit 0 (nothing is derived from it, its table is only scored on the fly).
+    const bool use16 = ctx->table16 && d_ovf != nullptr && !ctx->fuse_leaves;
     size_t needA = 0, needB = 0;
     for (int l = 0; l <= Lstar; l++) {
         uint64_t off = 0;
         for (size_t i = 0; i < layers[l].size(); i++) {
             auto &cs = layers[l][i];
             cs.off = off;
+            cs.t16 = false;
             if (l == Lstar && root_kind[i] == 2) continue;          // fused root
             if (l < Lstar && (cs.cube_mask & 1u) == 0) continue;    // leaf
-            off += (cs.cells + 3) / 4 * 4;
+            cs.t16 = use16 && l < Lstar && l >= ctx->table16_min_layer;   // root tables stay int32 (several kernels write them)
+            off += cs.t16 ? ((cs.cells + 1) / 2 + 3) / 4 * 4 : (cs.cells + 3) / 4 * 4;
         }
         if (((Lstar - l) & 1) == 0) needA = std::max<size_t>(needA, off); else needB = std::max<size_t>(needB, off);
         if (l < Lstar) {
@@ -1237,7 +1252,8 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                             if (it == Lc.end() || it->cube_mask != cm) return ctx->fail(URLGPU_ERR_INTERNAL, "cube: child of a fused root missing");
                             cr.child_off[b] = it->off;
                             cr.child_acc[b] = (uint32_t)(it - Lc.begin());
-                            if (b > 0) ctx->st.k1_bytes_written += 4.0 * (double)it->cells; // only children that have children of their own are stored
+                            if (it->t16) cr.child16 |= 1u << b;
+                            if (b > 0) ctx->st.k1_bytes_written += (it->t16 ? 2.0 : 4.0) * (double)it->cells; // only children that have children of their own are stored
                         }
                         fused_root[big_idx[i]] = 1;
                     } else cr.table_off = big[i].table_off;
@@ -1278,7 +1294,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 const size_t smem = ((size_t)RB + 2 * seg_cap + 1) * sizeof(int);
                 const unsigned grid = (unsigned)rchunk;
                 switch (rv) {
-#define URLGPU_ROOT_ARGS tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, bufP, bufC, dacc.as<long long>() + acc_off[Lstar > 0 ? Lstar - 1 : 0], RB, seg_cap
+#define URLGPU_ROOT_ARGS tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, bufP, bufC, dacc.as<long long>() + acc_off[Lstar > 0 ? Lstar - 1 : 0], RB, seg_cap, d_ovf
 #define URLGPU_ROOT(RVV)                                                                             \
     do {                                                                                             \
         if (ctx->root_warps == 8) bic_root_kernel<RVV, 8><<<grid, 256, smem, s>>>(URLGPU_ROOT_ARGS); \
@@ -1387,12 +1403,13 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             pr.acc_index = (uint32_t)(acc_off[l] + order[k]);
             pr.leaf = (cs.cube_mask & 1u) == 0; // lowest missing bit is 0: nothing is derived from this set
             pr.leaf_acc = kNoLeafAcc;
+            pr.fmt = (P[cs.parent].t16 ? 1u : 0u) | (cs.t16 ? 2u : 0u);
             if (!pr.leaf && leaf_child[order[k]] != kNoLeafAcc) {
                 pr.leaf_acc = (uint32_t)(acc_off[l - 1] + leaf_child[order[k]]);
                 by_pair[order[k]] = 1;
             }
-            ctx->st.k1_bytes_read += 4.0 * (double)cs.cells * (double)cs.r;
-            if (!pr.leaf) ctx->st.k1_bytes_written += 4.0 * (double)cs.cells;
+            ctx->st.k1_bytes_read += (P[cs.parent].t16 ? 2.0 : 4.0) * (double)cs.cells * (double)cs.r;
+            if (!pr.leaf) ctx->st.k1_bytes_written += (cs.t16 ? 2.0 : 4.0) * (double)cs.cells;
             const uint32_t cpb = cube_configs_per_block(pr.leaf_acc != kNoLeafAcc ? (uint32_t)r0 : 1u);
             chunk += (pr.child_configs + cpb - 1) / cpb;
             hp[k] = pr;
@@ -1407,10 +1424,10 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             const unsigned grid = (unsigned)chunk;
             cube_map_kernel<<<blocks_for(chunk, 256), 256, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), grid, dcmap.as<uint32_t>());
             switch (rv) {
-            case 2: cube_derive_kernel<2><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0); break;
-            case 3: cube_derive_kernel<3><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0); break;
-            case 4: cube_derive_kernel<4><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0); break;
-            default: cube_derive_kernel<0><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0); break;
+            case 2: cube_derive_kernel<2><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf); break;
+            case 3: cube_derive_kernel<3><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf); break;
+            case 4: cube_derive_kernel<4><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf); break;
+            default: cube_derive_kernel<0><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf); break;
             }
         }
         if (score) { int rc = finalize_layer(l); if (rc) return rc; }
@@ -1439,7 +1456,7 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
 
 // c <= 30 candidates: the mask-based K1 strategies; `om` says where a set's score goes (dense by mask, or rank space)
 static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
-                            uint64_t *n_scored, const RankSpace &om) {
+                            uint64_t *n_scored, const RankSpace &om, int *d_ovf = nullptr) {
     if (ctx->bic_mode == 0) {
         bool used = false;
         int rc = bic_score_family_tree(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used, om);
@@ -1447,7 +1464,7 @@ static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int
     }
     if (ctx->bic_mode != 1) {
         bool used = false;
-        int rc = bic_score_family_cube(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used, om);
+        int rc = bic_score_family_cube(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used, om, 0, 1, d_ovf);
         if (rc || used) return rc;
     }
     return bic_score_family_direct(ctx, variable, cand, K, d_table, d_llfixed, n_scored, om);
@@ -2164,7 +2181,13 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     cudaError_t e = pool_alloc(ctx, reinterpret_cast<void **>(&res->d_table), res->n_masks * sizeof(float));
     if (e != cudaSuccess) { delete res; return ctx->cuda_fail(e, "cudaMalloc(score table)", __LINE__); }
     cudaStream_t s = ctx->stream;
-    auto cleanup = [&](int code) { pool_free(ctx, res->d_table); delete res; return code; };
+    auto cleanup = [&](int code) { pool_free(ctx, res->d_table); if (res->d_ovf) pool_free(ctx, res->d_ovf); delete res; return code; };
+    res->is_bic = bic; res->filter_flags = filter_flags;
+    if (bic && ctx->table16 && c <= kMaxDenseCand && ctx->bic_mode == 2) {
+        e = pool_alloc(ctx, reinterpret_cast<void **>(&res->d_ovf), sizeof(int));
+        if (e != cudaSuccess) return cleanup(ctx->cuda_fail(e, "cudaMalloc(flag)", __LINE__));
+        cudaMemsetAsync(res->d_ovf, 0, sizeof(int), s);
+    }
     const double t_alloc = since(T0);
     if (rank) {
         const uint32_t total = (uint32_t)res->n_masks;
@@ -2172,12 +2195,12 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
         if (bic) {
             if (c <= kMaxDenseCand) { // the mask-based K1 strategies, writing by rank
                 fill_u32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), total, kSentinelBits);
-                rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored, res->rs);
+                rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored, res->rs, res->d_ovf);
             } else rc = bic_score_rank_direct(ctx, variable, cand, res->rs, 0, total, res->d_table);
         } else rc = cbic_score_rank(ctx, variable, cand, res->rs, lambda, 0, total, res->d_table, nullptr);
     } else {
         fill_u32_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), res->n_masks, kSentinelBits);
-        if (bic) rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored, RankSpace{});
+        if (bic) rc = bic_score_family(ctx, variable, cand, K, res->d_table, nullptr, &res->n_scored, RankSpace{}, res->d_ovf);
         else rc = cbic_score_family(ctx, variable, cand, K, lambda, res->d_table, nullptr, &res->n_scored);
     }
     if (rc) return cleanup(rc);
@@ -2262,8 +2285,21 @@ extern "C" int urlgpu_score_part(urlgpu_ctx *ctx, int variable, const uint64_t *
     bool done = false;
     if (bic && c <= kMaxDenseCand && ctx->bic_mode == 2) { // the cube path: part = a sub-forest of the root tables
         uint64_t ns = 0;
-        rc = bic_score_family_cube(ctx, variable, cand, K, d_out, nullptr, &ns, &done, rs, part, parts);
+        DevBuf flag(ctx);
+        if (ctx->table16) { CK(flag.alloc(sizeof(int))); CK(cudaMemsetAsync(flag.p, 0, sizeof(int), s)); }
+        rc = bic_score_family_cube(ctx, variable, cand, K, d_out, nullptr, &ns, &done, rs, part, parts, flag.as<int>());
         if (rc) return rc;
+        if (done && flag.p) { // 16-bit tables are speculative: check now (this entry point hands raw scores out)
+            int h = 0;
+            CK(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (h) {
+                ctx->st.table16_fallbacks++;
+                fill_u32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(d_out), total, kSentinelBits);
+                rc = bic_score_family_cube(ctx, variable, cand, K, d_out, nullptr, &ns, &done, rs, part, parts, nullptr);
+                if (rc) return rc;
+            }
+        }
     }
     if (!done) { // a contiguous range of the canonical numbering
         const uint64_t b0 = (uint64_t)total * part / parts, b1 = (uint64_t)total * (part + 1) / parts;
@@ -2437,7 +2473,8 @@ static int result_prefetch_impl(urlgpu_result *res) {
     CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_segcnt), (size_t)(res->rank_layout ? 1 : 32) * nseg * sizeof(uint32_t)));
     CK(pool_alloc(ctx, reinterpret_cast<void **>(&res->d_counts), (33 + 32) * sizeof(unsigned long long)));
     if (!ctx->free_pinned.empty()) { res->h_counts = ctx->free_pinned.back(); ctx->free_pinned.pop_back(); }
-    else CK(cudaHostAlloc(reinterpret_cast<void **>(&res->h_counts), 33 * sizeof(unsigned long long), cudaHostAllocDefault));
+    else CK(cudaHostAlloc(reinterpret_cast<void **>(&res->h_counts), 34 * sizeof(unsigned long long), cudaHostAllocDefault));
+    res->h_counts[33] = 0;
     res->ready = get_event(ctx);
     if (res->rank_layout) { // index order is the canonical order: one order-preserving compaction of the whole table
         Region rg(ctx, F_OTHER, 3);
@@ -2454,6 +2491,7 @@ static int result_prefetch_impl(urlgpu_result *res) {
         compact_write_kernel<<<nseg, kCompactThreads, 0, s>>>(res->d_table, res->n_masks, nseg, res->d_segcnt, res->d_counts + 33, res->d_masks, res->d_vals);
     }
     CK(cudaMemcpyAsync(res->h_counts, res->d_counts, 33 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if (res->d_ovf) CK(cudaMemcpyAsync(&res->h_counts[33], res->d_ovf, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(res->ready, s));
     CK(cudaGetLastError());
     res->prefetched = true;
@@ -2466,6 +2504,31 @@ static int result_wait_counts(urlgpu_result *res) {
     int rc = result_prefetch_impl(res);
     if (rc) return rc;
     CK(cudaEventSynchronize(res->ready));
+    if (res->d_ovf && (res->h_counts[33] & 0xffffffffull) != 0) {
+        // a cell count did not fit 16 bits somewhere in this variable's tables: the scores are discarded and the family is
+        // recomputed with 32-bit tables on the result's own table, then filtered and compacted again
+        ctx->st.table16_fallbacks++;
+        pool_free(ctx, res->d_ovf);
+        res->d_ovf = nullptr;
+        res->h_counts[33] = 0;
+        pool_free(ctx, res->d_masks); pool_free(ctx, res->d_vals); pool_free(ctx, res->d_segcnt); pool_free(ctx, res->d_counts);
+        res->d_masks = nullptr; res->d_vals = nullptr; res->d_segcnt = nullptr; res->d_counts = nullptr;
+        ctx->free_events.push_back(res->ready);
+        res->ready = nullptr;
+        ctx->free_pinned.push_back(res->h_counts);
+        res->h_counts = nullptr;
+        cudaStream_t s = ctx->stream;
+        fill_u32_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), res->n_masks, kSentinelBits);
+        uint64_t ns = 0;
+        rc = bic_score_family(ctx, res->variable, res->cand, res->max_parents, res->d_table, nullptr, &ns, res->rank_layout ? res->rs : RankSpace{}, nullptr);
+        if (rc) return rc;
+        rc = apply_filters(ctx, res, true, res->filter_flags);
+        if (rc) return rc;
+        res->prefetched = false;
+        rc = result_prefetch_impl(res);
+        if (rc) return rc;
+        CK(cudaEventSynchronize(res->ready));
+    }
     res->n_stored = res->h_counts[32];
     for (int l = 0; l < 32; l++) res->layer_count[l] = res->h_counts[l];
     if (res->n_stored > std::min<uint64_t>(res->n_scored, res->n_masks)) return ctx->fail(URLGPU_ERR_INTERNAL, "result: more stored entries than scored sets");
@@ -2539,6 +2602,7 @@ extern "C" int urlgpu_result_free(urlgpu_result *res) {
     cudaSetDevice(ctx->device);
     // stream-ordered reuse: the pool hands these blocks to later work on the same stream, no sync needed
     if (res->d_table) pool_free(ctx, res->d_table);
+    if (res->d_ovf) pool_free(ctx, res->d_ovf);
     if (res->d_masks) pool_free(ctx, res->d_masks);
     if (res->d_vals) pool_free(ctx, res->d_vals);
     if (res->d_segcnt) pool_free(ctx, res->d_segcnt);
