@@ -428,6 +428,7 @@ def run_gpu(args):
                   "parallelism": f"configs[3] itself: codes broadcast over NCCL, 60 variables dealt to {world} ranks by predicted cost (LPT), caches gathered to rank 0"}
 
     mem_free, mem_total = torch.cuda.mem_get_info()
+    t16_fallbacks = int(pool.stats().get("table16_fallbacks", 0))   # after the e2e arm, which reads every cache (the flag is checked on first read)
     if rank == 0:
         peak, peak_src = load_peaks()
         fam = {"count": st["ms_count"], "cube": st["ms_cube"], "tree": st["ms_tree"], "cbic": st["ms_cbic"], "accept": st["ms_accept"],
@@ -502,7 +503,7 @@ def run_gpu(args):
                                            else "variables striped v % N") + f", N={world}; "
                                           f"{T} context(s)/stream(s) per GPU, one host thread each (the reference's -t workers)",
                            "l2": "flushed between steps (256 MB write)", "dominant_family": dom,
-                           "table16_fallbacks": int(pool.stats().get("table16_fallbacks", 0)) if pool is not None else None,
+                           "table16_fallbacks": t16_fallbacks,
                            "hbm_in_use_gb": round((mem_total - mem_free) / 1e9, 1)},
                 "e2e": e2e, "gpu_launches": int(launches_total), "clocks": sampler.summary(), "roofline": roofline,
                 "cpu_baseline": cpu, **extra, **({"scaling_strong": strong} if strong else {})}

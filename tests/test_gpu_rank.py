@@ -229,8 +229,8 @@ def test_family_parts_merge_to_the_whole(pkg):
             bits = np.stack([a.view(np.uint32) for a in arrs])
             scored = bits != NOT_SCORED
             assert np.all(scored.sum(axis=0) == 1), "every set belongs to exactly one part"
-            if st == pkg.BIC and K >= 9:
-                assert all(s.sum() > 0 for s in scored), "no empty part for a big family"
+            if st == pkg.BIC and parts == 2 and total > 50000:
+                assert all(s.sum() > total // 8 for s in scored), "both halves of a big family carry a real share of it"
             merged = np.min(np.stack([a.view(np.int32) for a in arrs]), axis=0).view(np.float32)
             for flags in (0, pkg.PRUNE_DOMINATED):
                 want = eng.score_variable(v, nb, K, st, lam=2.0, flags=flags)

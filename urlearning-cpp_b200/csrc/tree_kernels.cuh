@@ -500,11 +500,13 @@ template <int RV, int NW>
 __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const CubeRoot *__restrict__ roots, const uint32_t *__restrict__ cta_root,
                                                                 const long long *__restrict__ qlog, int *__restrict__ tables, int *__restrict__ child_tables,
                                                                 long long *__restrict__ acc_out, uint32_t table_budget /*cells*/, uint32_t seg_cap,
-                                                                int *__restrict__ ovf_flag) {
+                                                                int *__restrict__ ovf_flag, int qn /*entries of qlog*/) {
     extern __shared__ __align__(16) int s_dyn[];              // [table_budget] slice table, then segbeg[seg_cap], segoff[seg_cap + 1]
     __shared__ CubeRoot cr;
     __shared__ uint16_t s_lut[8 * 256];
     __shared__ unsigned long long s_cacc[kRootMaxChild]; // per-child exact sums of this CTA
+    constexpr int kQRoot = 256;                          // two CTAs of this kernel share an SM's shared memory: a 2 KB cache
+    __shared__ long long s_q[kQRoot];                    // qlog[0 .. kQRoot) (bic_kernels.cuh: the score gather)
     constexpr int kRootThreads = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rv = RV > 0 ? RV : tv.rv;
@@ -517,6 +519,7 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
     __syncthreads();
     const TreeRoot &rt = cr.t;
     const int z = rt.z;
+    if (cr.nchild != 0 && cr.score != 0) qcache_load<kQRoot>(s_q, qlog, qn);   // visible after the barriers of the counting phase
     if (tid < kRootMaxChild) s_cacc[tid] = 0;
     const uint32_t S0 = rt.H * (uint32_t)rv * tv.pre[z];
     const uint32_t si = blockIdx.x - rt.chunk0;
@@ -659,8 +662,8 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
                     if (score && nij > 1) {
 #pragma unroll
                         for (int k = 0; k < RV; k++)
-                            if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
-                        acc -= __ldg(&qlog[nij]);
+                            if (cnt[k] > 1) acc += qlog_at<kQRoot>(s_q, qlog, cnt[k]);
+                        acc -= qlog_at<kQRoot>(s_q, qlog, nij);
                     }
                 }
             };

@@ -1294,7 +1294,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 const size_t smem = ((size_t)RB + 2 * seg_cap + 1) * sizeof(int);
                 const unsigned grid = (unsigned)rchunk;
                 switch (rv) {
-#define URLGPU_ROOT_ARGS tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, bufP, bufC, dacc.as<long long>() + acc_off[Lstar > 0 ? Lstar - 1 : 0], RB, seg_cap, d_ovf
+#define URLGPU_ROOT_ARGS tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, bufP, bufC, dacc.as<long long>() + acc_off[Lstar > 0 ? Lstar - 1 : 0], RB, seg_cap, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)
 #define URLGPU_ROOT(RVV)                                                                             \
     do {                                                                                             \
         if (ctx->root_warps == 8) bic_root_kernel<RVV, 8><<<grid, 256, smem, s>>>(URLGPU_ROOT_ARGS); \
@@ -1404,6 +1404,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             pr.leaf = (cs.cube_mask & 1u) == 0; // lowest missing bit is 0: nothing is derived from this set
             pr.leaf_acc = kNoLeafAcc;
             pr.fmt = (P[cs.parent].t16 ? 1u : 0u) | (cs.t16 ? 2u : 0u);
+            pr.magic = pr.Bc > 1 ? 0xFFFFFFFFu / pr.Bc : 0;
             if (!pr.leaf && leaf_child[order[k]] != kNoLeafAcc) {
                 pr.leaf_acc = (uint32_t)(acc_off[l - 1] + leaf_child[order[k]]);
                 by_pair[order[k]] = 1;
@@ -1424,10 +1425,10 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             const unsigned grid = (unsigned)chunk;
             cube_map_kernel<<<blocks_for(chunk, 256), 256, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), grid, dcmap.as<uint32_t>());
             switch (rv) {
-            case 2: cube_derive_kernel<2><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf); break;
-            case 3: cube_derive_kernel<3><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf); break;
-            case 4: cube_derive_kernel<4><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf); break;
-            default: cube_derive_kernel<0><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf); break;
+            case 2: cube_derive_kernel<2><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
+            case 3: cube_derive_kernel<3><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
+            case 4: cube_derive_kernel<4><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
+            default: cube_derive_kernel<0><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
             }
         }
         if (score) { int rc = finalize_layer(l); if (rc) return rc; }
