@@ -274,19 +274,6 @@ __global__ void bic_store_rule_kernel(float *__restrict__ scores, uint64_t n_mas
 }
 
 
-// The score of a table is a gather from qlog[] by cell count.  Through L1 a warp-wide gather with 32 different addresses is
-// served sector by sector; most counts at the deep layers are tiny, so the first kQCache entries are kept in shared memory
-// (32 banks: full rate, equal addresses broadcast) and only larger counts go to the global table.
-constexpr int kQCache = 512;
-template <int N = kQCache>
-__device__ __forceinline__ void qcache_load(long long *s_q, const long long *__restrict__ qlog, int qn /*entries of qlog*/) {
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s_q[i] = i < qn ? __ldg(&qlog[i]) : 0;
-}
-template <int N = kQCache>
-__device__ __forceinline__ long long qlog_at(const long long *s_q, const long long *__restrict__ qlog, int cnt) {
-    return cnt < N ? s_q[cnt] : __ldg(&qlog[cnt]);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // K1 "cube": derive a child table by summing one parent digit out, and score it in the same pass.
 //
@@ -387,8 +374,7 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
                                                                    int r0 /*arity of cube bit 0*/, int *__restrict__ ovf_flag /*16-bit tables: a count did not fit*/,
                                                                    int qn /*entries of qlog*/) {
     __shared__ long long red[32];
-    __shared__ long long s_q[kQCache];
-    if (score_child) { qcache_load(s_q, qlog, qn); __syncthreads(); }
+    (void)qn;
     const CubePair pr = pairs[__ldg(&block_pair[blockIdx.x])];
     const int rv = RV > 0 ? RV : rv_dyn;
     long long *__restrict__ acc_out = score_child ? acc_all : nullptr;
@@ -456,8 +442,8 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
             if (nij > 1) { // q[0] = q[1] = 0
 #pragma unroll
                 for (int k = 0; k < RV; k++)
-                    if (cnt[k] > 1) acc += qlog_at(s_q, qlog, cnt[k]);
-                acc -= qlog_at(s_q, qlog, nij);
+                    if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
+                acc -= __ldg(&qlog[nij]);
             }
         };
         // kCubeUnroll configurations per thread and iteration: r * kCubeUnroll independent 128-bit loads in flight.

@@ -505,8 +505,6 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
     __shared__ CubeRoot cr;
     __shared__ uint16_t s_lut[8 * 256];
     __shared__ unsigned long long s_cacc[kRootMaxChild]; // per-child exact sums of this CTA
-    constexpr int kQRoot = 256;                          // two CTAs of this kernel share an SM's shared memory: a 2 KB cache
-    __shared__ long long s_q[kQRoot];                    // qlog[0 .. kQRoot) (bic_kernels.cuh: the score gather)
     constexpr int kRootThreads = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rv = RV > 0 ? RV : tv.rv;
@@ -519,7 +517,7 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
     __syncthreads();
     const TreeRoot &rt = cr.t;
     const int z = rt.z;
-    if (cr.nchild != 0 && cr.score != 0) qcache_load<kQRoot>(s_q, qlog, qn);   // visible after the barriers of the counting phase
+    (void)qn;
     if (tid < kRootMaxChild) s_cacc[tid] = 0;
     const uint32_t S0 = rt.H * (uint32_t)rv * tv.pre[z];
     const uint32_t si = blockIdx.x - rt.chunk0;
@@ -662,8 +660,8 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
                     if (score && nij > 1) {
 #pragma unroll
                         for (int k = 0; k < RV; k++)
-                            if (cnt[k] > 1) acc += qlog_at<kQRoot>(s_q, qlog, cnt[k]);
-                        acc -= qlog_at<kQRoot>(s_q, qlog, nij);
+                            if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
+                        acc -= __ldg(&qlog[nij]);
                     }
                 }
             };
