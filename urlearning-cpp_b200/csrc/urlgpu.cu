@@ -927,7 +927,13 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     const auto T0 = tnow();
     const int c = (int)cand.size();
     const int Kc = std::min(K, c);
-    const int rv = ctx->card[variable];
+    // Table layout arity.  A child of arity 3 is laid out as if it had a fourth value that never occurs: configurations are then
+    // 16 bytes (8 in uint16 tables) and every kernel of this path moves them with one aligned vector access per lane.  With
+    // 12-byte configurations each lane issued three scalar accesses and L1 fetched every sector three times (ncu: 9 of 32
+    // bytes used per sector, L1/TEX throughput 90 % — the limiter of cube_derive_kernel<3>).  The empty cells contribute nothing
+    // to any sum; the penalty uses the true arity (cube_finalize_kernel, ci_res).  URLGPU_PAD3=0 restores 12-byte configurations.
+    static const bool pad3 = !(getenv("URLGPU_PAD3") && atoi(getenv("URLGPU_PAD3")) == 0);
+    const int rv = (ctx->card[variable] == 3 && pad3) ? 4 : ctx->card[variable];
     const uint64_t n = (uint64_t)ctx->n;
     if (c == 0) return URLGPU_OK; // only the empty set: the direct path handles it
     // cube order: ascending arity, ties by variable index
@@ -939,6 +945,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     for (int i = 0; i < c; i++) { cube_vars[i] = cand[perm[i]]; ccard[i] = (uint64_t)ctx->card[cube_vars[i]]; }
     for (int i = 0; i < c; i++) prefix[i + 1] = std::min<uint64_t>(prefix[i] * ccard[i], (uint64_t)1 << 40);
     CandInfo ci_cube = make_candinfo(ctx, variable, cube_vars, K);
+    ci_cube.rv = rv;                               // layout arity: the counting kernels index x_v + rv * paIdx
     CandInfo ci_res = make_candinfo(ctx, variable, cand, K);
     BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
     const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
