@@ -927,12 +927,13 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     const auto T0 = tnow();
     const int c = (int)cand.size();
     const int Kc = std::min(K, c);
-    // Table layout arity.  A child of arity 3 is laid out as if it had a fourth value that never occurs: configurations are then
-    // 16 bytes (8 in uint16 tables) and every kernel of this path moves them with one aligned vector access per lane.  With
-    // 12-byte configurations each lane issued three scalar accesses and L1 fetched every sector three times (ncu: 9 of 32
-    // bytes used per sector, L1/TEX throughput 90 % — the limiter of cube_derive_kernel<3>).  The empty cells contribute nothing
-    // to any sum; the penalty uses the true arity (cube_finalize_kernel, ci_res).  URLGPU_PAD3=0 restores 12-byte configurations.
-    static const bool pad3 = !(getenv("URLGPU_PAD3") && atoi(getenv("URLGPU_PAD3")) == 0);
+    // Table layout arity (opt-in, URLGPU_PAD3=1).  A child of arity 3 can be laid out as if it had a fourth value that never occurs:
+    // configurations are then 16 bytes (8 in uint16 tables) and every kernel of this path moves them with one aligned vector
+    // access per lane instead of three scalar ones (ncu on the 12-byte layout: 9 of 32 bytes used per L1 sector).  The empty
+    // cells contribute nothing to any sum; the penalty uses the true arity (cube_finalize_kernel, ci_res).  Bit-exact, but
+    // measured slower at configs[3] (301 -> 332 ms per step): the kernels are bound by instruction issue, not by L1 sectors,
+    // and a third more cells are walked and a third more root slices counted.  Off by default.
+    static const bool pad3 = getenv("URLGPU_PAD3") && atoi(getenv("URLGPU_PAD3")) != 0;
     const int rv = (ctx->card[variable] == 3 && pad3) ? 4 : ctx->card[variable];
     const uint64_t n = (uint64_t)ctx->n;
     if (c == 0) return URLGPU_OK; // only the empty set: the direct path handles it
