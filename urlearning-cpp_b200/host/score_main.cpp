@@ -189,6 +189,33 @@ int main(int argc, char **argv) {
             }
         }
 
+        // Which thread scores which variable.  The reference stripes variable % threadCount (:137); families differ in size by orders
+        // of magnitude, so the variables are dealt out longest-processing-time-first on the family size sum_{l<=K} C(c, l) instead
+        // (ties by index: deterministic), each thread's list in decreasing size.
+        std::vector<std::vector<int>> work(o.threadCount);
+        {
+            std::vector<double> cost(p);
+            for (int v = 0; v < p; v++) {
+                Varset nb = skeleton.get_neighbors(v), all = nb;
+                for (int j = 0; j < p; j++) if (nb.get(j) && j != v) all = all | skeleton.get_neighbors(j);
+                all.clear(v);
+                const int c = all.cardinality();
+                double fam = 0, b = 1;
+                for (int l = 0; l <= maxParents && l <= c; l++) { fam += b; b = b * (c - l) / (l + 1); }
+                cost[v] = fam;
+            }
+            std::vector<int> order(p);
+            for (int v = 0; v < p; v++) order[v] = v;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+            std::vector<double> load(o.threadCount, 0.0);
+            for (int v : order) {
+                int best = 0;
+                for (int t = 1; t < o.threadCount; t++) if (load[t] < load[best]) best = t;
+                work[best].push_back(v);
+                load[best] += cost[v];
+            }
+        }
+
         std::vector<std::string> blocks(p);
         std::vector<uint64_t> scored(p, 0);
         std::vector<std::string> errors(o.threadCount);
@@ -245,10 +272,11 @@ int main(int argc, char **argv) {
                     }
                     out += "\n";
                 };
-                // software pipeline of depth one: variable v+1 is enqueued before v's cache is read back
+                // software pipeline of depth one: variable v+1 is enqueued before v's cache is read back.  The thread takes its
+                // variables (work[thread], dealt out below) largest family first, so the engine's table buffers are allocated
+                // once at their final size; every block lands in blocks[variable], so the file order does not depend on this
                 scoring::ScoreCalculator::Pending prev;
-                for (int variable = 0; variable < p; variable++) {
-                    if (variable % o.threadCount != thread) continue; // :137
+                for (int variable : work[thread]) {
                     Varset orig;
                     scoring::ScoreCalculator::Pending cur = scoreCalculator.beginScores(variable, neighbors_of(variable, orig));
                     if (prev.res) emit(prev);
