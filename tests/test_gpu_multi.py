@@ -26,7 +26,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 p, n, K = 24, 40000, 5
 codes, card, edges, _ = pkg.datagen.discrete_bn(p=p, n=n, seed=7, window=3, max_indegree=2)
 half = p // world
-mine = torch.from_numpy(codes[rank * half:(rank + 1) * half]).cuda()      # this rank's block of columns
+mine = torch.from_numpy(np.ascontiguousarray(codes[rank * half:(rank + 1) * half])).cuda()      # this rank's block of columns
 full = torch.empty((p, n), dtype=torch.uint8, device="cuda")
 dist.all_gather_into_tensor(full, mine)
 torch.cuda.synchronize()
@@ -49,10 +49,12 @@ eng.close()
 '''
 
 
-def test_two_rank_nccl_pss_identical_to_single_process(pkg, engine, tmp_path):
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_nccl_pss_identical_to_single_process(pkg, engine, tmp_path, nranks):
+    """the .pss is byte-identical at 1, 2, 4 and 8 ranks (p = 24 is divisible by each)"""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
     p, n, K = 24, 40000, 5
     codes, card, edges, _ = pkg.datagen.discrete_bn(p=p, n=n, seed=7, window=3, max_indegree=2)
     engine.set_discrete(codes, card)
@@ -67,8 +69,8 @@ def test_two_rank_nccl_pss_identical_to_single_process(pkg, engine, tmp_path):
     worker.write_text(WORKER)
     multi = str(tmp_path / "multi.pss")
     port = 29600 + os.getpid() % 300
-    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                           "--master-port", str(port), str(worker), ROOT, multi], timeout=600)
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr", "127.0.0.1",
+                           "--master-port", str(port + nranks), str(worker), ROOT, multi], timeout=600)
     assert hashlib.sha256(open(multi, "rb").read()).hexdigest() == hashlib.sha256(open(single, "rb").read()).hexdigest()
 
 
@@ -127,7 +129,8 @@ eng.close()
 
 def test_two_rank_nccl_parent_set_range_shards(pkg, tmp_path):
     """cBIC over 69 candidates per variable, sharded by (variable, parent-set range) over two ranks: row-sharded Gram, ranges
-    scored into NCCL buffers, one all-to-all to the owners, filters, gather to rank 0: the .pss equals the one-process one"""
+    scored into NCCL buffers, one all-to-all to the owners, filters, gather to rank 0: the .pss equals the one-process one
+    (two ranks: the one-process run sums the same two Gram shards in the same order, so the Gram bits are the same)"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")

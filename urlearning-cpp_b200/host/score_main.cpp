@@ -13,6 +13,7 @@
 #include <iostream>
 #include <memory>
 #include <thread>
+#include <unistd.h>
 
 #include "fast_io.hpp"
 #include "gpu_scoring.hpp"
@@ -116,6 +117,20 @@ int main(int argc, char **argv) {
         printf("Has header: '%s'\n", o.hasHeader ? "true" : "false");
         printf("Enable end-of-scoring pruning: '%s'\n", o.prune ? "true" : "False");
 
+        // CUDA start-up (driver initialisation, one context per worker thread) costs about a second on a fresh process: it runs on a
+        // side thread while the CSV is parsed
+        int ndev = 0;
+        std::vector<std::unique_ptr<scoring::GpuContext>> gpus(o.threadCount);
+        std::string initError;
+        std::thread initThread([&] {
+            try {
+                ndev = urlgpu_device_count();
+                if (ndev < 1) throw std::runtime_error("urlgpu: no CUDA device available; the score path has no CPU fallback");
+                for (int t = 0; t < o.threadCount; t++) gpus[t].reset(new scoring::GpuContext(t % ndev));
+            } catch (const std::exception &e) { initError = e.what(); }
+        });
+        struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{initThread};
+
         printf("Parsing input file.\n");
         // RecordFile::read + BayesianNetwork::initialize in one parallel pass (fast_io.hpp): value indices in first-appearance order
         ParsedCsv csv = parse_csv(o.inputFile, o.delimiter, o.hasHeader);
@@ -150,8 +165,8 @@ int main(int argc, char **argv) {
             else skeleton.read_matrix_file(o.skeletonFile, p);
         } else skeleton.set_variable_count(p);
 
-        int ndev = urlgpu_device_count();
-        if (ndev < 1) throw std::runtime_error("urlgpu: no CUDA device available; the score path has no CPU fallback");
+        initThread.join();
+        if (!initError.empty()) throw std::runtime_error(initError);
 
         // device input, built once: packed codes (BIC) or the FP64 matrix (cBIC; mlpack::data::Load parses numbers, BIC_OLS.cpp:48)
         const bool isBic = sf == "bic";
@@ -175,10 +190,8 @@ int main(int argc, char **argv) {
         }
         // one context per worker thread (-t), thread t on device t % ndev; the first context of a device holds the data, the
         // others borrow its device copy (BIC) or install its Gram (cBIC): one upload per device, not one per thread
-        std::vector<std::unique_ptr<scoring::GpuContext>> gpus(o.threadCount);
         std::vector<std::unique_ptr<scoring::ScoringFunction>> functions(o.threadCount);
         for (int t = 0; t < o.threadCount; t++) {
-            gpus[t].reset(new scoring::GpuContext(t % ndev));
             const int owner = t % ndev;
             if (t == owner) {
                 if (isBic) functions[t].reset(new scoring::GpuBICScoringFunction(*gpus[t], codes.data(), recordCount, p, card.data()));
@@ -298,14 +311,17 @@ int main(int argc, char **argv) {
         out << "META parent_limit=" << maxParents << "\nMETA score_type=" << sf << "\nMETA ess=" << lexicalFloat(o.ess) << "\n\n"; // :388
         for (int v = 0; v < p; v++) out.write(blocks[v].data(), (std::streamsize)blocks[v].size());
         out.close();
-        functions.clear();
-        gpus.clear();
         const auto t3 = std::chrono::steady_clock::now();
         uint64_t total = 0;
         for (auto s : scored) total += s;
         auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
         printf("Scored %llu parent sets in %.3f s (%.3e sets/s); parse %.3f s, init %.3f s, write %.3f s, total %.3f s wall\n", (unsigned long long)total,
                sec(t1, t2), total / std::max(1e-9, sec(t1, t2)), sec(t0, tParsed), sec(tParsed, t1), sec(t2, t3), sec(t0, t3));
+        // the file is complete and closed: leave without tearing the engines down (returning tens of GB of pooled device memory
+        // block by block takes longer than scoring hepatitis; the driver reclaims everything at process exit)
+        fflush(stdout);
+        fflush(stderr);
+        _exit(0);
     } catch (const std::exception &e) {
         fprintf(stderr, "score: %s\n", e.what());
         return 1;
