@@ -52,7 +52,9 @@ typedef enum { URLGPU_BIC = 0, URLGPU_CBIC = 1 } urlgpu_score_t;
 enum {
     URLGPU_KEEP_ALL = 0,          /* store rule of the shipped `score` only (score_calculator.cpp:59,111; BIC_OLS.cpp:213-249) */
     URLGPU_PRUNE_DOMINATED = 2,   /* additionally drop S if a stored subset scores at least as well (score_calculator.cpp:150-197) */
-    URLGPU_CBIC_NO_ACCEPT = 4     /* cBIC: skip the in-line acceptance test, store every set's -the_score (diagnostics) */
+    URLGPU_CBIC_NO_ACCEPT = 4,    /* cBIC: skip the in-line acceptance test, store every set's -the_score (diagnostics) */
+    URLGPU_CBIC_ACCEPT_LITERAL = 8 /* cBIC: the acceptance test AS WRITTEN (BIC_OLS.cpp:125-172 with arma::uvec zero-filled, Armadillo >= 10.5;
+                                      SURVEY.md Q5) instead of the default "clean" recursion; sets of at most 12 parents */
 };
 
 /* One context = one device + one stream.  Thread-compatible: use one context per host thread. */

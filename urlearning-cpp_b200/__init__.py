@@ -24,7 +24,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liburlgpu.so")
 
 BIC, CBIC = 0, 1
-KEEP_ALL, PRUNE_DOMINATED, CBIC_NO_ACCEPT = 0, 2, 4
+KEEP_ALL, PRUNE_DOMINATED, CBIC_NO_ACCEPT, CBIC_ACCEPT_LITERAL = 0, 2, 4, 8
 
 # every symbol include/urlgpu.h declares (tests check the built library exports all of them)
 ABI_SYMBOLS = [

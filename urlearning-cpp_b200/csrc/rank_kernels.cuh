@@ -415,4 +415,106 @@ __global__ void rank_bic_finalize_kernel(BicData d, RankSpace rs, RankCand rc, c
     scores[idx] = bic_finalize(acc[i], pen, d.base);
 }
 
+
+// ------------------------------------------------------------------------------------------------ K4, literal form
+// find_best_subset_score AS WRITTEN (BIC_OLS.cpp:125-172) under Armadillo >= 10.5, where arma::uvec(n) is
+// zero-filled: the vector of remaining parents handed to each recursive call is only partly filled, its tail names
+// variable 0, and VARSET_CLEAR is an XOR (typedefs.h:657), so a zero entry TOGGLES variable 0: subsets that are not
+// subsets get looked up and half-explored sets are marked `checked`.  This kernel emulates that recursion, one thread per
+// parent set, with an explicit stack and a private `checked` bitset, so that `score --accept=literal-zero` reproduces the
+// cache of the reference as compiled today (the default "clean" DP restates the evident intent of the same lines).
+// Sets live in a LOCAL universe: bit i < k = the i-th member of S (ascending), bit k = variable 0 when it is not a member.
+// Dependencies: a look-up can reach a set of S's own layer only by replacing a member with variable 0; such a set contains
+// variable 0 (the lowest candidate), so a layer is processed in two launches: sets containing candidate 0, then the rest.
+constexpr int kLiteralMaxK = 12;
+
+struct LiteralFrame {
+    uint16_t parents, thin;
+    uint8_t np, idx, i, j, inner, var;
+    float best;
+    uint8_t pv[kLiteralMaxK], nv[kLiteralMaxK];
+};
+
+__global__ void __launch_bounds__(128) accept_literal_kernel(RankSpace enumr /*rank space used to enumerate the layer*/, RankSpace lay /*layout of `table`*/, int layer,
+                                                             int zero_cand /*compact position of variable 0 among the candidates, -1: not a candidate*/,
+                                                             int phase /*0: only sets with candidate 0, 1: only sets without, 2: all*/, float *__restrict__ table,
+                                                             LiteralFrame *__restrict__ frames /*[threads][kLiteralMaxK + 1]*/, uint32_t *__restrict__ checked /*[threads][256]*/) {
+    const uint32_t n_layer = enumr.layer_base[layer + 1] - enumr.layer_base[layer];
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_layer) return;
+    uint8_t e[kMaxRankLayers];
+    rs_unrank(enumr.binom, enumr.bstride, enumr.c, layer, r, e);
+    uint64_t S = 0;
+    for (int i = 0; i < layer; i++) S |= (uint64_t)1 << e[i];
+    const bool has0 = zero_cand >= 0 && ((S >> zero_cand) & 1);
+    if (phase == 0 && !has0) return;
+    if (phase == 1 && has0) return;
+    const uint64_t idx = out_index(lay, S);
+    const float ts = table[idx];
+    if (is_sentinel(ts)) return;
+    const int k = layer;
+    if (k == 0) { table[idx] = -ts; return; }
+    if (ts > 0.0f) { table[idx] = -ts; return; }                    // BIC_OLS.cpp:213-224: "bad" set, stored by the caller
+    if (ts == 0.0f) { table[idx] = sentinel(); return; }            // returned as -0.0: neither side stores it
+    // ---- best = find_best_subset_score(parents, cache, parent_vec, num_parents, checked) ----
+    LiteralFrame *st = frames + (size_t)r * (kLiteralMaxK + 1);
+    uint32_t *chk = checked + (size_t)r * 256;                       // 2^(k+1) <= 8192 bits
+    for (int w = 0; w < ((1 << (k + 1)) + 31) / 32; w++) chk[w] = 0;
+    chk[0] = 1u;                                                     // checked.insert(empty set) (:231)
+    const int zpos = has0 ? 0 : k;                                   // local position of variable 0 (a member is local bit 0: it is the lowest index)
+    auto lookup = [&](uint32_t local, float &val) -> bool {          // cache.find(local set)
+        uint64_t m = 0;
+        for (int i = 0; i < k; i++) if ((local >> i) & 1) m |= (uint64_t)1 << e[i];
+        if ((local >> k) & 1) { if (zero_cand < 0) return false; m |= (uint64_t)1 << zero_cand; }
+        if (__popcll(m) > lay.K && lay.binom) return false;
+        const float x = table[out_index(lay, m)];
+        if (is_sentinel(x)) return false;
+        val = x;
+        return true;
+    };
+    int sp = 0;
+    st[0].parents = (uint16_t)((1u << k) - 1); st[0].np = (uint8_t)k; st[0].idx = 0; st[0].inner = 0; st[0].best = 0.0f;
+    for (int i = 0; i < k; i++) st[0].pv[i] = (uint8_t)i;
+    float result = 0.0f;
+    while (true) {
+        LiteralFrame &F = st[sp];
+        if (!F.inner) {
+            if (F.idx == F.np) {                                     // return best_score
+                const float ret = F.best;
+                if (sp == 0) { result = ret; break; }
+                sp--;
+                LiteralFrame &G = st[sp];
+                chk[G.thin >> 5] |= 1u << (G.thin & 31);             // checked.insert(thin_parents) (:166)
+                if (ret > G.best) G.best = ret;
+                G.i++;
+                continue;
+            }
+            F.var = F.pv[F.idx];
+            const uint16_t thin = F.parents ^ (uint16_t)(1u << F.var);   // VARSET_CLEAR is XOR
+            if ((chk[thin >> 5] >> (thin & 31)) & 1u) { F.idx++; continue; }
+            float val;
+            if (lookup(thin, val)) { if (val > F.best) F.best = val; F.idx++; continue; }
+            F.thin = thin; F.inner = 1; F.i = 0; F.j = 0;
+            for (int q = 0; q < kLiteralMaxK; q++) F.nv[q] = (uint8_t)zpos;   // arma::uvec(num_parents - 1), zero-filled: variable 0
+        }
+        bool called = false;
+        while (F.i < F.np) {
+            if (F.var == F.pv[F.i]) { F.i++; continue; }
+            F.nv[F.j++] = F.pv[F.i];
+            LiteralFrame &N = st[sp + 1];                            // find_best_subset_score(thin_parents, cache, new_parent_vec, num_parents - 1, ...)
+            N.parents = F.thin; N.np = (uint8_t)(F.np - 1); N.idx = 0; N.inner = 0; N.best = 0.0f;
+            for (int q = 0; q < kLiteralMaxK; q++) N.pv[q] = F.nv[q];
+            sp++;
+            called = true;
+            break;
+        }
+        if (called) continue;
+        F.inner = 0;
+        F.idx++;
+    }
+    // :233-249 with bic_threshold = 0
+    const float nv = -ts;
+    table[idx] = result >= nv ? sentinel() : nv;
+}
+
 } // namespace urlgpu

@@ -2125,11 +2125,49 @@ static bool choose_rank_layout(urlgpu_ctx *ctx, int c, int K, bool bic) {
     return c >= 16 && (double)family_size(c, Kc) * 8.0 < std::ldexp(1.0, c);
 }
 
+// K4 as written (URLGPU_CBIC_ACCEPT_LITERAL): accept_literal_kernel, layer by layer, two launches per layer when variable 0
+// is a candidate (rank_kernels.cuh)
+static int run_accept_literal(urlgpu_ctx *ctx, urlgpu_result *res) {
+    cudaStream_t s = ctx->stream;
+    const int c = res->c, K = res->max_parents;
+    if (K > kLiteralMaxK) return ctx->fail(URLGPU_ERR_LIMIT, "literal-zero acceptance emulates the reference's recursion per parent set and handles sets of at most " +
+                                                              std::to_string(kLiteralMaxK) + " parents");
+    if (c > 62) return ctx->fail(URLGPU_ERR_LIMIT, "literal-zero acceptance handles at most 62 candidates");
+    RankSpace enumr{};
+    int rc = make_rank_space(ctx, c, K, enumr);
+    if (rc) return rc;
+    const RankSpace lay = res->rank_layout ? res->rs : RankSpace{};
+    uint32_t widest = 0;
+    for (int l = 0; l <= K; l++) widest = std::max(widest, enumr.layer_base[l + 1] - enumr.layer_base[l]);
+    if ((uint64_t)widest * (sizeof(LiteralFrame) * (kLiteralMaxK + 1) + 1024) > ((uint64_t)16 << 30))
+        return ctx->fail(URLGPU_ERR_LIMIT, "literal-zero acceptance: the widest layer of this family needs more than 16 GB of per-set recursion state");
+    DevBuf frames(ctx), checked(ctx);
+    CK(frames.alloc((size_t)widest * (kLiteralMaxK + 1) * sizeof(LiteralFrame)));
+    CK(checked.alloc((size_t)widest * 256 * sizeof(uint32_t)));
+    const int zero_cand = (!res->cand.empty() && res->cand[0] == 0) ? 0 : -1;
+    {
+        Region rg(ctx, F_ACCEPT, (zero_cand >= 0 ? 2 : 1) * (K + 1));
+        for (int l = 0; l <= K; l++) {
+            const uint32_t nl = enumr.layer_base[l + 1] - enumr.layer_base[l];
+            if (nl == 0) continue;
+            for (int phase = (zero_cand >= 0 ? 0 : 2); phase <= (zero_cand >= 0 ? 1 : 2); phase++)
+                accept_literal_kernel<<<blocks_for(nl, 128), 128, 0, s>>>(enumr, lay, l, zero_cand, phase, res->d_table, frames.as<LiteralFrame>(), checked.as<uint32_t>());
+        }
+    }
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+
 // store rule / acceptance and the optional prune on a table of RAW scores (BIC: the score, cBIC: the_score)
 static int apply_filters(urlgpu_ctx *ctx, urlgpu_result *res, bool bic, unsigned filter_flags) {
     cudaStream_t s = ctx->stream;
     const int c = res->c, K = res->max_parents;
     int rc = URLGPU_OK;
+    if (!bic && (filter_flags & URLGPU_CBIC_ACCEPT_LITERAL) && !(filter_flags & URLGPU_CBIC_NO_ACCEPT)) {
+        if ((rc = run_accept_literal(ctx, res))) return rc;
+        if (filter_flags & URLGPU_PRUNE_DOMINATED) rc = res->rank_layout ? run_rank_dp<1>(ctx, res->rs, res->d_table) : run_prune(ctx, res->d_table, c, K);
+        return rc;
+    }
     if (res->rank_layout) {
         const RankSpace &rs = res->rs;
         const uint32_t total = (uint32_t)res->n_masks;

@@ -16,6 +16,9 @@ import torch
 import torch.distributed as dist
 
 
+_PINNED = {}
+
+
 def stripe(p: int, rank: int, world: int):
     """variables owned by ``rank`` (score_main.cpp:137)."""
     return [v for v in range(p) if v % world == rank]
@@ -88,8 +91,19 @@ def gather_caches(local: dict, p: int, words: int, device, dst: int = 0, owner=N
     if rank != dst:
         return None
     out = {}
+    host = None
+    if send.is_cuda:  # one page-locked landing buffer (kept between calls): pageable device->host copies run at a fraction of PCIe speed
+        need = world * send.numel()
+        host = _PINNED.get("buf")
+        if host is None or host.numel() < need:
+            host = torch.empty(need, dtype=torch.int64, pin_memory=True)
+            _PINNED["buf"] = host
+        host = host[:need].view(world, *send.shape)
+        for r in range(world):
+            host[r].copy_(recv[r], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
     for r in range(world):
-        buf = recv[r].cpu().numpy()
+        buf = host[r].numpy() if host is not None else recv[r].cpu().numpy()
         off = 0
         cr = all_counts[r].cpu().numpy()
         for v in range(p):

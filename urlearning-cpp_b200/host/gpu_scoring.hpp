@@ -185,7 +185,7 @@ public:
         urlgpu_ctx *ctx = scoringFunction->context();
         Pending pd;
         pd.variable = variable;
-        unsigned flags = pruneFlag ? URLGPU_PRUNE_DOMINATED : URLGPU_KEEP_ALL;
+        unsigned flags = (pruneFlag ? URLGPU_PRUNE_DOMINATED : URLGPU_KEEP_ALL) | extraFlags;
         check(ctx, urlgpu_score_variable(ctx, variable, neighbors.w, urlhost::kVarsetWords, maxParents, scoringFunction->scoreType(),
                                          scoringFunction->getLambda(), flags, &pd.res));
         int rc = urlgpu_result_prefetch(pd.res);
@@ -210,6 +210,7 @@ public:
         check(ctx, rc);
     }
     uint64_t lastScored = 0;
+    unsigned extraFlags = 0;   // e.g. URLGPU_CBIC_ACCEPT_LITERAL
 
 private:
     static void check(urlgpu_ctx *ctx, int rc) { if (rc != URLGPU_OK) throw std::runtime_error(std::string("urlgpu: ") + urlgpu_last_error(ctx)); }

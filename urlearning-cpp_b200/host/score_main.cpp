@@ -29,6 +29,7 @@ struct Options {
     int rMin = 5, maxParents = 0, threadCount = 1, runningTime = -1, which = 1;
     float ess = 1.0f;
     bool hasHeader = false, doNotPrune = false, prune = false, deCampos = false, adaptive = false, quiet = false;
+    std::string accept = "clean";   // cBIC acceptance test: "clean" (default) or "literal-zero" (BIC_OLS.cpp:125-172 as written)
 };
 
 void usage(const char *argv0) {
@@ -44,6 +45,7 @@ void usage(const char *argv0) {
               << "  -s [ --hasHeader ]         The first line of the input file gives the variable names.\n"
               << "  -o [ --doNotPrune ]        Accepted for compatibility (the reference ignores it).\n"
               << "  --prune                    Apply ScoreCalculator::prune (subset dominance) before writing.\n"
+              << "  --accept arg (=clean)      cBIC acceptance test: clean | literal-zero (the reference's recursion as written).\n"
               << "  -m, -e, -r, -w, -c, -a, --enableDeCamposPruning   accepted for compatibility.\n"
               << "  -h [ --help ]              Show this help message.\n";
 }
@@ -80,6 +82,7 @@ bool parse(int argc, char **argv, Options &o) {
         else if (takes("-p", "maxParents", v)) o.maxParents = atoi(v.c_str());
         else if (takes("-t", "threads", v)) o.threadCount = atoi(v.c_str());
         else if (takes("-r", "time", v)) o.runningTime = atoi(v.c_str());
+        else if (takes("", "accept", v)) o.accept = v;
         else if (a == "-a" || a == "--adaptive") o.adaptive = true;
         else if (a == "-s" || a == "--hasHeader") o.hasHeader = true;
         else if (a == "-o" || a == "--doNotPrune") o.doNotPrune = true;
@@ -104,6 +107,7 @@ int main(int argc, char **argv) {
     try {
         if (argc == 1 || !parse(argc, argv, o)) { usage(argv[0]); return 0; }
         if (o.threadCount < 1) o.threadCount = 1;
+        if (o.accept != "clean" && o.accept != "literal-zero" && o.accept != "literal") throw std::runtime_error("--accept takes clean or literal-zero");
         if (!o.constraintsFile.empty()) throw std::runtime_error("constraints files (-c) are not supported by the GPU score path");
         if (o.runningTime > 0) fprintf(stderr, "warning: -r (per-variable time limit) is ignored by the GPU score path\n");
 
@@ -237,6 +241,7 @@ int main(int argc, char **argv) {
             try {
                 scoring::ScoringFunction *scoringFunction = functions[thread].get();
                 scoring::ScoreCalculator scoreCalculator(scoringFunction, maxParents, p, o.prune);
+                scoreCalculator.extraFlags = (o.accept == "literal-zero" || o.accept == "literal") ? URLGPU_CBIC_ACCEPT_LITERAL : 0;
                 // two-hop candidate mask (:145-153)
                 auto neighbors_of = [&](int variable, Varset &orig) {
                     orig = skeleton.get_neighbors(variable);
