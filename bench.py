@@ -293,7 +293,7 @@ def run_gpu(args):
             # N > 1: the caches travel to rank 0 (the .pss writer) over NCCL inside the timed region
             got = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch=True, costs=costs)
             local = {v + shift: (to_global(m), sc) for v, (m, sc) in got.items()}
-            allc = D.gather_caches(local, p_global, words_global, "cuda", owner=owner_global)
+            allc = D.gather_caches(local, p_global, words_global, "cuda", owner=owner_global, copy=False)
             if rank == 0:
                 assert len(allc) == p_global
             return sum(len(sc) for _, sc in got.values())
@@ -414,7 +414,7 @@ def run_gpu(args):
                 pool.run(items_s, wl_s["K"], stype, flags=flags, fetch=False, costs=costs_s)
                 return 0
             got = pool.run(items_s, wl_s["K"], stype, flags=flags, fetch=True, costs=costs_s)
-            allc = D.gather_caches(got, wl_s["p"], words_s, "cuda", owner=owner_s)
+            allc = D.gather_caches(got, wl_s["p"], words_s, "cuda", owner=owner_s, copy=False)
             if rank == 0:
                 assert len(allc) == wl_s["p"]
             return sum(len(sc) for _, sc in got.values())
@@ -684,7 +684,7 @@ def run_gpu_cbic5(args):
 
     stored_box = [0]
 
-    def step():
+    def step(fetch=False):
         eng.shard_begin(x.data_ptr(), n_local, p)
         s1, _ = eng.shard_moments(None)
         mean = allsum(s1) / n_total
@@ -706,11 +706,11 @@ def run_gpu_cbic5(args):
         for v, t in full.items():
             res = eng.result_from_scores(v, nbs[v], K, pkg.CBIC, t.data_ptr(), n=sizes[v], flags=pkg.PRUNE_DOMINATED).prefetch()
             if prev is not None:
-                stored += prev.count()
+                stored += len(prev.fetch(pinned=True)[1]) if fetch else prev.count()
                 prev.free()
             prev = res
         if prev is not None:
-            stored += prev.count()
+            stored += len(prev.fetch(pinned=True)[1]) if fetch else prev.count()
             prev.free()
         stored_box[0] = stored
 
@@ -744,6 +744,35 @@ def run_gpu_cbic5(args):
     st = eng.stats()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    eng.enable_timing(False)
+
+    # ---- e2e: the rows start in page-locked HOST memory: every step uploads this rank's n/N rows (H2D inside the timed region)
+    # and reads every surviving (mask, score) list of the variables it owns back into the engine's page-locked result buffer
+    x_host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+    x_host.copy_(x)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        x.copy_(x_host, non_blocking=True)
+        step(fetch=True)
+
+    e2e_step()
+    nst = max(1, min(args.steps, 2))
+    barrier()
+    e0.record(stream)
+    for _ in range(nst):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    ems = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ems], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item())
+    words = pkg.mask_words_for(p)
+    e2e = {"value": sets_total * nst / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(p * n_total * 8),
+           "d2h_bytes_per_step": int((8 * words + 4) * stored), "steps": nst, "ms_per_step": ems / nst,
+           "note": "caches stay on their owner ranks (a .pss of %d entries is written per rank); no gather" % stored}
     if rank == 0:
         gram_tf = st["gram_flops"] / (st["ms_gram"] / 1e3) / 1e12 if st["ms_gram"] > 0 else None
         fp64 = eng.probe_fp64()
@@ -756,7 +785,7 @@ def run_gpu_cbic5(args):
                            "sets_per_step": sets_total, "stored_after_prune": stored,
                            "parallelism": f"rows sharded n/{world} for the Gram; scoring sharded by (variable, parent-set range): {world} contiguous pieces of the "
                                           f"concatenated family index space, one all-to-all of raw scores to the variables' owners, N={world}"},
-                "e2e": None, "gpu_launches": int(st["launches_total"]), "clocks": sampler.summary(),
+                "e2e": e2e, "gpu_launches": int(st["launches_total"]), "clocks": sampler.summary(),
                 "roofline": {"bound": "fp64", "kernel": "K2 gram_partial_kernel (TMA bulk copies -> shared memory -> DMMA m8n8k4.f64) + fixed-order combine", "achieved": gram_tf,
                              "peak": fp64["dmma"], "unit": "TFLOP/s", "frac": gram_tf / fp64["dmma"] if gram_tf else None, "traffic": None,
                              "peak_source": "measured in this run (urlgpu_probe_fp64: register-resident DMMA m8n8k4.f64 chains); DFMA: %.1f TFLOP/s" % fp64["dfma"],

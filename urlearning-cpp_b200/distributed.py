@@ -60,59 +60,77 @@ def broadcast_tensor(t: torch.Tensor | None, shape, dtype, device, src: int = 0)
     return buf
 
 
-def gather_caches(local: dict, p: int, words: int, device, dst: int = 0, owner=None):
+def _landing(key: str, numel: int, dtype, pinned: bool) -> torch.Tensor:
+    """a host buffer kept between calls (page-locked next to a GPU: pageable device->host copies run at a fraction of PCIe speed)"""
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < numel or buf.dtype != dtype:
+        buf = torch.empty(max(numel, 1), dtype=dtype, pin_memory=pinned)
+        _PINNED[key] = buf
+    return buf[:numel]
+
+
+def gather_caches(local: dict, p: int, words: int, device, dst: int = 0, owner=None, copy: bool = True):
     """local: {variable: (masks uint64 [n, words], scores float32 [n])} for the variables this rank owns
     (``owner[v]`` = its rank; default: the reference's striping v % world).
-    Returns the same dict for ALL p variables on rank ``dst`` (None elsewhere).  Two collectives: an all_gather of
-    the per-variable counts, then a padded gather of the packed (mask words, score bits) payload."""
+    Returns the same dict for ALL p variables on rank ``dst`` (None elsewhere).  Three collectives: an all_gather of
+    the per-variable counts, then one padded gather of the mask words and one of the scores (kept apart so that every
+    variable's block is a contiguous slice on both sides).  ``copy=False`` returns views into the landing buffers, valid
+    until the next call — what a writer that formats the blocks straight away wants."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    counts = torch.zeros(p, dtype=torch.int64, device=device)
-    for v, (m, s) in local.items():
-        counts[v] = len(s)
-    all_counts = [torch.zeros_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts)
+    on_gpu = torch.device(device).type == "cuda"
+    counts = torch.zeros(p, dtype=torch.int64)
     owned = sorted(local)
-    rows = int(sum(len(local[v][1]) for v in owned))
-    payload = np.zeros((rows, words + 1), dtype=np.int64)
+    for v in owned:
+        counts[v] = len(local[v][1])
+    counts = counts.to(device)
+    all_counts = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts)
+    all_counts = torch.stack(all_counts).cpu().numpy()          # [world, p]
+    per_rank = all_counts.sum(axis=1)
+    rows, width = int(per_rank[rank]), max(int(per_rank.max()), 1)
+    hm = _landing("send_m", width * words, torch.int64, on_gpu).view(width, words)
+    hs = _landing("send_s", width, torch.float32, on_gpu)
+    hm_np, hs_np = hm.numpy(), hs.numpy()
     off = 0
     for v in owned:
         m, s = local[v]
         k = len(s)
-        payload[off:off + k, :words] = np.ascontiguousarray(m, dtype=np.uint64).view(np.int64).reshape(k, words)
-        payload[off:off + k, words] = np.ascontiguousarray(s, dtype=np.float32).view(np.int32).astype(np.int64)
+        hm_np[off:off + k] = np.asarray(m).reshape(k, words).view(np.int64)
+        hs_np[off:off + k] = s
         off += k
-    per_rank = [int(c.sum().item()) for c in all_counts]
-    width = max(per_rank) if per_rank else 0
-    send = torch.zeros((max(width, 1), words + 1), dtype=torch.int64, device=device)
-    if rows:
-        send[:rows] = torch.from_numpy(payload).to(device)
-    recv = [torch.zeros_like(send) for _ in range(world)] if rank == dst else None
-    dist.gather(send, recv, dst=dst)
+    send_m = torch.empty((width, words), dtype=torch.int64, device=device)
+    send_s = torch.empty(width, dtype=torch.float32, device=device)
+    send_m[:rows].copy_(hm[:rows], non_blocking=True)
+    send_s[:rows].copy_(hs[:rows], non_blocking=True)
+    recv_m = [torch.empty_like(send_m) for _ in range(world)] if rank == dst else None
+    recv_s = [torch.empty_like(send_s) for _ in range(world)] if rank == dst else None
+    dist.gather(send_m, recv_m, dst=dst)
+    dist.gather(send_s, recv_s, dst=dst)
     if rank != dst:
+        if on_gpu:
+            torch.cuda.current_stream().synchronize()   # the landing buffers are reused by the next call
         return None
-    out = {}
-    host = None
-    if send.is_cuda:  # one page-locked landing buffer (kept between calls): pageable device->host copies run at a fraction of PCIe speed
-        need = world * send.numel()
-        host = _PINNED.get("buf")
-        if host is None or host.numel() < need:
-            host = torch.empty(need, dtype=torch.int64, pin_memory=True)
-            _PINNED["buf"] = host
-        host = host[:need].view(world, *send.shape)
-        for r in range(world):
-            host[r].copy_(recv[r], non_blocking=True)
+    total = int(per_rank.sum())
+    land_m = _landing("recv_m", max(total, 1) * words, torch.int64, on_gpu).view(-1, words)
+    land_s = _landing("recv_s", max(total, 1), torch.float32, on_gpu)
+    base = np.concatenate([[0], np.cumsum(per_rank)]).astype(np.int64)
+    for r in range(world):   # only the filled rows of every rank's padded block come to the host
+        k = int(per_rank[r])
+        if k:
+            land_m[int(base[r]):int(base[r]) + k].copy_(recv_m[r][:k], non_blocking=True)
+            land_s[int(base[r]):int(base[r]) + k].copy_(recv_s[r][:k], non_blocking=True)
+    if on_gpu:
         torch.cuda.current_stream().synchronize()
+    lm, ls = land_m.numpy().view(np.uint64), land_s.numpy()
+    out = {}
     for r in range(world):
-        buf = host[r].numpy() if host is not None else recv[r].cpu().numpy()
-        off = 0
-        cr = all_counts[r].cpu().numpy()
+        off = int(base[r])
         for v in range(p):
-            k = int(cr[v])
             if (owner[v] if owner is not None else v % world) != r:
                 continue
-            masks = buf[off:off + k, :words].astype(np.int64).view(np.uint64).reshape(k, words)
-            scores = buf[off:off + k, words].astype(np.int32).view(np.float32)
-            out[v] = (masks.copy(), scores.copy())
+            k = int(all_counts[r, v])
+            masks, scores = lm[off:off + k], ls[off:off + k]
+            out[v] = (masks.copy(), scores.copy()) if copy else (masks, scores)
             off += k
     return out
 
