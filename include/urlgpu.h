@@ -46,7 +46,9 @@ typedef enum {
     URLGPU_ERR_INTERNAL = -4
 } urlgpu_status;
 
-typedef enum { URLGPU_BIC = 0, URLGPU_CBIC = 1 } urlgpu_score_t;
+/* URLGPU_FNML: factorized NML on the same counts as BIC (scoring_function/fnml_scoring_function.{h,cpp}: log-likelihood
+ * minus sum_j log C(N_ij, r_v), no BIC penalty and no log-bound on the parent limit); needs urlgpu_set_discrete. */
+typedef enum { URLGPU_BIC = 0, URLGPU_CBIC = 1, URLGPU_FNML = 2 } urlgpu_score_t;
 
 /* filter_flags of urlgpu_score_variable (bit set) */
 enum {

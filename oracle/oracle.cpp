@@ -386,6 +386,131 @@ extern "C" int orc_bic_score_many(const uint8_t *codes, int64_t n, int p, const 
     return 0;
 }
 
+/* ------------------------------------------------------------ discrete fNML */
+
+/* fnml_scoring_function.h: `r2_1000` — the K=2 multinomial regret for N <= 1000.  The reference holds 12-digit decimal
+ * literals; as float32 they equal the exactly computed values in regret_r2.inc (tools/gen_regret_table.py,
+ * tests/test_fnml_tables.py compares them with the reference's header when it is present). */
+static const uint32_t k_r2_bits[1001] = {
+#include "regret_r2.inc"
+};
+/* fnml_scoring_function.h: reg2 */
+static float fnml_reg2(int N) {
+    if (N <= 1000) { float f; memcpy(&f, &k_r2_bits[N], 4); return f; }
+    const double pi = 3.1415926535897932384626433832795;
+    return exp(0.5 * log(N * pi / 2) + sqrt(8 / (9 * N * pi)) + (1.0 / 12 - 4 / (9 * pi)) / N);
+}
+/* fnml_scoring_function.h: reg — float32 recurrence C(N,k) = C(N,k-1) + C(N,k-2) / (k-2) * N */
+static float fnml_reg(int N, int K) {
+    if (K == 1) return 1.0;
+    else if (K == 2) return fnml_reg2(N);
+    float rk_2 = fnml_reg(N, 1);
+    float rk_1 = fnml_reg(N, 2);
+    float rk = 0;
+    for (int k = 3; k <= K; ++k) {
+        rk = rk_1 + rk_2 / (k - 2) * N;
+        rk_2 = rk_1;
+        rk_1 = rk;
+    }
+    return rk;
+}
+/* fnml_scoring_function.h: getRegretCache — one row: out[N] = (float)log(reg(N, r)), N = 0..n_max */
+extern "C" void orc_log_regret(int64_t n_max, int r, float *out) {
+    for (int64_t N = 0; N <= n_max; N++) out[N] = (float)std::log((double)fnml_reg((int)N, r));
+}
+
+struct FnmlCtx { BicCtx b; std::vector<std::vector<float>> regret; /* by arity, built on demand */ };
+static const std::vector<float> &fnml_row(FnmlCtx &c, int r) {
+    if ((int)c.regret.size() <= r) c.regret.resize(r + 1);
+    if (c.regret[r].empty()) { c.regret[r].resize(c.b.n + 1); orc_log_regret(c.b.n, r, c.regret[r].data()); }
+    return c.regret[r];
+}
+
+/* fnml_scoring_function.cpp:28-74 with enableDeCamposPruning off (score_main.cpp:112): LL - sum_j regret[r_v][N_ij].
+ * mode 0: the exact-integer contract (every float table entry in units of 2^-23, the regret entries rounded to that grid;
+ *         one rounding to float32 at the end) — independent of summation order.
+ * mode 1: literal float32: the log-likelihood as in orc_bic_score mode 1, tVal a float32 running sum over the parent
+ *         configurations with a positive count (ascending paIdx here; boost::unordered_map order there), score -= tVal. */
+static int fnml_score_one(const BicCtx &c, const std::vector<float> &reg, int v, uint64_t parents, int mode, std::vector<int32_t> &counts, float *score_out) {
+    int64_t cells = orc_bic_cells(c.card, c.p, v, parents);
+    if (cells < 0) return fail("contingency table too large");
+    counts.resize(cells);
+    if (orc_bic_counts(c.codes, c.n, c.p, c.card, v, parents, counts.data())) return -1;
+    const int rv = c.card[v];
+    if (mode == 0) {
+        int64_t fx = 0;
+        for (int64_t j = 0; j < cells; j += rv) {
+            int32_t nij = 0;
+            for (int k = 0; k < rv; k++) {
+                int32_t cnt = counts[j + k];
+                nij += cnt;
+                fx += (int64_t)std::ldexp((double)c.ilogi[cnt], 23);
+            }
+            if (nij > 0) {
+                fx -= (int64_t)std::ldexp((double)c.ilogi[nij], 23);
+                fx -= std::llrint(std::ldexp((double)reg[nij], 23));
+            }
+        }
+        *score_out = (float)std::ldexp((double)fx, -23);
+        return 0;
+    }
+    float ll;
+    { /* the log-likelihood of orc_bic_score mode 1 (penalty removed again would round twice: recompute) */
+        std::vector<int> vars;
+        for (int i = 0; i < c.p; i++) if (((parents >> i) & 1) || i == v) vars.push_back(i);
+        std::vector<int64_t> stride(vars.size());
+        int64_t b = rv;
+        for (size_t j = 0; j < vars.size(); j++) {
+            if (vars[j] == v) stride[j] = 1;
+            else { stride[j] = b; b *= c.card[vars[j]]; }
+        }
+        float score = 0;
+        std::vector<int> digit(vars.size(), 0);
+        while (true) {
+            int64_t idx = 0;
+            for (size_t j = 0; j < vars.size(); j++) idx += stride[j] * digit[j];
+            if (counts[idx] > 0) score += c.ilogi[counts[idx]];
+            int j = (int)vars.size() - 1;
+            while (j >= 0 && ++digit[j] == c.card[vars[j]]) { digit[j] = 0; j--; }
+            if (j < 0) break;
+        }
+        for (int64_t j = 0; j < cells; j += rv) {
+            int32_t nij = 0;
+            for (int k = 0; k < rv; k++) nij += counts[j + k];
+            if (nij > 0) score -= c.ilogi[nij];
+        }
+        ll = score;
+    }
+    float t = 0;
+    for (int64_t j = 0; j < cells; j += rv) {
+        int32_t nij = 0;
+        for (int k = 0; k < rv; k++) nij += counts[j + k];
+        if (nij > 0) t += reg[nij];
+    }
+    *score_out = ll - t;
+    return 0;
+}
+
+extern "C" int orc_fnml_score_many(const uint8_t *codes, int64_t n, int p, const int32_t *card, int v,
+                                   const uint64_t *parents, int64_t n_sets, int mode, int threads, float *out) {
+    FnmlCtx c{make_bic(codes, n, p, card), {}};
+    const std::vector<float> &reg = fnml_row(c, card[v]);
+    if (threads < 1) threads = 1;
+    std::vector<int> rc(threads, 0);
+    std::vector<std::string> errs(threads);
+    auto work = [&](int t) {
+        std::vector<int32_t> counts;
+        for (int64_t i = t; i < n_sets; i += threads)
+            if (fnml_score_one(c.b, reg, v, parents[i], mode, counts, &out[i])) { rc[t] = -1; errs[t] = g_err; return; }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    for (int t = 0; t < threads; t++) if (rc[t]) return fail(errs[t]);
+    return 0;
+}
+
 /* --------------------------------------------------------- continuous cBIC */
 
 /* arma::mean (arrayops::accumulate: two running sums over even/odd elements, then /n) */
@@ -637,14 +762,16 @@ static std::string lexical_float(float f) { /* boost::lexical_cast<std::string>(
 extern "C" int64_t orc_score_file(const orc_options *o) {
     std::string sf(o->function ? o->function : "BIC");
     for (auto &ch : sf) ch = (char)std::tolower((unsigned char)ch); /* score_main.cpp:294 */
-    bool is_bic = sf == "bic", is_cbic = sf == "cbic";
-    if (!is_bic && !is_cbic) return fail("oracle supports -f BIC|cBIC only");
+    const bool is_fnml = sf == "fnml";
+    const bool log_bound = sf == "bic";                     /* score_main.cpp:300-304: only BIC bounds the parent limit */
+    bool is_bic = sf == "bic" || is_fnml, is_cbic = sf == "cbic";   /* is_bic: discrete input */
+    if (!is_bic && !is_cbic) return fail("oracle supports -f BIC|fNML|cBIC only");
     orc_table *t = orc_read_csv(o->input, o->delimiter ? o->delimiter : ',', o->has_header);
     if (!t) return -1;
     const int p = t->p;
     const int64_t n = t->n;
     if (p > 63) { orc_table_free(t); return fail("p > 63 is not representable in the reference (uint64 varset)"); }
-    int maxParents = orc_effective_max_parents(o->max_parents, p, n, is_bic);
+    int maxParents = orc_effective_max_parents(o->max_parents, p, n, log_bound);
     std::vector<uint64_t> edges(p);
     int init = orc_read_skeleton(o->skeleton, p, edges.data());
     if (init < 0) { orc_table_free(t); return -1; }
@@ -675,10 +802,13 @@ extern "C" int64_t orc_score_file(const orc_options *o) {
         std::vector<float> val(m);
         std::vector<uint8_t> stored(m, 1);
         if (is_bic) {
-            BicCtx c = make_bic(codes.data(), n, p, card.data());
+            FnmlCtx fc{make_bic(codes.data(), n, p, card.data()), {}};
+            const BicCtx &c = fc.b;
+            const std::vector<float> *reg = is_fnml ? &fnml_row(fc, card[v]) : nullptr;
             std::vector<int32_t> cnt;
             for (int64_t i = 0; i < m; i++) {
-                if (bic_score_one(c, v, masks[i], o->bic_mode, cnt, &val[i], nullptr)) { rc[v] = -1; errs[v] = g_err; return; }
+                if (is_fnml ? fnml_score_one(c, *reg, v, masks[i], o->bic_mode, cnt, &val[i])
+                            : bic_score_one(c, v, masks[i], o->bic_mode, cnt, &val[i], nullptr)) { rc[v] = -1; errs[v] = g_err; return; }
                 stored[i] = masks[i] == 0 ? (val[i] < 1) : (val[i] < 0); /* score_calculator.cpp:59,111 */
             }
         } else {

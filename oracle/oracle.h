@@ -70,6 +70,13 @@ int orc_bic_score(const uint8_t *codes, int64_t n, int p, const int32_t *card, i
 int orc_bic_score_many(const uint8_t *codes, int64_t n, int p, const int32_t *card, int v,
                        const uint64_t *parents, int64_t n_sets, int mode, int threads, float *scores_out);
 
+/* ---------- discrete fNML (fnml_scoring_function.{h,cpp}) ---------- */
+/* one row of getRegretCache: out[N] = (float)log(reg(N, r)), N = 0..n_max */
+void orc_log_regret(int64_t n_max, int r, float *out);
+/* mode 0: exact-integer contract (float tables on the 2^-23 grid, one final rounding); mode 1: literal float32 sums */
+int orc_fnml_score_many(const uint8_t *codes, int64_t n, int p, const int32_t *card, int v,
+                        const uint64_t *parents, int64_t n_sets, int mode, int threads, float *scores_out);
+
 /* ---------- continuous cBIC (BIC_OLS.cpp) ---------- */
 /* BIC_OLS.cpp:66-80: centre, divide by sample std (N-1). z_out column-major n*p */
 void orc_standardise(const double *x, int64_t n, int p, double *z_out);
@@ -96,7 +103,7 @@ typedef struct orc_options {
     const char *input;      /* positional 1 */
     const char *output;     /* positional 2 */
     const char *skeleton;   /* -k, may be NULL */
-    const char *function;   /* -f: "BIC" | "cBIC" */
+    const char *function;   /* -f: "BIC" | "fNML" | "cBIC" */
     char delimiter;         /* -d */
     int has_header;         /* -s */
     int max_parents;        /* -p (0 = no limit) */

@@ -6,7 +6,8 @@ CXX = $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 # the reference's own flags (urlearning/Jamroot:14-45): -std=c++11 -fno-strict-aliasing; -w: its warnings are not ours
 CXXFLAGS = -std=c++11 -fno-strict-aliasing -O2 -fPIC -w -pthread -I shim -I $(REF)
 SRC = base/bayesian_network.cpp base/skeleton.cpp ad_tree/ad_tree.cpp ad_tree/ad_node.cpp ad_tree/vary_node.cpp \
-      scoring_function/log_likelihood_calculator.cpp scoring_function/bic_scoring_function.cpp scoring_function/score_calculator.cpp
+      scoring_function/log_likelihood_calculator.cpp scoring_function/bic_scoring_function.cpp scoring_function/score_calculator.cpp \
+      scoring_function/fnml_scoring_function.cpp scoring_function/bdeu_scoring_function.cpp
 # the search side (consumers of the .pss): the reader, the best-score structures, the static pattern database, the heap
 SEARCH_SRC = score_cache/score_cache.cpp score_cache/sparse_parent_list.cpp score_cache/sparse_parent_bitwise.cpp score_cache/sparse_parent_tree.cpp \
       heuristic/static_pattern_database.cpp priority_queue/priority_queue.cpp base/bayesian_network.cpp base/skeleton.cpp

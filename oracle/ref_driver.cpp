@@ -25,7 +25,9 @@
 #include "urlearning/base/record_file.h"
 #include "urlearning/base/skeleton.hpp"
 #include "urlearning/base/variable.h"
+#include "urlearning/scoring_function/bdeu_scoring_function.h"
 #include "urlearning/scoring_function/bic_scoring_function.h"
+#include "urlearning/scoring_function/fnml_scoring_function.h"
 #include "urlearning/scoring_function/log_likelihood_calculator.h"
 #include "urlearning/scoring_function/score_calculator.h"
 
@@ -37,6 +39,8 @@ struct Ref {
     scoring::LogLikelihoodCalculator *llc;
     scoring::BICScoringFunction *sf;
     std::vector<float> ilogi;
+    scoring::fNMLScoringFunction *fnml = NULL;                 /* built on first use */
+    std::vector<std::vector<float> *> *regret = NULL;
 };
 void flatten(scoring::ContingencyTableNode *ct, const std::vector<int> &vars, const std::vector<int> &card, size_t depth, int64_t idx, int64_t stride,
              int32_t *out) {
@@ -78,6 +82,30 @@ int ref_code(void *h, int v, int rec) {
 float ref_calculate_score(void *h, int variable, uint64_t parents) {
     FloatMap cache;
     return ((Ref *)h)->sf->calculateScore(variable, parents, cache);
+}
+
+/* fNMLScoringFunction::calculateScore (fnml_scoring_function.cpp:28-74), set up as score_main.cpp:336-355 does */
+float ref_fnml_score(void *h, int variable, uint64_t parents) {
+    Ref *r = (Ref *)h;
+    if (r->fnml == NULL) {
+        r->regret = scoring::getRegretCache(r->recordFile->size(), r->network->getMaxCardinality());
+        r->fnml = new scoring::fNMLScoringFunction(*r->network, r->llc, NULL, r->regret, false);
+    }
+    FloatMap cache;
+    return r->fnml->calculateScore(variable, parents, cache);
+}
+/* the reference's regret table entry regret->at(arity)->at(N) */
+float ref_regret(void *h, int arity, int N) {
+    Ref *r = (Ref *)h;
+    if (r->regret == NULL) ref_fnml_score(h, 0, 0);
+    return r->regret->at(arity)->at(N);
+}
+/* BDeuScoringFunction::calculateScore (bdeu_scoring_function.cpp:37-123), set up as score_main.cpp:357-360 does */
+float ref_bdeu_score(void *h, int variable, uint64_t parents, float ess) {
+    Ref *r = (Ref *)h;
+    scoring::BDeuScoringFunction sf(ess, *r->network, r->adTree, NULL, false);
+    FloatMap cache;
+    return sf.calculateScore(variable, parents, cache);
 }
 
 /* ADTree::makeContab (ad_tree.cpp:95-137) flattened: mixed radix over the set's variables in ascending index,

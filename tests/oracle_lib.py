@@ -57,6 +57,8 @@ def lib():
         L.orc_bic_counts.argtypes = [vp, i64, i32, vp, i32, u64, vp]
         L.orc_bic_score.argtypes = [vp, i64, i32, vp, i32, u64, i32, C.POINTER(C.c_float), C.POINTER(C.c_double)]
         L.orc_bic_score_many.argtypes = [vp, i64, i32, vp, i32, vp, i64, i32, i32, vp]
+        L.orc_log_regret.argtypes = [i64, i32, vp]
+        L.orc_fnml_score_many.argtypes = [vp, i64, i32, vp, i32, vp, i64, i32, i32, vp]
         L.orc_standardise.argtypes = [vp, i64, i32, vp]
         L.orc_gram.argtypes = [vp, i64, i32, vp]
         L.orc_cbic_the_score_residual.restype = C.c_double
@@ -163,6 +165,25 @@ def bic_score_many(codes, card, v, masks, mode=0, threads=8):
     out = np.zeros(len(masks), dtype=np.float32)
     if lib().orc_bic_score_many(codes.ctypes.data, n, p, card.ctypes.data, v, masks.ctypes.data, len(masks), mode, threads,
                                 out.ctypes.data):
+        raise RuntimeError(err())
+    return out
+
+
+def log_regret(n_max, r):
+    """one row of the reference's regret cache: (float)log(reg(N, r)), N = 0..n_max"""
+    out = np.zeros(n_max + 1, dtype=np.float32)
+    lib().orc_log_regret(n_max, r, out.ctypes.data)
+    return out
+
+
+def fnml_score_many(codes, card, v, masks, mode=0, threads=8):
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    card = np.ascontiguousarray(card, dtype=np.int32)
+    masks = np.ascontiguousarray(masks, dtype=np.uint64)
+    p, n = codes.shape
+    out = np.zeros(len(masks), dtype=np.float32)
+    if lib().orc_fnml_score_many(codes.ctypes.data, n, p, card.ctypes.data, v, masks.ctypes.data, len(masks), mode, threads,
+                                 out.ctypes.data):
         raise RuntimeError(err())
     return out
 

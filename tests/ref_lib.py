@@ -31,6 +31,12 @@ def lib():
         L.ref_code.argtypes = [vp, i32, i32]
         L.ref_calculate_score.restype = C.c_float
         L.ref_calculate_score.argtypes = [vp, i32, u64]
+        L.ref_fnml_score.restype = C.c_float
+        L.ref_fnml_score.argtypes = [vp, i32, u64]
+        L.ref_regret.restype = C.c_float
+        L.ref_regret.argtypes = [vp, i32, i32]
+        L.ref_bdeu_score.restype = C.c_float
+        L.ref_bdeu_score.argtypes = [vp, i32, u64, C.c_float]
         L.ref_contab.restype = i64
         L.ref_contab.argtypes = [vp, u64, vp, i64]
         L.ref_score_variable.restype = i64
@@ -59,6 +65,15 @@ class Reference:
 
     def calculate_score(self, v, parents):
         return np.float32(lib().ref_calculate_score(self.h, v, parents))
+
+    def fnml_score(self, v, parents):
+        return np.float32(lib().ref_fnml_score(self.h, v, parents))
+
+    def regret(self, arity, N):
+        return np.float32(lib().ref_regret(self.h, arity, N))
+
+    def bdeu_score(self, v, parents, ess=1.0):
+        return np.float32(lib().ref_bdeu_score(self.h, v, parents, ess))
 
     def contab(self, variables):
         cells = lib().ref_contab(self.h, variables, None, 0)

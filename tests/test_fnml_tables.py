@@ -1,0 +1,85 @@
+"""fNML: the regret tables and the oracle's fNML restatement, pinned against the reference's own
+code (oracle/_ref: fnml_scoring_function.cpp + getRegretCache compiled from /root/reference) and, for the K = 2 table,
+against the literals in the reference's header when it is present."""
+import os
+import re
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import ref_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEP = os.path.join(ROOT, "tests", "data", "hepatitis.clean.csv")
+REF_HEADER = "/root/reference/urlearning/scoring_function/fnml_scoring_function.h"
+R2_CRC = 0x85246587   # crc32 of the 1001 float32 bit patterns (tools/gen_regret_table.py)
+
+
+def read_inc(path):
+    bits = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{8})u", open(path).read())]
+    assert len(bits) == 1001
+    return bits
+
+
+def test_generated_r2_tables_are_identical_and_match_their_crc():
+    a = read_inc(os.path.join(ROOT, "oracle", "regret_r2.inc"))
+    b = read_inc(os.path.join(ROOT, "urlearning-cpp_b200", "csrc", "regret_r2.inc"))
+    assert a == b
+    assert zlib.crc32(struct.pack("<1001I", *a)) == R2_CRC
+    f = np.array(a, dtype=np.uint32).view(np.float32)
+    assert f[0] == 1 and f[1] == 2 and f[2] == 2.5 and f[3] == np.float32(26 / 9)   # C(N,2) by hand
+    assert np.all(np.diff(f) > 0)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HEADER), reason="reference sources not present")
+def test_r2_table_equals_the_reference_literals_as_float32():
+    src = open(REF_HEADER).read()
+    body = src[src.index("r2_1000[] = {") + len("r2_1000[] = {"):]
+    body = body[:body.index("};")]
+    ref = np.array([float(x) for x in re.findall(r"[-+0-9.eE]+", body)], dtype=np.float64).astype(np.float32)
+    mine = np.array(read_inc(os.path.join(ROOT, "oracle", "regret_r2.inc")), dtype=np.uint32).view(np.float32)
+    assert len(ref) == 1001 and np.array_equal(ref.view(np.uint32), mine.view(np.uint32))
+
+
+def test_log_regret_rows(orc):
+    r1 = orc.log_regret(50, 1)
+    assert np.all(r1 == 0)                                        # C(N, 1) = 1
+    r2 = orc.log_regret(2000, 2)
+    assert r2[0] == 0 and r2[1] == np.float32(np.log(2.0)) and r2[2] == np.float32(np.log(2.5))
+    assert abs(float(r2[1001]) - float(r2[1000])) < 1e-3          # Szpankowski's approximation joins the table smoothly
+    r3 = orc.log_regret(10, 3)
+    # C(N,3) = C(N,2) + N * C(N,1): N = 1 -> 3, N = 2 -> 4.5
+    assert r3[1] == np.float32(np.log(3.0)) and r3[2] == np.float32(np.log(np.float32(4.5)))
+
+
+@pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not built (reference sources were absent)")
+def test_regret_and_fnml_scores_against_the_reference(orc):
+    ref = ref_lib.Reference(HEP, has_header=True)
+    codes = ref.codes()
+    for r in sorted(set(int(c) for c in ref.card)):
+        mine = orc.log_regret(ref.n, r)
+        theirs = np.array([ref.regret(r, N) for N in range(ref.n + 1)], dtype=np.float32)
+        assert np.array_equal(mine.view(np.uint32), theirs.view(np.uint32)), r
+    rng = np.random.default_rng(5)
+    cases = [(0, 0), (0, 2), (19, 0)]
+    for _ in range(200):
+        k = int(rng.integers(0, 5))
+        cases.append((int(rng.integers(20)), sum(1 << int(i) for i in rng.choice(20, size=k, replace=False))))
+    worst, exact, n = 0.0, 0, 0
+    for v, m in cases:
+        m &= ~(1 << v)
+        r = ref.fnml_score(v, m)
+        q = orc.fnml_score_many(codes, ref.card, v, [m], mode=0, threads=1)[0]
+        lit = orc.fnml_score_many(codes, ref.card, v, [m], mode=1, threads=1)[0]
+        worst = max(worst, abs(float(r) - float(q)) / abs(float(r)), abs(float(r) - float(lit)) / abs(float(r)))
+        exact += int(r.view(np.uint32) == lit.view(np.uint32))
+        n += 1
+    assert worst < 3e-6            # float32 accumulation order (boost::unordered_map iteration) vs the exact contract
+    assert exact >= 0.4 * n
+
+
+def test_fnml_large_n_rows_use_the_approximation(orc):
+    r = orc.log_regret(5000, 4)
+    assert np.all(np.isfinite(r)) and np.all(np.diff(r[1:]) > 0)

@@ -25,6 +25,8 @@ struct BicData {
     const uint8_t *codes;   // [p][n_stride]
     int64_t n, n_stride;
     const long long *qlog;  // [n+2]
+    const long long *qcfg;  // [n+2] per-configuration term: qlog itself (BIC), qlog + the log-regret of the child's arity (fNML)
+    int cfg_min;            // configurations with at most this many records contribute nothing (BIC: 1, fNML: 0)
     float base;             // (float)(ln(N)/2)
 };
 
@@ -161,7 +163,7 @@ __device__ __forceinline__ void count_rows(const SetCols &sc, int64_t row0, int6
 // sum_cells q[n_ijk] - sum_j q[n_ij] over parent configurations [j0,j1)
 template <typename HistPtr>
 __device__ __forceinline__ long long score_configs(HistPtr hist, int rv, int64_t j0, int64_t j1, const long long *__restrict__ qlog,
-                                                   int tid, int nthreads) {
+                                                   const long long *__restrict__ qcfg, int cfg_min, int tid, int nthreads) {
     long long acc = 0;
     for (int64_t j = j0 + tid; j < j1; j += nthreads) {
         const int64_t b = j * rv;
@@ -171,7 +173,7 @@ __device__ __forceinline__ long long score_configs(HistPtr hist, int rv, int64_t
             nij += cnt;
             if (cnt > 1) acc += __ldg(&qlog[cnt]); // q[0] = q[1] = 0
         }
-        if (nij > 1) acc -= __ldg(&qlog[nij]);
+        if (nij > cfg_min) acc -= __ldg(&qcfg[nij]);
     }
     return acc;
 }
@@ -204,7 +206,7 @@ __global__ void bic_count_smem_kernel(BicData d, CandInfo ci, const uint32_t *__
         for (uint32_t i = threadIdx.x; i < sc.cells; i += blockDim.x) dst[i] = hist[i];
     }
     if (!scores && !acc_out) return;
-    long long acc = score_configs(hist, ci.rv, 0, sc.cells / ci.rv, d.qlog, threadIdx.x, blockDim.x);
+    long long acc = score_configs(hist, ci.rv, 0, sc.cells / ci.rv, d.qlog, d.qcfg, d.cfg_min, threadIdx.x, blockDim.x);
     acc = block_sum_ll(acc, red);
     if (threadIdx.x == 0) {
         if (scores) scores[out_index(om, mask)] = bic_finalize(acc, sc.tval, d.base);
@@ -244,7 +246,7 @@ __global__ void bic_score_tables_kernel(BicData d, CandInfo ci, const GlobalSet 
     if (j0 >= nconf) return;
     int64_t j1 = j0 + configs_per_chunk;
     if (j1 > nconf) j1 = nconf;
-    long long acc = score_configs(tables + gs.table_off, ci.rv, j0, j1, d.qlog, threadIdx.x, blockDim.x);
+    long long acc = score_configs(tables + gs.table_off, ci.rv, j0, j1, d.qlog, d.qcfg, d.cfg_min, threadIdx.x, blockDim.x);
     acc = block_sum_ll(acc, red);
     if (threadIdx.x == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[blockIdx.x]), (unsigned long long)acc);
 }
@@ -370,6 +372,7 @@ __global__ void cube_map_kernel(const CubePair *__restrict__ pairs, int npairs, 
 template <int RV>
 __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePair *__restrict__ pairs, const uint32_t *__restrict__ block_pair, const int *__restrict__ parent_tab,
                                                                    int *__restrict__ child_tab, int rv_dyn, const long long *__restrict__ qlog,
+                                                                   const long long *__restrict__ qcfg, int cfg_min,
                                                                    long long *__restrict__ acc_all, int score_child /*0: the children of this launch are ancestors only*/,
                                                                    int r0 /*arity of cube bit 0*/, int *__restrict__ ovf_flag /*16-bit tables: a count did not fit*/,
                                                                    int qn /*entries of qlog*/) {
@@ -393,11 +396,11 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
                 int nij = 0;
 #pragma unroll
                 for (int k = 0; k < RV; k++) nij += cnt[k];
-                if (nij > 1) {
+                if (nij > cfg_min) {
 #pragma unroll
                     for (int k = 0; k < RV; k++)
                         if (cnt[k] > 1) a += __ldg(&qlog[cnt[k]]);
-                    a -= __ldg(&qlog[nij]);
+                    a -= __ldg(&qcfg[nij]);
                 }
             };
             // thread = one group of r0 adjacent child configurations (the values of cube bit 0, the least significant
@@ -439,11 +442,11 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
             int nij = 0;
 #pragma unroll
             for (int k = 0; k < RV; k++) nij += cnt[k];
-            if (nij > 1) { // q[0] = q[1] = 0
+            if (nij > cfg_min) { // q[0] = q[1] = 0
 #pragma unroll
                 for (int k = 0; k < RV; k++)
                     if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
-                acc -= __ldg(&qlog[nij]);
+                acc -= __ldg(&qcfg[nij]);
             }
         };
         // kCubeUnroll configurations per thread and iteration: r * kCubeUnroll independent 128-bit loads in flight.
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
                 nij += cnt;
                 if (acc_out && cnt > 1) acc += __ldg(&qlog[cnt]);
             }
-            if (acc_out && nij > 1) acc -= __ldg(&qlog[nij]);
+            if (acc_out && nij > cfg_min) acc -= __ldg(&qcfg[nij]);
         }
     }
     if (acc_out) {

@@ -362,7 +362,7 @@ __global__ void rank_bic_count_smem_kernel(BicData d, RankSpace rs, RankCand rc,
     __syncthreads();
     count_rows(sc, 0, d.n, hist, threadIdx.x, blockDim.x);
     __syncthreads();
-    long long acc = score_configs(hist, rc.rv, 0, sc.cells / rc.rv, d.qlog, threadIdx.x, blockDim.x);
+    long long acc = score_configs(hist, rc.rv, 0, sc.cells / rc.rv, d.qlog, d.qcfg, d.cfg_min, threadIdx.x, blockDim.x);
     acc = block_sum_ll(acc, red);
     if (threadIdx.x == 0) scores[idx] = bic_finalize(acc, sc.tval, d.base);
 }
@@ -398,7 +398,7 @@ __global__ void rank_bic_score_tables_kernel(BicData d, int rv, const RankGlobal
     if (j0 >= nconf) return;
     int64_t j1 = j0 + configs_per_chunk;
     if (j1 > nconf) j1 = nconf;
-    long long acc = score_configs(tables + gs.table_off, rv, j0, j1, d.qlog, threadIdx.x, blockDim.x);
+    long long acc = score_configs(tables + gs.table_off, rv, j0, j1, d.qlog, d.qcfg, d.cfg_min, threadIdx.x, blockDim.x);
     acc = block_sum_ll(acc, red);
     if (threadIdx.x == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[blockIdx.x]), (unsigned long long)acc);
 }

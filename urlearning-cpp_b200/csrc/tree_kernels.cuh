@@ -155,7 +155,8 @@ __global__ void tree_map_kernel(const TreeRoot *__restrict__ roots, int nroots, 
 // `store` false: the table has no children (bit 0 dropped), it is only scored
 template <int RV>
 __device__ __forceinline__ long long tree_derive(const int *__restrict__ src, int *__restrict__ dst, uint32_t cfg_dst, uint32_t pre, uint32_t magic,
-                                                 uint32_t r, int rv_dyn, bool score, bool store, const long long *__restrict__ qlog, int lane) {
+                                                 uint32_t r, int rv_dyn, bool score, bool store, const long long *__restrict__ qlog,
+                                                 const long long *__restrict__ qcfg, int cfg_min, int lane) {
     long long acc = 0;
     for (uint32_t j = lane; j < cfg_dst; j += 32) {
         const uint32_t hi = fast_div(j, pre, magic), lo = j - hi * pre;
@@ -174,11 +175,11 @@ __device__ __forceinline__ long long tree_derive(const int *__restrict__ src, in
                 int nij = 0;
 #pragma unroll
                 for (int k = 0; k < RV; k++) nij += cnt[k];
-                if (nij > 1) { // q[0] = q[1] = 0: sparse tables skip the look-ups altogether
+                if (nij > cfg_min) { // q[0] = q[1] = 0: sparse tables skip the look-ups altogether
 #pragma unroll
                     for (int k = 0; k < RV; k++)
                         if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
-                    acc -= __ldg(&qlog[nij]);
+                    acc -= __ldg(&qcfg[nij]);
                 }
             }
         } else {
@@ -190,7 +191,7 @@ __device__ __forceinline__ long long tree_derive(const int *__restrict__ src, in
                 nij += cnt;
                 if (score && cnt > 1) acc += __ldg(&qlog[cnt]);
             }
-            if (score && nij > 1) acc -= __ldg(&qlog[nij]);
+            if (score && nij > cfg_min) acc -= __ldg(&qcfg[nij]);
         }
     }
     return acc;
@@ -276,7 +277,8 @@ __device__ __forceinline__ void tree_count_fragmented(const unsigned long long *
 // RV > 0: compile-time child arity (2,3,4); RV == 0: generic
 template <int RV>
 __global__ void __launch_bounds__(kTreeThreads) bic_tree_kernel(TreeVar tv, const TreeRoot *__restrict__ roots, const uint32_t *__restrict__ cta_root,
-                                                                const long long *__restrict__ qlog, long long *__restrict__ acc_out,
+                                                                const long long *__restrict__ qlog, const long long *__restrict__ qcfg, int cfg_min,
+                                                                long long *__restrict__ acc_out,
                                                                 uint32_t table_budget /*cells*/, uint32_t stack_budget /*cells, all warps*/) {
     extern __shared__ __align__(16) int s_dyn[];              // [table_budget] slice table, then the warps' stacks
     __shared__ TreeRoot rt;
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(kTreeThreads) bic_tree_kernel(TreeVar tv, cons
         const int *tab0 = s_dyn + (size_t)g * G * U0;
         const uint32_t cfg0 = units * tv.pre[z];                          // configurations of the group's level-0 table
         if (b1 < 0) {
-            long long acc = score_configs(tab0, rv, 0, cfg0, qlog, lane, 32);
+            long long acc = score_configs(tab0, rv, 0, cfg0, qlog, qcfg, cfg_min, lane, 32);
             acc = warp_sum_ll_redux(acc);
             if (lane == 0 && acc != 0) atomicAdd(&s_acc[0], (unsigned long long)acc);
             continue;
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(kTreeThreads) bic_tree_kernel(TreeVar tv, cons
             const int *src = lvl == 1 ? tab0 : stack + (size_t)G * s_loff[lvl - 1];
             int *dst = stack + (size_t)G * s_loff[lvl];
             const bool score = (int)rt.size - lvl <= tv.max_parents;
-            long long acc = tree_derive<RV>(src, dst, units * s_cfg[D], tv.pre[m], tv.magic[m], r, rv, score, m > 0, qlog, lane);
+            long long acc = tree_derive<RV>(src, dst, units * s_cfg[D], tv.pre[m], tv.magic[m], r, rv, score, m > 0, qlog, qcfg, cfg_min, lane);
             if (score) {
                 acc = warp_sum_ll_redux(acc);
                 if (lane == 0 && acc != 0) atomicAdd(&s_acc[D], (unsigned long long)acc);
@@ -498,7 +500,8 @@ __global__ void root_map_kernel(const CubeRoot *__restrict__ roots, int nroots, 
 
 template <int RV, int NW>
 __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const CubeRoot *__restrict__ roots, const uint32_t *__restrict__ cta_root,
-                                                                const long long *__restrict__ qlog, int *__restrict__ tables, int *__restrict__ child_tables,
+                                                                const long long *__restrict__ qlog, const long long *__restrict__ qcfg, int cfg_min,
+                                                                int *__restrict__ tables, int *__restrict__ child_tables,
                                                                 long long *__restrict__ acc_out, uint32_t table_budget /*cells*/, uint32_t seg_cap,
                                                                 int *__restrict__ ovf_flag, int qn /*entries of qlog*/) {
     extern __shared__ __align__(16) int s_dyn[];              // [table_budget] slice table, then segbeg[seg_cap], segoff[seg_cap + 1]
@@ -657,11 +660,11 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
                     int nij = 0;
 #pragma unroll
                     for (int k = 0; k < RV; k++) nij += cnt[k];
-                    if (score && nij > 1) {
+                    if (score && nij > cfg_min) {
 #pragma unroll
                         for (int k = 0; k < RV; k++)
                             if (cnt[k] > 1) acc += __ldg(&qlog[cnt[k]]);
-                        acc -= __ldg(&qlog[nij]);
+                        acc -= __ldg(&qcfg[nij]);
                     }
                 }
             };
@@ -686,7 +689,7 @@ __global__ void __launch_bounds__(NW * 32) bic_root_kernel(TreeVar tv, const Cub
                     nij += cnt;
                     if (score && cnt > 1) acc += __ldg(&qlog[cnt]);
                 }
-                if (score && nij > 1) acc -= __ldg(&qlog[nij]);
+                if (score && nij > cfg_min) acc -= __ldg(&qcfg[nij]);
             }
         }
         if (ovf) *ovf_flag = 1;

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -20,8 +21,11 @@
 #include "cbic_kernels.cuh"
 #include "rank_kernels.cuh"
 #include "spg_kernels.cuh"
+#include "regret.hpp"
 
 using namespace urlgpu;
+
+static inline bool is_discrete(int score_type) { return score_type == URLGPU_BIC || score_type == URLGPU_FNML; }
 
 namespace {
 
@@ -54,6 +58,10 @@ struct urlgpu_ctx {
     long long *d_qlog = nullptr;
     float base = 0.f;
     bool have_discrete = false;
+    // the discrete score the next K1 launches compute (select_discrete_score): per-configuration table, the smallest
+    // configuration count that contributes, the penalty constant
+    const long long *ds_qcfg = nullptr; int ds_cfg_min = 1; float ds_base = 0.f;
+    std::map<int, long long *> d_qfnml;   // fNML: arity -> qlog + log-regret table [n+2] (built on first use, owned by this context)
     bool borrowed_discrete = false; // d_codes/d_qlog belong to another context on the same device (urlgpu_share_discrete)
 
     // continuous data
@@ -279,6 +287,7 @@ struct urlgpu_result {
     // read (the flag travels with the compaction counters), and the variable is then recomputed with 32-bit tables
     int *d_ovf = nullptr;
     bool is_bic = false;
+    int score_type = URLGPU_BIC;
     unsigned filter_flags = 0;
     uint64_t n_masks = 0, n_scored = 0;   // n_masks = entries of d_table
     // compaction into canonical order (|S|, mask): enqueued on the context's stream by urlgpu_result_prefetch, no host sync
@@ -367,6 +376,8 @@ static void free_discrete(urlgpu_ctx *ctx) {
         if (ctx->d_codes) cudaFree(ctx->d_codes);
         if (ctx->d_qlog) cudaFree(ctx->d_qlog);
     }
+    for (auto &kv : ctx->d_qfnml) cudaFree(kv.second);
+    ctx->d_qfnml.clear();
     ctx->d_codes = nullptr; ctx->d_qlog = nullptr; ctx->have_discrete = false; ctx->borrowed_discrete = false;
 }
 static void free_continuous(urlgpu_ctx *ctx) {
@@ -481,6 +492,7 @@ static int set_discrete_common(urlgpu_ctx *ctx, const uint8_t *src, bool src_on_
         CK(cudaStreamSynchronize(ctx->stream)); // q goes out of scope
     } else CK(cudaStreamSynchronize(ctx->stream)); // the caller may reuse its buffer
     ctx->base = (float)(std::log((double)(int)n) / 2); // bic_scoring_function.cpp:13
+    ctx->ds_qcfg = ctx->d_qlog; ctx->ds_cfg_min = 1; ctx->ds_base = ctx->base;
     ctx->have_discrete = true;
     ctx->mem_free_sample = 0;
     return URLGPU_OK;
@@ -495,8 +507,43 @@ extern "C" int urlgpu_share_discrete(urlgpu_ctx *ctx, urlgpu_ctx *owner) {
     free_discrete(ctx);
     ctx->n = owner->n; ctx->p = owner->p; ctx->n_stride = owner->n_stride; ctx->card = owner->card;
     ctx->d_codes = owner->d_codes; ctx->d_qlog = owner->d_qlog; ctx->base = owner->base;
+    ctx->ds_qcfg = ctx->d_qlog; ctx->ds_cfg_min = 1; ctx->ds_base = ctx->base;
     ctx->have_discrete = true; ctx->borrowed_discrete = true;
     ctx->mem_free_sample = 0;
+    return URLGPU_OK;
+}
+
+// Chooses what the K1 kernels compute for `variable`: BIC (log_likelihood - tVal * ln(N)/2, bic_scoring_function.cpp:73) or
+// fNML (log_likelihood - sum_j log C(N_ij, r_v), fnml_scoring_function.cpp:28-74).  The fNML per-configuration table is
+// qlog[N] + round(2^23 * (float)log C(N, r_v)): the exact-integer contract of bic_kernels.cuh extended by one more float
+// table of the reference, so an fNML score is again independent of summation order, path and GPU count.
+static int select_discrete_score(urlgpu_ctx *ctx, int score_type, int variable) {
+    if (score_type != URLGPU_FNML) {
+        ctx->ds_qcfg = ctx->d_qlog; ctx->ds_cfg_min = 1; ctx->ds_base = ctx->base;
+        return URLGPU_OK;
+    }
+    const int r = ctx->card[variable];
+    auto it = ctx->d_qfnml.find(r);
+    if (it == ctx->d_qfnml.end()) {
+        const int64_t n = ctx->n;
+        std::vector<float> lr = regret::log_regret(n + 1, r);
+        std::vector<long long> q((size_t)n + 2);
+        q[0] = 0;
+        for (int64_t i = 0; i < n + 2; i++) {
+            if (!std::isfinite(lr[(size_t)i]))
+                return ctx->fail(URLGPU_ERR_LIMIT, "fNML: the regret C(N, r) of arity " + std::to_string(r) + " overflows float32 at N = " + std::to_string(i) +
+                                                   " (the reference would store -inf)");
+            long long ql = 0;
+            if (i > 0) { const float l = (float)((int)i * std::log((double)(int)i)); ql = (long long)std::ldexp((double)l, 23); }
+            q[(size_t)i] = ql + std::llrint(std::ldexp((double)lr[(size_t)i], 23));
+        }
+        long long *d = nullptr;
+        CK(cudaMalloc(&d, q.size() * sizeof(long long)));
+        CK(cudaMemcpyAsync(d, q.data(), q.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        it = ctx->d_qfnml.emplace(r, d).first;
+    }
+    ctx->ds_qcfg = it->second; ctx->ds_cfg_min = 0; ctx->ds_base = 0.f;
     return URLGPU_OK;
 }
 
@@ -799,7 +846,7 @@ static int bic_score_family_direct(urlgpu_ctx *ctx, int variable, const std::vec
     const uint64_t n_masks = (uint64_t)1 << c;
     const uint64_t fam = family_size(c, K);
     *n_scored = fam;
-    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
     CandInfo ci = make_candinfo(ctx, variable, cand, K);
     const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
 
@@ -948,7 +995,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     CandInfo ci_cube = make_candinfo(ctx, variable, cube_vars, K);
     ci_cube.rv = rv;                               // layout arity: the counting kernels index x_v + rv * paIdx
     CandInfo ci_res = make_candinfo(ctx, variable, cand, K);
-    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
     const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
 
     // ---- enumerate layers 0..Lmax (layers above Kc: only sets containing the lowest l-Kc cube bits) ----
@@ -1302,7 +1349,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
                 const size_t smem = ((size_t)RB + 2 * seg_cap + 1) * sizeof(int);
                 const unsigned grid = (unsigned)rchunk;
                 switch (rv) {
-#define URLGPU_ROOT_ARGS tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, bufP, bufC, dacc.as<long long>() + acc_off[Lstar > 0 ? Lstar - 1 : 0], RB, seg_cap, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)
+#define URLGPU_ROOT_ARGS tv, dcroots.as<CubeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, bufP, bufC, dacc.as<long long>() + acc_off[Lstar > 0 ? Lstar - 1 : 0], RB, seg_cap, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)
 #define URLGPU_ROOT(RVV)                                                                             \
     do {                                                                                             \
         if (ctx->root_warps == 8) bic_root_kernel<RVV, 8><<<grid, 256, smem, s>>>(URLGPU_ROOT_ARGS); \
@@ -1433,10 +1480,10 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
             const unsigned grid = (unsigned)chunk;
             cube_map_kernel<<<blocks_for(chunk, 256), 256, 0, s>>>(dpairs.as<CubePair>(), (int)hp.size(), grid, dcmap.as<uint32_t>());
             switch (rv) {
-            case 2: cube_derive_kernel<2><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
-            case 3: cube_derive_kernel<3><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
-            case 4: cube_derive_kernel<4><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
-            default: cube_derive_kernel<0><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
+            case 2: cube_derive_kernel<2><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
+            case 3: cube_derive_kernel<3><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
+            case 4: cube_derive_kernel<4><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
+            default: cube_derive_kernel<0><<<grid, kCubeThreads, 0, s>>>(dpairs.as<CubePair>(), dcmap.as<uint32_t>(), bufP, bufC, rv, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, dacc.as<long long>(), score, r0, d_ovf, (int)std::min<int64_t>(ctx->n + 2, 1 << 30)); break;
             }
         }
         if (score) { int rc = finalize_layer(l); if (rc) return rc; }
@@ -1488,9 +1535,9 @@ static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int
 // that fit the shared-memory budget.  The caller then takes the cube path.
 // ------------------------------------------------------------------------------------------------------------
 template <int RV>
-static void launch_tree(const TreeVar &tv, const TreeRoot *roots, const uint32_t *map, const long long *qlog, long long *acc, uint32_t budget, unsigned grid,
+static void launch_tree(const TreeVar &tv, const TreeRoot *roots, const uint32_t *map, const long long *qlog, const long long *qcfg, int cfg_min, long long *acc, uint32_t budget, unsigned grid,
                         size_t smem, cudaStream_t s) {
-    bic_tree_kernel<RV><<<grid, kTreeThreads, smem, s>>>(tv, roots, map, qlog, acc, budget, budget);
+    bic_tree_kernel<RV><<<grid, kTreeThreads, smem, s>>>(tv, roots, map, qlog, qcfg, cfg_min, acc, budget, budget);
 }
 
 static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
@@ -1629,7 +1676,7 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
     { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
     CandInfo ci_cube = make_candinfo(ctx, variable, cube_vars, K);
     CandInfo ci_res = make_candinfo(ctx, variable, cand, K);
-    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
     DevBuf dkeys(ctx), dhist(ctx), doff(ctx), dcursor(ctx), drows(ctx), droots(ctx), dmap(ctx), dacc(ctx), dperm(ctx), dtmp(ctx);
     CK(dkeys.alloc(n * sizeof(uint32_t)));
     CK(dhist.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
@@ -1678,10 +1725,10 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
         const size_t smem = (size_t)2 * B * sizeof(int);
         const unsigned grid = (unsigned)chunk;
         switch (rv) {
-        case 2: launch_tree<2>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, dacc.as<long long>(), B, grid, smem, s); break;
-        case 3: launch_tree<3>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, dacc.as<long long>(), B, grid, smem, s); break;
-        case 4: launch_tree<4>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, dacc.as<long long>(), B, grid, smem, s); break;
-        default: launch_tree<0>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, dacc.as<long long>(), B, grid, smem, s); break;
+        case 2: launch_tree<2>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, dacc.as<long long>(), B, grid, smem, s); break;
+        case 3: launch_tree<3>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, dacc.as<long long>(), B, grid, smem, s); break;
+        case 4: launch_tree<4>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, dacc.as<long long>(), B, grid, smem, s); break;
+        default: launch_tree<0>(tv, droots.as<TreeRoot>(), dmap.as<uint32_t>(), ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, dacc.as<long long>(), B, grid, smem, s); break;
         }
     }
     {
@@ -1986,7 +2033,7 @@ static int bic_score_rank_direct(urlgpu_ctx *ctx, int variable, const std::vecto
     cudaStream_t s = ctx->stream;
     const int c = rs.c;
     if (rs.K + 1 > kMaxCols) return ctx->fail(URLGPU_ERR_LIMIT, "BIC: more than 31 parents in one set");
-    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
     const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
     std::vector<int> hv(2 * (size_t)std::max(c, 1));
     for (int i = 0; i < c; i++) { hv[i] = cand[i]; hv[c + i] = ctx->card[cand[i]]; }
@@ -2193,12 +2240,13 @@ static int apply_filters(urlgpu_ctx *ctx, urlgpu_result *res, bool bic, unsigned
 }
 
 static int check_score_args(urlgpu_ctx *ctx, const char *who, int variable, const uint64_t *neighbors, int mask_words, int score_type, std::vector<int> &cand) {
-    const bool bic = score_type == URLGPU_BIC;
+    const bool bic = is_discrete(score_type);
     if (!bic && score_type != URLGPU_CBIC) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": unknown score type");
-    if (bic && !ctx->have_discrete) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": BIC needs urlgpu_set_discrete first");
+    if (bic && !ctx->have_discrete) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": BIC / fNML need urlgpu_set_discrete first");
     if (!bic && !ctx->have_gram) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": cBIC needs urlgpu_set_continuous first");
     const int p = bic ? ctx->p : ctx->cp;
     if (variable < 0 || variable >= p) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": variable out of range");
+    if (bic) { const int rc = select_discrete_score(ctx, score_type, variable); if (rc) return rc; }
     return candidates_from_mask(ctx, p, variable, neighbors, mask_words, cand);
 }
 
@@ -2210,7 +2258,7 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     const auto T0 = std::chrono::steady_clock::now();
     auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     CK(cudaSetDevice(ctx->device));
-    const bool bic = score_type == URLGPU_BIC;
+    const bool bic = is_discrete(score_type);
     std::vector<int> cand;
     int rc = check_score_args(ctx, "score_variable", variable, neighbors, mask_words, score_type, cand);
     if (rc) return rc;
@@ -2229,7 +2277,7 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     if (e != cudaSuccess) { delete res; return ctx->cuda_fail(e, "cudaMalloc(score table)", __LINE__); }
     cudaStream_t s = ctx->stream;
     auto cleanup = [&](int code) { pool_free(ctx, res->d_table); if (res->d_ovf) pool_free(ctx, res->d_ovf); delete res; return code; };
-    res->is_bic = bic; res->filter_flags = filter_flags;
+    res->is_bic = bic; res->score_type = score_type; res->filter_flags = filter_flags;
     if (bic && ctx->table16 && c <= kMaxDenseCand && ctx->bic_mode == 2) {
         e = pool_alloc(ctx, reinterpret_cast<void **>(&res->d_ovf), sizeof(int));
         if (e != cudaSuccess) return cleanup(ctx->cuda_fail(e, "cudaMalloc(flag)", __LINE__));
@@ -2283,7 +2331,7 @@ extern "C" int urlgpu_score_range(urlgpu_ctx *ctx, int variable, const uint64_t 
                                   uint64_t first, uint64_t count, float *scores, int on_device) {
     if (!ctx || !neighbors || !scores) return ctx ? ctx->fail(URLGPU_ERR_ARG, "score_range: null argument") : URLGPU_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    const bool bic = score_type == URLGPU_BIC;
+    const bool bic = is_discrete(score_type);
     std::vector<int> cand;
     int rc = check_score_args(ctx, "score_range", variable, neighbors, mask_words, score_type, cand);
     if (rc) return rc;
@@ -2314,7 +2362,7 @@ extern "C" int urlgpu_score_part(urlgpu_ctx *ctx, int variable, const uint64_t *
                                  int part, int parts, float *scores, int on_device) {
     if (!ctx || !neighbors || !scores || parts < 1 || part < 0 || part >= parts) return ctx ? ctx->fail(URLGPU_ERR_ARG, "score_part: bad argument") : URLGPU_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    const bool bic = score_type == URLGPU_BIC;
+    const bool bic = is_discrete(score_type);
     std::vector<int> cand;
     int rc = check_score_args(ctx, "score_part", variable, neighbors, mask_words, score_type, cand);
     if (rc) return rc;
@@ -2369,7 +2417,7 @@ extern "C" int urlgpu_result_from_scores(urlgpu_ctx *ctx, int variable, const ui
     if (!ctx || !neighbors || !scores || !out) return ctx ? ctx->fail(URLGPU_ERR_ARG, "result_from_scores: null argument") : URLGPU_ERR_ARG;
     *out = nullptr;
     CK(cudaSetDevice(ctx->device));
-    const bool bic = score_type == URLGPU_BIC;
+    const bool bic = is_discrete(score_type);
     std::vector<int> cand;
     int rc = check_score_args(ctx, "result_from_scores", variable, neighbors, mask_words, score_type, cand);
     if (rc) return rc;
@@ -2567,6 +2615,8 @@ static int result_wait_counts(urlgpu_result *res) {
         cudaStream_t s = ctx->stream;
         fill_u32_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), res->n_masks, kSentinelBits);
         uint64_t ns = 0;
+        rc = select_discrete_score(ctx, res->score_type, res->variable);   // a later call may have selected another score / arity
+        if (rc) return rc;
         rc = bic_score_family(ctx, res->variable, res->cand, res->max_parents, res->d_table, nullptr, &ns, res->rank_layout ? res->rs : RankSpace{}, nullptr);
         if (rc) return rc;
         rc = apply_filters(ctx, res, true, res->filter_flags);
@@ -2770,11 +2820,13 @@ extern "C" int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *p
                                 double *value64) {
     if (!ctx || !parents || !score) return ctx ? ctx->fail(URLGPU_ERR_ARG, "score_one: null argument") : URLGPU_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    const bool bic = score_type == URLGPU_BIC;
-    if (bic && !ctx->have_discrete) return ctx->fail(URLGPU_ERR_ARG, "score_one: BIC needs urlgpu_set_discrete first");
+    const bool bic = is_discrete(score_type);
+    if (!bic && score_type != URLGPU_CBIC) return ctx->fail(URLGPU_ERR_ARG, "score_one: unknown score type");
+    if (bic && !ctx->have_discrete) return ctx->fail(URLGPU_ERR_ARG, "score_one: BIC / fNML need urlgpu_set_discrete first");
     if (!bic && !ctx->have_gram) return ctx->fail(URLGPU_ERR_ARG, "score_one: cBIC needs urlgpu_set_continuous first");
     const int p = bic ? ctx->p : ctx->cp;
     if (variable < 0 || variable >= p) return ctx->fail(URLGPU_ERR_ARG, "score_one: variable out of range");
+    if (bic) { const int rc0 = select_discrete_score(ctx, score_type, variable); if (rc0) return rc0; }
     std::vector<int> cand;
     int rc = compact_of(ctx, p, variable, parents, mask_words, cand);
     if (rc) return rc;
@@ -2787,7 +2839,7 @@ extern "C" int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *p
         const uint32_t full = (uint32_t)(((uint64_t)1 << c) - 1);
         DevBuf out(ctx);
         CK(out.alloc(sizeof(float) + sizeof(long long) + 8));
-        BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+        BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
         CandInfo ci = make_candinfo(ctx, variable, cand, c);
         uint64_t cells = ci.rv;
         for (int b = 0; b < c; b++) { cells *= (uint64_t)ci.card[b]; if (cells > kCellLimit) return ctx->fail(URLGPU_ERR_LIMIT, "contingency table exceeds 2^30 cells"); }
@@ -2846,7 +2898,7 @@ extern "C" int urlgpu_contingency(urlgpu_ctx *ctx, int variable, const uint64_t 
     if (rc) return rc;
     const int c = (int)cand.size();
     if (c > kMaxDenseCand) return ctx->fail(URLGPU_ERR_LIMIT, "contingency: more than 30 parents in one set");
-    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->base};
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
     CandInfo ci = make_candinfo(ctx, variable, cand, c);
     uint64_t cells = ci.rv;
     for (int b = 0; b < c; b++) { cells *= (uint64_t)ci.card[b]; if (cells > kCellLimit) return ctx->fail(URLGPU_ERR_LIMIT, "contingency table exceeds 2^30 cells"); }

@@ -1,6 +1,6 @@
 // gpu_scoring.hpp — the reference's plugin/operator interface for the local-score path, backed by liburlgpu.
 //
-//   scoring::ScoringFunction      scoring_function/scoring_function.h:16-24  (calculateScore per set)
+//   scoring::ScoringFunction      scoring_function/scoring_function.h:16-24  (calculateScore per set; BIC, fNML, cBIC)
 //   scoring::ScoreCalculator      scoring_function/score_calculator.{h,cpp}  (calculateScores per variable, prune)
 //   FloatMap                      base/typedefs.h:816                        (per-variable score cache)
 //
@@ -97,6 +97,24 @@ public:
         return s;
     }
     int scoreType() const override { return URLGPU_BIC; }
+    urlgpu_ctx *context() override { return g.ctx; }
+private:
+    GpuContext &g;
+};
+
+// fNMLScoringFunction (fnml_scoring_function.cpp) on the device: the same counts as BIC, the regret tables instead of the penalty
+class GpufNMLScoringFunction : public ScoringFunction {
+public:
+    GpufNMLScoringFunction(GpuContext &g, const uint8_t *codes, int64_t recordCount, int p, const int32_t *card) : g(g) {
+        g.check(urlgpu_set_discrete(g.ctx, codes, recordCount, p, card));
+    }
+    GpufNMLScoringFunction(GpuContext &g, GpuContext &owner) : g(g) { g.check(urlgpu_share_discrete(g.ctx, owner.ctx)); }
+    float calculateScore(int variable, varset parents, FloatMap &) override {
+        float s;
+        g.check(urlgpu_score_one(g.ctx, variable, parents.w, urlhost::kVarsetWords, URLGPU_FNML, 0.0, &s, nullptr));
+        return s;
+    }
+    int scoreType() const override { return URLGPU_FNML; }
     urlgpu_ctx *context() override { return g.ctx; }
 private:
     GpuContext &g;
