@@ -47,8 +47,10 @@ typedef enum {
 } urlgpu_status;
 
 /* URLGPU_FNML: factorized NML on the same counts as BIC (scoring_function/fnml_scoring_function.{h,cpp}: log-likelihood
- * minus sum_j log C(N_ij, r_v), no BIC penalty and no log-bound on the parent limit); needs urlgpu_set_discrete. */
-typedef enum { URLGPU_BIC = 0, URLGPU_CBIC = 1, URLGPU_FNML = 2 } urlgpu_score_t;
+ * minus sum_j log C(N_ij, r_v), no BIC penalty and no log-bound on the parent limit); needs urlgpu_set_discrete.
+ * URLGPU_BDEU: BDeu on the same counts (scoring_function/bdeu_scoring_function.cpp:25-123, deCampos pruning off); the
+ * `lambda` argument of the scoring calls carries the equivalent sample size (score_main.cpp -e, default 1). */
+typedef enum { URLGPU_BIC = 0, URLGPU_CBIC = 1, URLGPU_FNML = 2, URLGPU_BDEU = 3 } urlgpu_score_t;
 
 /* filter_flags of urlgpu_score_variable (bit set) */
 enum {

@@ -511,6 +511,100 @@ extern "C" int orc_fnml_score_many(const uint8_t *codes, int64_t n, int p, const
     return 0;
 }
 
+/* ------------------------------------------------------------ discrete BDeu */
+
+/* bdeu_scoring_function.cpp:25-123 with enableDeCamposPruning off (score_main.cpp:112).
+ *   lg (:25-37): r = prod card(pa) (int); a_ij = ess / r (float / int); lg_ij = lgamma(a_ij) stored as float; a_ijk likewise
+ *   calculate (:125-168): every non-empty cell: score -= lg_ijk; score += (float)lgamma(a_ijk + n_ijk)   (float + int addition)
+ *   :115-118: every non-empty parent configuration: score += lg_ij; score -= lgamma(a_ij + n_ij)
+ * mode 0: every bracket [temp - lg_ijk], [lg_ij - lgamma(.)] in FP64, rounded to the 2^-30 grid, summed exactly, one final
+ *         rounding to float32 — the order-independent contract the device implements (bic_kernels.cuh score_configs_bdeu).
+ * mode 1: literal float32 running sum: cells in contingency-tree DFS order, then configurations in ascending paIdx
+ *         (boost::unordered_map order there). */
+static int bdeu_score_one(const BicCtx &c, float ess, int v, uint64_t parents, int mode, std::vector<int32_t> &counts, float *score_out) {
+    int64_t cells = orc_bic_cells(c.card, c.p, v, parents);
+    if (cells < 0) return fail("contingency table too large");
+    counts.resize(cells);
+    if (orc_bic_counts(c.codes, c.n, c.p, c.card, v, parents, counts.data())) return -1;
+    const int rv = c.card[v];
+    int r = 1;
+    for (int pa = 0; pa < c.p; pa++) if ((parents >> pa) & 1) r *= c.card[pa];
+    const float a_ij = ess / r;
+    int sg;
+    const float lg_ij = lgamma_r(a_ij, &sg);
+    r *= rv;
+    const float a_ijk = ess / r;
+    const float lg_ijk = lgamma_r(a_ijk, &sg);
+    if (mode == 0) {
+        int64_t fx = 0;
+        for (int64_t j = 0; j < cells; j += rv) {
+            int32_t nij = 0;
+            for (int k = 0; k < rv; k++) {
+                const int32_t cnt = counts[j + k];
+                nij += cnt;
+                if (cnt > 0) {
+                    const float temp = lgamma_r(a_ijk + cnt, &sg);
+                    fx += std::llrint(((double)temp - (double)lg_ijk) * 1073741824.0);
+                }
+            }
+            if (nij > 0) fx += std::llrint(((double)lg_ij - lgamma_r(a_ij + nij, &sg)) * 1073741824.0);
+        }
+        *score_out = (float)((double)fx * (1.0 / 1073741824.0));
+        return 0;
+    }
+    std::vector<int> vars;
+    for (int i = 0; i < c.p; i++) if (((parents >> i) & 1) || i == v) vars.push_back(i);
+    std::vector<int64_t> stride(vars.size());
+    int64_t b = rv;
+    for (size_t j = 0; j < vars.size(); j++) {
+        if (vars[j] == v) stride[j] = 1;
+        else { stride[j] = b; b *= c.card[vars[j]]; }
+    }
+    float score = 0;
+    std::vector<int> digit(vars.size(), 0);
+    while (true) {
+        int64_t idx = 0;
+        for (size_t j = 0; j < vars.size(); j++) idx += stride[j] * digit[j];
+        if (counts[idx] > 0) {
+            float temp = lgamma_r(a_ijk + counts[idx], &sg);
+            score -= lg_ijk;
+            score += temp;
+        }
+        int j = (int)vars.size() - 1;
+        while (j >= 0 && ++digit[j] == c.card[vars[j]]) { digit[j] = 0; j--; }
+        if (j < 0) break;
+    }
+    for (int64_t j = 0; j < cells; j += rv) {
+        int32_t nij = 0;
+        for (int k = 0; k < rv; k++) nij += counts[j + k];
+        if (nij > 0) {
+            score += lg_ij;
+            score -= lgamma_r(a_ij + nij, &sg);
+        }
+    }
+    *score_out = score;
+    return 0;
+}
+
+extern "C" int orc_bdeu_score_many(const uint8_t *codes, int64_t n, int p, const int32_t *card, int v, float ess,
+                                   const uint64_t *parents, int64_t n_sets, int mode, int threads, float *out) {
+    BicCtx c = make_bic(codes, n, p, card);
+    if (threads < 1) threads = 1;
+    std::vector<int> rc(threads, 0);
+    std::vector<std::string> errs(threads);
+    auto work = [&](int t) {
+        std::vector<int32_t> counts;
+        for (int64_t i = t; i < n_sets; i += threads)
+            if (bdeu_score_one(c, ess, v, parents[i], mode, counts, &out[i])) { rc[t] = -1; errs[t] = g_err; return; }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    for (int t = 0; t < threads; t++) if (rc[t]) return fail(errs[t]);
+    return 0;
+}
+
 /* --------------------------------------------------------- continuous cBIC */
 
 /* arma::mean (arrayops::accumulate: two running sums over even/odd elements, then /n) */
@@ -762,10 +856,10 @@ static std::string lexical_float(float f) { /* boost::lexical_cast<std::string>(
 extern "C" int64_t orc_score_file(const orc_options *o) {
     std::string sf(o->function ? o->function : "BIC");
     for (auto &ch : sf) ch = (char)std::tolower((unsigned char)ch); /* score_main.cpp:294 */
-    const bool is_fnml = sf == "fnml";
+    const bool is_fnml = sf == "fnml", is_bdeu = sf == "bdeu";
     const bool log_bound = sf == "bic";                     /* score_main.cpp:300-304: only BIC bounds the parent limit */
-    bool is_bic = sf == "bic" || is_fnml, is_cbic = sf == "cbic";   /* is_bic: discrete input */
-    if (!is_bic && !is_cbic) return fail("oracle supports -f BIC|fNML|cBIC only");
+    bool is_bic = sf == "bic" || is_fnml || is_bdeu, is_cbic = sf == "cbic";   /* is_bic: discrete input */
+    if (!is_bic && !is_cbic) return fail("oracle supports -f BIC|fNML|BDeu|cBIC only");
     orc_table *t = orc_read_csv(o->input, o->delimiter ? o->delimiter : ',', o->has_header);
     if (!t) return -1;
     const int p = t->p;
@@ -807,7 +901,8 @@ extern "C" int64_t orc_score_file(const orc_options *o) {
             const std::vector<float> *reg = is_fnml ? &fnml_row(fc, card[v]) : nullptr;
             std::vector<int32_t> cnt;
             for (int64_t i = 0; i < m; i++) {
-                if (is_fnml ? fnml_score_one(c, *reg, v, masks[i], o->bic_mode, cnt, &val[i])
+                if (is_bdeu ? bdeu_score_one(c, o->ess > 0 ? o->ess : 1.0f, v, masks[i], o->bic_mode, cnt, &val[i])
+                    : is_fnml ? fnml_score_one(c, *reg, v, masks[i], o->bic_mode, cnt, &val[i])
                             : bic_score_one(c, v, masks[i], o->bic_mode, cnt, &val[i], nullptr)) { rc[v] = -1; errs[v] = g_err; return; }
                 stored[i] = masks[i] == 0 ? (val[i] < 1) : (val[i] < 0); /* score_calculator.cpp:59,111 */
             }
@@ -858,7 +953,7 @@ extern "C" int64_t orc_score_file(const orc_options *o) {
     if (!out.good()) { orc_table_free(t); return fail("cannot open output file"); }
     /* score_main.cpp:387-388 */
     out << "META pss_version = 0.1\nMETA input_file=" << o->input << "\nMETA num_records=" << (int)n << "\n";
-    out << "META parent_limit=" << maxParents << "\nMETA score_type=" << sf << "\nMETA ess=" << lexical_float(1.0f) << "\n\n";
+    out << "META parent_limit=" << maxParents << "\nMETA score_type=" << sf << "\nMETA ess=" << lexical_float(o->ess > 0 ? o->ess : 1.0f) << "\n\n";
     int64_t total = 0;
     for (int v = 0; v < p; v++) { out << blocks[v]; total += counts[v]; }
     out.close();

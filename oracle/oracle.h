@@ -77,6 +77,11 @@ void orc_log_regret(int64_t n_max, int r, float *out);
 int orc_fnml_score_many(const uint8_t *codes, int64_t n, int p, const int32_t *card, int v,
                         const uint64_t *parents, int64_t n_sets, int mode, int threads, float *scores_out);
 
+/* ---------- discrete BDeu (bdeu_scoring_function.cpp:25-168) ---------- */
+/* mode 0: FP64 brackets on the 2^-30 grid, exact sum, one final rounding; mode 1: literal float32 running sum */
+int orc_bdeu_score_many(const uint8_t *codes, int64_t n, int p, const int32_t *card, int v, float ess,
+                        const uint64_t *parents, int64_t n_sets, int mode, int threads, float *scores_out);
+
 /* ---------- continuous cBIC (BIC_OLS.cpp) ---------- */
 /* BIC_OLS.cpp:66-80: centre, divide by sample std (N-1). z_out column-major n*p */
 void orc_standardise(const double *x, int64_t n, int p, double *z_out);
@@ -103,7 +108,7 @@ typedef struct orc_options {
     const char *input;      /* positional 1 */
     const char *output;     /* positional 2 */
     const char *skeleton;   /* -k, may be NULL */
-    const char *function;   /* -f: "BIC" | "fNML" | "cBIC" */
+    const char *function;   /* -f: "BIC" | "fNML" | "BDeu" | "cBIC" */
     char delimiter;         /* -d */
     int has_header;         /* -s */
     int max_parents;        /* -p (0 = no limit) */
@@ -113,6 +118,7 @@ typedef struct orc_options {
     int accept_mode;        /* cBIC: 0 clean, 1 literal-zero */
     int bic_mode;           /* 0 Q4 rule, 1 literal float32 */
     int cbic_from_gram;     /* 0 residual form (reference), 1 Gram/Cholesky form */
+    float ess;              /* -e: BDeu equivalent sample size (0 -> the default 1) */
 } orc_options;
 /* whole `score` run, canonical line order (|S|, mask). returns number of scores written, <0 on error */
 int64_t orc_score_file(const orc_options *opt);

@@ -103,9 +103,11 @@ float ref_regret(void *h, int arity, int N) {
 /* BDeuScoringFunction::calculateScore (bdeu_scoring_function.cpp:37-123), set up as score_main.cpp:357-360 does */
 float ref_bdeu_score(void *h, int variable, uint64_t parents, float ess) {
     Ref *r = (Ref *)h;
-    scoring::BDeuScoringFunction sf(ess, *r->network, r->adTree, NULL, false);
+    /* never freed, like everything else here: the function object holds a BayesianNetwork copy whose destructor would
+     * release the variables it shares with the original */
+    scoring::BDeuScoringFunction *sf = new scoring::BDeuScoringFunction(ess, *r->network, r->adTree, NULL, false);
     FloatMap cache;
-    return sf.calculateScore(variable, parents, cache);
+    return sf->calculateScore(variable, parents, cache);
 }
 
 /* ADTree::makeContab (ad_tree.cpp:95-137) flattened: mixed radix over the set's variables in ascending index,

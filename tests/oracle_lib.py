@@ -17,7 +17,7 @@ class Options(C.Structure):
     _fields_ = [("input", C.c_char_p), ("output", C.c_char_p), ("skeleton", C.c_char_p), ("function", C.c_char_p),
                 ("delimiter", C.c_char), ("has_header", C.c_int), ("max_parents", C.c_int), ("lambda_", C.c_double),
                 ("threads", C.c_int), ("prune", C.c_int), ("accept_mode", C.c_int), ("bic_mode", C.c_int),
-                ("cbic_from_gram", C.c_int)]
+                ("cbic_from_gram", C.c_int), ("ess", C.c_float)]
 
 
 _lib = None
@@ -59,6 +59,7 @@ def lib():
         L.orc_bic_score_many.argtypes = [vp, i64, i32, vp, i32, vp, i64, i32, i32, vp]
         L.orc_log_regret.argtypes = [i64, i32, vp]
         L.orc_fnml_score_many.argtypes = [vp, i64, i32, vp, i32, vp, i64, i32, i32, vp]
+        L.orc_bdeu_score_many.argtypes = [vp, i64, i32, vp, i32, C.c_float, vp, i64, i32, i32, vp]
         L.orc_standardise.argtypes = [vp, i64, i32, vp]
         L.orc_gram.argtypes = [vp, i64, i32, vp]
         L.orc_cbic_the_score_residual.restype = C.c_double
@@ -188,6 +189,18 @@ def fnml_score_many(codes, card, v, masks, mode=0, threads=8):
     return out
 
 
+def bdeu_score_many(codes, card, v, masks, ess=1.0, mode=0, threads=8):
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    card = np.ascontiguousarray(card, dtype=np.int32)
+    masks = np.ascontiguousarray(masks, dtype=np.uint64)
+    p, n = codes.shape
+    out = np.zeros(len(masks), dtype=np.float32)
+    if lib().orc_bdeu_score_many(codes.ctypes.data, n, p, card.ctypes.data, v, ess, masks.ctypes.data, len(masks), mode, threads,
+                                 out.ctypes.data):
+        raise RuntimeError(err())
+    return out
+
+
 def standardise(x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     p, n = x.shape
@@ -233,9 +246,9 @@ def prune(masks, scores, highest_completed_layer=64):
 
 
 def score_file(input, output, function="BIC", skeleton=None, has_header=False, max_parents=0, lam=0.5, threads=1,
-               prune=False, accept_mode=0, bic_mode=0, from_gram=False):
+               prune=False, accept_mode=0, bic_mode=0, from_gram=False, ess=0.0):
     o = Options(input.encode(), output.encode(), skeleton.encode() if skeleton else None, function.encode(), b",",
-                int(has_header), max_parents, lam, threads, int(prune), accept_mode, bic_mode, int(from_gram))
+                int(has_header), max_parents, lam, threads, int(prune), accept_mode, bic_mode, int(from_gram), ess)
     n = lib().orc_score_file(C.byref(o))
     if n < 0:
         raise RuntimeError(err())

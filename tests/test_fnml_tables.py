@@ -83,3 +83,37 @@ def test_regret_and_fnml_scores_against_the_reference(orc):
 def test_fnml_large_n_rows_use_the_approximation(orc):
     r = orc.log_regret(5000, 4)
     assert np.all(np.isfinite(r)) and np.all(np.diff(r[1:]) > 0)
+
+
+@pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not built (reference sources were absent)")
+@pytest.mark.parametrize("ess", [1.0, 10.0, 0.25])
+def test_bdeu_scores_against_the_reference(orc, ess):
+    """the oracle's BDeu (both modes) vs the reference's own BDeuScoringFunction::calculateScore: float32 running-sum noise"""
+    ref = ref_lib.Reference(HEP, has_header=True)
+    codes = ref.codes()
+    rng = np.random.default_rng(7)
+    cases = [(0, 0), (0, 2), (19, 0)]
+    for _ in range(150):
+        k = int(rng.integers(0, 5))
+        cases.append((int(rng.integers(20)), sum(1 << int(i) for i in rng.choice(20, size=k, replace=False))))
+    worst, exact, n = 0.0, 0, 0
+    for v, m in cases:
+        m &= ~(1 << v)
+        r = ref.bdeu_score(v, m, ess)
+        q = orc.bdeu_score_many(codes, ref.card, v, [m], ess=ess, mode=0, threads=1)[0]
+        lit = orc.bdeu_score_many(codes, ref.card, v, [m], ess=ess, mode=1, threads=1)[0]
+        worst = max(worst, abs(float(r) - float(q)) / abs(float(r)), abs(float(r) - float(lit)) / abs(float(r)))
+        exact += int(r.view(np.uint32) == lit.view(np.uint32))
+        n += 1
+    assert worst < 5e-6
+    assert exact >= 0.1 * n       # the configuration terms are added in boost::unordered_map order there, ascending here
+
+
+def test_bdeu_known_answer_by_hand(orc):
+    """two binary variables, 4 records (0,0),(0,1),(1,0),(1,1), ess = 1, X0 with parent X1: r = 2, a_ij = 1/2, a_ijk = 1/4,
+    every cell 1, every configuration 2:  4*(lgamma(1.25) - lgamma(0.25)) + 2*(lgamma(0.5) - lgamma(2.5))"""
+    from math import lgamma
+    codes = np.array([[0, 0, 1, 1], [0, 1, 0, 1]], dtype=np.uint8)
+    want = 4 * (lgamma(1.25) - lgamma(0.25)) + 2 * (lgamma(0.5) - lgamma(2.5))
+    got = orc.bdeu_score_many(codes, [2, 2], 0, [0b10], ess=1.0, mode=0, threads=1)[0]
+    assert abs(float(got) - want) < 1e-6 * abs(want)

@@ -23,7 +23,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liburlgpu.so")
 
-BIC, CBIC, FNML = 0, 1, 2
+BIC, CBIC, FNML, BDEU = 0, 1, 2, 3   # BDEU: the `lam` argument of the scoring calls is the equivalent sample size
 KEEP_ALL, PRUNE_DOMINATED, CBIC_NO_ACCEPT, CBIC_ACCEPT_LITERAL = 0, 2, 4, 8
 
 # every symbol include/urlgpu.h declares (tests check the built library exports all of them)

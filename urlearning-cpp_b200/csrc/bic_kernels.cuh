@@ -27,7 +27,9 @@ struct BicData {
     const long long *qlog;  // [n+2]
     const long long *qcfg;  // [n+2] per-configuration term: qlog itself (BIC), qlog + the log-regret of the child's arity (fNML)
     int cfg_min;            // configurations with at most this many records contribute nothing (BIC: 1, fNML: 0)
-    float base;             // (float)(ln(N)/2)
+    float base;             // (float)(ln(N)/2); 0 for fNML and BDeu (no penalty term)
+    float ess;              // > 0: BDeu with this equivalent sample size (direct-counting kernels only); 0: table look-ups
+    double acc_scale;       // the accumulator's unit: 2^-23 (BIC, fNML), 2^-30 (BDeu)
 };
 
 // Per-variable candidate description (kernel argument, by value).
@@ -178,10 +180,47 @@ __device__ __forceinline__ long long score_configs(HistPtr hist, int rv, int64_t
     return acc;
 }
 
-__device__ __forceinline__ float bic_finalize(long long acc, float tval, float base) {
+__device__ __forceinline__ float bic_finalize(long long acc, float tval, float base, double acc_scale = 1.0 / 8388608.0) {
     // acc * 2^-23 is exact in FP64 (|acc| < 2^53); one rounding to float32, then the float32 penalty
-    const float ll = __double2float_rn(__ll2double_rn(acc) * (1.0 / 8388608.0));
+    const float ll = __double2float_rn(__ll2double_rn(acc) * acc_scale);
     return __fsub_rn(ll, __fmul_rn(tval, base)); // bic_scoring_function.cpp:73, no FMA contraction
+}
+
+// BDeu (bdeu_scoring_function.cpp:25-123, enableDeCamposPruning off) over parent configurations [j0,j1) of a set with
+// `nconf` configurations in all:
+//   sum_{cells, n_ijk > 0} [ (float)lgamma(a_ijk (+) n_ijk) - (float)lgamma(a_ijk) ]  +  sum_{j, n_ij > 0} [ (float)lgamma(a_ij) - lgamma(a_ij (+) n_ij) ]
+// with a_ij = ess / r, a_ijk = ess / (r * r_v) in float32 and (+) the float32 addition the reference performs before
+// calling lgamma (:108, :117).  Contract: every bracket is evaluated in FP64, rounded to the 2^-30 grid and the grid values
+// are summed as exact integers — independent of summation order like the BIC contract; the reference itself keeps a
+// float32 running sum in contingency-tree / hash-map order.
+template <typename HistPtr>
+__device__ __forceinline__ long long score_configs_bdeu(HistPtr hist, int rv, int64_t nconf, int64_t j0, int64_t j1, float ess, int tid, int nthreads) {
+    const float a_ij = __fdiv_rn(ess, (float)(int)nconf);                 // :32 (float / int)
+    const float a_ijk = __fdiv_rn(ess, (float)(int)(nconf * rv));         // :35-36
+    const double lg_ij = (double)__double2float_rn(lgamma((double)a_ij));   // float members of `scratch`
+    const double lg_ijk = (double)__double2float_rn(lgamma((double)a_ijk));
+    long long acc = 0;
+    for (int64_t j = j0 + tid; j < j1; j += nthreads) {
+        const int64_t b = j * rv;
+        int nij = 0;
+        for (int k = 0; k < rv; k++) {
+            const int cnt = hist[b + k];
+            nij += cnt;
+            if (cnt > 0) {
+                const double temp = (double)__double2float_rn(lgamma((double)__fadd_rn(a_ijk, (float)cnt)));   // :105-108
+                acc += __double2ll_rn((temp - lg_ijk) * 1073741824.0);
+            }
+        }
+        if (nij > 0) acc += __double2ll_rn((lg_ij - lgamma((double)__fadd_rn(a_ij, (float)nij))) * 1073741824.0);   // :116-118
+    }
+    return acc;
+}
+
+// the per-set score sum of the direct-counting kernels: table look-ups (BIC, fNML) or BDeu's lgamma terms
+template <typename HistPtr>
+__device__ __forceinline__ long long score_configs_of(const BicData &d, HistPtr hist, int rv, int64_t nconf, int64_t j0, int64_t j1, int tid, int nthreads) {
+    if (d.ess > 0.f) return score_configs_bdeu(hist, rv, nconf, j0, j1, d.ess, tid, nthreads);
+    return score_configs(hist, rv, j0, j1, d.qlog, d.qcfg, d.cfg_min, tid, nthreads);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -206,10 +245,10 @@ __global__ void bic_count_smem_kernel(BicData d, CandInfo ci, const uint32_t *__
         for (uint32_t i = threadIdx.x; i < sc.cells; i += blockDim.x) dst[i] = hist[i];
     }
     if (!scores && !acc_out) return;
-    long long acc = score_configs(hist, ci.rv, 0, sc.cells / ci.rv, d.qlog, d.qcfg, d.cfg_min, threadIdx.x, blockDim.x);
+    long long acc = score_configs_of(d, hist, ci.rv, sc.cells / ci.rv, 0, sc.cells / ci.rv, threadIdx.x, blockDim.x);
     acc = block_sum_ll(acc, red);
     if (threadIdx.x == 0) {
-        if (scores) scores[out_index(om, mask)] = bic_finalize(acc, sc.tval, d.base);
+        if (scores) scores[out_index(om, mask)] = bic_finalize(acc, sc.tval, d.base, d.acc_scale);
         if (ll_fixed) ll_fixed[out_index(om, mask)] = acc;
         if (acc_out) acc_out[blockIdx.x] = acc;
     }
@@ -246,7 +285,7 @@ __global__ void bic_score_tables_kernel(BicData d, CandInfo ci, const GlobalSet 
     if (j0 >= nconf) return;
     int64_t j1 = j0 + configs_per_chunk;
     if (j1 > nconf) j1 = nconf;
-    long long acc = score_configs(tables + gs.table_off, ci.rv, j0, j1, d.qlog, d.qcfg, d.cfg_min, threadIdx.x, blockDim.x);
+    long long acc = score_configs_of(d, tables + gs.table_off, ci.rv, nconf, j0, j1, threadIdx.x, blockDim.x);
     acc = block_sum_ll(acc, red);
     if (threadIdx.x == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[blockIdx.x]), (unsigned long long)acc);
 }
@@ -260,7 +299,7 @@ __global__ void bic_finalize_kernel(BicData d, CandInfo ci, const GlobalSet *__r
     for (int b = 0; b < ci.c; b++)
         if ((mask >> b) & 1) pen = __fmul_rn(pen, (float)ci.card[b]);
     const uint64_t o = out_index(om, mask);
-    scores[o] = bic_finalize(acc[i], pen, d.base);
+    scores[o] = bic_finalize(acc[i], pen, d.base, d.acc_scale);
     if (ll_fixed) ll_fixed[o] = acc[i];
 }
 
@@ -539,7 +578,7 @@ __global__ void cube_finalize_kernel(BicData d, CandInfo ci_res, const uint32_t 
     for (int b = 0; b < ci_res.c; b++)
         if ((mask >> b) & 1) pen = __fmul_rn(pen, (float)ci_res.card[b]);
     const uint64_t o = out_index(om, mask);
-    scores[o] = bic_finalize(acc[i], pen, d.base);
+    scores[o] = bic_finalize(acc[i], pen, d.base, d.acc_scale);
     if (ll_fixed) ll_fixed[o] = acc[i];
 }
 

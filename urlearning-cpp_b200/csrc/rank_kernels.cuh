@@ -362,9 +362,9 @@ __global__ void rank_bic_count_smem_kernel(BicData d, RankSpace rs, RankCand rc,
     __syncthreads();
     count_rows(sc, 0, d.n, hist, threadIdx.x, blockDim.x);
     __syncthreads();
-    long long acc = score_configs(hist, rc.rv, 0, sc.cells / rc.rv, d.qlog, d.qcfg, d.cfg_min, threadIdx.x, blockDim.x);
+    long long acc = score_configs_of(d, hist, rc.rv, sc.cells / rc.rv, 0, sc.cells / rc.rv, threadIdx.x, blockDim.x);
     acc = block_sum_ll(acc, red);
-    if (threadIdx.x == 0) scores[idx] = bic_finalize(acc, sc.tval, d.base);
+    if (threadIdx.x == 0) scores[idx] = bic_finalize(acc, sc.tval, d.base, d.acc_scale);
 }
 
 // global tier: tables in an L2-resident scratch batch (twins of bic_count_global_kernel / bic_score_tables_kernel / bic_finalize_kernel)
@@ -398,7 +398,7 @@ __global__ void rank_bic_score_tables_kernel(BicData d, int rv, const RankGlobal
     if (j0 >= nconf) return;
     int64_t j1 = j0 + configs_per_chunk;
     if (j1 > nconf) j1 = nconf;
-    long long acc = score_configs(tables + gs.table_off, rv, j0, j1, d.qlog, d.qcfg, d.cfg_min, threadIdx.x, blockDim.x);
+    long long acc = score_configs_of(d, tables + gs.table_off, rv, nconf, j0, j1, threadIdx.x, blockDim.x);
     acc = block_sum_ll(acc, red);
     if (threadIdx.x == 0 && acc != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc_out[blockIdx.x]), (unsigned long long)acc);
 }
@@ -412,7 +412,7 @@ __global__ void rank_bic_finalize_kernel(BicData d, RankSpace rs, RankCand rc, c
     rs_unrank(rs.binom, rs.bstride, rs.c, l, idx - rs.layer_base[l], e);
     float pen = (float)(rc.rv - 1);
     for (int j = 0; j < l; j++) pen = __fmul_rn(pen, (float)__ldg(rc.card + e[j]));
-    scores[idx] = bic_finalize(acc[i], pen, d.base);
+    scores[idx] = bic_finalize(acc[i], pen, d.base, d.acc_scale);
 }
 
 

@@ -461,7 +461,7 @@ __global__ void tree_finalize_kernel(BicData d, CandInfo ci_res, const TreeRoot 
     for (int b = 0; b < ci_res.c; b++)
         if ((rm >> b) & 1) pen = __fmul_rn(pen, (float)ci_res.card[b]);
     const uint64_t o = out_index(om, rm);
-    scores[o] = bic_finalize(acc[i], pen, d.base);
+    scores[o] = bic_finalize(acc[i], pen, d.base, d.acc_scale);
     if (ll_fixed) ll_fixed[o] = acc[i];
 }
 

@@ -25,7 +25,7 @@
 
 using namespace urlgpu;
 
-static inline bool is_discrete(int score_type) { return score_type == URLGPU_BIC || score_type == URLGPU_FNML; }
+static inline bool is_discrete(int score_type) { return score_type == URLGPU_BIC || score_type == URLGPU_FNML || score_type == URLGPU_BDEU; }
 
 namespace {
 
@@ -61,6 +61,7 @@ struct urlgpu_ctx {
     // the discrete score the next K1 launches compute (select_discrete_score): per-configuration table, the smallest
     // configuration count that contributes, the penalty constant
     const long long *ds_qcfg = nullptr; int ds_cfg_min = 1; float ds_base = 0.f;
+    float ds_ess = 0.f; double ds_scale = 1.0 / 8388608.0;   // BDeu: equivalent sample size (> 0) and the 2^-30 accumulator unit
     std::map<int, long long *> d_qfnml;   // fNML: arity -> qlog + log-regret table [n+2] (built on first use, owned by this context)
     bool borrowed_discrete = false; // d_codes/d_qlog belong to another context on the same device (urlgpu_share_discrete)
 
@@ -517,7 +518,16 @@ extern "C" int urlgpu_share_discrete(urlgpu_ctx *ctx, urlgpu_ctx *owner) {
 // fNML (log_likelihood - sum_j log C(N_ij, r_v), fnml_scoring_function.cpp:28-74).  The fNML per-configuration table is
 // qlog[N] + round(2^23 * (float)log C(N, r_v)): the exact-integer contract of bic_kernels.cuh extended by one more float
 // table of the reference, so an fNML score is again independent of summation order, path and GPU count.
-static int select_discrete_score(urlgpu_ctx *ctx, int score_type, int variable) {
+static int select_discrete_score(urlgpu_ctx *ctx, int score_type, int variable, double param) {
+    ctx->ds_ess = 0.f; ctx->ds_scale = 1.0 / 8388608.0;
+    if (score_type == URLGPU_BDEU) {
+        // BDeu (bdeu_scoring_function.cpp): lgamma terms evaluated in the direct-counting kernels (score_configs_bdeu); `param` = ess
+        if (!(param > 0) || !std::isfinite(param)) return ctx->fail(URLGPU_ERR_ARG, "BDeu: the equivalent sample size (the lambda argument) must be positive");
+        if (ctx->n > 100000000) return ctx->fail(URLGPU_ERR_LIMIT, "BDeu: more than 1e8 records overflow the 2^-30 fixed-point accumulator");
+        ctx->ds_qcfg = ctx->d_qlog; ctx->ds_cfg_min = 1; ctx->ds_base = 0.f;
+        ctx->ds_ess = (float)param; ctx->ds_scale = 1.0 / 1073741824.0;
+        return URLGPU_OK;
+    }
     if (score_type != URLGPU_FNML) {
         ctx->ds_qcfg = ctx->d_qlog; ctx->ds_cfg_min = 1; ctx->ds_base = ctx->base;
         return URLGPU_OK;
@@ -846,7 +856,7 @@ static int bic_score_family_direct(urlgpu_ctx *ctx, int variable, const std::vec
     const uint64_t n_masks = (uint64_t)1 << c;
     const uint64_t fam = family_size(c, K);
     *n_scored = fam;
-    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base, ctx->ds_ess, ctx->ds_scale};
     CandInfo ci = make_candinfo(ctx, variable, cand, K);
     const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
 
@@ -995,7 +1005,7 @@ static int bic_score_family_cube(urlgpu_ctx *ctx, int variable, const std::vecto
     CandInfo ci_cube = make_candinfo(ctx, variable, cube_vars, K);
     ci_cube.rv = rv;                               // layout arity: the counting kernels index x_v + rv * paIdx
     CandInfo ci_res = make_candinfo(ctx, variable, cand, K);
-    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base, ctx->ds_ess, ctx->ds_scale};
     const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
 
     // ---- enumerate layers 0..Lmax (layers above Kc: only sets containing the lowest l-Kc cube bits) ----
@@ -1513,6 +1523,7 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
 // c <= 30 candidates: the mask-based K1 strategies; `om` says where a set's score goes (dense by mask, or rank space)
 static int bic_score_family(urlgpu_ctx *ctx, int variable, const std::vector<int> &cand, int K, float *d_table, long long *d_llfixed,
                             uint64_t *n_scored, const RankSpace &om, int *d_ovf = nullptr) {
+    if (ctx->ds_ess > 0.f) return bic_score_family_direct(ctx, variable, cand, K, d_table, d_llfixed, n_scored, om);   // BDeu: one table per set
     if (ctx->bic_mode == 0) {
         bool used = false;
         int rc = bic_score_family_tree(ctx, variable, cand, K, d_table, d_llfixed, n_scored, &used, om);
@@ -1676,7 +1687,7 @@ static int bic_score_family_tree(urlgpu_ctx *ctx, int variable, const std::vecto
     { int rc_ = stage_begin(ctx); if (rc_) return rc_; }
     CandInfo ci_cube = make_candinfo(ctx, variable, cube_vars, K);
     CandInfo ci_res = make_candinfo(ctx, variable, cand, K);
-    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base, ctx->ds_ess, ctx->ds_scale};
     DevBuf dkeys(ctx), dhist(ctx), doff(ctx), dcursor(ctx), drows(ctx), droots(ctx), dmap(ctx), dacc(ctx), dperm(ctx), dtmp(ctx);
     CK(dkeys.alloc(n * sizeof(uint32_t)));
     CK(dhist.alloc(((size_t)Pd + 1) * sizeof(uint32_t)));
@@ -2033,7 +2044,7 @@ static int bic_score_rank_direct(urlgpu_ctx *ctx, int variable, const std::vecto
     cudaStream_t s = ctx->stream;
     const int c = rs.c;
     if (rs.K + 1 > kMaxCols) return ctx->fail(URLGPU_ERR_LIMIT, "BIC: more than 31 parents in one set");
-    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base, ctx->ds_ess, ctx->ds_scale};
     const uint32_t tier1_cells = (uint32_t)((ctx->smem_optin - 2048) / sizeof(int));
     std::vector<int> hv(2 * (size_t)std::max(c, 1));
     for (int i = 0; i < c; i++) { hv[i] = cand[i]; hv[c + i] = ctx->card[cand[i]]; }
@@ -2239,14 +2250,15 @@ static int apply_filters(urlgpu_ctx *ctx, urlgpu_result *res, bool bic, unsigned
     return rc;
 }
 
-static int check_score_args(urlgpu_ctx *ctx, const char *who, int variable, const uint64_t *neighbors, int mask_words, int score_type, std::vector<int> &cand) {
+static int check_score_args(urlgpu_ctx *ctx, const char *who, int variable, const uint64_t *neighbors, int mask_words, int score_type, std::vector<int> &cand,
+                            double param = 1.0) {
     const bool bic = is_discrete(score_type);
     if (!bic && score_type != URLGPU_CBIC) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": unknown score type");
     if (bic && !ctx->have_discrete) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": BIC / fNML need urlgpu_set_discrete first");
     if (!bic && !ctx->have_gram) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": cBIC needs urlgpu_set_continuous first");
     const int p = bic ? ctx->p : ctx->cp;
     if (variable < 0 || variable >= p) return ctx->fail(URLGPU_ERR_ARG, std::string(who) + ": variable out of range");
-    if (bic) { const int rc = select_discrete_score(ctx, score_type, variable); if (rc) return rc; }
+    if (bic) { const int rc = select_discrete_score(ctx, score_type, variable, param); if (rc) return rc; }
     return candidates_from_mask(ctx, p, variable, neighbors, mask_words, cand);
 }
 
@@ -2260,7 +2272,7 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     CK(cudaSetDevice(ctx->device));
     const bool bic = is_discrete(score_type);
     std::vector<int> cand;
-    int rc = check_score_args(ctx, "score_variable", variable, neighbors, mask_words, score_type, cand);
+    int rc = check_score_args(ctx, "score_variable", variable, neighbors, mask_words, score_type, cand, lambda);
     if (rc) return rc;
     const int c = (int)cand.size();
     int K = std::max(0, std::min(max_parents, c));
@@ -2278,7 +2290,7 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     cudaStream_t s = ctx->stream;
     auto cleanup = [&](int code) { pool_free(ctx, res->d_table); if (res->d_ovf) pool_free(ctx, res->d_ovf); delete res; return code; };
     res->is_bic = bic; res->score_type = score_type; res->filter_flags = filter_flags;
-    if (bic && ctx->table16 && c <= kMaxDenseCand && ctx->bic_mode == 2) {
+    if (bic && ctx->ds_ess == 0.f && ctx->table16 && c <= kMaxDenseCand && ctx->bic_mode == 2) {
         e = pool_alloc(ctx, reinterpret_cast<void **>(&res->d_ovf), sizeof(int));
         if (e != cudaSuccess) return cleanup(ctx->cuda_fail(e, "cudaMalloc(flag)", __LINE__));
         cudaMemsetAsync(res->d_ovf, 0, sizeof(int), s);
@@ -2333,7 +2345,7 @@ extern "C" int urlgpu_score_range(urlgpu_ctx *ctx, int variable, const uint64_t 
     CK(cudaSetDevice(ctx->device));
     const bool bic = is_discrete(score_type);
     std::vector<int> cand;
-    int rc = check_score_args(ctx, "score_range", variable, neighbors, mask_words, score_type, cand);
+    int rc = check_score_args(ctx, "score_range", variable, neighbors, mask_words, score_type, cand, lambda);
     if (rc) return rc;
     RankSpace rs{};
     rc = make_rank_space(ctx, (int)cand.size(), std::max(0, max_parents), rs);
@@ -2364,7 +2376,7 @@ extern "C" int urlgpu_score_part(urlgpu_ctx *ctx, int variable, const uint64_t *
     CK(cudaSetDevice(ctx->device));
     const bool bic = is_discrete(score_type);
     std::vector<int> cand;
-    int rc = check_score_args(ctx, "score_part", variable, neighbors, mask_words, score_type, cand);
+    int rc = check_score_args(ctx, "score_part", variable, neighbors, mask_words, score_type, cand, lambda);
     if (rc) return rc;
     const int c = (int)cand.size();
     const int K = std::max(0, std::min(max_parents, c));
@@ -2378,7 +2390,7 @@ extern "C" int urlgpu_score_part(urlgpu_ctx *ctx, int variable, const uint64_t *
     if (!on_device) { CK(tmp.alloc((size_t)total * sizeof(float))); d_out = tmp.as<float>(); }
     fill_u32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(d_out), total, kSentinelBits);
     bool done = false;
-    if (bic && c <= kMaxDenseCand && ctx->bic_mode == 2) { // the cube path: part = a sub-forest of the root tables
+    if (bic && ctx->ds_ess == 0.f && c <= kMaxDenseCand && ctx->bic_mode == 2) { // the cube path: part = a sub-forest of the root tables
         uint64_t ns = 0;
         DevBuf flag(ctx);
         if (ctx->table16) { CK(flag.alloc(sizeof(int))); CK(cudaMemsetAsync(flag.p, 0, sizeof(int), s)); }
@@ -2615,7 +2627,7 @@ static int result_wait_counts(urlgpu_result *res) {
         cudaStream_t s = ctx->stream;
         fill_u32_kernel<<<blocks_for(res->n_masks, 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(res->d_table), res->n_masks, kSentinelBits);
         uint64_t ns = 0;
-        rc = select_discrete_score(ctx, res->score_type, res->variable);   // a later call may have selected another score / arity
+        rc = select_discrete_score(ctx, res->score_type, res->variable, 1.0);   // a later call may have selected another score / arity (never BDeu: no cube path)
         if (rc) return rc;
         rc = bic_score_family(ctx, res->variable, res->cand, res->max_parents, res->d_table, nullptr, &ns, res->rank_layout ? res->rs : RankSpace{}, nullptr);
         if (rc) return rc;
@@ -2826,7 +2838,7 @@ extern "C" int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *p
     if (!bic && !ctx->have_gram) return ctx->fail(URLGPU_ERR_ARG, "score_one: cBIC needs urlgpu_set_continuous first");
     const int p = bic ? ctx->p : ctx->cp;
     if (variable < 0 || variable >= p) return ctx->fail(URLGPU_ERR_ARG, "score_one: variable out of range");
-    if (bic) { const int rc0 = select_discrete_score(ctx, score_type, variable); if (rc0) return rc0; }
+    if (bic) { const int rc0 = select_discrete_score(ctx, score_type, variable, lambda); if (rc0) return rc0; }
     std::vector<int> cand;
     int rc = compact_of(ctx, p, variable, parents, mask_words, cand);
     if (rc) return rc;
@@ -2839,7 +2851,7 @@ extern "C" int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *p
         const uint32_t full = (uint32_t)(((uint64_t)1 << c) - 1);
         DevBuf out(ctx);
         CK(out.alloc(sizeof(float) + sizeof(long long) + 8));
-        BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
+        BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base, ctx->ds_ess, ctx->ds_scale};
         CandInfo ci = make_candinfo(ctx, variable, cand, c);
         uint64_t cells = ci.rv;
         for (int b = 0; b < c; b++) { cells *= (uint64_t)ci.card[b]; if (cells > kCellLimit) return ctx->fail(URLGPU_ERR_LIMIT, "contingency table exceeds 2^30 cells"); }
@@ -2853,7 +2865,7 @@ extern "C" int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *p
         CK(cudaMemcpyAsync(score, d_sc, sizeof(float), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(&fx, d_ll, sizeof fx, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        if (value64) *value64 = std::ldexp((double)fx, -23);
+        if (value64) *value64 = (double)fx * ctx->ds_scale;
     } else {
         if (c > 200) return ctx->fail(URLGPU_ERR_LIMIT, "score_one: more than 200 parents in one set");
         const int p_ = ctx->cp;
@@ -2898,7 +2910,7 @@ extern "C" int urlgpu_contingency(urlgpu_ctx *ctx, int variable, const uint64_t 
     if (rc) return rc;
     const int c = (int)cand.size();
     if (c > kMaxDenseCand) return ctx->fail(URLGPU_ERR_LIMIT, "contingency: more than 30 parents in one set");
-    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base};
+    BicData bd{ctx->d_codes, ctx->n, ctx->n_stride, ctx->d_qlog, ctx->ds_qcfg, ctx->ds_cfg_min, ctx->ds_base, ctx->ds_ess, ctx->ds_scale};
     CandInfo ci = make_candinfo(ctx, variable, cand, c);
     uint64_t cells = ci.rv;
     for (int b = 0; b < c; b++) { cells *= (uint64_t)ci.card[b]; if (cells > kCellLimit) return ctx->fail(URLGPU_ERR_LIMIT, "contingency table exceeds 2^30 cells"); }

@@ -1,6 +1,6 @@
 // gpu_scoring.hpp — the reference's plugin/operator interface for the local-score path, backed by liburlgpu.
 //
-//   scoring::ScoringFunction      scoring_function/scoring_function.h:16-24  (calculateScore per set; BIC, fNML, cBIC)
+//   scoring::ScoringFunction      scoring_function/scoring_function.h:16-24  (calculateScore per set; BIC, fNML, BDeu, cBIC)
 //   scoring::ScoreCalculator      scoring_function/score_calculator.{h,cpp}  (calculateScores per variable, prune)
 //   FloatMap                      base/typedefs.h:816                        (per-variable score cache)
 //
@@ -118,6 +118,26 @@ public:
     urlgpu_ctx *context() override { return g.ctx; }
 private:
     GpuContext &g;
+};
+
+// BDeuScoringFunction (bdeu_scoring_function.cpp, deCampos pruning off) on the device; getLambda() carries the equivalent sample size
+class GpuBDeuScoringFunction : public ScoringFunction {
+public:
+    GpuBDeuScoringFunction(GpuContext &g, float ess, const uint8_t *codes, int64_t recordCount, int p, const int32_t *card) : g(g), ess(ess) {
+        g.check(urlgpu_set_discrete(g.ctx, codes, recordCount, p, card));
+    }
+    GpuBDeuScoringFunction(GpuContext &g, float ess, GpuContext &owner) : g(g), ess(ess) { g.check(urlgpu_share_discrete(g.ctx, owner.ctx)); }
+    float calculateScore(int variable, varset parents, FloatMap &) override {
+        float s;
+        g.check(urlgpu_score_one(g.ctx, variable, parents.w, urlhost::kVarsetWords, URLGPU_BDEU, ess, &s, nullptr));
+        return s;
+    }
+    int scoreType() const override { return URLGPU_BDEU; }
+    double getLambda() const override { return ess; }
+    urlgpu_ctx *context() override { return g.ctx; }
+private:
+    GpuContext &g;
+    float ess;
 };
 
 // BIC_OLS_Function (BIC_OLS.cpp) on the device

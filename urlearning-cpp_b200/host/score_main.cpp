@@ -1,7 +1,7 @@
 // score_main.cpp — the `score` binary: same command line and .pss output as the reference's
 // urlearning/score/score_main.cpp:209-403, with the inner scoring loop replaced by liburlgpu (B200).
 //
-// Differences, all documented in DESIGN.md: only -f BIC, -f fNML and -f cBIC are offered (the path this engine
+// Differences, all documented in DESIGN.md: only -f BIC, -f fNML, -f BDeu and -f cBIC are offered (the path this engine
 // accelerates); .pss lines are written in canonical (|S|, mask) order instead of boost::unordered_map order;
 // pruning is opt-in through --prune because the reference's call is commented out (score_main.cpp:166-171);
 // -t selects the number of worker threads, thread t driving device t % (visible devices); an unreadable
@@ -39,7 +39,7 @@ void usage(const char *argv0) {
               << "  -d [ --delimiter ] arg (=,) The delimiter of the input file.\n"
               << "  -l [ --lambda ] arg        The lambda in cBIC.\n"
               << "  -k [ --skeleton ] arg      The file specifying the skeleton superstructure\n"
-              << "  -f [ --function ] arg (=BIC) The scoring function to use (BIC | fNML | cBIC).\n"
+              << "  -f [ --function ] arg (=BIC) The scoring function to use (BIC | fNML | BDeu | cBIC).\n"
               << "  -p [ --maxParents ] arg (=0) The maximum number of parents for any variable. A value less than 1 means no limit.\n"
               << "  -t [ --threads ] arg (=1)  Worker threads; thread t drives GPU t mod (visible GPUs).\n"
               << "  -s [ --hasHeader ]         The first line of the input file gives the variable names.\n"
@@ -158,8 +158,8 @@ int main(int argc, char **argv) {
         if (sf == "bic") {
             int maxParentCount = (int)std::log(2 * (int)recordCount / std::log((double)(int)recordCount)); // :301
             if (maxParentCount < maxParents) maxParents = maxParentCount;
-        } else if (sf != "cbic" && sf != "fnml") {
-            throw std::runtime_error("Invalid scoring function.  The GPU score path offers 'BIC', 'fNML' and 'cBIC'.");
+        } else if (sf != "cbic" && sf != "fnml" && sf != "bdeu") {
+            throw std::runtime_error("Invalid scoring function.  The GPU score path offers 'BIC', 'fNML', 'BDeu' and 'cBIC'.");
         }
 
         printf("Skeleton file %s\n", o.skeletonFile.c_str());
@@ -173,8 +173,8 @@ int main(int argc, char **argv) {
         if (!initError.empty()) throw std::runtime_error(initError);
 
         // device input, built once: packed codes (BIC) or the FP64 matrix (cBIC; mlpack::data::Load parses numbers, BIC_OLS.cpp:48)
-        const bool isFnml = sf == "fnml";
-        const bool isBic = sf == "bic" || isFnml;   // discrete input: packed codes
+        const bool isFnml = sf == "fnml", isBdeu = sf == "bdeu";
+        const bool isBic = sf == "bic" || isFnml || isBdeu;   // discrete input: packed codes
         std::vector<uint8_t> codes;
         std::vector<double> x;
         if (isBic) {
@@ -199,11 +199,13 @@ int main(int argc, char **argv) {
         for (int t = 0; t < o.threadCount; t++) {
             const int owner = t % ndev;
             if (t == owner) {
-                if (isFnml) functions[t].reset(new scoring::GpufNMLScoringFunction(*gpus[t], codes.data(), recordCount, p, card.data()));
+                if (isBdeu) functions[t].reset(new scoring::GpuBDeuScoringFunction(*gpus[t], o.ess, codes.data(), recordCount, p, card.data()));
+                else if (isFnml) functions[t].reset(new scoring::GpufNMLScoringFunction(*gpus[t], codes.data(), recordCount, p, card.data()));
                 else if (isBic) functions[t].reset(new scoring::GpuBICScoringFunction(*gpus[t], codes.data(), recordCount, p, card.data()));
                 else functions[t].reset(new scoring::GpuBICOLSFunction(*gpus[t], x.data(), recordCount, p, o.lambda));
             } else {
-                if (isFnml) functions[t].reset(new scoring::GpufNMLScoringFunction(*gpus[t], *gpus[owner]));
+                if (isBdeu) functions[t].reset(new scoring::GpuBDeuScoringFunction(*gpus[t], o.ess, *gpus[owner]));
+                else if (isFnml) functions[t].reset(new scoring::GpufNMLScoringFunction(*gpus[t], *gpus[owner]));
                 else if (isBic) functions[t].reset(new scoring::GpuBICScoringFunction(*gpus[t], *gpus[owner]));
                 else functions[t].reset(new scoring::GpuBICOLSFunction(*gpus[t], *gpus[owner], recordCount, p, o.lambda));
             }
