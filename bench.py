@@ -483,6 +483,10 @@ def run_gpu(args):
         # the rest of BASELINE.json's metric ("BIC & cBIC ...; score-file wall time"), measured by the same default command
         extra = {}
         if world == 1 and is_bic and not args.no_subrecords:
+            try:
+                extra["other_scores"] = measure_other_scores(pkg, D, torch, pool, wl, flags)
+            except Exception as ex:
+                extra["other_scores"] = {"error": repr(ex)}
             pool.close()
             pool = None
             import tempfile
@@ -529,6 +533,34 @@ def fast_write_csv(path, codes):
     buf[:, 1::2] = ord(",")
     buf[:, -1] = ord("\n")
     buf.tofile(path)
+
+
+def measure_other_scores(pkg, D, torch, pool, wl, flags, steps=3):
+    """the other discrete scores on K1's counts, device-resident like `value`.  fNML: configs[3] itself (same
+    kernels as BIC, the regret table as the per-configuration table).  BDeu (ess = 1): the configs[3] network sampled at
+    n = 2e4 with -p 6 — BDeu runs on the direct-counting kernels (one table per set), at the sample sizes it is used with."""
+    out = []
+    small_codes, small_card, _, _ = pkg.datagen.discrete_bn(p=60, n=20_000, seed=4)
+    items = [(v, wl["nbs"][v]) for v in range(wl["p"])]
+    for name, codes, card, K, stype, lam, note in (
+            ("fNML", wl["codes"], wl["card"], wl["K"], pkg.FNML, 0.0, "configs[3] data and skeleton, -p %d (fNML has no log-bound), prune" % wl["K"]),
+            ("BDeu", small_codes, small_card, 6, pkg.BDEU, 1.0, "configs[3] network sampled at n=2e4, -p 6, ess=1, prune")):
+        pool.set_discrete(np.ascontiguousarray(codes), card)
+        costs = [D.family_cost(card, v, wl["nbs"][v], K) for v in range(wl["p"])]
+        sets = sum(family_size(bin(wl["nbs"][v] & ~(1 << v)).count("1"), K) for v in range(wl["p"]))
+        pool.run(items, K, stype, lam=lam, flags=flags, costs=costs)
+        pool.reset_stats()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            pool.run(items, K, stype, lam=lam, flags=flags, costs=costs)   # returns after every context has drained
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out.append({"score": name, "workload": note, "sets_per_step": sets, "ms_per_step": ms, "value": sets / ms * 1e3, "unit": UNIT, "steps": steps,
+                    "gpu_launches": int(pool.stats()["launches_total"])})
+    return out
 
 
 def measure_cbic_subrecord(pkg, torch, device):

@@ -409,7 +409,7 @@ __global__ void cube_map_kernel(const CubePair *__restrict__ pairs, int npairs, 
 }
 
 template <int RV>
-__global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePair *__restrict__ pairs, const uint32_t *__restrict__ block_pair, const int *__restrict__ parent_tab,
+__global__ void __launch_bounds__(kCubeThreads, RV == 4 ? 5 : 6) cube_derive_kernel(const CubePair *__restrict__ pairs, const uint32_t *__restrict__ block_pair, const int *__restrict__ parent_tab,
                                                                    int *__restrict__ child_tab, int rv_dyn, const long long *__restrict__ qlog,
                                                                    const long long *__restrict__ qcfg, int cfg_min,
                                                                    long long *__restrict__ acc_all, int score_child /*0: the children of this launch are ancestors only*/,
@@ -446,17 +446,17 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
             // digit): the group's sum is the configuration of child \ {bit 0}
             for (uint32_t jb = j0 + threadIdx.x * (uint32_t)r0; jb < j1; jb += kCubeThreads * (uint32_t)r0) {
                 const uint32_t hi = jb / pr.Bc, lo = jb - hi * pr.Bc;
-                const uint64_t pc0 = (uint64_t)lo + (uint64_t)hi * pr.r * pr.Bc;
+                const uint32_t pc0 = lo + hi * pr.r * pr.Bc;
                 int cnt[4][RV], sum[RV];
 #pragma unroll
                 for (int t = 0; t < 4; t++)
-                    if (t < r0) load_cfg<RV>(P + (pc0 + t) * RV, cnt[t]);
+                    if (t < r0) load_cfg<RV>(P + (pc0 + t) * (uint32_t)RV, cnt[t]);
                 for (uint32_t a = 1; a < pr.r; a++) {
 #pragma unroll
                     for (int t = 0; t < 4; t++)
                         if (t < r0) {
                             int tt[RV];
-                            load_cfg<RV>(P + (pc0 + (uint64_t)a * pr.Bc + t) * RV, tt);
+                            load_cfg<RV>(P + (pc0 + a * pr.Bc + t) * (uint32_t)RV, tt);
 #pragma unroll
                             for (int k = 0; k < RV; k++) cnt[t][k] += tt[k];
                         }
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
 #pragma unroll
                 for (int t = 0; t < 4; t++)
                     if (t < r0) {
-                        store_cfg<RV>(Cc + (uint64_t)(jb + t) * RV, cnt[t]);
+                        store_cfg<RV>(Cc + (jb + t) * (uint32_t)RV, cnt[t]);
                         if (acc_out) score_cfg(cnt[t], acc);
 #pragma unroll
                         for (int k = 0; k < RV; k++) sum[k] += cnt[t][k];
@@ -497,7 +497,10 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
             bool ovf = false;
             for (uint32_t j = j0 + threadIdx.x; j < j1; j += kCubeUnroll * kCubeThreads) {
                 uint32_t jj[kCubeUnroll];
-                uint64_t pc[kCubeUnroll];
+                // configuration indices fit 32 bits (a table has at most 2^30 cells): one IMAD + one IMAD.WIDE per address.  Arity 4 keeps
+                // 64-bit indices: ptxas allocates 44 registers for that form and 58 (or spills) for the 32-bit one
+                using idx_t = std::conditional_t<RV == 4, uint64_t, uint32_t>;
+                idx_t pc[kCubeUnroll];
                 bool on[kCubeUnroll];
                 int cnt[kCubeUnroll][RV];
 #pragma unroll
@@ -506,17 +509,17 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
                     on[u] = jj[u] < j1;
                     const uint32_t ju = on[u] ? jj[u] : j;
                     const uint32_t hi = fast_div(ju, pr.Bc, pr.magic), lo = ju - hi * pr.Bc;
-                    pc[u] = (uint64_t)lo + (uint64_t)hi * pr.r * pr.Bc;
+                    pc[u] = (idx_t)lo + (idx_t)hi * pr.r * pr.Bc;
                 }
 #pragma unroll
                 for (int u = 0; u < kCubeUnroll; u++) {
-                    if constexpr (P16) load_cfg16<RV>(Ph + pc[u] * RV, cnt[u]); else load_cfg<RV>(P + pc[u] * RV, cnt[u]);
+                    if constexpr (P16) load_cfg16<RV>(Ph + pc[u] * (idx_t)RV, cnt[u]); else load_cfg<RV>(P + pc[u] * (idx_t)RV, cnt[u]);
                 }
                 for (uint32_t a = 1; a < pr.r; a++) {
                     int t[kCubeUnroll][RV];
 #pragma unroll
                     for (int u = 0; u < kCubeUnroll; u++) {
-                        if constexpr (P16) load_cfg16<RV>(Ph + (pc[u] + (uint64_t)a * pr.Bc) * RV, t[u]); else load_cfg<RV>(P + (pc[u] + (uint64_t)a * pr.Bc) * RV, t[u]);
+                        if constexpr (P16) load_cfg16<RV>(Ph + (pc[u] + (idx_t)a * pr.Bc) * (idx_t)RV, t[u]); else load_cfg<RV>(P + (pc[u] + (idx_t)a * pr.Bc) * (idx_t)RV, t[u]);
                     }
 #pragma unroll
                     for (int u = 0; u < kCubeUnroll; u++)
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(kCubeThreads) cube_derive_kernel(const CubePai
                 for (int u = 0; u < kCubeUnroll; u++) {
                     if (!on[u]) continue;
                     if (!pr.leaf) {
-                        if constexpr (C16) ovf |= store_cfg16<RV>(Ch + (uint64_t)jj[u] * RV, cnt[u]); else store_cfg<RV>(Cc + (uint64_t)jj[u] * RV, cnt[u]);
+                        if constexpr (C16) ovf |= store_cfg16<RV>(Ch + (idx_t)jj[u] * (idx_t)RV, cnt[u]); else store_cfg<RV>(Cc + (idx_t)jj[u] * (idx_t)RV, cnt[u]);
                     }
                     if (acc_out) score_cfg(cnt[u]);
                 }
