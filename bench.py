@@ -804,7 +804,7 @@ def run_gpu_cbic5(args):
     words = pkg.mask_words_for(p)
     e2e = {"value": sets_total * nst / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(p * n_total * 8),
            "d2h_bytes_per_step": int((8 * words + 4) * stored), "steps": nst, "ms_per_step": ems / nst,
-           "note": "caches stay on their owner ranks (a .pss of %d entries is written per rank); no gather" % stored}
+           "note": "every surviving cache is read back on its owner rank (%d entries over all ranks); no gather" % stored}
     if rank == 0:
         gram_tf = st["gram_flops"] / (st["ms_gram"] / 1e3) / 1e12 if st["ms_gram"] > 0 else None
         fp64 = eng.probe_fp64()
