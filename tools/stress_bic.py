@@ -1,4 +1,4 @@
-"""randomised parity sweep of the BIC path against the oracle (development aid): random shapes, arities (incl. arity-1
+"""randomised parity sweep of the BIC / fNML path against the oracle (development aid): random shapes, arities (incl. arity-1
 columns), skeletons, parent limits, all K1 modes and root-kernel budgets; prints the first mismatch and exits non-zero"""
 import importlib, os, sys, time
 import numpy as np
@@ -35,10 +35,11 @@ while time.time() < t_end:
         cells = int(card[v]) * int(np.prod(sorted(card[[i for i in range(p) if i != v and (nb >> i) & 1]])[::-1][:K])) if K else 1
         if cells > (1 << 24):
             continue
-        res = eng.score_variable(v, nb, K, pkg.BIC, flags=flags)
+        fnml = rng.random() < 0.35 and int(card[v]) <= 7   # fNML on the same kernels (regret tables of wide children overflow float32)
+        res = eng.score_variable(v, nb, K, pkg.FNML if fnml else pkg.BIC, flags=flags)
         masks, scores = res.fetch(); res.free()
         om = orc.enumerate_sets(v, nb, p, K)
-        osc = orc.bic_score_many(codes, card, v, om)
+        osc = orc.fnml_score_many(codes, card, v, om) if fnml else orc.bic_score_many(codes, card, v, om)
         stored = np.array([(s < 1) if m == 0 else (s < 0) for m, s in zip(om, osc)])
         om, osc = om[stored], osc[stored]
         if flags:
@@ -47,7 +48,7 @@ while time.time() < t_end:
         ok = [int(m[0]) for m in masks] == [int(om[i]) for i in order] and np.array_equal(scores.view(np.uint32), osc[order].view(np.uint32))
         cases += 1
         if not ok:
-            print("MISMATCH", env, dict(p=p, n=n, ar=ar, v=v, K=K, skel=use_skel, flags=flags, card=card.tolist()))
+            print("MISMATCH", env, dict(p=p, n=n, ar=ar, v=v, K=K, skel=use_skel, flags=flags, fnml=fnml, card=card.tolist()))
             sys.exit(1)
     eng.close()
 print(f"stress OK: {cases} (variable, family) cases, seed {seed}")
