@@ -701,7 +701,9 @@ def run_gpu_cbic5(args):
     sets_total = sum(sizes)
     pieces, owner = D.plan_ranges(sizes, world)
     my_total = sum(c for _, _, c in pieces[rank])
-    score_buf = torch.empty(max(1, my_total), dtype=torch.float32, device="cuda")
+    board = D.PeerScoreBoard(eng, sizes, owner) if args.exchange == "p2p" else None
+    score_buf = torch.empty(max(1, my_total), dtype=torch.float32, device="cuda") if board is None else None
+    owned = [v for v in range(p) if owner[v] == rank]
 
     def allsum(a):
         if world == 1:
@@ -726,17 +728,24 @@ def run_gpu_cbic5(args):
         eng.shard_finish(mean, dev, n_total)
         g = allsum(eng.gram())
         eng.set_gram(g, n_total)
-        mine, off = {}, 0
-        for (v, first, count) in pieces[rank]:
-            t = score_buf[off:off + count]
-            eng.score_range(v, nbs[v], K, pkg.CBIC, first, count, lam=lam, out_device_ptr=t.data_ptr())
-            mine[(v, first, count)] = t
-            off += count
-        full = D.exchange_ranges(pieces, owner, sizes, mine, "cuda")
+        if board is not None:
+            # the K3 kernels store every piece straight into its owner's score board (peer memory over NVLink); a barrier follows
+            for (v, first, count) in pieces[rank]:
+                eng.score_range(v, nbs[v], K, pkg.CBIC, first, count, lam=lam, out_device_ptr=board.target(v, first))
+            board.fence()
+            full = {v: board.target(v) for v in owned}
+        else:
+            mine, off = {}, 0
+            for (v, first, count) in pieces[rank]:
+                t = score_buf[off:off + count]
+                eng.score_range(v, nbs[v], K, pkg.CBIC, first, count, lam=lam, out_device_ptr=t.data_ptr())
+                mine[(v, first, count)] = t
+                off += count
+            full = {v: t.data_ptr() for v, t in D.exchange_ranges(pieces, owner, sizes, mine, "cuda").items()}
         stored = 0
         prev = None
-        for v, t in full.items():
-            res = eng.result_from_scores(v, nbs[v], K, pkg.CBIC, t.data_ptr(), n=sizes[v], flags=pkg.PRUNE_DOMINATED).prefetch()
+        for v, ptr in full.items():
+            res = eng.result_from_scores(v, nbs[v], K, pkg.CBIC, ptr, n=sizes[v], flags=pkg.PRUNE_DOMINATED).prefetch()
             if prev is not None:
                 stored += len(prev.fetch(pinned=True)[1]) if fetch else prev.count()
                 prev.free()
@@ -816,7 +825,8 @@ def run_gpu_cbic5(args):
                                        f"{maxdeg}, 2-hop candidates ({min(cs)}..{max(cs)} per variable), explicit -p {K}, cBIC lambda=2, accept + prune",
                            "sets_per_step": sets_total, "stored_after_prune": stored,
                            "parallelism": f"rows sharded n/{world} for the Gram; scoring sharded by (variable, parent-set range): {world} contiguous pieces of the "
-                                          f"concatenated family index space, one all-to-all of raw scores to the variables' owners, N={world}"},
+                                          f"concatenated family index space, " + ("every piece scored straight into its owner's memory over NVLink (CUDA IPC peer mapping), one barrier"
+                                                                               if board is not None else "one all-to-all of raw scores to the variables' owners") + f", N={world}"},
                 "e2e": e2e, "gpu_launches": int(st["launches_total"]), "clocks": sampler.summary(),
                 "roofline": {"bound": "fp64", "kernel": "K2 gram_partial_kernel (TMA bulk copies -> shared memory -> DMMA m8n8k4.f64) + fixed-order combine", "achieved": gram_tf,
                              "peak": fp64["dmma"], "unit": "TFLOP/s", "frac": gram_tf / fp64["dmma"] if gram_tf else None, "traffic": None,
@@ -827,6 +837,8 @@ def run_gpu_cbic5(args):
                                            "prune": st["ms_prune"]}},
                 "cpu_baseline": None}
         print(json.dumps(line))
+    if board is not None:
+        board.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -921,6 +933,9 @@ def main():
                          "fixed); strong = configs[3] itself split over the ranks")
     ap.add_argument("--n5", type=int, default=10_000_000, help="total rows of the cbic5 workload")
     ap.add_argument("--k5", type=int, default=4, help="explicit parent limit (-p) of the cbic5 workload")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="cbic5: how the raw scores reach their owners: p2p = scored straight into the owner's memory over NVLink "
+                         "(CUDA IPC peer mapping, urlgpu_peer_*), nccl = local buffer + one all-to-all")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-subrecords", action="store_true", help="skip the cBIC configs[2] and score-file wall-time sub-records of the default line")

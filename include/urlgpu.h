@@ -139,6 +139,19 @@ int urlgpu_result_from_scores(urlgpu_ctx *ctx, int variable, const uint64_t *nei
 int urlgpu_score_part(urlgpu_ctx *ctx, int variable, const uint64_t *neighbors, int mask_words, int max_parents, int score_type,
                       double lambda, int part, int parts, float *scores, int on_device);
 
+/* Peer memory for the exchange step of the range shards: instead of scoring into a local send buffer and moving the pieces
+ * with an all-to-all, a rank can score a piece STRAIGHT INTO ITS OWNER'S MEMORY over NVLink.  The owner allocates its score
+ * board with urlgpu_peer_alloc and publishes the 64-byte handle (any transport: one all-gather); every other rank (one
+ * process per GPU) maps it with urlgpu_peer_open — CUDA IPC with lazily enabled peer access — and passes the mapped
+ * address + offset as the on_device destination of urlgpu_score_range.  The scoring kernels then store through NVSwitch
+ * while they compute; the only synchronisation left is a barrier before the owner filters.  No reference counterpart
+ * (the reference's threads share one address space, score_main.cpp:132-171). */
+#define URLGPU_PEER_HANDLE_BYTES 64
+int urlgpu_peer_alloc(urlgpu_ctx *ctx, uint64_t bytes, void **dev_ptr, unsigned char handle[URLGPU_PEER_HANDLE_BYTES]);
+int urlgpu_peer_open(urlgpu_ctx *ctx, const unsigned char handle[URLGPU_PEER_HANDLE_BYTES], void **dev_ptr);
+int urlgpu_peer_close(urlgpu_ctx *ctx, void *dev_ptr);   /* a pointer from urlgpu_peer_open */
+int urlgpu_peer_free(urlgpu_ctx *ctx, void *dev_ptr);    /* a pointer from urlgpu_peer_alloc */
+
 /* Single parent set, same value ScoringFunction::calculateScore returns (BIC: the score; cBIC: -the_score).
  * value64 (optional): BIC: exact log-likelihood before the float rounding; cBIC: the_score in FP64. */
 int urlgpu_score_one(urlgpu_ctx *ctx, int variable, const uint64_t *parents, int mask_words, int score_type,

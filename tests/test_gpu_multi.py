@@ -77,7 +77,7 @@ def test_nccl_pss_identical_to_single_process(pkg, engine, tmp_path, nranks):
 RANGE_WORKER = r'''
 import importlib, os, sys
 import numpy as np, torch, torch.distributed as dist
-ROOT = sys.argv[1]; out = sys.argv[2]
+ROOT = sys.argv[1]; out = sys.argv[2]; exchange = sys.argv[3]
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("urlearning-cpp_b200")
 D = importlib.import_module("urlearning-cpp_b200.distributed")
@@ -106,18 +106,31 @@ eng.set_gram(allsum(eng.gram()), n)
 nbs = [(1 << p) - 1] * p
 sizes = [eng.family_size(v, nbs[v], K, pkg.CBIC) for v in range(p)]
 pieces, owner = D.plan_ranges(sizes, world)
-mine = {}
-for (v, first, count) in pieces[rank]:
-    t = torch.empty(count, dtype=torch.float32, device="cuda")
-    eng.score_range(v, nbs[v], K, pkg.CBIC, first, count, lam=lam, out_device_ptr=t.data_ptr())
-    mine[(v, first, count)] = t
-eng.synchronize()
-full = D.exchange_ranges(pieces, owner, sizes, mine, "cuda")
 local_caches = {}
-for v, t in full.items():
-    res = eng.result_from_scores(v, nbs[v], K, pkg.CBIC, t.data_ptr(), n=sizes[v], flags=pkg.PRUNE_DOMINATED)
-    local_caches[v] = res.fetch()
-    res.free()
+if exchange == "p2p":
+    # every piece is scored straight into its owner's memory over NVLink (CUDA IPC peer mapping); no collective
+    board = D.PeerScoreBoard(eng, sizes, owner)
+    for (v, first, count) in pieces[rank]:
+        eng.score_range(v, nbs[v], K, pkg.CBIC, first, count, lam=lam, out_device_ptr=board.target(v, first))
+    board.fence()
+    for v in range(p):
+        if owner[v] == rank:
+            res = eng.result_from_scores(v, nbs[v], K, pkg.CBIC, board.target(v), n=sizes[v], flags=pkg.PRUNE_DOMINATED)
+            local_caches[v] = res.fetch()
+            res.free()
+    board.close()
+else:
+    mine = {}
+    for (v, first, count) in pieces[rank]:
+        t = torch.empty(count, dtype=torch.float32, device="cuda")
+        eng.score_range(v, nbs[v], K, pkg.CBIC, first, count, lam=lam, out_device_ptr=t.data_ptr())
+        mine[(v, first, count)] = t
+    eng.synchronize()
+    full = D.exchange_ranges(pieces, owner, sizes, mine, "cuda")
+    for v, t in full.items():
+        res = eng.result_from_scores(v, nbs[v], K, pkg.CBIC, t.data_ptr(), n=sizes[v], flags=pkg.PRUNE_DOMINATED)
+        local_caches[v] = res.fetch()
+        res.free()
 caches = D.gather_caches(local_caches, p, 2, "cuda", owner=owner)
 if rank == 0:
     pkg.pss.write_pss(out, "synthetic.csv", n, K, "cBIC", [f"V{i}" for i in range(p)], [n] * p, caches)
@@ -127,10 +140,13 @@ eng.close()
 '''
 
 
-def test_two_rank_nccl_parent_set_range_shards(pkg, tmp_path):
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_two_rank_nccl_parent_set_range_shards(pkg, tmp_path, exchange):
     """cBIC over 69 candidates per variable, sharded by (variable, parent-set range) over two ranks: row-sharded Gram, ranges
-    scored into NCCL buffers, one all-to-all to the owners, filters, gather to rank 0: the .pss equals the one-process one
-    (two ranks: the one-process run sums the same two Gram shards in the same order, so the Gram bits are the same)"""
+    scored into NCCL buffers and moved with one all-to-all ("nccl"), or scored straight into the owner's memory over NVLink
+    through a CUDA-IPC peer mapping with only a barrier ("p2p", urlgpu_peer_*); filters, gather to rank 0: the .pss equals
+    the one-process one (two ranks: the one-process run sums the same two Gram shards in the same order, so the Gram bits
+    are the same)"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -162,5 +178,5 @@ def test_two_rank_nccl_parent_set_range_shards(pkg, tmp_path):
     multi = str(tmp_path / "multi.pss")
     port = 29900 + os.getpid() % 300
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                           "--master-port", str(port), str(worker), ROOT, multi], timeout=600)
+                           "--master-port", str(port + (7 if exchange == "p2p" else 0)), str(worker), ROOT, multi, exchange], timeout=600)
     assert hashlib.sha256(open(multi, "rb").read()).hexdigest() == hashlib.sha256(open(single, "rb").read()).hexdigest()

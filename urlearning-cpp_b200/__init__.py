@@ -36,6 +36,7 @@ ABI_SYMBOLS = [
     "urlgpu_score_one", "urlgpu_contingency", "urlgpu_prune", "urlgpu_stats_reset", "urlgpu_stats_get",
     "urlgpu_stats_enable_timing", "urlgpu_probe_fp64", "urlgpu_family_size", "urlgpu_score_range", "urlgpu_result_from_scores", "urlgpu_score_part",
     "urlgpu_spg_build", "urlgpu_spg_query", "urlgpu_spg_free",
+    "urlgpu_peer_alloc", "urlgpu_peer_open", "urlgpu_peer_close", "urlgpu_peer_free",
 ]
 
 
@@ -108,6 +109,10 @@ def load_library():
     lib.urlgpu_spg_build.argtypes = [vp, vp, vp, u64, i32, i32, P(vp)]
     lib.urlgpu_spg_query.argtypes = [vp, vp, u64, vp, vp, vp]
     lib.urlgpu_spg_free.argtypes = [vp]
+    lib.urlgpu_peer_alloc.argtypes = [vp, u64, P(vp), vp]
+    lib.urlgpu_peer_open.argtypes = [vp, vp, P(vp)]
+    lib.urlgpu_peer_close.argtypes = [vp, vp]
+    lib.urlgpu_peer_free.argtypes = [vp, vp]
     lib.urlgpu_family_size.argtypes = [vp, i32, vp, i32, i32, i32, P(u64)]
     lib.urlgpu_score_range.argtypes = [vp, i32, vp, i32, i32, i32, C.c_double, u64, u64, vp, i32]
     lib.urlgpu_score_part.argtypes = [vp, i32, vp, i32, i32, i32, C.c_double, i32, i32, vp, i32]
@@ -442,6 +447,26 @@ class Engine:
 
     def enable_timing(self, on: bool = True):
         self._check(self.lib.urlgpu_stats_enable_timing(self._h, int(on)))
+
+    def peer_alloc(self, nbytes: int):
+        """a device buffer other ranks can map (urlgpu_peer_alloc) -> (device pointer, 64-byte handle)"""
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64)()
+        self._check(self.lib.urlgpu_peer_alloc(self._h, int(nbytes), C.byref(p), h))
+        return p.value, bytes(h)
+
+    def peer_open(self, handle: bytes) -> int:
+        """map another rank's buffer into this process (CUDA IPC, peer access over NVLink) -> device pointer"""
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self.lib.urlgpu_peer_open(self._h, h, C.byref(p)))
+        return p.value
+
+    def peer_close(self, ptr: int):
+        self._check(self.lib.urlgpu_peer_close(self._h, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int):
+        self._check(self.lib.urlgpu_peer_free(self._h, C.c_void_p(ptr)))
 
     def probe_fp64(self) -> dict:
         """measured FP64 issue rates of this device in TFLOP/s: {'dfma': ..., 'dmma': ...}"""

@@ -2705,6 +2705,46 @@ extern "C" void urlgpu_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
 
+// ---- peer memory (include/urlgpu.h): score boards that other ranks' kernels write through NVLink ---------------------
+extern "C" int urlgpu_peer_alloc(urlgpu_ctx *ctx, uint64_t bytes, void **dev_ptr, unsigned char handle[URLGPU_PEER_HANDLE_BYTES]) {
+    if (!ctx || !dev_ptr || !handle) return ctx ? ctx->fail(URLGPU_ERR_ARG, "peer_alloc: null argument") : URLGPU_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == URLGPU_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+    CK(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    CK(cudaMalloc(&p, bytes ? bytes : 1));     // its own allocation: an IPC handle names a whole cudaMalloc block
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return ctx->cuda_fail(e, "cudaIpcGetMemHandle", __LINE__); }
+    memcpy(handle, &h, sizeof h);
+    *dev_ptr = p;
+    return URLGPU_OK;
+}
+extern "C" int urlgpu_peer_open(urlgpu_ctx *ctx, const unsigned char handle[URLGPU_PEER_HANDLE_BYTES], void **dev_ptr) {
+    if (!ctx || !dev_ptr || !handle) return ctx ? ctx->fail(URLGPU_ERR_ARG, "peer_open: null argument") : URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = p;
+    return URLGPU_OK;
+}
+extern "C" int urlgpu_peer_close(urlgpu_ctx *ctx, void *dev_ptr) {
+    if (!ctx) return URLGPU_ERR_ARG;
+    if (!dev_ptr) return URLGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaIpcCloseMemHandle(dev_ptr));
+    return URLGPU_OK;
+}
+extern "C" int urlgpu_peer_free(urlgpu_ctx *ctx, void *dev_ptr) {
+    if (!ctx) return URLGPU_ERR_ARG;
+    if (!dev_ptr) return URLGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(dev_ptr));
+    return URLGPU_OK;
+}
+
 extern "C" int urlgpu_result_free(urlgpu_result *res) {
     if (!res) return URLGPU_OK;
     urlgpu_ctx *ctx = res->ctx;

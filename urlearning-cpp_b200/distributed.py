@@ -202,3 +202,51 @@ def exchange_ranges(pieces, owner, sizes, my_scores, device):
                 out[v][first:first + count] = recv[pos:pos + count]
                 pos += count
     return out
+
+
+class PeerScoreBoard:
+    """The exchange step of the range shards without a collective: every rank owns one device buffer holding the raw-score
+    arrays of the variables it owns (``urlgpu_peer_alloc``) and maps the buffers of all other ranks (CUDA IPC, peer access
+    over NVLink / NVSwitch).  ``target(v, first)`` is then the address — local or on a peer GPU — that
+    ``urlgpu_score_range(..., out_device_ptr=...)`` scores a piece into, so the scoring kernels store straight into the
+    owner's memory while they compute; ``fence()`` (stream sync + barrier) replaces the all-to-all of
+    :func:`exchange_ranges`.  One process per GPU on one node; needs the NCCL (or any) process group only for the handle
+    all-gather and the barrier."""
+
+    def __init__(self, eng, sizes, owner):
+        self.eng, self.sizes, self.owner = eng, [int(s) for s in sizes], list(owner)
+        self.world, self.rank = (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
+        self.offset, fill = [0] * len(sizes), [0] * self.world
+        for v, s in enumerate(self.sizes):         # every rank computes the same layout
+            self.offset[v] = fill[self.owner[v]]
+            fill[self.owner[v]] += (s + 63) // 64 * 64
+        self.base = [None] * self.world
+        self.base[self.rank], handle = eng.peer_alloc(4 * max(1, fill[self.rank]))
+        if self.world > 1:
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+            allh = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allh, mine)
+            for r in range(self.world):
+                if r != self.rank:
+                    self.base[r] = eng.peer_open(bytes(allh[r].cpu().tolist()))
+            dist.barrier()
+
+    def target(self, v: int, first: int = 0) -> int:
+        """device address of entry ``first`` of variable v's raw-score array, in its owner's memory"""
+        return self.base[self.owner[v]] + 4 * (self.offset[v] + int(first))
+
+    def fence(self):
+        """all pieces have landed: this rank's kernels are done and so are everybody else's"""
+        self.eng.synchronize()
+        if self.world > 1:
+            dist.barrier()
+
+    def close(self):
+        self.fence()
+        for r in range(self.world):
+            if self.base[r] is not None:
+                if r == self.rank:
+                    self.eng.peer_free(self.base[r])
+                else:
+                    self.eng.peer_close(self.base[r])
+            self.base[r] = None
