@@ -291,12 +291,22 @@ def run_gpu(args):
         stream.synchronize()
         if fetch and world > 1 and is_bic:
             # N > 1: the caches travel to rank 0 (the .pss writer) over NCCL inside the timed region
-            got = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch=True, costs=costs)
-            local = {v + shift: (to_global(m), sc) for v, (m, sc) in got.items()}
-            allc = D.gather_caches(local, p_global, words_global, "cuda", owner=owner_global, copy=False)
+            if args.gather == "p2p":
+                # the compacted caches go from every GPU straight into rank 0's device memory over NVLink (CUDA IPC mapping,
+                # urlgpu_result_fetch_device), rank 0 reads the whole area back once
+                kept = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch="keep", costs=costs)
+                allc = D.gather_results_p2p(eng, kept, p_global, words_global, owner=owner_global, shift=shift, copy=False)
+                nst_ = sum(r.count() for r in kept.values())
+                for r in kept.values():
+                    r.free()
+            else:
+                got = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch=True, costs=costs)
+                local = {v + shift: (to_global(m), sc) for v, (m, sc) in got.items()}
+                allc = D.gather_caches(local, p_global, words_global, "cuda", owner=owner_global, copy=False)
+                nst_ = sum(len(sc) for _, sc in got.values())
             if rank == 0:
                 assert len(allc) == p_global
-            return sum(len(sc) for _, sc in got.values())
+            return nst_
         out = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch="pinned" if fetch else False, costs=costs)
         return sum(out.values()) if fetch else 0
 
@@ -390,7 +400,9 @@ def run_gpu(args):
         e2e = {"value": total_sets * nst / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int((8 * words + 4) * stored // nst), "steps": nst, "ms_per_step": ems / nst}
         if world > 1:
-            e2e["gather_to_rank0"] = "NCCL, inside the timed region: %d bytes per step" % int((8 * (words_global + 1)) * stored // nst)
+            e2e["gather_to_rank0"] = ("%s, inside the timed region: %d bytes per step" % (
+                "device to device over NVLink into rank 0's memory (CUDA IPC peer mapping), then one D2H on rank 0" if args.gather == "p2p"
+                else "NCCL gather of host-packed blocks", int((8 * words_global + 4) * stored // nst)))
 
     # ---- strong-scaling sub-record of every N > 1 weak line: configs[3] ITSELF split over the ranks (codes broadcast over NCCL,
     # variables dealt out by predicted cost, device-resident timing like `value`, then one e2e pass with the NCCL gather)
@@ -413,11 +425,19 @@ def run_gpu(args):
             if not fetch:
                 pool.run(items_s, wl_s["K"], stype, flags=flags, fetch=False, costs=costs_s)
                 return 0
-            got = pool.run(items_s, wl_s["K"], stype, flags=flags, fetch=True, costs=costs_s)
-            allc = D.gather_caches(got, wl_s["p"], words_s, "cuda", owner=owner_s, copy=False)
+            if args.gather == "p2p":
+                kept = pool.run(items_s, wl_s["K"], stype, flags=flags, fetch="keep", costs=costs_s)
+                allc = D.gather_results_p2p(eng, kept, wl_s["p"], words_s, owner=owner_s, copy=False)
+                nst_ = sum(r.count() for r in kept.values())
+                for r in kept.values():
+                    r.free()
+            else:
+                got = pool.run(items_s, wl_s["K"], stype, flags=flags, fetch=True, costs=costs_s)
+                allc = D.gather_caches(got, wl_s["p"], words_s, "cuda", owner=owner_s, copy=False)
+                nst_ = sum(len(sc) for _, sc in got.values())
             if rank == 0:
                 assert len(allc) == wl_s["p"]
-            return sum(len(sc) for _, sc in got.values())
+            return nst_
         step_s()
         nss = max(1, min(args.steps, 5))
         sms, _ = timed(nss, step_s)
@@ -516,6 +536,7 @@ def run_gpu(args):
                 "cpu_baseline": cpu, **extra, **({"scaling_strong": strong} if strong else {})}
         print(json.dumps(line))
     if world > 1:
+        D.release_boards()
         dist.barrier()
         dist.destroy_process_group()
     if pool is not None:
@@ -933,6 +954,9 @@ def main():
                          "fixed); strong = configs[3] itself split over the ranks")
     ap.add_argument("--n5", type=int, default=10_000_000, help="total rows of the cbic5 workload")
     ap.add_argument("--k5", type=int, default=4, help="explicit parent limit (-p) of the cbic5 workload")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1, e2e arm: how the caches reach rank 0: p2p = written by every GPU straight into rank 0's device memory over "
+                         "NVLink (urlgpu_result_fetch_device), nccl = fetched to the host, packed, NCCL gather")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="cbic5: how the raw scores reach their owners: p2p = scored straight into the owner's memory over NVLink "
                          "(CUDA IPC peer mapping, urlgpu_peer_*), nccl = local buffer + one all-to-all")

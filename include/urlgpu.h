@@ -112,6 +112,13 @@ int urlgpu_result_scored(urlgpu_result *res, uint64_t *n_scored);  /* candidate 
 /* canonical order: (|S| ascending, mask ascending as an integer).  masks: n*mask_words words. */
 int urlgpu_result_fetch(urlgpu_result *res, uint64_t offset, uint64_t n, uint64_t *masks, float *scores);
 int urlgpu_result_free(urlgpu_result *res);
+/* The same entries into DEVICE memory: this device's, or a buffer on another GPU mapped with urlgpu_peer_open (the gather of
+ * the per-variable caches to the rank that writes the .pss then runs over NVLink without touching the host).  Masks get
+ * mask_words_out words; variable_shift is added to every variable index (0 unless the data set is one block of a larger one). */
+int urlgpu_result_fetch_device(urlgpu_result *res, uint64_t offset, uint64_t n, int mask_words_out, int variable_shift,
+                               uint64_t *d_masks, float *d_scores);
+/* copy `bytes` from a device address (e.g. a board other ranks filled) into host memory */
+int urlgpu_copy_to_host(urlgpu_ctx *ctx, void *dst_host, const void *src_device, uint64_t bytes);
 /* page-locked host memory for large result payloads (urlgpu_result_fetch copies into it at PCIe speed; pageable
  * destinations work too but go through the driver's staging copy).  NULL on failure. */
 void *urlgpu_host_alloc(uint64_t bytes);

@@ -34,15 +34,25 @@ eng = pkg.Engine(local)
 eng.set_discrete_device(full.data_ptr(), n, p, card)
 nbs = [pkg.two_hop_neighbors(edges, p, v) for v in range(p)]
 owner = D.assign_lpt([D.family_cost(card, v, nbs[v], K) for v in range(p)], world)
-local_caches = {}
+local_caches, kept = {}, {}
 for v in range(p):
     if owner[v] == rank:
         res = eng.score_variable(v, nbs[v], K, pkg.BIC, flags=pkg.PRUNE_DOMINATED)
         local_caches[v] = res.fetch()
-        res.free()
+        kept[v] = res
 caches = D.gather_caches(local_caches, p, 1, "cuda", owner=owner)
+# the same gather without the host bounce: every rank writes its compacted caches into rank 0's device memory over NVLink
+# (twice: the second call reuses the mapped board)
+for _ in range(2):
+    direct = D.gather_results_p2p(eng, kept, p, 1, owner=owner)
+for r in kept.values():
+    r.free()
 if rank == 0:
-    pkg.pss.write_pss(out, "synthetic.csv", n, K, "BIC", [f"V{i}" for i in range(p)], card, caches)
+    assert sorted(direct) == sorted(caches) == list(range(p))
+    for v in range(p):
+        assert np.array_equal(direct[v][0], caches[v][0]) and np.array_equal(direct[v][1].view(np.uint32), caches[v][1].view(np.uint32)), v
+    pkg.pss.write_pss(out, "synthetic.csv", n, K, "BIC", [f"V{i}" for i in range(p)], card, direct)
+D.release_boards()
 dist.barrier()
 dist.destroy_process_group()
 eng.close()

@@ -37,6 +37,7 @@ ABI_SYMBOLS = [
     "urlgpu_stats_enable_timing", "urlgpu_probe_fp64", "urlgpu_family_size", "urlgpu_score_range", "urlgpu_result_from_scores", "urlgpu_score_part",
     "urlgpu_spg_build", "urlgpu_spg_query", "urlgpu_spg_free",
     "urlgpu_peer_alloc", "urlgpu_peer_open", "urlgpu_peer_close", "urlgpu_peer_free",
+    "urlgpu_result_fetch_device", "urlgpu_copy_to_host",
 ]
 
 
@@ -109,6 +110,8 @@ def load_library():
     lib.urlgpu_spg_build.argtypes = [vp, vp, vp, u64, i32, i32, P(vp)]
     lib.urlgpu_spg_query.argtypes = [vp, vp, u64, vp, vp, vp]
     lib.urlgpu_spg_free.argtypes = [vp]
+    lib.urlgpu_result_fetch_device.argtypes = [vp, u64, u64, i32, i32, vp, vp]
+    lib.urlgpu_copy_to_host.argtypes = [vp, vp, vp, u64]
     lib.urlgpu_peer_alloc.argtypes = [vp, u64, P(vp), vp]
     lib.urlgpu_peer_open.argtypes = [vp, vp, P(vp)]
     lib.urlgpu_peer_close.argtypes = [vp, vp]
@@ -202,6 +205,15 @@ class Result:
         if n:
             self._eng._check(self._eng.lib.urlgpu_result_fetch(self._h, 0, n, masks.ctypes.data, scores.ctypes.data))
         return masks, scores
+
+    def fetch_device(self, masks_ptr: int, scores_ptr: int, words_out: int | None = None, shift: int = 0) -> int:
+        """write the stored entries (canonical order) to device addresses — local or peer-mapped (Engine.peer_open): masks as
+        ``words_out`` words with every variable index shifted by ``shift``, scores as float32.  -> number of entries"""
+        n = self.count()
+        if n:
+            self._eng._check(self._eng.lib.urlgpu_result_fetch_device(self._h, 0, n, int(words_out or self.words), int(shift),
+                                                                      C.c_void_p(masks_ptr), C.c_void_p(scores_ptr)))
+        return n
 
     def free(self):
         if self._h is not None:
@@ -448,6 +460,10 @@ class Engine:
     def enable_timing(self, on: bool = True):
         self._check(self.lib.urlgpu_stats_enable_timing(self._h, int(on)))
 
+    def copy_to_host(self, host: np.ndarray, dev_ptr: int, nbytes: int):
+        """bytes at a device address -> a (preferably page-locked) host array"""
+        self._check(self.lib.urlgpu_copy_to_host(self._h, host.ctypes.data, C.c_void_p(dev_ptr), int(nbytes)))
+
     def peer_alloc(self, nbytes: int):
         """a device buffer other ranks can map (urlgpu_peer_alloc) -> (device pointer, 64-byte handle)"""
         p = C.c_void_p()
@@ -578,7 +594,8 @@ class EnginePool:
         longest first, else round robin).  fetch=True -> {variable: (masks, scores)}, read back one variable behind the
         one being scored (urlgpu_result_prefetch); fetch="pinned" -> {variable: stored entries}, every cache is read back
         into the context's page-locked result buffer (overwritten by the next one: for drivers that consume each cache as
-        it arrives); fetch=False -> {variable: sets scored}, results dropped on the device.
+        it arrives); fetch="keep" -> {variable: Result} with the compaction enqueued (for device-side consumers such as
+        distributed.gather_results_p2p; the caller frees them); fetch=False -> {variable: sets scored}, results dropped on the device.
         contexts: use only the first `contexts` contexts (1 = strictly serial kernels, for per-kernel timing)."""
         T = len(self.engines) if contexts is None else max(1, min(contexts, len(self.engines)))
         order = sorted(range(len(items)), key=lambda i: (-(costs[i] if costs is not None else 0.0), i))
@@ -597,6 +614,8 @@ class EnginePool:
                 return len(res.fetch(pinned=True)[1])
             return res.fetch()
 
+        keep = fetch == "keep"   # -> {variable: Result}, compaction enqueued, results alive: the caller reads and frees them
+
         def work(t):
             eng = self.engines[t]
             try:
@@ -604,7 +623,9 @@ class EnginePool:
                 for i in lists[t]:
                     v, nb = items[i]
                     res = eng.score_variable(v, nb, max_parents, score_type, lam=lam, flags=flags)
-                    if fetch:
+                    if keep:
+                        out[v] = res.prefetch()
+                    elif fetch:
                         res.prefetch()
                         if prev is not None:
                             out[prev[0]] = take(prev[1])

@@ -2695,6 +2695,48 @@ extern "C" int urlgpu_result_fetch(urlgpu_result *res, uint64_t offset, uint64_t
     return URLGPU_OK;
 }
 
+// The same entries into DEVICE memory — this device's or a peer-mapped buffer on another GPU (urlgpu_peer_open): the expansion
+// kernel writes the wide masks straight to the destination, the scores follow with one device-to-device copy.  Masks are
+// written with `mask_words_out` words and every variable index shifted up by `variable_shift` (a data set that is one block
+// of a larger one: the gathered cache then names the global variables).
+extern "C" int urlgpu_result_fetch_device(urlgpu_result *res, uint64_t offset, uint64_t n, int mask_words_out, int variable_shift, uint64_t *d_masks, float *d_scores) {
+    if (!res) return URLGPU_ERR_ARG;
+    urlgpu_ctx *ctx = res->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int rc = result_wait_counts(res);
+    if (rc) return rc;
+    if (offset + n > res->n_stored) return ctx->fail(URLGPU_ERR_ARG, "result_fetch_device: range exceeds the stored count");
+    if (variable_shift < 0 || mask_words_out < 1) return ctx->fail(URLGPU_ERR_ARG, "result_fetch_device: bad mask width or shift");
+    for (int v : res->cand)
+        if ((v + variable_shift) / 64 >= mask_words_out) return ctx->fail(URLGPU_ERR_ARG, "result_fetch_device: mask_words_out is too small for the shifted variables");
+    if (n == 0) return URLGPU_OK;
+    cudaStream_t cs = ctx->copy_stream;
+    if (d_masks) {
+        if (!ctx->d_fetch_cand) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_fetch_cand), (kMaxRankCand + 2) * sizeof(int)));
+        std::vector<int> shifted(res->cand);
+        for (int &v : shifted) v += variable_shift;
+        if (!shifted.empty()) CK(cudaMemcpyAsync(ctx->d_fetch_cand, shifted.data(), shifted.size() * sizeof(int), cudaMemcpyHostToDevice, cs));
+        if (res->rank_layout)
+            rank_expand_kernel<<<blocks_for(n, 256), 256, rs_binom_bytes(res->rs), cs>>>(res->rs, res->d_masks + offset, n, ctx->d_fetch_cand, mask_words_out, d_masks);
+        else
+            expand_masks_kernel<<<blocks_for(n, 256), 256, 0, cs>>>(res->d_masks + offset, n, ctx->d_fetch_cand, res->c, mask_words_out, d_masks);
+    }
+    if (d_scores) CK(cudaMemcpyAsync(d_scores, res->d_vals + offset, n * sizeof(float), cudaMemcpyDefault, cs));
+    CK(cudaStreamSynchronize(cs));   // `shifted` goes out of scope; the caller may publish the destination after this returns
+    CK(cudaGetLastError());
+    return URLGPU_OK;
+}
+// plain copy out of a device buffer named by address (e.g. a score board others filled): the binding has no other way to read one
+extern "C" int urlgpu_copy_to_host(urlgpu_ctx *ctx, void *dst_host, const void *src_device, uint64_t bytes) {
+    if (!ctx || (bytes && (!dst_host || !src_device))) return ctx ? ctx->fail(URLGPU_ERR_ARG, "copy_to_host: null argument") : URLGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (bytes) {
+        CK(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+    }
+    return URLGPU_OK;
+}
+
 // page-locked host memory for result payloads: device->host copies into it run at PCIe speed and need no staging copy
 extern "C" void *urlgpu_host_alloc(uint64_t bytes) {
     void *p = nullptr;

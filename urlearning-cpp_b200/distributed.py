@@ -250,3 +250,84 @@ class PeerScoreBoard:
                 else:
                     self.eng.peer_close(self.base[r])
             self.base[r] = None
+
+
+_BOARD = {}
+
+
+def _cache_board(eng, total: int, words: int, dst: int):
+    """rank dst's device landing area for gathered caches ([cap * words] mask words, then [cap] scores), mapped by every
+    rank; (re)allocated collectively when `total` entries do not fit — every rank sees the same `total`, so all take the
+    same branch.  -> (address of the area in THIS process, cap)"""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    b = _BOARD.get(dst)
+    if b is not None and b["cap"] >= total and b["words"] == words:
+        return b["ptr"], b["cap"]
+    if b is not None:
+        dist.barrier()
+        (b["eng"].peer_free if rank == dst else b["eng"].peer_close)(b["ptr"])
+    cap = int(total * 1.5) + 4096
+    handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    ptr = None
+    if rank == dst:
+        ptr, h = eng.peer_alloc(cap * (8 * words + 4))
+        handle = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
+    dist.broadcast(handle, src=dst)
+    if rank != dst:
+        ptr = eng.peer_open(bytes(handle.cpu().tolist()))
+    _BOARD[dst] = {"ptr": ptr, "cap": cap, "words": words, "eng": eng}
+    return ptr, cap
+
+
+def gather_results_p2p(eng, results: dict, p: int, words: int, dst: int = 0, owner=None, shift: int = 0, copy: bool = True):
+    """:func:`gather_caches` without the host bounce: ``results`` = {variable: Result} still on the device (the variables this
+    rank owns, local numbering; ``shift`` is added to every variable index, for a rank whose data set is one block of a larger
+    one).  Every rank writes its compacted caches straight into rank ``dst``'s device memory over NVLink
+    (``urlgpu_result_fetch_device`` into a CUDA-IPC mapping), one barrier, and ``dst`` copies the whole area to page-locked
+    host memory once.  Returns {global variable: (masks uint64 [n, words], scores float32 [n])} on ``dst``, None elsewhere."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = torch.zeros(p, dtype=torch.int64)
+    owned = sorted(results)
+    for v in owned:
+        counts[v + shift] = results[v].count()
+    counts = counts.cuda()
+    all_counts = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts)
+    all_counts = torch.stack(all_counts).cpu().numpy()
+    per_rank = all_counts.sum(axis=1)
+    base = np.concatenate([[0], np.cumsum(per_rank)]).astype(np.int64)
+    total = int(per_rank.sum())
+    ptr, cap = _cache_board(eng, total, words, dst)
+    off = int(base[rank])
+    for v in owned:
+        off += results[v].fetch_device(ptr + 8 * words * off, ptr + 8 * words * cap + 4 * off, words, shift)
+    dist.barrier()            # every rank's stores have completed (fetch_device returns after its copy stream drained)
+    if rank != dst:
+        return None
+    land_m = _landing("recv_m", max(total, 1) * words, torch.int64, True).view(-1, words)
+    land_s = _landing("recv_s", max(total, 1), torch.float32, True)
+    lm, ls = land_m.numpy(), land_s.numpy()
+    eng.copy_to_host(lm, ptr, 8 * words * total)
+    eng.copy_to_host(ls, ptr + 8 * words * cap, 4 * total)
+    lm = lm.view(np.uint64)
+    out = {}
+    for r in range(world):
+        o = int(base[r])
+        for v in range(p):
+            k = int(all_counts[r, v])
+            if k == 0 and (owner[v] if owner is not None else v % world) != r:
+                continue
+            out[v] = (lm[o:o + k].copy(), ls[o:o + k].copy()) if copy else (lm[o:o + k], ls[o:o + k])
+            o += k
+    return out
+
+
+def release_boards():
+    """free / unmap the gather boards (collective: call on every rank before the engines close)"""
+    if not _BOARD:
+        return
+    dist.barrier()
+    rank = dist.get_rank()
+    for dst, b in list(_BOARD.items()):
+        (b["eng"].peer_free if rank == dst else b["eng"].peer_close)(b["ptr"])
+    _BOARD.clear()
