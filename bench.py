@@ -294,7 +294,13 @@ def run_gpu(args):
             if args.gather == "p2p":
                 # the compacted caches go from every GPU straight into rank 0's device memory over NVLink (CUDA IPC mapping,
                 # urlgpu_result_fetch_device), rank 0 reads the whole area back once
+                t0_ = time.perf_counter()
                 kept = pool.run(items, wl["K"], stype, lam=lam, flags=flags, fetch="keep", costs=costs)
+                if os.environ.get("URLGPU_GATHER_TIMING"):
+                    t1_ = time.perf_counter()
+                    torch.cuda.synchronize()
+                    t2_ = time.perf_counter()
+                    print("[step rank %d] pool.run(keep) %.1f ms, device sync after it %.1f ms (wall %.3f)" % (rank, 1e3 * (t1_ - t0_), 1e3 * (t2_ - t1_), time.time() % 100), flush=True)
                 allc = D.gather_results_p2p(eng, kept, p_global, words_global, owner=owner_global, shift=shift, copy=False)
                 nst_ = sum(r.count() for r in kept.values())
                 for r in kept.values():
@@ -351,6 +357,7 @@ def run_gpu(args):
         step()
     sampler = ClockSampler(local)
     sampler.start()
+    t16_warm = int(pool.stats().get("table16_fallbacks", 0))   # variables whose speculative 16-bit tables overflowed during the warm-up (remembered: 32-bit from then on)
     pool.reset_stats()
     ms, _ = timed(args.steps, step)
     launches_total = pool.stats()["launches_total"]
@@ -382,11 +389,16 @@ def run_gpu(args):
         host = pinned.numpy()
 
         def e2e_step():
+            t0 = time.perf_counter()
             if is_bic:
                 pool.set_discrete(host, wl["card"])  # one upload per GPU; the pool's other contexts borrow the device copy
             else:
                 pool.set_continuous(host)
-            return step(fetch=True)
+            t1 = time.perf_counter()
+            out = step(fetch=True)
+            if os.environ.get("URLGPU_GATHER_TIMING"):
+                print("[e2e_step rank %d] upload %.1f ms, step+gather %.1f ms" % (rank, 1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t1)), flush=True)
+            return out
 
         e2e_step()
         nst = max(1, min(args.steps, 3))
@@ -448,7 +460,11 @@ def run_gpu(args):
                   "parallelism": f"configs[3] itself: codes broadcast over NCCL, 60 variables dealt to {world} ranks by predicted cost (LPT), caches gathered to rank 0"}
 
     mem_free, mem_total = torch.cuda.mem_get_info()
-    t16_fallbacks = int(pool.stats().get("table16_fallbacks", 0))   # after the e2e arm, which reads every cache (the flag is checked on first read)
+    t16_fallbacks = int(pool.stats().get("table16_fallbacks", 0))   # timed regions (value, roofline pass, e2e), summed over the ranks
+    if world > 1:
+        t = torch.tensor([t16_fallbacks, t16_warm], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        t16_fallbacks, t16_warm = int(t[0].item()), int(t[1].item())
     if rank == 0:
         peak, peak_src = load_peaks()
         fam = {"count": st["ms_count"], "cube": st["ms_cube"], "tree": st["ms_tree"], "cbic": st["ms_cbic"], "accept": st["ms_accept"],
@@ -530,7 +546,7 @@ def run_gpu(args):
                                            else "variables striped v % N") + f", N={world}; "
                                           f"{T} context(s)/stream(s) per GPU, one host thread each (the reference's -t workers)",
                            "l2": "flushed between steps (256 MB write)", "dominant_family": dom,
-                           "table16_fallbacks": t16_fallbacks,
+                           "table16_fallbacks": t16_fallbacks, "table16_fallbacks_warmup": t16_warm,
                            "hbm_in_use_gb": round((mem_total - mem_free) / 1e9, 1)},
                 "e2e": e2e, "gpu_launches": int(launches_total), "clocks": sampler.summary(), "roofline": roofline,
                 "cpu_baseline": cpu, **extra, **({"scaling_strong": strong} if strong else {})}

@@ -311,7 +311,7 @@ def test_speculative_16bit_tables_and_their_fallback(pkg, orc):
     for v in (0, 11):
         _check_variable(pkg, orc, eng, skew, card, None, v, 10)
         _check_variable(pkg, orc, eng, skew, card, None, v, 10, flags=pkg.PRUNE_DOMINATED)
-    assert eng.stats()["table16_fallbacks"] >= 2
+    assert eng.stats()["table16_fallbacks"] == 2   # once per variable: its later scorings go straight to 32-bit tables
     eng.close()
     codes, card2, edges, _ = pkg.datagen.discrete_bn(p=14, n=90001, seed=31, arities=(2, 3, 4), window=6, max_indegree=3)
     forced = engine_with_env(pkg, {"URLGPU_BIC_MODE": "cube", "URLGPU_TABLE16_MINLAYER": "1"})

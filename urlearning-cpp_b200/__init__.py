@@ -632,10 +632,20 @@ class EnginePool:
                             prev[1].free()
                         prev = (v, res)
                     else:
+                        # nothing is read back, but every result is still completed on the device: the compaction runs and the
+                        # count is awaited one variable behind, which is also where a speculative 16-bit table that
+                        # overflowed is noticed and the variable recomputed (result_wait_counts)
                         out[v] = res.scored()
-                        res.free()
+                        res.prefetch()
+                        if prev is not None:
+                            prev[1].count()
+                            prev[1].free()
+                        prev = (v, res)
                 if prev is not None:
-                    out[prev[0]] = take(prev[1])
+                    if fetch:
+                        out[prev[0]] = take(prev[1])
+                    else:
+                        prev[1].count()
                     prev[1].free()
                 eng.synchronize()
             except Exception as ex:

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -63,6 +64,7 @@ struct urlgpu_ctx {
     const long long *ds_qcfg = nullptr; int ds_cfg_min = 1; float ds_base = 0.f;
     float ds_ess = 0.f; double ds_scale = 1.0 / 8388608.0;   // BDeu: equivalent sample size (> 0) and the 2^-30 accumulator unit
     std::map<int, long long *> d_qfnml;   // fNML: arity -> qlog + log-regret table [n+2] (built on first use, owned by this context)
+    std::set<int> t16_overflowed;         // variables whose speculative 16-bit tables overflowed once: scored with 32-bit tables from then on
     bool borrowed_discrete = false; // d_codes/d_qlog belong to another context on the same device (urlgpu_share_discrete)
 
     // continuous data
@@ -468,7 +470,7 @@ static int set_discrete_common(urlgpu_ctx *ctx, const uint8_t *src, bool src_on_
         if (cardinality[i] < 1 || cardinality[i] > 256) return ctx->fail(URLGPU_ERR_ARG, "set_discrete: cardinality must be in 1..256");
     // a data set of the same shape re-uses the device buffers, and the log table depends on n only
     const bool same_shape = ctx->have_discrete && !ctx->borrowed_discrete && ctx->n == n && ctx->p == p;
-    if (!same_shape) free_discrete(ctx);
+    if (!same_shape) { free_discrete(ctx); ctx->t16_overflowed.clear(); }
     ctx->have_discrete = false;
     ctx->n = n; ctx->p = p;
     ctx->n_stride = (n + 15) / 16 * 16;
@@ -2290,7 +2292,7 @@ extern "C" int urlgpu_score_variable(urlgpu_ctx *ctx, int variable, const uint64
     cudaStream_t s = ctx->stream;
     auto cleanup = [&](int code) { pool_free(ctx, res->d_table); if (res->d_ovf) pool_free(ctx, res->d_ovf); delete res; return code; };
     res->is_bic = bic; res->score_type = score_type; res->filter_flags = filter_flags;
-    if (bic && ctx->ds_ess == 0.f && ctx->table16 && c <= kMaxDenseCand && ctx->bic_mode == 2) {
+    if (bic && ctx->ds_ess == 0.f && ctx->table16 && c <= kMaxDenseCand && ctx->bic_mode == 2 && !ctx->t16_overflowed.count(variable)) {
         e = pool_alloc(ctx, reinterpret_cast<void **>(&res->d_ovf), sizeof(int));
         if (e != cudaSuccess) return cleanup(ctx->cuda_fail(e, "cudaMalloc(flag)", __LINE__));
         cudaMemsetAsync(res->d_ovf, 0, sizeof(int), s);
@@ -2615,6 +2617,7 @@ static int result_wait_counts(urlgpu_result *res) {
         // a cell count did not fit 16 bits somewhere in this variable's tables: the scores are discarded and the family is
         // recomputed with 32-bit tables on the result's own table, then filtered and compacted again
         ctx->st.table16_fallbacks++;
+        ctx->t16_overflowed.insert(res->variable);   // a hint only (32-bit tables are always right): kept while the data set keeps its shape
         pool_free(ctx, res->d_ovf);
         res->d_ovf = nullptr;
         res->h_counts[33] = 0;

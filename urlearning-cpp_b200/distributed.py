@@ -253,6 +253,18 @@ class PeerScoreBoard:
 
 
 _BOARD = {}
+_SIDE = {}
+
+
+def _side_group():
+    """A gloo (CPU, TCP on localhost) group for the few bytes of control traffic of the peer-memory paths: counts, handles and
+    barriers.  Measured on 4 and 8 B200s: the first NCCL collective after a ~300 ms compute phase takes 55-60 ms whatever its
+    size (later ones < 1 ms), which was most of the gather's cost; the gloo round trips take ~0.2 ms and involve no GPU."""
+    g = _SIDE.get("g")
+    if g is None:
+        g = dist.new_group(backend="gloo")      # collective: every rank reaches its first peer-memory gather together
+        _SIDE["g"] = g
+    return g
 
 
 def _cache_board(eng, total: int, words: int, dst: int):
@@ -263,18 +275,19 @@ def _cache_board(eng, total: int, words: int, dst: int):
     b = _BOARD.get(dst)
     if b is not None and b["cap"] >= total and b["words"] == words:
         return b["ptr"], b["cap"]
+    g = _side_group()
     if b is not None:
-        dist.barrier()
+        dist.barrier(group=g)
         (b["eng"].peer_free if rank == dst else b["eng"].peer_close)(b["ptr"])
     cap = int(total * 1.5) + 4096
-    handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    handle = torch.zeros(64, dtype=torch.uint8)
     ptr = None
     if rank == dst:
         ptr, h = eng.peer_alloc(cap * (8 * words + 4))
-        handle = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
-    dist.broadcast(handle, src=dst)
+        handle = torch.tensor(list(h), dtype=torch.uint8)
+    dist.broadcast(handle, src=dst, group=g)
     if rank != dst:
-        ptr = eng.peer_open(bytes(handle.cpu().tolist()))
+        ptr = eng.peer_open(bytes(handle.tolist()))
     _BOARD[dst] = {"ptr": ptr, "cap": cap, "words": words, "eng": eng}
     return ptr, cap
 
@@ -285,23 +298,33 @@ def gather_results_p2p(eng, results: dict, p: int, words: int, dst: int = 0, own
     one).  Every rank writes its compacted caches straight into rank ``dst``'s device memory over NVLink
     (``urlgpu_result_fetch_device`` into a CUDA-IPC mapping), one barrier, and ``dst`` copies the whole area to page-locked
     host memory once.  Returns {global variable: (masks uint64 [n, words], scores float32 [n])} on ``dst``, None elsewhere."""
+    import os, time
+    dbg = os.environ.get("URLGPU_GATHER_TIMING")
+    tt = [time.perf_counter()]
     world, rank = dist.get_world_size(), dist.get_rank()
     counts = torch.zeros(p, dtype=torch.int64)
     owned = sorted(results)
     for v in owned:
         counts[v + shift] = results[v].count()
-    counts = counts.cuda()
+    tt.append(time.perf_counter())
+    g = _side_group()
     all_counts = [torch.empty_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts)
-    all_counts = torch.stack(all_counts).cpu().numpy()
+    dist.all_gather(all_counts, counts, group=g)      # CPU tensors over gloo: see _side_group
+    all_counts = torch.stack(all_counts).numpy()
     per_rank = all_counts.sum(axis=1)
     base = np.concatenate([[0], np.cumsum(per_rank)]).astype(np.int64)
     total = int(per_rank.sum())
+    tt.append(time.perf_counter())
     ptr, cap = _cache_board(eng, total, words, dst)
     off = int(base[rank])
     for v in owned:
         off += results[v].fetch_device(ptr + 8 * words * off, ptr + 8 * words * cap + 4 * off, words, shift)
-    dist.barrier()            # every rank's stores have completed (fetch_device returns after its copy stream drained)
+    tt.append(time.perf_counter())
+    dist.barrier(group=g)     # every rank's stores have completed (fetch_device returns after its copy stream drained)
+    tt.append(time.perf_counter())
+    if dbg and rank in (0, 1):
+        print("[gather_results_p2p rank %d] counts %.1f ms, all_gather %.1f, stores %.1f, barrier %.1f" % (
+            rank, *[1e3 * (tt[i + 1] - tt[i]) for i in range(4)]), flush=True)
     if rank != dst:
         return None
     land_m = _landing("recv_m", max(total, 1) * words, torch.int64, True).view(-1, words)
@@ -309,6 +332,8 @@ def gather_results_p2p(eng, results: dict, p: int, words: int, dst: int = 0, own
     lm, ls = land_m.numpy(), land_s.numpy()
     eng.copy_to_host(lm, ptr, 8 * words * total)
     eng.copy_to_host(ls, ptr + 8 * words * cap, 4 * total)
+    if dbg:
+        print("[gather_results_p2p rank %d] D2H of %d bytes %.1f ms" % (rank, (8 * words + 4) * total, 1e3 * (time.perf_counter() - tt[-1])), flush=True)
     lm = lm.view(np.uint64)
     out = {}
     for r in range(world):
@@ -326,7 +351,7 @@ def release_boards():
     """free / unmap the gather boards (collective: call on every rank before the engines close)"""
     if not _BOARD:
         return
-    dist.barrier()
+    dist.barrier(group=_side_group())
     rank = dist.get_rank()
     for dst, b in list(_BOARD.items()):
         (b["eng"].peer_free if rank == dst else b["eng"].peer_close)(b["ptr"])
