@@ -151,3 +151,35 @@ def test_two_rank_gloo_range_exchange(tmp_path):
     mp.spawn(_range_worker, args=(2, port, out), nprocs=2, join=True)
     r = json.load(open(out))
     assert r["ok"] and r["owned"] == [0, 1, 2, 3, 4]
+
+
+def test_peer_score_board_layout_single_process():
+    """PeerScoreBoard's address arithmetic (no process group, a stand-in engine): every variable's array starts 64 scores
+    aligned inside its owner's buffer, pieces land at first * 4 bytes, and close() releases what was allocated"""
+    import importlib
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
+
+    class FakeEngine:
+        def __init__(self):
+            self.allocated, self.freed, self.syncs = [], [], 0
+
+        def peer_alloc(self, nbytes):
+            self.allocated.append(nbytes)
+            return 1 << 20, bytes(64)
+
+        def peer_free(self, ptr):
+            self.freed.append(ptr)
+
+        def synchronize(self):
+            self.syncs += 1
+
+    eng = FakeEngine()
+    sizes = [100, 64, 1, 1000]
+    board = D.PeerScoreBoard(eng, sizes, owner=[0, 0, 0, 0])
+    assert eng.allocated == [4 * (128 + 64 + 64 + 1024)]
+    base = 1 << 20
+    assert [board.target(v) for v in range(4)] == [base, base + 4 * 128, base + 4 * 192, base + 4 * 256]
+    assert board.target(3, 10) == base + 4 * (256 + 10)
+    board.fence()
+    board.close()
+    assert eng.freed == [base] and eng.syncs >= 2
