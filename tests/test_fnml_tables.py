@@ -117,3 +117,24 @@ def test_bdeu_known_answer_by_hand(orc):
     want = 4 * (lgamma(1.25) - lgamma(0.25)) + 2 * (lgamma(0.5) - lgamma(2.5))
     got = orc.bdeu_score_many(codes, [2, 2], 0, [0b10], ess=1.0, mode=0, threads=1)[0]
     assert abs(float(got) - want) < 1e-6 * abs(want)
+
+
+def test_product_regret_builder_equals_the_oracle(orc, tmp_path):
+    """the engine's host-side table builder (csrc/regret.hpp, compiled here with g++ as plain C++) against the oracle's
+    restatement, bit for bit: arities 1..9, N up to 3000 (the exact K=2 row, Szpankowski's approximation above 1000, the
+    float32 recurrence), and an arity whose regret overflows float32"""
+    import ctypes as C
+    import subprocess
+    so = str(tmp_path / "regret_probe.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "tests", "regret_probe.cpp")])
+    lib = C.CDLL(so)
+    lib.probe_log_regret.argtypes = [C.c_int64, C.c_int, C.c_void_p]
+    for r in range(1, 10):
+        mine = np.zeros(3001, dtype=np.float32)
+        lib.probe_log_regret(3000, r, mine.ctypes.data)
+        assert np.array_equal(mine.view(np.uint32), orc.log_regret(3000, r).view(np.uint32)), r
+    wide = np.zeros(200001, dtype=np.float32)
+    lib.probe_log_regret(200000, 60, wide.ctypes.data)
+    ref = orc.log_regret(200000, 60)
+    assert np.array_equal(wide.view(np.uint32), ref.view(np.uint32)) and not np.all(np.isfinite(wide))
