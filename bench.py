@@ -301,7 +301,15 @@ def run_gpu(args):
                     torch.cuda.synchronize()
                     t2_ = time.perf_counter()
                     print("[step rank %d] pool.run(keep) %.1f ms, device sync after it %.1f ms (wall %.3f)" % (rank, 1e3 * (t1_ - t0_), 1e3 * (t2_ - t1_), time.time() % 100), flush=True)
-                allc = D.gather_results_p2p(eng, kept, p_global, words_global, owner=owner_global, shift=shift, copy=False)
+                try:
+                    allc = D.gather_results_p2p(eng, kept, p_global, words_global, owner=owner_global, shift=shift, copy=False)
+                except D.PeerMemoryUnavailable as ex:     # raised on every rank together: all switch to the NCCL gather
+                    if rank == 0:
+                        print("bench: peer memory unavailable (%s): using --gather nccl" % ex, file=sys.stderr)
+                    args.gather = "nccl"
+                    for r in kept.values():
+                        r.free()
+                    return step(fetch=True)
                 nst_ = sum(r.count() for r in kept.values())
                 for r in kept.values():
                     r.free()
@@ -439,7 +447,13 @@ def run_gpu(args):
                 return 0
             if args.gather == "p2p":
                 kept = pool.run(items_s, wl_s["K"], stype, flags=flags, fetch="keep", costs=costs_s)
-                allc = D.gather_results_p2p(eng, kept, wl_s["p"], words_s, owner=owner_s, copy=False)
+                try:
+                    allc = D.gather_results_p2p(eng, kept, wl_s["p"], words_s, owner=owner_s, copy=False)
+                except D.PeerMemoryUnavailable:
+                    args.gather = "nccl"
+                    for r in kept.values():
+                        r.free()
+                    return step_s(True)
                 nst_ = sum(r.count() for r in kept.values())
                 for r in kept.values():
                     r.free()
@@ -738,7 +752,13 @@ def run_gpu_cbic5(args):
     sets_total = sum(sizes)
     pieces, owner = D.plan_ranges(sizes, world)
     my_total = sum(c for _, _, c in pieces[rank])
-    board = D.PeerScoreBoard(eng, sizes, owner) if args.exchange == "p2p" else None
+    board = None
+    if args.exchange == "p2p":
+        try:
+            board = D.PeerScoreBoard(eng, sizes, owner)
+        except D.PeerMemoryUnavailable as ex:     # raised on every rank together
+            if rank == 0:
+                print("bench: peer memory unavailable (%s): using --exchange nccl" % ex, file=sys.stderr)
     score_buf = torch.empty(max(1, my_total), dtype=torch.float32, device="cuda") if board is None else None
     owned = [v for v in range(p) if owner[v] == rank]
 

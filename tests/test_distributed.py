@@ -183,3 +183,151 @@ def test_peer_score_board_layout_single_process():
     board.fence()
     board.close()
     assert eng.freed == [base] and eng.syncs >= 2
+
+
+# ---- the control flow of the peer-memory gather on CPU: stand-in engines whose "device memory" is a file under /dev/shm ----------
+class _ShmEngine:
+    """peer_alloc creates a file, the 64-byte handle carries its name, peer_open maps it by name: both ranks then address the
+    same bytes, as CUDA IPC does for device memory.  `fail_open` makes the mapping fail, as a box without peer access would."""
+    def __init__(self, tag, fail_open=False):
+        self.tag, self.fail_open, self.maps, self.next = tag, fail_open, {}, 1 << 30
+
+    def _map(self, name, nbytes=None):
+        path = "/dev/shm/" + name
+        if nbytes is not None:
+            with open(path, "wb") as f:
+                f.truncate(nbytes)
+        mm = np.memmap(path, dtype=np.uint8, mode="r+")
+        base, self.next = self.next, self.next + ((len(mm) + 4095) // 4096 + 1) * 4096
+        self.maps[base] = (mm, path)
+        return base
+
+    def peer_alloc(self, nbytes):
+        name = "urlgpu_test_%s_%d" % (self.tag, os.getpid())
+        return self._map(name, nbytes), name.encode().ljust(64, b"\0")
+
+    def peer_open(self, handle):
+        if self.fail_open:
+            raise RuntimeError("peer access is not available")
+        return self._map(handle.rstrip(b"\0").decode())
+
+    def peer_close(self, ptr):
+        self.maps.pop(ptr)
+
+    def peer_free(self, ptr):
+        _, path = self.maps.pop(ptr)
+        os.unlink(path)
+
+    def view(self, ptr, nbytes):
+        for base, (mm, _) in self.maps.items():
+            if base <= ptr < base + len(mm):
+                return mm[ptr - base:ptr - base + nbytes]
+        raise KeyError(ptr)
+
+    def copy_to_host(self, host, ptr, nbytes):
+        if nbytes:
+            host.reshape(-1).view(np.uint8)[:nbytes] = self.view(ptr, nbytes)
+
+    def synchronize(self):
+        pass
+
+
+class _FakeResult:
+    def __init__(self, eng, masks, scores):
+        self.eng, self.masks, self.scores = eng, np.ascontiguousarray(masks, dtype=np.uint64), np.ascontiguousarray(scores, dtype=np.float32)
+
+    def count(self):
+        return len(self.scores)
+
+    def fetch_device(self, masks_ptr, scores_ptr, words_out=None, shift=0):
+        n = len(self.scores)
+        wide = np.zeros((n, words_out), dtype=np.uint64)
+        wide[:, 0] = self.masks.reshape(n, -1)[:, 0] << np.uint64(shift)     # the tests shift by less than 64 - p
+        self.eng.view(masks_ptr, 8 * words_out * n)[:] = wide.reshape(-1).view(np.uint8)
+        self.eng.view(scores_ptr, 4 * n)[:] = self.scores.view(np.uint8)
+        return n
+
+
+def _p2p_worker(rank, world, port, fail):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
+    eng = _ShmEngine("r%d" % rank, fail_open=(fail and rank == 1))
+    rng = np.random.default_rng(5)
+    p, words = 6, 2
+    owner = [0, 1, 0, 1, 1, 0]
+    full = {v: (rng.integers(1, 1 << 20, size=(10 + 3 * v, 1)).astype(np.uint64), rng.standard_normal(10 + 3 * v).astype(np.float32)) for v in range(p)}
+    mine = {v: _FakeResult(eng, *full[v]) for v in range(p) if owner[v] == rank}
+    if fail:
+        try:
+            D.gather_results_p2p(eng, mine, p, words, owner=owner)
+            raise AssertionError("the gather should have been refused on every rank")
+        except D.PeerMemoryUnavailable:
+            pass
+        # ... and every rank can fall back to the host gather in step
+        local = {v: (np.concatenate([full[v][0], np.zeros_like(full[v][0])], axis=1), full[v][1]) for v in mine}
+        got = D.gather_caches(local, p, words, "cpu", owner=owner)
+    else:
+        for _ in range(2):           # the second round reuses the mapped board
+            got = D.gather_results_p2p(eng, mine, p, words, owner=owner)
+        big = {v: _FakeResult(eng, np.tile(full[v][0], (40, 1)), np.tile(full[v][1], 40)) for v in mine}
+        grown = D.gather_results_p2p(eng, big, p, words, owner=owner)     # does not fit: the board is re-created collectively
+        if rank == 0:
+            assert all(len(grown[v][1]) == 40 * len(full[v][1]) for v in range(p))
+        D.release_boards()
+    if rank == 0:
+        assert sorted(got) == list(range(p))
+        for v in range(p):
+            assert np.array_equal(got[v][0][:, 0], full[v][0][:, 0]) and not got[v][0][:, 1].any()
+            assert np.array_equal(got[v][1].view(np.uint32), full[v][1].view(np.uint32))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_memory_gather_control_flow_on_cpu():
+    """gather_results_p2p with stand-in engines (shared files instead of CUDA IPC): counts and barriers over the gloo side
+    group, slices by rank and variable, board reuse and collective growth, the result equal to the inputs"""
+    mp.spawn(_p2p_worker, args=(2, 29871 + os.getpid() % 50, False), nprocs=2, join=True)
+
+
+def test_peer_memory_failure_is_agreed_on_by_all_ranks():
+    """a rank that cannot map the board makes EVERY rank raise PeerMemoryUnavailable (no deadlock), and the NCCL/gloo gather
+    then works in step"""
+    mp.spawn(_p2p_worker, args=(2, 29931 + os.getpid() % 50, True), nprocs=2, join=True)
+
+
+def _board_worker(rank, world, port, fail):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    D = importlib.import_module("urlearning-cpp_b200.distributed")
+    eng = _ShmEngine("b%d" % rank, fail_open=(fail and rank == 0))
+    sizes = [1000, 37, 5000, 64]
+    pieces, owner = D.plan_ranges(sizes, world, min_chunk=1)
+    if fail:
+        try:
+            D.PeerScoreBoard(eng, sizes, owner)
+            raise AssertionError("the board should have been refused on every rank")
+        except D.PeerMemoryUnavailable:
+            pass
+    else:
+        board = D.PeerScoreBoard(eng, sizes, owner)
+        truth = {v: np.arange(sizes[v], dtype=np.float32) + 1000 * v for v in range(len(sizes))}
+        for (v, first, count) in pieces[rank]:       # "score" my pieces straight into the owners' memory
+            eng.view(board.target(v, first), 4 * count)[:] = truth[v][first:first + count].view(np.uint8)
+        board.fence()
+        for v in range(len(sizes)):
+            if owner[v] == rank:
+                got = np.frombuffer(bytes(eng.view(board.target(v), 4 * sizes[v])), dtype=np.float32)
+                assert np.array_equal(got, truth[v]), v
+        board.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_score_board_two_ranks_on_cpu():
+    """PeerScoreBoard over two gloo ranks with the shared-file stand-in: every piece written through target() lands in its
+    owner's array; a rank that cannot map makes both ranks raise PeerMemoryUnavailable"""
+    mp.spawn(_board_worker, args=(2, 29991 + os.getpid() % 50, False), nprocs=2, join=True)
+    mp.spawn(_board_worker, args=(2, 30051 + os.getpid() % 50, True), nprocs=2, join=True)

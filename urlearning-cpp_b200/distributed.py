@@ -19,6 +19,11 @@ import torch.distributed as dist
 _PINNED = {}
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """CUDA IPC / peer access could not be set up on some rank.  Raised on EVERY rank together (the ranks agree through a
+    collective before anyone proceeds), so callers can fall back to the NCCL forms in step."""
+
+
 def stripe(p: int, rank: int, world: int):
     """variables owned by ``rank`` (score_main.cpp:137)."""
     return [v for v in range(p) if v % world == rank]
@@ -221,15 +226,30 @@ class PeerScoreBoard:
             self.offset[v] = fill[self.owner[v]]
             fill[self.owner[v]] += (s + 63) // 64 * 64
         self.base = [None] * self.world
-        self.base[self.rank], handle = eng.peer_alloc(4 * max(1, fill[self.rank]))
+        ok, why, handle = 1, "", bytes(64)
+        try:
+            self.base[self.rank], handle = eng.peer_alloc(4 * max(1, fill[self.rank]))
+        except Exception as ex:      # reported below, on every rank
+            ok, why = 0, repr(ex)
         if self.world > 1:
-            mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+            g = _side_group()
+            mine = torch.tensor(list(handle), dtype=torch.uint8)
             allh = [torch.empty_like(mine) for _ in range(self.world)]
-            dist.all_gather(allh, mine)
+            dist.all_gather(allh, mine, group=g)
             for r in range(self.world):
-                if r != self.rank:
-                    self.base[r] = eng.peer_open(bytes(allh[r].cpu().tolist()))
-            dist.barrier()
+                if r != self.rank and ok and bool(allh[r].any()):
+                    try:
+                        self.base[r] = eng.peer_open(bytes(allh[r].tolist()))
+                    except Exception as ex:
+                        ok, why = 0, repr(ex)
+                elif r != self.rank:
+                    ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=g)      # agreement: all proceed or all give up
+            ok = int(flag.item())
+        if not ok:
+            self._release()
+            raise PeerMemoryUnavailable("peer score board: " + (why or "another rank could not allocate or map it"))
 
     def target(self, v: int, first: int = 0) -> int:
         """device address of entry ``first`` of variable v's raw-score array, in its owner's memory"""
@@ -241,15 +261,18 @@ class PeerScoreBoard:
         if self.world > 1:
             dist.barrier()
 
-    def close(self):
-        self.fence()
+    def _release(self):
         for r in range(self.world):
             if self.base[r] is not None:
-                if r == self.rank:
-                    self.eng.peer_free(self.base[r])
-                else:
-                    self.eng.peer_close(self.base[r])
+                try:
+                    (self.eng.peer_free if r == self.rank else self.eng.peer_close)(self.base[r])
+                except Exception:
+                    pass
             self.base[r] = None
+
+    def close(self):
+        self.fence()
+        self._release()
 
 
 _BOARD = {}
@@ -279,15 +302,34 @@ def _cache_board(eng, total: int, words: int, dst: int):
     if b is not None:
         dist.barrier(group=g)
         (b["eng"].peer_free if rank == dst else b["eng"].peer_close)(b["ptr"])
+        _BOARD.pop(dst, None)
     cap = int(total * 1.5) + 4096
     handle = torch.zeros(64, dtype=torch.uint8)
-    ptr = None
+    ptr, ok, why = None, 1, ""
     if rank == dst:
-        ptr, h = eng.peer_alloc(cap * (8 * words + 4))
-        handle = torch.tensor(list(h), dtype=torch.uint8)
+        try:
+            ptr, h = eng.peer_alloc(cap * (8 * words + 4))
+            handle = torch.tensor(list(h), dtype=torch.uint8)
+        except Exception as ex:
+            ok, why = 0, repr(ex)
     dist.broadcast(handle, src=dst, group=g)
     if rank != dst:
-        ptr = eng.peer_open(bytes(handle.tolist()))
+        if bool(handle.any()):
+            try:
+                ptr = eng.peer_open(bytes(handle.tolist()))
+            except Exception as ex:
+                ok, why = 0, repr(ex)
+        else:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=g)      # agreement: all proceed or all give up
+    if int(flag.item()) == 0:
+        if ptr is not None:
+            try:
+                (eng.peer_free if rank == dst else eng.peer_close)(ptr)
+            except Exception:
+                pass
+        raise PeerMemoryUnavailable("gather board: " + (why or "another rank could not allocate or map it"))
     _BOARD[dst] = {"ptr": ptr, "cap": cap, "words": words, "eng": eng}
     return ptr, cap
 
@@ -327,8 +369,9 @@ def gather_results_p2p(eng, results: dict, p: int, words: int, dst: int = 0, own
             rank, *[1e3 * (tt[i + 1] - tt[i]) for i in range(4)]), flush=True)
     if rank != dst:
         return None
-    land_m = _landing("recv_m", max(total, 1) * words, torch.int64, True).view(-1, words)
-    land_s = _landing("recv_s", max(total, 1), torch.float32, True)
+    pin = torch.cuda.is_available()
+    land_m = _landing("recv_m", max(total, 1) * words, torch.int64, pin).view(-1, words)
+    land_s = _landing("recv_s", max(total, 1), torch.float32, pin)
     lm, ls = land_m.numpy(), land_s.numpy()
     eng.copy_to_host(lm, ptr, 8 * words * total)
     eng.copy_to_host(ls, ptr + 8 * words * cap, 4 * total)
