@@ -416,7 +416,8 @@ static float fnml_reg(int N, int K) {
 }
 /* fnml_scoring_function.h: getRegretCache — one row: out[N] = (float)log(reg(N, r)), N = 0..n_max */
 extern "C" void orc_log_regret(int64_t n_max, int r, float *out) {
-    for (int64_t N = 0; N <= n_max; N++) out[N] = (float)std::log((double)fnml_reg((int)N, r));
+    /* log(float) in C++ is the float overload (logf): the reference includes <math.h> and passes reg()'s float result */
+    for (int64_t N = 0; N <= n_max; N++) out[N] = std::log(fnml_reg((int)N, r));
 }
 
 struct FnmlCtx { BicCtx b; std::vector<std::vector<float>> regret; /* by arity, built on demand */ };
@@ -519,8 +520,8 @@ extern "C" int orc_fnml_score_many(const uint8_t *codes, int64_t n, int p, const
  *   :115-118: every non-empty parent configuration: score += lg_ij; score -= lgamma(a_ij + n_ij)
  * mode 0: every bracket [temp - lg_ijk], [lg_ij - lgamma(.)] in FP64, rounded to the 2^-30 grid, summed exactly, one final
  *         rounding to float32 — the order-independent contract the device implements (bic_kernels.cuh score_configs_bdeu).
- * mode 1: literal float32 running sum: cells in contingency-tree DFS order, then configurations in ascending paIdx
- *         (boost::unordered_map order there). */
+ * mode 1: literal float32 running sum with lgammaf (lgamma(float) under <math.h> in C++ is the float overload): cells in
+ *         contingency-tree DFS order, then configurations in ascending paIdx (boost::unordered_map order there). */
 static int bdeu_score_one(const BicCtx &c, float ess, int v, uint64_t parents, int mode, std::vector<int32_t> &counts, float *score_out) {
     int64_t cells = orc_bic_cells(c.card, c.p, v, parents);
     if (cells < 0) return fail("contingency table too large");
@@ -560,14 +561,16 @@ static int bdeu_score_one(const BicCtx &c, float ess, int v, uint64_t parents, i
         if (vars[j] == v) stride[j] = 1;
         else { stride[j] = b; b *= c.card[vars[j]]; }
     }
+    /* the reference's calls are lgamma(float): under <math.h> in C++ that is the float overload, lgammaf */
+    const float lg_ij_f = lgammaf_r(a_ij, &sg), lg_ijk_f = lgammaf_r(a_ijk, &sg);
     float score = 0;
     std::vector<int> digit(vars.size(), 0);
     while (true) {
         int64_t idx = 0;
         for (size_t j = 0; j < vars.size(); j++) idx += stride[j] * digit[j];
         if (counts[idx] > 0) {
-            float temp = lgamma_r(a_ijk + counts[idx], &sg);
-            score -= lg_ijk;
+            float temp = lgammaf_r(a_ijk + counts[idx], &sg);
+            score -= lg_ijk_f;
             score += temp;
         }
         int j = (int)vars.size() - 1;
@@ -578,8 +581,8 @@ static int bdeu_score_one(const BicCtx &c, float ess, int v, uint64_t parents, i
         int32_t nij = 0;
         for (int k = 0; k < rv; k++) nij += counts[j + k];
         if (nij > 0) {
-            score += lg_ij;
-            score -= lgamma_r(a_ij + nij, &sg);
+            score += lg_ij_f;
+            score -= lgammaf_r(a_ij + nij, &sg);
         }
     }
     *score_out = score;

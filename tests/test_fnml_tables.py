@@ -138,3 +138,30 @@ def test_product_regret_builder_equals_the_oracle(orc, tmp_path):
     lib.probe_log_regret(200000, 60, wide.ctypes.data)
     ref = orc.log_regret(200000, 60)
     assert np.array_equal(wide.view(np.uint32), ref.view(np.uint32)) and not np.all(np.isfinite(wide))
+
+
+@pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not built (reference sources were absent)")
+def test_regret_fnml_bdeu_against_the_reference_at_n_3000(orc, pkg, tmp_path):
+    """a synthetic network with 3000 records: the regret rows beyond N = 1000 (Szpankowski's approximation + the float32
+    recurrence) are bit-equal to the reference's compiled getRegretCache, and fNML / BDeu scores agree to accumulation noise"""
+    codes, card, edges, _ = pkg.datagen.discrete_bn(p=8, n=3000, seed=23, arities=(2, 3, 4), window=3, max_indegree=2)
+    path = str(tmp_path / "syn.csv")
+    pkg.datagen.write_csv(path, codes)
+    ref = ref_lib.Reference(path)
+    assert ref.n == 3000 and np.array_equal(ref.codes(), codes)       # first-appearance coding of the generator's columns
+    for r in sorted(set(int(c) for c in ref.card)):
+        mine = orc.log_regret(ref.n, r)
+        theirs = np.array([ref.regret(r, N) for N in range(ref.n + 1)], dtype=np.float32)
+        assert np.array_equal(mine.view(np.uint32), theirs.view(np.uint32)), r
+    rng = np.random.default_rng(11)
+    worst_f = worst_b = 0.0
+    for _ in range(120):
+        v = int(rng.integers(8))
+        k = int(rng.integers(0, 4))
+        m = sum(1 << int(i) for i in rng.choice(8, size=k, replace=False)) & ~(1 << v)
+        rf, rb = float(ref.fnml_score(v, m)), float(ref.bdeu_score(v, m, 1.0))
+        of = float(orc.fnml_score_many(codes, ref.card, v, [m], mode=0, threads=1)[0])
+        ob = float(orc.bdeu_score_many(codes, ref.card, v, [m], ess=1.0, mode=0, threads=1)[0])
+        worst_f = max(worst_f, abs(rf - of) / abs(rf))
+        worst_b = max(worst_b, abs(rb - ob) / abs(rb))
+    assert worst_f < 2e-5 and worst_b < 5e-5      # float32 running sums (and, for BDeu, lgammaf) over up to 256 cells at N = 3000 (SURVEY Q4: ~1e-5)

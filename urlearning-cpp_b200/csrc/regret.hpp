@@ -5,7 +5,7 @@
 // fNML(v | S) = LL(v | S) - sum_j log C(N_ij, r_v)   (fnml_scoring_function.cpp:28-74, no BIC penalty), with
 // C(N, 1) = 1, C(N, 2) = the K=2 regret (tabulated exactly for N <= 1000, Szpankowski's approximation above) and the
 // linear recurrence C(N, k) = C(N, k-1) + N/(k-2) C(N, k-2), evaluated in float32 in the reference's operation order.
-// The table entry is log() of that float, rounded to float32 — the reference's `regret->at(r)->at(N)`.
+// The table entry is logf() of that float — the reference's `regret->at(r)->at(N)`.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -49,7 +49,8 @@ inline float reg(int N, int K) {
 // out[N] = (float)log(reg(N, r)) for N = 0..n_max.  r = 0 is never looked up (an arity is at least 1).
 inline std::vector<float> log_regret(int64_t n_max, int r) {
     std::vector<float> out((size_t)n_max + 1);
-    for (int64_t N = 0; N <= n_max; N++) out[(size_t)N] = (float)std::log((double)reg((int)N, r));
+    // log of a float: the float overload (logf), as in the reference (`log(scoring::reg(n, r))` under <math.h>)
+    for (int64_t N = 0; N <= n_max; N++) { const float x = reg((int)N, r); out[(size_t)N] = std::log(x); }
     return out;
 }
 
