@@ -13,6 +13,7 @@
  *   urlsearch_astar         astar() / run_astar_on_one_scc                 astar/astar_main.cpp:216-546, 548-645
  *                           with heuristics::StaticPatternDatabase         heuristic/static_pattern_database.cpp:83-248
  *                           and PriorityQueue / CompareNodeStar            priority_queue/priority_queue-inl.h, base/node.h:124-135
+ *   urlsearch_triplet       the Triplet A* driver: astar(), process_triple  astar/triplet_astar.cpp:991-1622, 811-989
  * All functions return 0 (or a count) on success and a negative value on error (message via urlsearch_last_error).
  */
 #ifndef URLSEARCH_H
@@ -35,6 +36,10 @@ int64_t urlsearch_entries(urlsearch_cache *c, int variable, uint64_t *masks, flo
 int urlsearch_best_scores(urlsearch_cache *c, const char *type, int variable, const uint64_t *queries, int64_t nq, float *best, uint64_t *parents);
 /* skeleton_file NULL or "": no skeleton.  parents[v] = optimal parent set; returns the number of components searched. */
 int urlsearch_astar(urlsearch_cache *c, const char *type, int pd_count, const char *skeleton_file, float *total_cost, uint64_t *parents, int *nodes_expanded);
+/* Triplet A*: directed[i*p + j] = 1 iff i -> j, both directions set for an undirected edge (the reference's <netFile>.csv,
+ * README.md:40-45).  A skeleton file is required.  stats (optional, 5 ints): triples searched, colliders found, edges found
+ * outside the skeleton, edges oriented by the rules, A* nodes expanded. */
+int urlsearch_triplet(urlsearch_cache *c, const char *type, int pd_count, const char *skeleton_file, int32_t *directed, int *stats);
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,16 @@ SRC = base/bayesian_network.cpp base/skeleton.cpp ad_tree/ad_tree.cpp ad_tree/ad
 SEARCH_SRC = score_cache/score_cache.cpp score_cache/sparse_parent_list.cpp score_cache/sparse_parent_bitwise.cpp score_cache/sparse_parent_tree.cpp \
       heuristic/static_pattern_database.cpp priority_queue/priority_queue.cpp base/bayesian_network.cpp base/skeleton.cpp
 OUT = _ref
-all: $(OUT)/libref_bic.so $(OUT)/libref_search.so
+# the Triplet A* driver (astar/triplet_astar.cpp) as a binary: its main() is renamed away, ref_triplet_driver.cpp supplies one
+TRIPLET_SRC = heuristic/static_pattern_database.cpp heuristic/dynamic_pattern_database.cpp heuristic/combined_pattern_database.cpp \
+      heuristic/file_pattern_database.cpp priority_queue/priority_queue.cpp base/bayesian_network.cpp base/skeleton.cpp \
+      score_cache/score_cache.cpp score_cache/sparse_parent_list.cpp score_cache/sparse_parent_bitwise.cpp score_cache/sparse_parent_tree.cpp
+all: $(OUT)/libref_bic.so $(OUT)/libref_search.so $(OUT)/ref_triplet
+$(OUT)/ref_triplet: ref_triplet_driver.cpp $(REF)/urlearning/astar/triplet_astar.cpp $(addprefix $(REF)/urlearning/,$(TRIPLET_SRC)) $(wildcard shim/boost/*.hpp) $(wildcard shim/boost/*/*.hpp)
+	@mkdir -p $(OUT)
+	$(CXX) -std=c++11 -fno-strict-aliasing -O1 -w -pthread -include set -include map -include fstream -I shim -I $(REF) -Dmain=ref_triplet_unused_main -c $(REF)/urlearning/astar/triplet_astar.cpp -o $(OUT)/triplet_astar.o
+	$(CXX) -std=c++11 -fno-strict-aliasing -O1 -w -pthread -include set -include map -include fstream -I shim -I $(REF) -o $@ ref_triplet_driver.cpp $(OUT)/triplet_astar.o $(addprefix $(REF)/urlearning/,$(TRIPLET_SRC))
+	@rm -f $(OUT)/triplet_astar.o
 $(OUT)/libref_search.so: ref_search_driver.cpp $(addprefix $(REF)/urlearning/,$(SEARCH_SRC)) $(wildcard shim/boost/*.hpp)
 	@mkdir -p $(OUT)
 	$(CXX) $(CXXFLAGS) -shared -Wl,-Bsymbolic -o $@ ref_search_driver.cpp $(addprefix $(REF)/urlearning/,$(SEARCH_SRC))

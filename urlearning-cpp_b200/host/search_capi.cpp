@@ -2,6 +2,7 @@
 #include <memory>
 
 #include "search_host.hpp"
+#include "triplet_host.hpp"
 #include "urlearning_host.hpp"
 #include "urlsearch.h"
 
@@ -89,6 +90,30 @@ int urlsearch_astar(urlsearch_cache *c, const char *type, int pd_count, const ch
             for (int v = 0; v < p; v++) if ((comp >> v) & 1) parents[v] = r.parents[v];
         }
         return (int)comps.size();
+    } catch (const std::exception &e) { c->err = e.what(); return -1; }
+}
+
+// astar/triplet_astar.cpp:991-1622 — the Triplet A* driver (host/triplet_host.hpp)
+int urlsearch_triplet(urlsearch_cache *c, const char *type, int pd_count, const char *skeleton_file, int32_t *directed /*[p*p], row-major: [i*p+j] = 1 iff i -> j*/,
+                      int *stats /*optional [5]: triples, colliders, edges outside the skeleton, edges oriented by rules, nodes expanded*/) {
+    try {
+        const int p = c->cache.getVariableCount();
+        if (!skeleton_file || !*skeleton_file) throw std::runtime_error("Triplet A* needs a skeleton file");
+        auto own = make_spgs(c, type ? type : "list");
+        std::vector<BestScoreCalculator *> spgs;
+        for (auto &o : own) spgs.push_back(o.get());
+        urlhost::Skeleton sk;
+        const std::string sf = skeleton_file;
+        if (sf.find(".arc") + 4 == sf.size()) sk.read_arc_list_file(sf, p);
+        else sk.read_matrix_file(sf, p);
+        std::vector<varset> rows;
+        for (int v = 0; v < p; v++) rows.push_back(sk.get_neighbors(v).w[0]);
+        TripletDriver driver(p, spgs, rows, std::max(1, pd_count));
+        const TripletResult r = driver.run();
+        for (int i = 0; i < p; i++)
+            for (int j = 0; j < p; j++) directed[i * p + j] = r.directed[i][j];
+        if (stats) { stats[0] = r.triplesRun; stats[1] = r.vStructures; stats[2] = r.unfaithfulEdges; stats[3] = r.orientedByRules; stats[4] = (int)r.nodesExpanded; }
+        return 0;
     } catch (const std::exception &e) { c->err = e.what(); return -1; }
 }
 

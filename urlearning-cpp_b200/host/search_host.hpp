@@ -362,8 +362,10 @@ struct AstarResult {
 };
 
 // astar_main.cpp:216-546 for one connected component `the_scc` of the skeleton (edges empty: no skeleton restriction)
+// reopenClosed: the Triplet driver's copy of this loop (astar/triplet_astar.cpp:283-674) lacks the "closed nodes stay closed"
+// line and pushes a closed node again when it finds a better g for it (:541-555)
 inline AstarResult run_astar_on_one_scc(int variableCount, std::vector<BestScoreCalculator *> &spgs, const StaticPatternDatabase &heuristic, varset ancestors,
-                                        varset the_scc, const std::vector<varset> &edges) {
+                                        varset the_scc, const std::vector<varset> &edges, bool reopenClosed = false) {
     AstarResult out;
     std::unordered_map<varset, Node *> generatedNodes;
     PriorityQueue openList;
@@ -396,9 +398,14 @@ inline AstarResult run_astar_on_one_scc(int variableCount, std::vector<BestScore
                 continue;
             }
             Node *succ = slot;
-            if (succ->pqPos == -2) continue; // consistent heuristic: closed nodes stay closed
+            if (succ->pqPos == -2 && !reopenClosed) continue; // consistent heuristic: closed nodes stay closed
             const float g = u->g + spgs[leaf]->getScore(variables);
-            if (g < succ->g) { succ->leaf = (uint8_t)leaf; succ->g = g; openList.update(succ); }
+            if (g < succ->g) {
+                succ->leaf = (uint8_t)leaf;
+                succ->g = g;
+                if (succ->pqPos == -2) { succ->pqPos = 0; openList.push(succ); }
+                else openList.update(succ);
+            }
         }
     }
     if (goal) { // reconstructSolution (:140-166)

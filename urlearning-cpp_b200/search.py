@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liburlsearch.so")
 ABI_SYMBOLS = ["urlsearch_open", "urlsearch_close", "urlsearch_last_error", "urlsearch_variable_count", "urlsearch_name", "urlsearch_arity",
-               "urlsearch_meta", "urlsearch_entries", "urlsearch_best_scores", "urlsearch_astar"]
+               "urlsearch_meta", "urlsearch_entries", "urlsearch_best_scores", "urlsearch_astar", "urlsearch_triplet"]
 FLT_MAX = float(np.finfo(np.float32).max)
 _lib = None
 
@@ -39,6 +39,7 @@ def load_library():
         L.urlsearch_entries.argtypes = [vp, i32, vp, vp, i64]
         L.urlsearch_best_scores.argtypes = [vp, C.c_char_p, i32, vp, i64, vp, vp]
         L.urlsearch_astar.argtypes = [vp, C.c_char_p, i32, C.c_char_p, C.POINTER(C.c_float), vp, C.POINTER(C.c_int)]
+        L.urlsearch_triplet.argtypes = [vp, C.c_char_p, i32, C.c_char_p, vp, vp]
         _lib = L
     return _lib
 
@@ -80,6 +81,15 @@ class ScoreCache:
         if rc < 0:
             raise RuntimeError(self.lib.urlsearch_last_error(self._h).decode())
         return cost.value, parents, nodes.value, rc
+
+    def triplet(self, skeleton: str, kind: str = "list", pd_count: int = 2):
+        """Triplet A* (astar/triplet_astar.cpp) -> (M int32 [p, p] with M[i, j] = 1 iff i -> j, both set for an undirected edge;
+        stats dict)"""
+        m = np.zeros((self.p, self.p), dtype=np.int32)
+        st = np.zeros(5, dtype=np.int32)
+        if self.lib.urlsearch_triplet(self._h, kind.encode(), pd_count, skeleton.encode(), m.ctypes.data, st.ctypes.data) < 0:
+            raise RuntimeError(self.lib.urlsearch_last_error(self._h).decode())
+        return m, dict(zip(("triples", "colliders", "unfaithful_edges", "oriented_by_rules", "nodes_expanded"), (int(x) for x in st)))
 
     def close(self):
         if self._h:
