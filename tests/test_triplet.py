@@ -114,3 +114,23 @@ def test_against_the_compiled_reference_driver(orc, pkg, exe, tmp_path, seed):
         assert open(str(tmp_path / "mine.csv")).read() == open(str(tmp_path / "ref.csv")).read(), (seed, case, p, n, continuous, density)
         checked += 1
     assert checked >= 4
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ref_triplet not built (reference sources were absent)")
+@pytest.mark.parametrize("density,diag", [(0.12, False), (0.2, True)])
+def test_hepatitis_against_the_compiled_reference_driver(orc, exe, tmp_path, density, diag):
+    """configs[0]'s data (p = 20, discrete BIC) under a seeded sparse skeleton: clusters of up to ~15 variables, dozens of
+    triples, edges outside the skeleton, orientation rules — the same matrix as the reference's driver"""
+    rng = np.random.default_rng(int(density * 100))
+    p = 20
+    a = np.triu((rng.random((p, p)) < density).astype(int), 1)
+    a = a + a.T + (np.eye(p, dtype=int) if diag else 0)
+    skel = str(tmp_path / "skel.csv")
+    np.savetxt(skel, a, delimiter=",", fmt="%d")
+    pss = str(tmp_path / "hep.pss")
+    orc.score_file(os.path.join(DATA, "hepatitis.clean.csv"), pss, "BIC", skeleton=skel, has_header=True)
+    subprocess.check_call([REF, pss, skel, str(tmp_path / "ref")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call([exe, pss, "-k", skel, "-n", str(tmp_path / "mine"), "--quiet"])
+    mine, ref = _matrix(str(tmp_path / "mine.csv")), _matrix(str(tmp_path / "ref.csv"))
+    assert np.array_equal(mine, ref)      # (these two inputs hold a few exactly tied entries; the optima do not hinge on them)
+    assert mine.shape == (p, p) and mine.sum() > 0
