@@ -13,9 +13,13 @@
  * path.  The oracle is pinned against (a) oracle/_ref — the
  * reference's own BIC/AD-tree/enumeration/prune sources compiled against shim
  * headers (see oracle/Makefile, oracle/shim/), and (b) the Figure_1/2 golden
- * DAG/MEC matrices (MEC-level).  The cBIC arithmetic lives in mlpack/Armadillo
- * (absent, unpinned versions) and is restated from their published algorithm:
- * for cBIC the header says "parity unpinned" except through (b).
+ * DAG/MEC matrices (MEC-level).  For cBIC, oracle/_ref/libref_cbic.so compiles the
+ * reference's own BIC_OLS.cpp + score_calculator.cpp over a minimal Armadillo / mlpack
+ * (oracle/shim_arma): the standardisation, the score formula, the acceptance recursion
+ * as written and the store loop are PINNED to that compiled code (tests/test_ref_pin_cbic.py:
+ * key sets and values bit-equal).  The floating-point arithmetic INSIDE mlpack/Armadillo
+ * (absent, unpinned versions) is restated from their published algorithms on both sides:
+ * that part stays "parity unpinned" except through (b).
  */
 #ifndef URL_ORACLE_H
 #define URL_ORACLE_H

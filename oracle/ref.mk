@@ -16,7 +16,13 @@ OUT = _ref
 TRIPLET_SRC = heuristic/static_pattern_database.cpp heuristic/dynamic_pattern_database.cpp heuristic/combined_pattern_database.cpp \
       heuristic/file_pattern_database.cpp priority_queue/priority_queue.cpp base/bayesian_network.cpp base/skeleton.cpp \
       score_cache/score_cache.cpp score_cache/sparse_parent_list.cpp score_cache/sparse_parent_bitwise.cpp score_cache/sparse_parent_tree.cpp
-all: $(OUT)/libref_bic.so $(OUT)/libref_search.so $(OUT)/ref_triplet
+# the continuous-BIC scoring function (BIC_OLS.cpp) over a minimal Armadillo / mlpack (shim_arma/): pins the reference's own code
+# around the regression, see ref_cbic_driver.cpp
+CBIC_SRC = base/bayesian_network.cpp scoring_function/BIC_OLS.cpp scoring_function/score_calculator.cpp
+all: $(OUT)/libref_bic.so $(OUT)/libref_search.so $(OUT)/ref_triplet $(OUT)/libref_cbic.so
+$(OUT)/libref_cbic.so: ref_cbic_driver.cpp $(addprefix $(REF)/urlearning/,$(CBIC_SRC)) $(wildcard shim/boost/*.hpp) shim_arma/armadillo $(wildcard shim_arma/mlpack/*.hpp) $(wildcard shim_arma/mlpack/methods/linear_regression/*.hpp)
+	@mkdir -p $(OUT)
+	$(CXX) -std=c++11 -fno-strict-aliasing -O2 -fPIC -w -pthread -I shim_arma -I shim -I $(REF) -shared -Wl,-Bsymbolic -o $@ ref_cbic_driver.cpp $(addprefix $(REF)/urlearning/,$(CBIC_SRC))
 $(OUT)/ref_triplet: ref_triplet_driver.cpp $(REF)/urlearning/astar/triplet_astar.cpp $(addprefix $(REF)/urlearning/,$(TRIPLET_SRC)) $(wildcard shim/boost/*.hpp) $(wildcard shim/boost/*/*.hpp)
 	@mkdir -p $(OUT)
 	$(CXX) -std=c++11 -fno-strict-aliasing -O1 -w -pthread -include set -include map -include fstream -I shim -I $(REF) -Dmain=ref_triplet_unused_main -c $(REF)/urlearning/astar/triplet_astar.cpp -o $(OUT)/triplet_astar.o
