@@ -19,7 +19,16 @@ TRIPLET_SRC = heuristic/static_pattern_database.cpp heuristic/dynamic_pattern_da
 # the continuous-BIC scoring function (BIC_OLS.cpp) over a minimal Armadillo / mlpack (shim_arma/): pins the reference's own code
 # around the regression, see ref_cbic_driver.cpp
 CBIC_SRC = base/bayesian_network.cpp scoring_function/BIC_OLS.cpp scoring_function/score_calculator.cpp
-all: $(OUT)/libref_bic.so $(OUT)/libref_search.so $(OUT)/ref_triplet $(OUT)/libref_cbic.so
+# the `score` binary itself: the reference's score/score_main.cpp with its own main(), every scoring function of this project's
+# path behind it (BIC, fNML, BDeu over its AD-tree; cBIC over shim_arma), Boost replaced by working shims (program_options
+# parses, thread runs)
+SCORE_SRC = score/score_main.cpp base/bayesian_network.cpp base/skeleton.cpp ad_tree/ad_tree.cpp ad_tree/ad_node.cpp ad_tree/vary_node.cpp \
+      scoring_function/log_likelihood_calculator.cpp scoring_function/bic_scoring_function.cpp scoring_function/fnml_scoring_function.cpp \
+      scoring_function/bdeu_scoring_function.cpp scoring_function/score_calculator.cpp scoring_function/BIC_OLS.cpp
+all: $(OUT)/libref_bic.so $(OUT)/libref_search.so $(OUT)/ref_triplet $(OUT)/libref_cbic.so $(OUT)/ref_score
+$(OUT)/ref_score: $(addprefix $(REF)/urlearning/,$(SCORE_SRC)) $(wildcard shim/boost/*.hpp) shim_arma/armadillo $(wildcard shim_arma/mlpack/*.hpp) $(wildcard shim_arma/urlearning/scoring_function/*.h)
+	@mkdir -p $(OUT)
+	$(CXX) -std=c++11 -fno-strict-aliasing -O2 -w -pthread -include set -include map -include fstream -I shim_arma -I shim -I $(REF) -o $@ $(addprefix $(REF)/urlearning/,$(SCORE_SRC))
 $(OUT)/libref_cbic.so: ref_cbic_driver.cpp $(addprefix $(REF)/urlearning/,$(CBIC_SRC)) $(wildcard shim/boost/*.hpp) shim_arma/armadillo $(wildcard shim_arma/mlpack/*.hpp) $(wildcard shim_arma/mlpack/methods/linear_regression/*.hpp)
 	@mkdir -p $(OUT)
 	$(CXX) -std=c++11 -fno-strict-aliasing -O2 -fPIC -w -pthread -I shim_arma -I shim -I $(REF) -shared -Wl,-Bsymbolic -o $@ ref_cbic_driver.cpp $(addprefix $(REF)/urlearning/,$(CBIC_SRC))

@@ -1,5 +1,5 @@
-// Shim: just enough of boost::asio / boost::thread / boost::bind for scoring_function/score_calculator.cpp to
-// compile.  The per-variable time limit (-r) is not exercised through oracle/_ref: async_wait never fires.
+// Shim: just enough of boost::asio / boost::thread / boost::bind for scoring_function/score_calculator.cpp and the drivers'
+// main() functions.  The per-variable time limit (-r) is not exercised through oracle/_ref: async_wait never fires.
 #pragma once
 #include <functional>
 #include <thread>
@@ -20,9 +20,12 @@ public:
 template <class T> inline std::reference_wrapper<T> ref(T &t) { return std::ref(t); }
 struct bound_nothing { void operator()() const {} };
 template <class... A> inline bound_nothing bind(A &&...) { return bound_nothing(); }
-class thread {
+class thread { // a real thread (score_main.cpp's workers must run); detached on destruction like boost::thread
 public:
-    template <class F> explicit thread(F) {}
-    void join() {}
+    template <class F, class... A> explicit thread(F f, A... a) : t(f, a...) {}
+    ~thread() { if (t.joinable()) t.detach(); }
+    void join() { if (t.joinable()) t.join(); }
+private:
+    std::thread t;
 };
 } // namespace boost
