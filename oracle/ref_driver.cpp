@@ -10,8 +10,9 @@
  * resulting FloatMap back.  It pins the oracle: counts, enumeration, store rule, prune and (to float32
  * summation-order noise) scores are compared against the real reference code in tests/test_ref_pin.py.
  *
- * The continuous path (BIC_OLS.cpp) needs mlpack + Armadillo and is NOT built: "parity unpinned" for cBIC
- * beyond the Figure_1/2 golden DAG/MEC files.
+ * The continuous path (BIC_OLS.cpp) needs mlpack + Armadillo: it is built separately over a minimal shim of the two
+ * (ref_cbic_driver.cpp -> libref_cbic.so), which pins the reference's own code around the regression; the arithmetic
+ * inside mlpack / Armadillo stays "parity unpinned" beyond the Figure_1/2 golden DAG/MEC files.
  */
 #include <cstdint>
 #include <cstring>
