@@ -4,7 +4,8 @@
 namespace scoring {
 class AdaptiveLassoEntropyScoringFunction : public ScoringFunction {
 public:
-    AdaptiveLassoEntropyScoringFunction(datastructures::BayesianNetwork &, int, std::string, double, Constraints *, bool, bool, const datastructures::Skeleton * = NULL) { throw std::runtime_error("the lasso scoring functions are not built in this pin"); }
-    float calculateScore(int, varset, FloatMap &) { return 0; }
+    AdaptiveLassoEntropyScoringFunction(datastructures::BayesianNetwork &, int, std::string, double, Constraints *, bool, bool, const datastructures::Skeleton * = NULL) {}
+    float calculateScore(int, varset, FloatMap &) { throw std::runtime_error("the lasso scoring functions are not built in this pin"); }
+    void post_processing(std::vector<int> &, std::vector<varset> &) {}
 };
 }

@@ -1,5 +1,5 @@
 // shim: score_main.cpp can construct the lasso scoring functions (mlpack LARS); they are outside this project's path.  These
-// declarations let the reference's main() compile; choosing -f lasso / adaptive throws.  TEST INFRASTRUCTURE.
+// declarations let the reference's main() compile; scoring with -f lasso / adaptive throws; astar's print-only post-processing is a no-op.  TEST INFRASTRUCTURE.
 #pragma once
 #include <stdexcept>
 #include <string>
@@ -10,7 +10,8 @@
 namespace scoring {
 class LassoEntropyScoringFunction : public ScoringFunction {
 public:
-    LassoEntropyScoringFunction(datastructures::BayesianNetwork &, int, std::string, double, Constraints *, bool) { throw std::runtime_error("the lasso scoring functions are not built in this pin"); }
-    float calculateScore(int, varset, FloatMap &) { return 0; }
+    LassoEntropyScoringFunction(datastructures::BayesianNetwork &, int, std::string, double, Constraints *, bool) {}
+    float calculateScore(int, varset, FloatMap &) { throw std::runtime_error("the lasso scoring functions are not built in this pin"); }
+    void post_processing(std::vector<int> &, std::vector<varset> &) {}   // print-only in the reference (astar_main.cpp:482-491)
 };
 }
