@@ -110,6 +110,9 @@ int main(int argc, char **argv) {
         if (o.accept != "clean" && o.accept != "literal-zero" && o.accept != "literal") throw std::runtime_error("--accept takes clean or literal-zero");
         if (!o.constraintsFile.empty()) throw std::runtime_error("constraints files (-c) are not supported by the GPU score path");
         if (o.runningTime > 0) fprintf(stderr, "warning: -r (per-variable time limit) is ignored by the GPU score path\n");
+        if (o.deCampos)
+            fprintf(stderr, "warning: --enableDeCamposPruning (experimental in the reference: it drops a few sets while scoring, 7 of 23 200 on hepatitis) "
+                            "is not implemented; every set is scored\n");
 
         printf("URLearning, Score Calculator (urlgpu / B200)\n");
         printf("Input file: '%s'\n", o.inputFile.c_str());
